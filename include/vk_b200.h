@@ -1,0 +1,180 @@
+/* vk_b200.h -- C-ABI of libvk_b200.so: Vision-Kit's YOLO detection data path on B200.
+ *
+ * The reference (ArkarPhyo1310/Vision-Kit) has no FFI layer: its boundary is the Python
+ * call surface.  The host shims in vision_kit_b200/ keep that surface and
+ * reach the kernels only through the entry points declared here, loaded with ctypes.
+ * Each entry point cites the reference lines it replaces (paths relative to
+ * /root/reference/vision_kit/).
+ *
+ * Conventions
+ *   - return 0 = OK; < 0 = invalid argument (VK_E_*); > 0 = a cudaError_t.
+ *     vk_last_error() returns a thread-local message for the last non-zero return.
+ *   - the library never allocates or frees device memory: outputs and workspaces are
+ *     caller-owned device buffers (sizes from the vk_*_workspace_bytes helpers).
+ *   - all device work is enqueued on the given stream; no entry point synchronises.
+ *   - "host" pointers are read before the call returns; "dev" pointers are device memory.
+ *   - no CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef VK_B200_H_
+#define VK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vk_stream_t; /* a cudaStream_t (torch.cuda.current_stream().cuda_stream) */
+
+#define VK_OK 0
+#define VK_E_ARG (-1)      /* bad argument */
+#define VK_E_WORKSPACE (-2) /* workspace too small */
+#define VK_E_LIMIT (-3)    /* a compiled-in limit was exceeded (VK_MAX_*) */
+
+#define VK_MAX_LEVELS 4
+#define VK_MAX_ANCHORS 8     /* anchors per level */
+#define VK_MAX_NMS 32768     /* largest max_nms (reference: 30000 / 10000) */
+#define VK_MAX_DET 1024      /* largest max_det (reference default 300) */
+#define VK_MAX_SEGMENTS 2048 /* candidate segments per image (64 rows each) */
+
+/* ---------------------------------------------------------------- library info */
+int vk_version(void);                    /* 100*major + minor */
+const char* vk_last_error(void);         /* thread-local, never NULL */
+uint64_t vk_launch_count(void);          /* kernels launched by this library so far */
+int vk_build_arch(void);                 /* 100 => sm_100a */
+
+/* ---------------------------------------------------------------- letterbox
+ * Replaces utils/image_proc.py:12-60 `resize` (= demo/processing.py:59-97
+ * `ImageProcessor.resize`) and the normalise step of demo/processing.py:45-52
+ * `preprocess` / core/train/det_trainer.py:74-75.
+ */
+typedef struct VkLbGeom {
+    double ratio;          /* image_proc.py:27-31 */
+    double pad_w, pad_h;   /* the (dw, dh) the reference returns (:55,60): halved when letterbox */
+    int32_t new_w, new_h;  /* :34-35, banker's rounding */
+    int32_t top, bottom, left, right; /* :46-53 */
+    int32_t out_h, out_w;  /* canvas = new + pads (img_sz unless auto) */
+    int32_t needs_resize;  /* :42 */
+    int32_t reserved;
+} VkLbGeom;
+
+/* Host-only scalar set-up, float64 exactly as the reference's Python. */
+int vk_letterbox_geometry(int src_h, int src_w, int img_h, int img_w, int stride,
+                          int letterbox, int scaleup, int auto_, VkLbGeom* out);
+
+typedef struct VkLbDesc {  /* one source image; 48 bytes */
+    const uint8_t* src;    /* dev, HWC uint8, 3 channels */
+    int64_t pitch;         /* bytes between source rows */
+    int32_t src_h, src_w;
+    int32_t new_h, new_w;  /* resized interior (== src size when no resize) */
+    int32_t top, left;     /* interior origin on the canvas */
+    int32_t reserved0, reserved1;
+} VkLbDesc;
+
+#define VK_LB_F32_NCHW 0   /* float32 (B,3,H,W), value/255 (true division) */
+#define VK_LB_BF16_NCHW 1  /* bfloat16 (B,3,H,W), RN(float32(value/255)) */
+#define VK_LB_U8_NHWC 2    /* uint8 (B,H,W,3), what `resize` returns */
+
+size_t vk_letterbox_workspace_bytes(int batch, int out_h, int out_w);
+
+/* descs_host: `batch` descriptors (host).  descs_dev: the same array already on the
+ * device, or NULL to have the library upload descs_host into the workspace.
+ * swap_rb: 1 = source is BGR, write RGB (cv2.cvtColor BGR2RGB, demo/processing.py:47).
+ * pad_rgb: border colour in OUTPUT channel order, 0x00BBGGRR-style packing c0|c1<<8|c2<<16.
+ * Resize arithmetic = OpenCV INTER_LINEAR 8-bit fixed point, bit-exact. */
+int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* descs_dev, int batch,
+                       int out_h, int out_w, int swap_rb, uint32_t pad_rgb, int dst_fmt,
+                       void* dst, void* ws, size_t ws_bytes, vk_stream_t stream);
+
+/* ---------------------------------------------------------------- Detect decode
+ * Replaces the eval branch of models/heads/yolov5.py:54-78 and
+ * models/heads/yolov7.py:62-90 after the 1x1 conv.
+ */
+#define VK_HEAD_V5 0 /* xy = (s*2 + (g-0.5))*stride   yolov5.py:68,88 */
+#define VK_HEAD_V7 1 /* xy = (s*2 - 0.5 + g)*stride   yolov7.py:80,95 */
+
+typedef struct VkHeadCfg {
+    int32_t variant;             /* VK_HEAD_V5 | VK_HEAD_V7 */
+    int32_t nl, na, nc;          /* levels, anchors per level, classes; no = nc + 5 */
+    int32_t ny[VK_MAX_LEVELS], nx[VK_MAX_LEVELS];
+    float stride[VK_MAX_LEVELS];
+    float anchors[VK_MAX_LEVELS][2 * VK_MAX_ANCHORS]; /* pixels: (w,h) per anchor */
+} VkHeadCfg;
+
+int vk_head_rows(const VkHeadCfg* cfg);  /* sum_l na*ny*nx (25200 at 640) */
+
+/* levels[l]: dev float32 (B, na*no, ny_l, nx_l) contiguous.  pred: dev float32
+ * (B, rows, no).  raw[l]: dev float32 (B, na, ny_l, nx_l, no) or raw == NULL to skip the
+ * permuted logits copy the reference also returns (yolov5.py:60,78). */
+int vk_detect_decode(const VkHeadCfg* cfg, const float* const* levels, int batch,
+                     float* pred, float* const* raw, vk_stream_t stream);
+
+/* ---------------------------------------------------------------- candidates
+ * Confidence filter of utils/image_proc.py:99-151 (= demo/processing.py:110-164):
+ * obj > conf, cls *= obj, cxcywh->xyxy (utils/bboxes.py:103-111), multi-label
+ * `nonzero` or best-class `max`, optional class filter.
+ *
+ * A candidate set lives in caller-owned device buffers described by VkCandBuf.  Candidates
+ * are written in segments (one per kernel tile); the canonical order of the reference
+ * (row ascending, class ascending) is segment order x in-segment order.
+ */
+typedef struct VkCandBuf {
+    uint64_t* cand;      /* dev [batch][cap]: low 32 = score bits, high 32 = row*nc + cls */
+    float* boxes;        /* dev [batch][rows][4] xyxy of rows that produced candidates */
+    int32_t* counts;     /* dev [batch] candidates per image (may exceed cap => overflow) */
+    int32_t* seg_base;   /* dev [batch][segs] first slot of each segment */
+    int32_t* seg_count;  /* dev [batch][segs] */
+    int32_t cap;         /* candidate slots per image */
+    int32_t rows;        /* prediction rows per image */
+    int32_t segs;        /* segments per image (vk_filter_segments / vk_decode_filter_segments) */
+    int32_t nc;
+} VkCandBuf;
+
+int vk_filter_segments(int rows);                    /* for vk_filter_pred */
+int vk_decode_filter_segments(const VkHeadCfg* cfg); /* for vk_decode_filter */
+
+/* class_mask: dev uint32[(nc+31)/32] bitmap of allowed classes or NULL (classes=None). */
+int vk_filter_pred(const float* pred, int batch, int rows, int nc, float conf_thres,
+                   int multi_label, const uint32_t* class_mask, const VkCandBuf* out,
+                   vk_stream_t stream);
+
+/* Fused Detect decode + confidence filter straight from the conv outputs: the
+ * (B, rows, no) prediction tensor is never materialised. */
+int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch,
+                     float conf_thres, int multi_label, const uint32_t* class_mask,
+                     const VkCandBuf* out, vk_stream_t stream);
+
+/* ---------------------------------------------------------------- NMS
+ * utils/image_proc.py:154-182: top-max_nms cut by score (stable), class offset
+ * cls*max_wh, torchvision.ops.nms greedy suppression, [:max_det].
+ * iou_thres is the python float; the comparison is made the way torchvision's CPU kernel
+ * makes it (float32 IoU promoted to double).
+ *
+ * dets: dev float32 (B, max_det, 6) [x1,y1,x2,y2,conf,cls], rows >= det_counts[b] zeroed.
+ * keep_idx: dev int64 (B, max_det) or NULL -- indices torchvision.ops.nms returned
+ *   (into the candidate list the reference handed it), -1 padded.
+ * status: dev int32[batch] or NULL; bit0 = candidate buffer overflowed (results invalid).
+ */
+size_t vk_nms_workspace_bytes(int batch, int max_nms);
+
+int vk_nms_batched(const VkCandBuf* cand, int batch, float conf_unused, double iou_thres,
+                   int agnostic, int max_nms, int max_det, float max_wh, float* dets,
+                   int32_t* det_counts, int64_t* keep_idx, int32_t* status, void* ws,
+                   size_t ws_bytes, vk_stream_t stream);
+
+/* ---------------------------------------------------------------- small ops */
+/* utils/image_proc.py:63-80 `scale_coords` (+ utils/bboxes.py:50-59 `clip_coords`):
+ * in place on n rows of `row_stride` floats, columns 0..3 = xyxy.  clip_w/clip_h < 0
+ * skips the clip (demo/processing.py:99-105). */
+int vk_scale_coords(float* coords, int n, int row_stride, float pad_w, float pad_h,
+                    float gain, int subtract_pad, float clip_w, float clip_h,
+                    vk_stream_t stream);
+
+/* utils/bboxes.py:103-111 `cxcywh_to_xyxy` on n rows of 4 floats (out may alias in). */
+int vk_cxcywh_to_xyxy(const float* in, float* out, int n, vk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VK_B200_H_ */

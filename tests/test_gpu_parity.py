@@ -1,0 +1,380 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the golden
+fixtures generated from the live reference.  Integer/byte/index work is compared bit-exact;
+the Detect decode within 1e-5 relative (north_star tolerance)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port, restate
+from tests.golden.make_golden import LETTERBOX_CASES, NMS_CASES, case_seed
+from vision_kit_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DECODE_RTOL = 1e-5      # north_star: boxes/scores within 1e-5 relative fp32
+DECODE_ATOL = 1e-6
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def vk(cuda, vk_lib):
+    from vision_kit_b200 import heads, image_proc, ops, processing
+    import types
+    return types.SimpleNamespace(ops=ops, image_proc=image_proc, processing=processing, heads=heads)
+
+
+# --------------------------------------------------------------------------- letterbox
+@pytest.fixture(scope="module")
+def lb_gold(golden_dir):
+    return (json.load(open(os.path.join(golden_dir, "letterbox.json"))),
+            np.load(os.path.join(golden_dir, "letterbox.npz")))
+
+
+@pytest.mark.parametrize("case", LETTERBOX_CASES, ids=[c[0] for c in LETTERBOX_CASES])
+def test_letterbox_golden(case, lb_gold, vk):
+    name, h, w, sz, kw, full = case
+    meta, blob = lb_gold
+    m = meta[name]
+    img = synth.image_u8(h, w, case_seed(name))
+    out, (ratio, pad) = vk.image_proc.resize(sz, img.copy(), **kw)
+    assert list(out.shape) == m["shape"]
+    assert ratio == m["ratio"] and [float(pad[0]), float(pad[1])] == m["pad"]
+    if full:
+        assert np.array_equal(out, blob[name])
+    assert sha(out) == m["sha"]
+    ip = vk.processing.ImageProcessor(img_sz=sz, **kw)
+    ten, (r2, p2) = ip.preprocess(img.copy(), is_BGR=True)
+    assert list(ten.shape) == m["pre_shape"] and r2 == m["ratio"]
+    assert sha(ten.cpu().numpy()) == m["pre_sha"]          # fp32 value/255 bit-exact
+
+
+def test_letterbox_mixed_batch_vs_cv2(vk, cuda):
+    sizes = synth.mixed_sizes(24, seed=5)
+    imgs = [synth.image_u8(h, w, 100 + i) for i, (h, w) in enumerate(sizes)]
+    srcs = [torch.from_numpy(im).to(cuda) for im in imgs]
+    for dtype in (torch.float32, torch.bfloat16, torch.uint8):
+        out, rps = vk.ops.letterbox_batch(srcs, (640, 640), swap_rb=True, dtype=dtype)
+        out = out.cpu()
+        for i, im in enumerate(imgs):
+            exp_t, (ratio, pad) = ref_port.preprocess(im, (640, 640), is_bgr=True)
+            assert rps[i][0] == ratio and tuple(rps[i][1]) == tuple(pad)
+            if dtype == torch.float32:
+                assert torch.equal(out[i], exp_t[0]), f"image {i} {sizes[i]}"
+            elif dtype == torch.bfloat16:
+                assert torch.equal(out[i], exp_t[0].to(torch.bfloat16)), f"image {i} {sizes[i]}"
+            else:
+                exp_u8, _ = ref_port.letterbox(np.ascontiguousarray(im[:, :, ::-1]), (640, 640))
+                assert np.array_equal(out[i].numpy(), exp_u8), f"image {i} {sizes[i]}"
+
+
+def test_letterbox_norm255_all_values(vk, cuda):
+    # every uint8 value through both kernel paths (vector copy path and general path)
+    row = np.arange(256, dtype=np.uint8)
+    img = np.stack([np.roll(row, k) for k in range(3)], -1)[None].repeat(4, 0)      # (4,256,3)
+    img = np.ascontiguousarray(np.concatenate([img, img], 1))                      # (4,512,3)
+    src = torch.from_numpy(img).to(cuda)
+    exp = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))) / 255
+    out, _ = vk.ops.letterbox_batch([src], (4, 512), dtype=torch.float32)           # vector path
+    assert torch.equal(out[0].cpu(), exp)
+    out, _ = vk.ops.letterbox_batch([src[:, 1:]], (4, 512), letterbox=False, dtype=torch.float32)  # general
+    assert torch.equal(out[0, :, :, :511].cpu(), exp[:, :, 1:])
+
+
+def test_letterbox_random_sizes_vs_cv2(vk, cuda):
+    rng = np.random.Generator(np.random.PCG64(11))
+    for k in range(40):
+        h, w = int(rng.integers(8, 900)), int(rng.integers(8, 900))
+        sz = (int(rng.integers(32, 700)), int(rng.integers(32, 700)))
+        kw = dict(letterbox=bool(rng.integers(0, 2)), scaleup=bool(rng.integers(0, 2)))
+        img = synth.image_u8(h, w, 1000 + k)
+        exp, (ratio, pad) = ref_port.letterbox(img, sz, **kw)
+        out, (r2, p2) = vk.image_proc.resize(sz, img, **kw)
+        assert r2 == ratio and tuple(p2) == tuple(pad)
+        assert np.array_equal(out, exp), f"{(h, w)} -> {sz} {kw}"
+
+
+# --------------------------------------------------------------------------- decode
+def _cfg(vk, variant, img=640, nc=80):
+    anchors = synth.V5_ANCHORS if variant == "v5" else synth.V7_ANCHORS
+    grids = [(img // s, img // s) for s in synth.STRIDES]
+    return vk.ops.head_cfg(variant, nc, anchors, synth.STRIDES, grids), anchors
+
+
+@pytest.mark.parametrize("variant", ["v5", "v7"])
+def test_decode_golden_and_port(variant, golden_dir, vk, cuda):
+    g = np.load(os.path.join(golden_dir, "decode.npz"))
+    cfg, anchors = _cfg(vk, variant, img=64)
+    lv = synth.head_logits(2, seed=11, img=64)
+    pred, raws = vk.ops.detect_decode(cfg, [torch.from_numpy(x).to(cuda) for x in lv], want_raw=True)
+    np.testing.assert_allclose(pred.cpu().numpy(), g[f"{variant}_small_pred"], rtol=DECODE_RTOL, atol=DECODE_ATOL)
+    assert np.array_equal(raws[0].cpu().numpy(), g[f"{variant}_small_raw0"])
+    cfg, anchors = _cfg(vk, variant, img=640)
+    lv = synth.head_logits(1, seed=12, img=640)
+    pred = vk.ops.detect_decode(cfg, [torch.from_numpy(x).to(cuda) for x in lv])
+    np.testing.assert_allclose(pred.cpu().numpy()[:, ::97], g[f"{variant}_640_rows"], rtol=DECODE_RTOL, atol=DECODE_ATOL)
+    # full tensor + permuted raws against the library port (same torch ops as the reference)
+    lv = synth.head_logits(3, seed=13, img=640, clusters=10)
+    pred, raws = vk.ops.detect_decode(cfg, [torch.from_numpy(x).to(cuda) for x in lv], want_raw=True)
+    exp, exp_raws = ref_port.detect_decode([torch.from_numpy(x) for x in lv], anchors, synth.STRIDES, variant)
+    np.testing.assert_allclose(pred.cpu().numpy(), exp.numpy(), rtol=DECODE_RTOL, atol=DECODE_ATOL)
+    for a, b in zip(raws, exp_raws):
+        assert torch.equal(a.cpu(), b)
+
+
+def test_decode_odd_grid_and_classes(vk, cuda):
+    # 21x21 / 441-cell grids are not multiples of 4 or 64: scalar loads and ragged tiles
+    for nc, img in ((3, 672), (17, 336), (1, 96)):
+        anchors = synth.V5_ANCHORS
+        grids = [(img // s, img // s) for s in synth.STRIDES]
+        cfg = vk.ops.head_cfg("v5", nc, anchors, synth.STRIDES, grids)
+        lv = synth.head_logits(2, seed=nc, nc=nc, img=img)
+        pred, raws = vk.ops.detect_decode(cfg, [torch.from_numpy(x).to(cuda) for x in lv], want_raw=True)
+        exp, exp_raws = ref_port.detect_decode([torch.from_numpy(x) for x in lv], anchors, synth.STRIDES, "v5")
+        np.testing.assert_allclose(pred.cpu().numpy(), exp.numpy(), rtol=DECODE_RTOL, atol=DECODE_ATOL)
+        for a, b in zip(raws, exp_raws):
+            assert torch.equal(a.cpu(), b)
+
+
+def test_heads_module_matches_port(vk, cuda):
+    torch.manual_seed(0)
+    for variant, cls in (("v5", vk.heads.YoloV5Head), ("v7", vk.heads.YoloV7Head)):
+        head = cls(width=0.25) if variant == "v5" else cls(deploy=True)
+        head = head.to(cuda).eval()
+        chs = [m.in_channels for m in head.m]
+        x = [torch.randn(2, c, 64 // s * 2, 64 // s * 2, device=cuda) for c, s in zip(chs, (8, 16, 32))]
+        with torch.no_grad():
+            pred, raws = head(x)
+            feats = [head.m[i](x[i]).cpu() for i in range(3)]
+        anchors = synth.V5_ANCHORS if variant == "v5" else synth.V7_ANCHORS
+        exp, exp_raws = ref_port.detect_decode(feats, anchors, synth.STRIDES, variant)
+        np.testing.assert_allclose(pred.cpu().numpy(), exp.numpy(), rtol=DECODE_RTOL, atol=1e-5)
+        assert len(raws) == 3 and tuple(raws[0].shape) == tuple(exp_raws[0].shape)
+        head.export = True
+        with torch.no_grad():
+            out = head(x)
+        assert isinstance(out, tuple) and len(out) == 1 and torch.equal(out[0], pred)
+
+
+# --------------------------------------------------------------------------- filter + NMS
+@pytest.fixture(scope="module")
+def nms_gold(golden_dir):
+    return (json.load(open(os.path.join(golden_dir, "nms.json"))),
+            np.load(os.path.join(golden_dir, "nms.npz")))
+
+
+@pytest.mark.parametrize("case", NMS_CASES, ids=[c[0] for c in NMS_CASES])
+def test_nms_golden(case, nms_gold, vk, cuda):
+    name, rows, batch, mode, clusters, kw = case
+    meta, blob = nms_gold
+    p = synth.prediction(batch, rows, seed=case_seed(name), mode=mode, clusters=clusters,
+                         img=64 if rows == 252 else 640)
+    pt = torch.from_numpy(p).to(cuda)
+    before = pt.clone()
+    run_kw = dict(conf_thres=kw.get("conf_thres", 0.25), iou_thres=kw.get("iou_thres", 0.45),
+                  classes=kw.get("classes"), agnostic=kw.get("agnostic", False),
+                  multi_label=kw.get("multi_label", False), labels=(), max_det=kw.get("max_det", 300))
+    dets, keeps = vk.image_proc._run_nms(pt, max_nms=30000, want_keep=True, **run_kw)
+    assert torch.equal(pt, before), "nms mutated its input"
+    out = vk.image_proc.nms(pt, **kw)
+    for i in range(batch):
+        assert dets[i].shape[0] == meta[name]["counts"][i], f"count img {i}"
+        assert np.array_equal(keeps[i].cpu().numpy(), blob[f"{name}_keep{i}"]), f"keep img {i}"
+        assert np.array_equal(dets[i].cpu().numpy(), blob[f"{name}_dets{i}"]), f"dets img {i}"
+        assert torch.equal(out[i], dets[i])
+    # demo copy: ImageProcessor.nms, max_nms = 10000 (demo/processing.py:119)
+    ip = vk.processing.ImageProcessor(conf_thres=run_kw["conf_thres"], iou_thres=run_kw["iou_thres"],
+                                      filtered_classes=run_kw["classes"], agnostic=run_kw["agnostic"],
+                                      multi_label=run_kw["multi_label"], max_det=run_kw["max_det"])
+    out2 = ip.nms(pt)
+    for i in range(batch):
+        assert np.array_equal(out2[i].cpu().numpy(), blob[f"{name}_ipdets{i}"]), f"ip img {i}"
+
+
+@pytest.mark.parametrize("mode,kw", [
+    ("demo", dict(conf_thres=0.25, iou_thres=0.45)),
+    ("eval", dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)),
+    ("eval", dict(conf_thres=0.05, iou_thres=0.3, multi_label=True, agnostic=True, max_det=40)),
+])
+def test_nms_vs_port_random(mode, kw, vk, cuda):
+    p = synth.prediction(3, 3000, seed=21, mode=mode, clusters=12)
+    p[1, :, 4] = 0.0                                     # an image with no candidates
+    outs, keeps = ref_port.nms(torch.from_numpy(p.copy()), return_keep=True, **kw)
+    run_kw = dict(classes=None, agnostic=False, multi_label=False, labels=(), max_det=300)
+    run_kw.update(kw)
+    dets, k2 = vk.image_proc._run_nms(torch.from_numpy(p).to(cuda), max_nms=30000, want_keep=True, **run_kw)
+    for i in range(3):
+        assert np.array_equal(k2[i].cpu().numpy(), keeps[i].numpy()), f"keep img {i}"
+        assert np.array_equal(dets[i].cpu().numpy(), outs[i].numpy()), f"dets img {i}"
+    assert dets[1].shape == (0, 6)
+
+
+def test_nms_cut_ties_are_stable(vk, cuda):
+    # many equal scores straddling a small max_nms cut: lowest candidate index wins
+    p = synth.prediction(2, 2000, seed=8, mode="eval")
+    p[..., 5:] = np.round(p[..., 5:] * 16) / 16          # heavy score ties
+    p[..., 4] = 1.0
+    kw = dict(conf_thres=0.05, iou_thres=0.5, multi_label=True)
+    outs, keeps = ref_port.nms(torch.from_numpy(p.copy()), return_keep=True, max_nms=700, **kw)
+    dets, k2 = vk.image_proc._run_nms(torch.from_numpy(p).to(cuda), classes=None, agnostic=False, labels=(),
+                                      max_det=300, max_nms=700, want_keep=True, **kw)
+    for i in range(2):
+        assert np.array_equal(k2[i].cpu().numpy(), keeps[i].numpy())
+        assert np.array_equal(dets[i].cpu().numpy(), outs[i].numpy())
+
+
+def test_nms_labels_and_asserts(vk, cuda):
+    p = synth.prediction(2, 500, seed=4, mode="demo", clusters=3)
+    pt = torch.from_numpy(p).to(cuda)
+    with pytest.raises(AssertionError):
+        vk.image_proc.nms(pt, conf_thres=1.5)
+    with pytest.raises(RuntimeError):
+        vk.image_proc.nms(torch.from_numpy(p))           # CPU tensor: no fallback
+    labels = [torch.tensor([[3.0, 100.0, 120.0, 40.0, 50.0]]), torch.zeros((0, 5))]
+    out = vk.image_proc.nms(pt, labels=labels)
+    # restated: utils/image_proc.py:122-128 appends [box, 1.0, one-hot] rows
+    x = p.copy()
+    v = np.zeros((1, 85), np.float32); v[0, :4] = [100, 120, 40, 50]; v[0, 4] = 1; v[0, 8] = 1
+    exp0 = restate.nms_image(np.concatenate([x[0], v]))[0]
+    assert np.array_equal(out[0].cpu().numpy(), exp0)
+    assert np.array_equal(out[1].cpu().numpy(), restate.nms_image(x[1])[0])
+
+
+# --------------------------------------------------------------------------- fused path
+@pytest.mark.parametrize("variant,kw", [
+    ("v5", dict(conf_thres=0.25, iou_thres=0.45, multi_label=False)),
+    ("v7", dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)),
+    ("v5", dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, agnostic=True)),
+])
+def test_fused_decode_filter_equals_two_step_and_oracle(variant, kw, vk, cuda):
+    cfg, anchors = _cfg(vk, variant)
+    lv = synth.head_logits(3, seed=31, clusters=25)
+    dev = [torch.from_numpy(x).to(cuda) for x in lv]
+    kw = dict(kw)
+    iou = kw.pop("iou_thres"); agn = kw.pop("agnostic", False)
+    # two-step: materialised pred -> filter -> nms
+    pred = vk.ops.detect_decode(cfg, dev)
+    buf = vk.ops.filter_pred(pred, kw["conf_thres"], kw["multi_label"])
+    a = vk.ops.nms_batched(buf, iou, agn, want_keep=True)
+    # fused: logits -> candidates -> nms
+    buf2 = vk.ops.decode_filter(cfg, dev, kw["conf_thres"], kw["multi_label"])
+    b = vk.ops.nms_batched(buf2, iou, agn, want_keep=True)
+    assert torch.equal(buf.counts, buf2.counts)
+    assert torch.equal(a.counts, b.counts) and torch.equal(a.dets, b.dets) and torch.equal(a.keep, b.keep)
+    assert int(a.status.sum()) == 0
+    # oracle on OUR pred tensor: integer/index work must be bit-exact (SURVEY.md §7 protocol ii)
+    outs, keeps = ref_port.nms(pred.cpu(), iou_thres=iou, agnostic=agn, return_keep=True, **kw)
+    for i in range(3):
+        k = int(a.counts[i])
+        assert k == outs[i].shape[0]
+        assert np.array_equal(a.keep[i, :k].cpu().numpy(), keeps[i].numpy())
+        assert np.array_equal(a.dets[i, :k].cpu().numpy(), outs[i].numpy())
+    # end to end against the oracle's own decode (protocol iii): same counts, boxes within 1e-5
+    exp_pred, _ = ref_port.detect_decode([torch.from_numpy(x) for x in lv], anchors, synth.STRIDES, variant)
+    outs2 = ref_port.nms(exp_pred, iou_thres=iou, agnostic=agn, **kw)
+    for i in range(3):
+        k = int(a.counts[i])
+        if k == outs2[i].shape[0]:
+            np.testing.assert_allclose(a.dets[i, :k].cpu().numpy(), outs2[i].numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_head_forward_nms(vk, cuda):
+    torch.manual_seed(1)
+    head = vk.heads.YoloV5Head(width=0.25).to(cuda).eval()
+    x = [torch.randn(2, m.in_channels, 640 // s, 640 // s, device=cuda) * 3 for m, s in zip(head.m, (8, 16, 32))]
+    with torch.no_grad():
+        pred, _ = head(x)
+        out = head.forward_nms(x, conf_thres=0.05, iou_thres=0.5)
+    ref = vk.image_proc.nms(pred, conf_thres=0.05, iou_thres=0.5)
+    for i in range(2):
+        assert torch.equal(out.dets[i, : int(out.counts[i])], ref[i])
+
+
+# --------------------------------------------------------------------------- small ops
+def test_scale_coords_golden(golden_dir, vk, cuda):
+    g = np.load(os.path.join(golden_dir, "scale_coords.npz"))
+    for name, img0 in (("bus", (1080, 810)), ("wide", (375, 1242)), ("same", (640, 640))):
+        t = torch.from_numpy(g[f"{name}_in"].copy()).to(cuda)
+        ret = vk.image_proc.scale_coords((640, 640), t[:, :4], img0)
+        assert np.array_equal(t.cpu().numpy(), g[f"{name}_inplace"])
+        assert np.array_equal(ret.cpu().numpy(), g[f"{name}_ret"])
+        ip = vk.processing.ImageProcessor()
+        ip.resize(synth.image_u8(img0[0], img0[1], 3))
+        t2 = torch.from_numpy(g[f"{name}_in"].copy()).to(cuda)
+        r2 = ip.scale_coords(t2)
+        assert r2 is t2 and np.array_equal(t2.cpu().numpy(), g[f"{name}_demo"])
+
+
+def test_cxcywh_and_clip(vk, cuda):
+    from vision_kit_b200 import bboxes
+    rng = np.random.Generator(np.random.PCG64(2))
+    b = (rng.random((1000, 4), dtype=np.float32) * np.float32(640))
+    out = bboxes.cxcywh_to_xyxy(torch.from_numpy(b).to(cuda)).cpu().numpy()
+    assert np.array_equal(out, restate.cxcywh_to_xyxy(b))
+    t = torch.from_numpy(b - np.float32(100)).to(cuda)
+    bboxes.clip_coords(t, (300, 400))
+    e = b - np.float32(100)
+    e[:, [0, 2]] = e[:, [0, 2]].clip(0, 400); e[:, [1, 3]] = e[:, [1, 3]].clip(0, 300)
+    assert np.array_equal(t.cpu().numpy(), e)
+
+
+# --------------------------------------------------------------------------- full-size properties
+def _check_nms_properties(dets, counts, iou_thr, agnostic, max_det):
+    import torchvision
+    for i in range(dets.shape[0]):
+        k = int(counts[i])
+        assert 0 <= k <= max_det
+        d = dets[i, :k]
+        assert bool((d[1:, 4] <= d[:-1, 4]).all()), "scores not descending"
+        assert bool((dets[i, k:] == 0).all())
+        if k > 1:
+            off = d[:, 5:6] * (0 if agnostic else 7680)
+            iou = torchvision.ops.box_iou(d[:, :4] + off, d[:, :4] + off)
+            iou.fill_diagonal_(0)
+            assert float(iou.max()) <= iou_thr + 1e-6, "a kept pair overlaps more than the threshold"
+
+
+def test_config2_full_size_properties(vk, cuda):
+    # BASELINE config 2: B=64, demo-mode NMS, 640x640 sources (identity letterbox)
+    B = 64
+    imgs = torch.from_numpy(synth.images_u8(B, 640, 640, seed=0)).to(cuda)
+    out, rps = vk.ops.letterbox_batch(list(imgs), (640, 640), swap_rb=True)
+    exp = imgs.permute(0, 3, 1, 2).flip(1).float() / 255
+    assert torch.equal(out, exp)
+    lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=2, clusters=20)]
+    cfg, _ = _cfg(vk, "v5")
+    r1 = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.25, False), 0.45)
+    r2 = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.25, False), 0.45)
+    assert torch.equal(r1.dets, r2.dets) and torch.equal(r1.counts, r2.counts)      # deterministic
+    assert int(r1.counts.min()) > 0 and int(r1.status.sum()) == 0
+    _check_nms_properties(r1.dets, r1.counts, 0.45, False, 300)
+    pred = vk.ops.detect_decode(cfg, lv)
+    ref = vk.image_proc.nms(pred)
+    for i in range(B):
+        assert torch.equal(ref[i], r1.dets[i, : int(r1.counts[i])])
+
+
+def test_config3_eval_mode_properties(vk, cuda):
+    # BASELINE config 3 shape at a batch the oracle-free checks finish quickly
+    B = 8
+    lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=3, clusters=20)]
+    cfg, _ = _cfg(vk, "v5")
+    buf = vk.ops.decode_filter(cfg, lv, 0.001, True)
+    assert int(buf.counts.min()) > 30000, "workload must exercise the max_nms cut"
+    r1 = vk.ops.nms_batched(buf, 0.6, want_keep=True)
+    r2 = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.001, True), 0.6, want_keep=True)
+    assert torch.equal(r1.dets, r2.dets) and torch.equal(r1.keep, r2.keep)
+    assert int(r1.status.sum()) == 0
+    _check_nms_properties(r1.dets, r1.counts, 0.6, False, 300)
+    # image 0 against the oracle (one image of ~200k candidates takes the CPU a few seconds)
+    pred = vk.ops.detect_decode(cfg, [t[:1] for t in lv])
+    outs, keeps = ref_port.nms(pred.cpu(), conf_thres=0.001, iou_thres=0.6, multi_label=True, return_keep=True)
+    k = int(r1.counts[0])
+    assert np.array_equal(r1.keep[0, :k].cpu().numpy(), keeps[0].numpy())
+    assert np.array_equal(r1.dets[0, :k].cpu().numpy(), outs[0].numpy())

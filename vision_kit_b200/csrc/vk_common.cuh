@@ -1,0 +1,123 @@
+// Shared host/device helpers of libvk_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/vk_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvk_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace vk {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+int fail_arg(const char* fmt, ...);        // sets message, returns VK_E_ARG
+int fail_code(int code, const char* fmt, ...);
+int check_launch(const char* what);        // cudaGetLastError -> return code
+void count_launch(int n = 1);
+
+inline cudaStream_t as_stream(vk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+// 128-bit streaming load that does not allocate in L1 (data is touched once).
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const void* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const void* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+// streaming stores (evict-first: the output is not re-read by this kernel)
+__device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_f32(void* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(void* p, uint2 v) {
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// The sigmoid every kernel of the path shares, so that the fused decode+filter and the
+// two-step decode -> filter paths produce identical bits.  ex2.approx + fast divide:
+// relative error < 2e-6 for |x| < 40, inside the 1e-5 decode tolerance.
+__device__ __forceinline__ float sigmoidf_vk(float x) {
+    return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+
+// Detect decode of one element; every product/sum rounded separately.
+//   c: 0=cx 1=cy 2=w 3=h >=4: probability.  g: grid index of that axis.  anchor: pixels.
+__device__ __forceinline__ float decode_elem(float logit, int c, float g, float stride,
+                                             float anchor, int variant) {
+    const float s = sigmoidf_vk(logit);
+    if (c >= 4) return s;
+    const float t = __fmul_rn(s, 2.0f);
+    if (c < 2) {
+        const float u = (variant == VK_HEAD_V5)
+                            ? __fadd_rn(t, __fsub_rn(g, 0.5f))            // yolov5.py:68,88
+                            : __fadd_rn(__fsub_rn(t, 0.5f), g);           // yolov7.py:80
+        return __fmul_rn(u, stride);
+    }
+    return __fmul_rn(__fmul_rn(t, t), anchor);                            // yolov5.py:69
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of one int per thread over a block of up to 1024 threads.
+// `wsum` is shared scratch of 33 ints.  Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ int block_excl_scan(int v, int* wsum, int* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    const int inc = warp_incl_scan(v, lane);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = (lane < nw) ? wsum[lane] : 0;
+        int xi = warp_incl_scan(x, lane);
+        wsum[lane] = xi - x;
+        if (lane == 31) wsum[32] = xi;
+    }
+    __syncthreads();
+    const int r = wsum[w] + inc - v;
+    *total = wsum[32];
+    __syncthreads();
+    return r;
+}
+#endif  // __CUDACC__
+
+}  // namespace vk
