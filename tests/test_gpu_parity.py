@@ -345,8 +345,9 @@ def test_config2_full_size_properties(vk, cuda):
     B = 64
     imgs = torch.from_numpy(synth.images_u8(B, 640, 640, seed=0)).to(cuda)
     out, rps = vk.ops.letterbox_batch(list(imgs), (640, 640), swap_rb=True)
-    exp = imgs.permute(0, 3, 1, 2).flip(1).float() / 255
-    assert torch.equal(out, exp)
+    # expectation on the CPU: torch's CUDA `x / 255` multiplies by a reciprocal (1 ulp off)
+    exp = imgs.cpu().permute(0, 3, 1, 2).flip(1).float() / 255
+    assert torch.equal(out.cpu(), exp)
     lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=2, clusters=20)]
     cfg, _ = _cfg(vk, "v5")
     r1 = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.25, False), 0.45)

@@ -1,0 +1,94 @@
+"""Batched device pipeline of the hot path with pre-allocated buffers: what a serving or
+eval loop calls once per batch.
+
+    pipe = DetectPipeline("v5", batch=64)
+    x = pipe.preprocess(srcs)            # uint8 HWC CUDA sources -> (B,3,640,640) input tensor
+    feats = model_backbone_and_convs(x)  # the reference's PyTorch modules (not part of this repo)
+    out = pipe.postprocess(feats)        # fused decode + filter + NMS -> NmsOut (device tensors)
+    dets = pipe.to_list(out)             # the reference's list[(k,6)] (one synchronisation)
+
+Replaces, per batch, demo/processing.py:45-52 + models/heads/*.py eval forward +
+utils/image_proc.py:83-187, with no host synchronisation between the three kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops, synth
+
+
+class DetectPipeline:
+    def __init__(self, variant: str = "v5", nc: int = 80, img_sz=(640, 640), batch: int = 64,
+                 conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None, agnostic: bool = False,
+                 multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
+                 anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
+                 swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False):
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if isinstance(img_sz, int):
+            img_sz = (img_sz, img_sz)
+        self.img_sz, self.batch, self.dtype, self.color, self.swap_rb = tuple(img_sz), batch, dtype, color, swap_rb
+        self.conf_thres, self.iou_thres, self.classes = conf_thres, iou_thres, classes
+        self.agnostic, self.multi_label, self.max_det, self.max_nms = agnostic, multi_label, max_det, max_nms
+        if anchors is None:
+            anchors = synth.V5_ANCHORS if variant == "v5" else synth.V7_ANCHORS
+        grids = [(img_sz[0] // int(s), img_sz[1] // int(s)) for s in strides]
+        self.cfg = ops.head_cfg(variant, nc, anchors, strides, grids)
+        self.rows = ops.head_rows(self.cfg)
+        import ctypes as C
+        segs = _lib.lib().vk_decode_filter_segments(C.byref(self.cfg))
+        ml = bool(multi_label) and nc > 1
+        cap = cand_cap or ops.default_cap(self.rows, nc, ml)
+        self.cand = ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device)
+        self.out = ops.NmsOut(
+            torch.empty((batch, max_det, 6), dtype=torch.float32, device=self.device),
+            torch.empty((batch,), dtype=torch.int32, device=self.device),
+            torch.empty((batch, max_det), dtype=torch.int64, device=self.device) if want_keep else None,
+            torch.empty((batch,), dtype=torch.int32, device=self.device))
+        self.nms_ws = torch.empty(_lib.lib().vk_nms_workspace_bytes(batch, max_nms), dtype=torch.uint8,
+                                  device=self.device)
+        self.input = torch.empty((batch, 3, img_sz[0], img_sz[1]), dtype=dtype, device=self.device)
+        self.plan: Optional[ops.LetterboxPlan] = None
+
+    # -- letterbox + normalise
+    def plan_sources(self, srcs: Sequence[torch.Tensor]) -> ops.LetterboxPlan:
+        """Builds (and uploads) the descriptors for a set of source buffers.  The plan stays
+        valid while those buffers do: a loop that refills a fixed staging buffer plans once."""
+        if len(srcs) != self.batch:
+            raise ValueError(f"expected {self.batch} sources, got {len(srcs)}")
+        self.plan = ops.LetterboxPlan(srcs, self.img_sz, upload=True)
+        return self.plan
+
+    def preprocess(self, srcs: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        if srcs is not None:
+            self.plan_sources(srcs)
+        self.plan.run(self.input, swap_rb=self.swap_rb, color=self.color)
+        return self.input
+
+    def ratio_pads(self):
+        return self.plan.ratio_pads()
+
+    # -- fused Detect decode + confidence filter + NMS
+    def filter(self, feats: Sequence[torch.Tensor]) -> ops.CandBuf:
+        return ops.decode_filter(self.cfg, feats, self.conf_thres, self.multi_label, self.classes,
+                                 buf=self.cand)
+
+    def nms(self) -> ops.NmsOut:
+        return ops.nms_batched(self.cand, self.iou_thres, self.agnostic, self.max_nms, self.max_det,
+                               out=self.out, ws=self.nms_ws)
+
+    def postprocess(self, feats: Sequence[torch.Tensor]) -> ops.NmsOut:
+        self.filter(feats)
+        return self.nms()
+
+    # -- drop-in layout: decode to the (B, rows, no) tensor, then filter + NMS from it
+    def postprocess_materialised(self, feats: Sequence[torch.Tensor]):
+        pred = ops.detect_decode(self.cfg, feats)
+        buf = ops.filter_pred(pred, self.conf_thres, self.multi_label, self.classes)
+        return pred, ops.nms_batched(buf, self.iou_thres, self.agnostic, self.max_nms, self.max_det)
+
+    @staticmethod
+    def to_list(out: ops.NmsOut) -> List[torch.Tensor]:
+        counts = out.counts.cpu().tolist()
+        return [out.dets[i, :k] for i, k in enumerate(counts)]
