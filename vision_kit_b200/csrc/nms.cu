@@ -67,6 +67,7 @@ struct NmsScratch {              // lives after the sort arrays in dynamic share
     union {
         struct {                 // A1-A3
             int segoff[VK_MAX_SEGMENTS + 1];
+            int segbase[VK_MAX_SEGMENTS];
             union {
                 int hist[kHistBins];
                 struct { int gt[VK_MAX_SEGMENTS]; int eq[VK_MAX_SEGMENTS]; } c;
@@ -81,6 +82,7 @@ struct NmsScratch {              // lives after the sort arrays in dynamic share
             uint8_t csup[kChunk];
             uint8_t newk[kChunk];
         } b;
+        unsigned long long xchg[kNmsThreads];  // A4 (small sorts): cross-warp exchange
     };
 };
 
@@ -126,7 +128,9 @@ nms_image_kernel(const NmsArgs A) {
             int c = 0;
             if (t < A.segs) {
                 c = seg_count[t];
-                if (c > 0) c = max(0, min(c, A.cap - seg_base[t]));  // overflowed tail was never written
+                const int sb = seg_base[t];
+                X.a.segbase[t] = sb;
+                if (c > 0) c = max(0, min(c, A.cap - sb));  // overflowed tail was never written
             }
             int total;
             const int ex = block_excl_scan(c, wsum, &total);
@@ -179,11 +183,25 @@ nms_image_kernel(const NmsArgs A) {
     }
 
     // ---------------- A3: ordered compaction into shared memory
+    // sel[pos] = row*nc + cls of the candidate at compacted position pos
     const int M = cut ? K : n;
-    if (cut) {
+    if (!cut) {
+        // every candidate is selected: one thread per canonical position, segment by binary search
+        for (int p = tid; p < n; p += kNmsThreads) {
+            int lo = 0, hi = A.segs;            // last t with segoff[t] <= p
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (X.a.segoff[mid] <= p) lo = mid; else hi = mid;
+            }
+            const uint64_t cd = cand[X.a.segbase[lo] + (p - X.a.segoff[lo])];
+            skey[p] = order_key((uint32_t)cd);
+            spos[p] = (uint16_t)p;
+            sel[p] = (uint32_t)(cd >> 32);
+        }
+    } else {
         for (int t = warp; t < A.segs; t += kNmsWarps) {
             const int cnt = X.a.segoff[t + 1] - X.a.segoff[t];
-            const int base = seg_base[t];
+            const int base = X.a.segbase[t];
             int gt = 0, eq = 0;
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 const int j = j0 + lane;
@@ -208,39 +226,32 @@ nms_image_kernel(const NmsArgs A) {
             carry_gt += tg; carry_eq += te;
         }
         __syncthreads();
-    }
-    for (int t = warp; t < A.segs; t += kNmsWarps) {
-        const int cnt = X.a.segoff[t + 1] - X.a.segoff[t];
-        if (cnt == 0) continue;
-        const int base = seg_base[t];
-        int eq_before = 0, pos0;
-        if (cut) {
-            eq_before = X.a.u.c.eq[t];
-            pos0 = X.a.u.c.gt[t] + min(eq_before, need_eq);
-        } else {
-            pos0 = X.a.segoff[t];
-        }
-        for (int j0 = 0; j0 < cnt; j0 += 32) {
-            const int j = j0 + lane;
-            const bool ok = j < cnt;
-            uint32_t key = 0;
-            if (ok) key = order_key((uint32_t)cand[base + j]);
-            bool take = ok;
-            if (cut) {
+        for (int t = warp; t < A.segs; t += kNmsWarps) {
+            const int cnt = X.a.segoff[t + 1] - X.a.segoff[t];
+            if (cnt == 0) continue;
+            const int base = X.a.segbase[t];
+            int eq_before = X.a.u.c.eq[t];
+            int pos0 = X.a.u.c.gt[t] + min(eq_before, need_eq);
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int j = j0 + lane;
+                const bool ok = j < cnt;
+                uint64_t cd = 0;
+                if (ok) cd = cand[base + j];
+                const uint32_t key = order_key((uint32_t)cd);
                 const bool is_eq = ok && key == tval;
                 const unsigned em = __ballot_sync(0xffffffffu, is_eq);
                 const int eq_rank = eq_before + __popc(em & ((1u << lane) - 1u));
-                take = ok && (key > tval || (is_eq && eq_rank < need_eq));
+                const bool take = ok && (key > tval || (is_eq && eq_rank < need_eq));
                 eq_before += __popc(em);
+                const unsigned tm = __ballot_sync(0xffffffffu, take);
+                const int pos = pos0 + __popc(tm & ((1u << lane) - 1u));
+                if (take) {
+                    skey[pos] = key;
+                    spos[pos] = (uint16_t)pos;
+                    sel[pos] = (uint32_t)(cd >> 32);
+                }
+                pos0 += __popc(tm);
             }
-            const unsigned tm = __ballot_sync(0xffffffffu, take);
-            const int pos = pos0 + __popc(tm & ((1u << lane) - 1u));
-            if (take) {
-                skey[pos] = key;
-                spos[pos] = (uint16_t)pos;
-                sel[pos] = (uint32_t)(base + j);
-            }
-            pos0 += __popc(tm);
         }
     }
     int Ps = 32;
@@ -249,21 +260,49 @@ nms_image_kernel(const NmsArgs A) {
     __syncthreads();
 
     // ---------------- A4: bitonic sort, "before" = higher score, then lower position
-    for (int k = 2; k <= Ps; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < (Ps >> 1); i += kNmsThreads) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const uint32_t ka = skey[lo], kb = skey[hi];
-                const uint16_t pa = spos[lo], pb = spos[hi];
-                const bool hi_before_lo = (kb > ka) || (kb == ka && pb < pa);
-                const bool descending_block = (lo & k) == 0;  // final order: "before" first
-                if (hi_before_lo == descending_block) {
-                    skey[lo] = kb; skey[hi] = ka;
-                    spos[lo] = pb; spos[hi] = pa;
+    if (Ps <= kNmsThreads) {
+        // one element per thread in a register: composite = score<<16 | (0xffff - pos), sorted
+        // descending; strides below 32 exchange by shuffle, the rest through shared memory
+        unsigned long long v = 0ull;
+        if (tid < Ps) v = ((unsigned long long)skey[tid] << 16) | (unsigned long long)(0xffffu - spos[tid]);
+        __syncthreads();   // skey/spos read before the scratch is reused as exchange buffer
+        for (int k = 2; k <= Ps; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long o;
+                if (j >= 32) {
+                    X.xchg[tid] = v;
+                    __syncthreads();
+                    o = X.xchg[tid ^ j];
+                    __syncthreads();
+                } else {
+                    o = __shfl_xor_sync(0xffffffffu, v, j);
                 }
+                const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
+                v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
             }
-            __syncthreads();
+        }
+        if (tid < Ps) {
+            skey[tid] = (uint32_t)(v >> 16);
+            spos[tid] = (uint16_t)(0xffffu - (uint32_t)(v & 0xffffull));
+        }
+        __syncthreads();
+    } else {
+        for (int k = 2; k <= Ps; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < (Ps >> 1); i += kNmsThreads) {
+                    const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                    const int hi = lo | j;
+                    const uint32_t ka = skey[lo], kb = skey[hi];
+                    const uint16_t pa = spos[lo], pb = spos[hi];
+                    const bool hi_before_lo = (kb > ka) || (kb == ka && pb < pa);
+                    const bool descending_block = (lo & k) == 0;  // final order: "before" first
+                    if (hi_before_lo == descending_block) {
+                        skey[lo] = kb; skey[hi] = ka;
+                        spos[lo] = pb; spos[hi] = pa;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
 
@@ -277,8 +316,7 @@ nms_image_kernel(const NmsArgs A) {
         const int cn = min(kChunk, M - chunk0);
         if (tid < kChunk) {
             if (tid < cn) {
-                const uint32_t phys = sel[spos[chunk0 + tid]];
-                const uint32_t idx = (uint32_t)(cand[phys] >> 32);
+                const uint32_t idx = sel[spos[chunk0 + tid]];
                 const uint32_t row = idx / (uint32_t)A.nc;
                 const float cls = (float)(idx - row * (uint32_t)A.nc);
                 const float4 bx = boxes[row];
@@ -327,21 +365,34 @@ nms_image_kernel(const NmsArgs A) {
             }
         }
         __syncthreads();
-        if (warp == 0) {  // phase 3: sequential resolve, lanes 0..7 hold the 256 alive bits
-            uint32_t alive = 0;
-            if (lane < kChunkWords)
-                for (int bit = 0; bit < 32; ++bit) {
-                    const int j = lane * 32 + bit;
-                    if (j < cn && !X.b.csup[j]) alive |= 1u << bit;
-                }
+        if (warp == 0) {  // phase 3: sequential resolve; every lane carries all 256 alive bits
+            uint32_t alive[kChunkWords];
+#pragma unroll
+            for (int wd = 0; wd < kChunkWords; ++wd) {
+                // lane `bit` of each ballot = "box wd*32+bit is a live candidate"
+                const int j = wd * 32 + lane;
+                alive[wd] = __ballot_sync(0xffffffffu, j < cn && !X.b.csup[j]);
+            }
             int kept = kept0, newc = 0;
-            for (int i = 0; i < cn; ++i) {
-                const uint32_t wv = __shfl_sync(0xffffffffu, alive, i >> 5);
-                if ((wv >> (i & 31)) & 1u) {
-                    if (lane == 0) X.b.newk[newc] = (uint8_t)i;
-                    ++newc; ++kept;
-                    if (lane < kChunkWords) alive &= ~X.b.mask[i][lane];
-                    if (kept >= A.max_det) break;
+            bool done = false;
+            const uint4* mrow = reinterpret_cast<const uint4*>(&X.b.mask[0][0]);
+            uint4 n0 = mrow[0], n1 = mrow[1];
+#pragma unroll
+            for (int wd = 0; wd < kChunkWords; ++wd) {
+                if (done || wd * 32 >= cn) break;
+                const int lim = min(32, cn - wd * 32);
+                for (int bit = 0; bit < lim; ++bit) {
+                    const int i = wd * 32 + bit;
+                    const uint4 m0 = n0, m1 = n1;
+                    const int nx = min(i + 1, kChunk - 1);   // prefetch the next row
+                    n0 = mrow[2 * nx]; n1 = mrow[2 * nx + 1];
+                    if ((alive[wd] >> bit) & 1u) {
+                        if (lane == 0) X.b.newk[newc] = (uint8_t)i;
+                        ++newc; ++kept;
+                        alive[0] &= ~m0.x; alive[1] &= ~m0.y; alive[2] &= ~m0.z; alive[3] &= ~m0.w;
+                        alive[4] &= ~m1.x; alive[5] &= ~m1.y; alive[6] &= ~m1.z; alive[7] &= ~m1.w;
+                        if (kept >= A.max_det) { done = true; break; }
+                    }
                 }
             }
             if (lane == 0) { s_kept = kept; s_newcount = newc; }
@@ -354,14 +405,12 @@ nms_image_kernel(const NmsArgs A) {
                 const int slot = kept0 + tid;
                 X.b.kbox[slot] = X.b.cbox[i];
                 X.b.karea[slot] = X.b.carea[i];
-                const uint32_t phys = sel[spos[chunk0 + i]];
-                const uint64_t cd = cand[phys];
-                const uint32_t idx = (uint32_t)(cd >> 32);
+                const uint32_t idx = sel[spos[chunk0 + i]];
                 const uint32_t row = idx / (uint32_t)A.nc;
                 const float4 bx = boxes[row];
                 float* o = dets + (size_t)slot * 6;     // image_proc.py:182 output[xi] = x[i]
                 o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-                o[4] = __uint_as_float((uint32_t)cd);
+                o[4] = __uint_as_float(unorder_key(skey[chunk0 + i]));
                 o[5] = (float)(idx - row * (uint32_t)A.nc);
                 if (keep_out) keep_out[slot] = cut ? (int64_t)(chunk0 + i) : (int64_t)spos[chunk0 + i];
             }
