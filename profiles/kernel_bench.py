@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Per-kernel roofline table on the GPU box (CUDA events, warm, inputs > L2 where possible):
+letterbox (identity / mixed-size resize, f32 / bf16), Detect decode (materialised, +raw),
+filter_pred, fused decode_filter and NMS in demo and eval mode.
+
+    python profiles/kernel_bench.py [--batch 64] > gpurun_out/kernels.json
+"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from vision_kit_b200 import _lib, ops, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--iters", type=int, default=30)
+args = ap.parse_args()
+B = args.batch
+dev = torch.device("cuda:0")
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+res = {}
+
+
+def timeit(fn, iters=args.iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, ms, nbytes, note=""):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    res[name] = {"ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 2), "GBps": round(gbs, 1),
+                 "frac_of_measured_peak": round(gbs / PEAK, 3), "images_per_s": round(B / (ms * 1e-3)), "note": note}
+    print(f"{name:34s} {ms*1e3:9.1f} us  {gbs:8.1f} GB/s  {gbs/PEAK:6.3f} of peak  {B/(ms*1e-3):12.0f} img/s  {note}", file=sys.stderr)
+
+
+# ---- letterbox
+imgs = torch.from_numpy(synth.images_u8(B, 640, 640, seed=0)).to(dev)
+for dt, nm, sz in ((torch.float32, "f32", 4), (torch.bfloat16, "bf16", 2)):
+    plan = ops.LetterboxPlan(list(imgs), (640, 640))
+    out = torch.empty((B, 3, 640, 640), dtype=dt, device=dev)
+    ms = timeit(lambda: plan.run(out, swap_rb=True))
+    report(f"letterbox identity 640 {nm}", ms, B * (640 * 640 * 3 + 3 * 640 * 640 * sz))
+sizes = synth.mixed_sizes(B, seed=5)
+srcs = [torch.from_numpy(synth.image_u8(h, w, 50 + i)).to(dev) for i, (h, w) in enumerate(sizes)]
+src_bytes = sum(h * w * 3 for h, w in sizes)
+for dt, nm, sz in ((torch.float32, "f32", 4), (torch.bfloat16, "bf16", 2)):
+    plan = ops.LetterboxPlan(srcs, (640, 640))
+    out = torch.empty((B, 3, 640, 640), dtype=dt, device=dev)
+    ms = timeit(lambda: plan.run(out, swap_rb=True))
+    report(f"letterbox mixed 480-1280 {nm}", ms, src_bytes + B * 3 * 640 * 640 * sz, "config 5 sources")
+# pure up-scale and exact 2x
+for (h, w), nm in (((480, 480), "up 480"), ((1280, 1280), "down 2x 1280")):
+    s2 = [torch.from_numpy(synth.image_u8(h, w, 7)).to(dev) for _ in range(B)]
+    plan = ops.LetterboxPlan(s2, (640, 640))
+    out = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev)
+    ms = timeit(lambda: plan.run(out, swap_rb=True))
+    report(f"letterbox {nm} f32", ms, B * (h * w * 3 + 3 * 640 * 640 * 4))
+del srcs, s2
+
+# ---- decode / filter / nms
+grids = [(640 // s, 640 // s) for s in synth.STRIDES]
+cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)
+lv = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
+in_bytes = B * 25200 * 85 * 4
+ms = timeit(lambda: ops.detect_decode(cfg, lv))
+report("detect_decode -> pred", ms, 2 * in_bytes)
+ms = timeit(lambda: ops.detect_decode(cfg, lv, want_raw=True))
+report("detect_decode -> pred + raw", ms, 3 * in_bytes, "the reference's full return value")
+pred = ops.detect_decode(cfg, lv)
+for mode, conf, ml, iou in (("demo", 0.25, False, 0.45), ("eval", 0.001, True, 0.6)):
+    buf = ops.filter_pred(pred, conf, ml)
+    ncand = int(buf.counts.sum())
+    ms = timeit(lambda: ops.filter_pred(pred, conf, ml, buf=buf))
+    report(f"filter_pred {mode}", ms, in_bytes + 8 * ncand, f"{ncand // B} candidates/img; bytes = full pred read")
+    buf2 = ops.decode_filter(cfg, lv, conf, ml)
+    ms = timeit(lambda: ops.decode_filter(cfg, lv, conf, ml, buf=buf2))
+    report(f"decode_filter {mode}", ms, in_bytes + 8 * ncand)
+    outb = ops.nms_batched(buf2, iou)
+    ws = torch.empty(_lib.lib().vk_nms_workspace_bytes(B, 30000), dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: ops.nms_batched(buf2, iou, out=outb, ws=ws), iters=10)
+    report(f"nms {mode}", ms, 24 * ncand + B * 300 * 24, f"{int(outb.counts.sum()) // B} dets/img")
+# plain logits (no planted clusters): SURVEY.md §8d base workload
+lv0 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=0)]
+buf3 = ops.decode_filter(cfg, lv0, 0.25, False)
+ms = timeit(lambda: ops.decode_filter(cfg, lv0, 0.25, False, buf=buf3))
+report("decode_filter demo (no clusters)", ms, in_bytes + 8 * int(buf3.counts.sum()), f"{int(buf3.counts.sum()) // B} candidates/img")
+print(json.dumps({"batch": B, "peak_GBps": PEAK, "kernels": res}))

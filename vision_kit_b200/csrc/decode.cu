@@ -26,6 +26,7 @@ struct HeadDev {
     int variant, nl, na, nc, no, rows, tiles;
     int ny[VK_MAX_LEVELS], nx[VK_MAX_LEVELS], nynx[VK_MAX_LEVELS];
     int row_base[VK_MAX_LEVELS], tile_start[VK_MAX_LEVELS + 1], tpa[VK_MAX_LEVELS];
+    int group_start[VK_MAX_LEVELS + 1];  // first block of each level for the chosen group size
     float stride[VK_MAX_LEVELS];
     float anchors[VK_MAX_LEVELS][2 * VK_MAX_ANCHORS];
     const float* lv[VK_MAX_LEVELS];
@@ -104,8 +105,22 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred) {
 }
 
 // ---------------------------------------------------------------------------------------
-// confidence filter back-end shared by the fused and the drop-in kernels
+// confidence filter: one block walks a GROUP of up to 8 consecutive tiles of one plane.
+//
+//   stage A  objectness of the whole group (<= 512 rows, 2 per thread, one DRAM round trip),
+//            ordered list of surviving rows per tile
+//   stage B  tiles with <= 8 survivors are "sparse": their rows (<= 64 for the group) are
+//            gathered into one staging buffer in a single round trip, evaluated, and their
+//            candidates claimed with ONE atomicAdd for the group
+//   stage C  the remaining "dense" tiles are loaded whole (coalesced planes / rows), one tile
+//            at a time, each with its own atomicAdd
+//
+// At demo thresholds (0.7 % of rows survive) a group costs ~3 dependent memory round trips
+// instead of 3 per tile; at eval thresholds every tile is dense and HBM-bound.
 // ---------------------------------------------------------------------------------------
+constexpr int kGroupMax = 8;
+constexpr int kItems = kTileS;  // rows evaluated per back-end call (64)
+
 struct FilterArgs {
     float conf;
     int multi_label;
@@ -116,62 +131,95 @@ struct FilterArgs {
     int32_t* seg_base;
     int32_t* seg_count;
     int cap, rows, segs, nc;
+    int group;                   // tiles per block, 1..kGroupMax
 };
 
 struct FilterSmem {
-    float obj[kTileS];
-    int cnt[kTileS];
-    int excl[kTileS];
-    int list[kTileS];   // passing rows, ascending
-    float best_v[kTileS];
-    int best_j[kTileS];
-    int npass, base;
+    float obj[kGroupMax * kTileS];
+    short tile_list[kGroupMax][kTileS];  // surviving rows of each tile, ascending
+    int wcnt[2 * kWarps];
+    int tile_np[kGroupMax];
+    int tile_first[kGroupMax + 1];       // first sparse item of each tile
+    int it_ai[kItems];                   // accessor index (staging slot or tile row)
+    int it_row[kItems];                  // prediction row within the image
+    float it_obj[kItems];
+    int it_cnt[kItems];
+    int it_excl[kItems + 1];
+    float it_bv[kItems];
+    int it_bj[kItems];
+    int base;
 };
 
 __device__ __forceinline__ bool class_allowed(const uint32_t* m, int c) {
     return m == nullptr || ((__ldg(m + (c >> 5)) >> (c & 31)) & 1u);
 }
 
-// Ordered list of the rows whose flag is set (warps 0 and 1 cover kTileS = 64 rows).
-__device__ __forceinline__ void build_pass_list(FilterSmem& S, bool pass) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __shared__ int first_half;
-    if (w < 2) {
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (w == 0 && lane == 0) first_half = __popc(m);
-        __syncwarp();
-        // second warp needs the first warp's count: publish through shared memory below
-        S.cnt[threadIdx.x] = 0;
-        if (pass) S.excl[threadIdx.x] = __popc(m & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    if (w < 2 && pass) S.list[S.excl[threadIdx.x] + (w ? first_half : 0)] = threadIdx.x;
-    __syncthreads();
+__device__ __forceinline__ float4 xyxy_from_cxcywh(float cx, float cy, float w, float h) {
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // utils/bboxes.py:103-111
+    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
 }
 
-// Phases 2-4: evaluate passing rows, claim slots, write candidates.
-//   val(r, c): class probability (c in [0, nc)) of tile row r -- already multiplied? no: raw prob.
-//   put(r, c, v) / get(r, c): scratch for the product (aliases the tile).
-//   box(r): xyxy of tile row r.
-template <class Tile>
-__device__ __forceinline__ void filter_backend(FilterSmem& S, Tile& T, const FilterArgs& A, int b,
-                                               int seg, int row0) {
+// ---- accessors: where the 5+nc values of item `ai` live and how they turn into numbers
+struct PlaneGeom {       // fused path: what is needed to decode a box from logits
+    int variant, nx, s0; // s0: spatial index of the group's first row inside its plane
+    float stride, aw, ah;
+    __device__ __forceinline__ float4 box(float l0, float l1, float l2, float l3, int sp) const {
+        const int gy = sp / nx, gx = sp - gy * nx;
+        return xyxy_from_cxcywh(decode_elem(l0, 0, (float)gx, stride, aw, variant),
+                                decode_elem(l1, 1, (float)gy, stride, ah, variant),
+                                decode_elem(l2, 2, 0.f, stride, aw, variant),
+                                decode_elem(l3, 3, 0.f, stride, ah, variant));
+    }
+};
+struct LogitTile {       // dense tile of logits [no][kTilePitch]; ai = row inside the tile
+    float* t; PlaneGeom g; int tile_s0;
+    __device__ __forceinline__ float prob(int ai, int c) const { return sigmoidf_vk(t[(5 + c) * kTilePitch + ai]); }
+    __device__ __forceinline__ void put(int ai, int c, float v) { t[(5 + c) * kTilePitch + ai] = v; }
+    __device__ __forceinline__ float get(int ai, int c) const { return t[(5 + c) * kTilePitch + ai]; }
+    __device__ __forceinline__ float4 box(int ai) const {
+        return g.box(t[ai], t[kTilePitch + ai], t[2 * kTilePitch + ai], t[3 * kTilePitch + ai], tile_s0 + ai);
+    }
+};
+struct LogitStage {      // gathered rows of logits [slot][no]; sp[slot] = spatial index in the plane
+    float* t; int no; PlaneGeom g; const int* sp;
+    __device__ __forceinline__ float prob(int ai, int c) const { return sigmoidf_vk(t[ai * no + 5 + c]); }
+    __device__ __forceinline__ void put(int ai, int c, float v) { t[ai * no + 5 + c] = v; }
+    __device__ __forceinline__ float get(int ai, int c) const { return t[ai * no + 5 + c]; }
+    __device__ __forceinline__ float4 box(int ai) const {
+        const float* p = t + ai * no;
+        return g.box(p[0], p[1], p[2], p[3], sp[ai]);
+    }
+};
+struct PredRows {        // decoded prediction rows [ai][no] (dense tile or gathered rows alike)
+    float* t; int no;
+    __device__ __forceinline__ float prob(int ai, int c) const { return t[ai * no + 5 + c]; }
+    __device__ __forceinline__ void put(int ai, int c, float v) { t[ai * no + 5 + c] = v; }
+    __device__ __forceinline__ float get(int ai, int c) const { return t[ai * no + 5 + c]; }
+    __device__ __forceinline__ float4 box(int ai) const {
+        const float* p = t + ai * no;
+        return xyxy_from_cxcywh(p[0], p[1], p[2], p[3]);
+    }
+};
+
+// Evaluates S.it_*[0..n_items): class products, per-item candidate counts, one atomicAdd for
+// the lot, then the ordered candidate writes.  Ends with S.it_excl[0..n_items] valid and
+// S.base = first claimed slot.  All threads of the block must call it.
+template <class Acc>
+__device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const FilterArgs& A, int b, int n_items) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nc = A.nc;
-    const int npass = S.npass;
-    // phase 2
-    for (int i = w; i < npass; i += kWarps) {
-        const int r = S.list[i];
-        const float obj = S.obj[r];
+    for (int i = w; i < n_items; i += kWarps) {
+        const int ai = S.it_ai[i];
+        const float obj = S.it_obj[i];
         int count = 0;
         if (A.multi_label) {
             for (int c0 = 0; c0 < nc; c0 += 32) {
                 const int c = c0 + lane;
                 bool flag = false;
                 if (c < nc) {
-                    const float prod = __fmul_rn(T.prob(r, c), obj);      // image_proc.py:135
-                    flag = (prod > A.conf) && class_allowed(A.class_mask, c);  // :141,151
-                    T.put(r, c, flag ? prod : -1.0f);
+                    const float prod = __fmul_rn(T.prob(ai, c), obj);               // image_proc.py:135
+                    flag = (prod > A.conf) && class_allowed(A.class_mask, c);       // :141,151
+                    T.put(ai, c, flag ? prod : -1.0f);
                 }
                 count += __popc(__ballot_sync(0xffffffffu, flag));
             }
@@ -181,49 +229,44 @@ __device__ __forceinline__ void filter_backend(FilterSmem& S, Tile& T, const Fil
             for (int c0 = 0; c0 < nc; c0 += 32) {
                 const int c = c0 + lane;
                 if (c < nc) {
-                    const float prod = __fmul_rn(T.prob(r, c), obj);
-                    if (prod > bv) { bv = prod; bj = c; }     // first max within the lane
+                    const float prod = __fmul_rn(T.prob(ai, c), obj);
+                    if (prod > bv) { bv = prod; bj = c; }      // first max within the lane
                 }
             }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {                     // first max across lanes
+            for (int o = 16; o; o >>= 1) {                      // first max across lanes (:145)
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
                 const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
                 if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
             }
-            const bool sel = (bj != 0x7fffffff) && (bv > A.conf) && class_allowed(A.class_mask, bj);  // :145-151
+            const bool sel = (bj != 0x7fffffff) && (bv > A.conf) && class_allowed(A.class_mask, bj);  // :147,151
             count = sel ? 1 : 0;
-            if (lane == 0) { S.best_v[r] = bv; S.best_j[r] = bj; }
+            if (lane == 0) { S.it_bv[i] = bv; S.it_bj[i] = bj; }
         }
-        if (lane == 0) S.cnt[r] = count;
+        if (lane == 0) S.it_cnt[i] = count;
     }
     __syncthreads();
-    // phase 3: exclusive scan of the 64 row counts, one atomic per tile
-    if (w == 0) {
-        const int a = S.cnt[2 * lane], c = S.cnt[2 * lane + 1];
+    if (w == 0) {   // exclusive scan of <= 64 counts, one atomic
+        const int i0 = 2 * lane, i1 = 2 * lane + 1;
+        const int a = (i0 < n_items) ? S.it_cnt[i0] : 0, c = (i1 < n_items) ? S.it_cnt[i1] : 0;
         const int inc = warp_incl_scan(a + c, lane);
-        S.excl[2 * lane] = inc - a - c;
-        S.excl[2 * lane + 1] = inc - c;
+        S.it_excl[i0] = inc - a - c;
+        S.it_excl[i1] = inc - c;
         if (lane == 31) {
-            const int total = inc;
-            const int base = total ? atomicAdd(A.counts + b, total) : 0;
-            S.base = base;
-            A.seg_base[(size_t)b * A.segs + seg] = base;
-            A.seg_count[(size_t)b * A.segs + seg] = total;
+            S.it_excl[kItems] = inc;
+            S.base = inc ? atomicAdd(A.counts + b, inc) : 0;
         }
     }
     __syncthreads();
-    // phase 4
     uint64_t* cand = A.cand + (size_t)b * A.cap;
-    for (int i = w; i < npass; i += kWarps) {
-        const int r = S.list[i];
-        if (S.cnt[r] == 0) continue;
-        const int row = row0 + r;
-        int pos = S.base + S.excl[r];
+    for (int i = w; i < n_items; i += kWarps) {
+        if (S.it_cnt[i] == 0) continue;
+        const int ai = S.it_ai[i], row = S.it_row[i];
+        int pos = S.base + S.it_excl[i];
         if (A.multi_label) {
             for (int c0 = 0; c0 < nc; c0 += 32) {
                 const int c = c0 + lane;
-                const float v = (c < nc) ? T.get(r, c) : -1.0f;
+                const float v = (c < nc) ? T.get(ai, c) : -1.0f;
                 const bool flag = v >= 0.0f;
                 const unsigned m = __ballot_sync(0xffffffffu, flag);
                 const int p = pos + __popc(m & ((1u << lane) - 1u));
@@ -232,159 +275,251 @@ __device__ __forceinline__ void filter_backend(FilterSmem& S, Tile& T, const Fil
                 pos += __popc(m);
             }
         } else if (lane == 0 && pos < A.cap) {
-            cand[pos] = ((uint64_t)(uint32_t)(row * nc + S.best_j[r]) << 32) | __float_as_uint(S.best_v[r]);
+            cand[pos] = ((uint64_t)(uint32_t)(row * nc + S.it_bj[i]) << 32) | __float_as_uint(S.it_bv[i]);
         }
-        if (lane == 0) A.boxes[(size_t)b * A.rows + row] = T.box(r);
+        if (lane == 0) A.boxes[(size_t)b * A.rows + row] = T.box(ai);
+    }
+    __syncthreads();
+}
+
+// Stage A for both kernels: S.obj holds the group's objectness (-1 for rows past the end).
+// Builds the per-tile ordered survivor lists and counts.  Returns the group's survivor count.
+__device__ __forceinline__ int survivors(FilterSmem& S, float conf, int ntiles) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool pa = S.obj[threadIdx.x] > conf;                 // image_proc.py:99
+    const bool pb = S.obj[threadIdx.x + kDecThreads] > conf;
+    const unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+    if (lane == 0) { S.wcnt[w] = __popc(ma); S.wcnt[kWarps + w] = __popc(mb); }
+    const int total = __syncthreads_count(pa) + __syncthreads_count(pb);
+    if (total == 0) return 0;
+    const unsigned lt = (1u << lane) - 1u;
+    if (pa) S.tile_list[w >> 1][__popc(ma & lt) + ((w & 1) ? S.wcnt[w - 1] : 0)] = (short)(threadIdx.x & 63);
+    if (pb) S.tile_list[4 + (w >> 1)][__popc(mb & lt) + ((w & 1) ? S.wcnt[kWarps + w - 1] : 0)] = (short)(threadIdx.x & 63);
+    if (threadIdx.x < kGroupMax) {
+        const int k = threadIdx.x;
+        const int base = (k < 4) ? 2 * k : kWarps + 2 * (k - 4);
+        S.tile_np[k] = (k < ntiles) ? S.wcnt[base] + S.wcnt[base + 1] : 0;
+    }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ bool tile_is_sparse(int np, int nvalid) { return np > 0 && np * 8 <= nvalid; }
+
+// Lays the sparse tiles' survivors out as items 0..n (staging slot = item index).
+// Returns n (<= 64).  tile_nvalid(k) = rows of tile k.
+template <class NV>
+__device__ __forceinline__ int plan_sparse_items(FilterSmem& S, int ntiles, int row0_group, NV tile_nvalid) {
+    if (threadIdx.x <= kGroupMax) {
+        int run = 0;
+        for (int k = 0; k < (int)threadIdx.x; ++k)
+            if (k < ntiles && tile_is_sparse(S.tile_np[k], tile_nvalid(k))) run += S.tile_np[k];
+        S.tile_first[threadIdx.x] = run;
+    }
+    __syncthreads();
+    const int run = S.tile_first[kGroupMax];
+    if (threadIdx.x < run) {
+        int k = 0;
+#pragma unroll
+        for (int q = 1; q < kGroupMax; ++q)
+            if ((int)threadIdx.x >= S.tile_first[q]) k = q;
+        const int r = S.tile_list[k][threadIdx.x - S.tile_first[k]];
+        S.it_ai[threadIdx.x] = threadIdx.x;
+        S.it_row[threadIdx.x] = row0_group + k * kTileS + r;
+        S.it_obj[threadIdx.x] = S.obj[k * kTileS + r];
+    }
+    __syncthreads();
+    return run;
+}
+
+// Items of one dense tile: its survivors, accessor index = row inside the tile.
+__device__ __forceinline__ int plan_dense_items(FilterSmem& S, int k, int row0_group) {
+    const int np = S.tile_np[k];
+    if (threadIdx.x < np) {
+        const int r = S.tile_list[k][threadIdx.x];
+        S.it_ai[threadIdx.x] = r;
+        S.it_row[threadIdx.x] = row0_group + k * kTileS + r;
+        S.it_obj[threadIdx.x] = S.obj[k * kTileS + r];
+    }
+    return np;
+}
+
+__device__ __forceinline__ void write_empty_segments(const FilterArgs& A, int b, int seg0, int ntiles) {
+    if (threadIdx.x < ntiles) {
+        A.seg_base[(size_t)b * A.segs + seg0 + threadIdx.x] = 0;
+        A.seg_count[(size_t)b * A.segs + seg0 + threadIdx.x] = 0;
     }
 }
 
-__device__ __forceinline__ float4 xyxy_from_cxcywh(float cx, float cy, float w, float h) {
-    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // utils/bboxes.py:103-111
-    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+// Segment table entries of the group's sparse and empty tiles after filter_items().
+template <class NV>
+__device__ __forceinline__ void write_sparse_segments(FilterSmem& S, const FilterArgs& A, int b, int seg0,
+                                                      int ntiles, int n_items, NV tile_nvalid) {
+    if (threadIdx.x < ntiles) {
+        const int k = threadIdx.x;
+        const int np = S.tile_np[k];
+        const bool sparse = tile_is_sparse(np, tile_nvalid(k));
+        if (sparse || np == 0) {
+            int sb = 0, sc = 0;
+            if (sparse && n_items > 0) {
+                const int f = S.tile_first[k];
+                const int e0 = S.it_excl[f];
+                const int e1 = (f + np >= n_items) ? S.it_excl[kItems] : S.it_excl[f + np];
+                sb = S.base + e0;
+                sc = e1 - e0;
+            }
+            A.seg_base[(size_t)b * A.segs + seg0 + k] = sb;
+            A.seg_count[(size_t)b * A.segs + seg0 + k] = sc;
+        }
+    }
 }
 
-// tile of logits [no][kTilePitch] (fused path)
-struct LogitTile {
-    float* t;
-    int variant, nx, s0;
-    float stride, aw, ah;
-    __device__ __forceinline__ float prob(int r, int c) const { return sigmoidf_vk(t[(5 + c) * kTilePitch + r]); }
-    __device__ __forceinline__ void put(int r, int c, float v) { t[(5 + c) * kTilePitch + r] = v; }
-    __device__ __forceinline__ float get(int r, int c) const { return t[(5 + c) * kTilePitch + r]; }
-    __device__ __forceinline__ float4 box(int r) const {
-        const int sp = s0 + r;
-        const int gy = sp / nx, gx = sp - gy * nx;
-        const float cx = decode_elem(t[0 * kTilePitch + r], 0, (float)gx, stride, aw, variant);
-        const float cy = decode_elem(t[1 * kTilePitch + r], 1, (float)gy, stride, ah, variant);
-        const float w = decode_elem(t[2 * kTilePitch + r], 2, 0.f, stride, aw, variant);
-        const float h = decode_elem(t[3 * kTilePitch + r], 3, 0.f, stride, ah, variant);
-        return xyxy_from_cxcywh(cx, cy, w, h);
+__device__ __forceinline__ void write_dense_segment(FilterSmem& S, const FilterArgs& A, int b, int seg) {
+    if (threadIdx.x == 0) {
+        A.seg_base[(size_t)b * A.segs + seg] = S.base;
+        A.seg_count[(size_t)b * A.segs + seg] = S.it_excl[kItems];
     }
-};
-
-// tile of decoded prediction rows [kTileS][no] (drop-in path)
-struct PredTile {
-    float* t;
-    int no;
-    __device__ __forceinline__ float prob(int r, int c) const { return t[r * no + 5 + c]; }
-    __device__ __forceinline__ void put(int r, int c, float v) { t[r * no + 5 + c] = v; }
-    __device__ __forceinline__ float get(int r, int c) const { return t[r * no + 5 + c]; }
-    __device__ __forceinline__ float4 box(int r) const {
-        const float* p = t + r * no;
-        return xyxy_from_cxcywh(p[0], p[1], p[2], p[3]);
-    }
-};
+}
 
 __global__ void __launch_bounds__(kDecThreads)
 decode_filter_kernel(const HeadDev H, const FilterArgs A) {
-    extern __shared__ float tile[];  // [no][kTilePitch]
+    extern __shared__ float buf[];  // dense tile [no][kTilePitch] or staging [64][no]
     __shared__ FilterSmem S;
-    const int b = blockIdx.y, seg = blockIdx.x;
-    const TileLoc q = locate_tile(H, seg);
-    const int no = H.no, nynx = H.nynx[q.l];
-    const float* __restrict__ in = H.lv[q.l] + ((size_t)(b * H.na + q.a) * no) * nynx + q.s0;
+    __shared__ int s_sp[kItems];
+    const int b = blockIdx.y;
+    const int G = A.group;
+    // locate the group: planes are (level, anchor); groups never straddle a plane
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < VK_MAX_LEVELS; ++i)
+        if (i < H.nl && (int)blockIdx.x >= H.group_start[i]) l = i;
+    const int rel = blockIdx.x - H.group_start[l];
+    const int gpa = ceil_div(H.tpa[l], G);
+    const int a = rel / gpa;
+    const int tile0 = (rel - a * gpa) * G;                 // first tile of the group inside the plane
+    const int ntiles = min(G, H.tpa[l] - tile0);
+    const int s0 = tile0 * kTileS;
+    const int no = H.no, nynx = H.nynx[l];
+    const int nrows = min(ntiles * kTileS, nynx - s0);
+    const int row0 = H.row_base[l] + a * nynx + s0;
+    const int seg0 = H.tile_start[l] + a * H.tpa[l] + tile0;
+    const float* __restrict__ in = H.lv[l] + ((size_t)(b * H.na + a) * no) * nynx + s0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    auto tile_nvalid = [&](int k) { return min(kTileS, nrows - k * kTileS); };
 
-    // phase 0: objectness plane of the tile (coalesced), image_proc.py:99
-    bool pass = false;
-    if (threadIdx.x < kTileS) {
-        float obj = 0.f;
-        if (threadIdx.x < q.nvalid) {
-            obj = sigmoidf_vk(ld_stream_f32(in + (size_t)4 * nynx + threadIdx.x));
-            pass = obj > A.conf;
-        }
-        S.obj[threadIdx.x] = obj;
+    // stage A: objectness plane of the group (coalesced)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = threadIdx.x + h * kDecThreads;
+        S.obj[r] = (r < nrows) ? sigmoidf_vk(ld_stream_f32(in + (size_t)4 * nynx + r)) : -1.0f;
     }
-    const int npass = __syncthreads_count(pass);
-    if (npass == 0) {
-        if (threadIdx.x == 0) {
-            A.seg_base[(size_t)b * A.segs + seg] = 0;
-            A.seg_count[(size_t)b * A.segs + seg] = 0;
-        }
+    __syncthreads();
+    if (survivors(S, A.conf, ntiles) == 0) {
+        write_empty_segments(A, b, seg0, ntiles);
         return;
     }
-    if (threadIdx.x == 0) S.npass = npass;
-    build_pass_list(S, pass);
+    const PlaneGeom geom{H.variant, H.nx[l], s0, H.stride[l], H.anchors[l][2 * a], H.anchors[l][2 * a + 1]};
 
-    // phase 1: bring the logits of the surviving rows into shared memory
-    if (npass * 8 > q.nvalid) {  // dense: coalesced planes
-        const bool vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[q.l]) & 15) == 0);
+    // stage B: sparse tiles, one gather for the whole group
+    const int n_sparse = plan_sparse_items(S, ntiles, row0, tile_nvalid);
+    if (n_sparse > 0) {
+        for (int i = w; i < n_sparse; i += kWarps) {
+            const int sp = S.it_row[i] - row0;              // row inside the group
+            if (lane == 0) s_sp[i] = s0 + sp;
+            for (int c = lane; c < no; c += 32) buf[i * no + c] = __ldg(in + (size_t)c * nynx + sp);
+        }
+        __syncthreads();
+        LogitStage T{buf, no, geom, s_sp};
+        filter_items(S, T, A, b, n_sparse);
+    }
+    write_sparse_segments(S, A, b, seg0, ntiles, n_sparse, tile_nvalid);
+    __syncthreads();
+
+    // stage C: dense tiles, coalesced plane loads
+    const bool vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[l]) & 15) == 0);
+    for (int k = 0; k < ntiles; ++k) {
+        const int np = S.tile_np[k], nv = tile_nvalid(k);
+        if (np == 0 || tile_is_sparse(np, nv)) continue;
+        const float* __restrict__ tin = in + k * kTileS;
         if (vec) {
             for (int e = threadIdx.x; e < no * (kTileS / 4); e += kDecThreads) {
                 const int c = e >> 4, s = (e & 15) << 2;
-                if (s < q.nvalid) {
-                    const float4 v = ld_stream_f4(in + (size_t)c * nynx + s);
-                    float* d = tile + c * kTilePitch + s;
+                if (s < nv) {
+                    const float4 v = ld_stream_f4(tin + (size_t)c * nynx + s);
+                    float* d = buf + c * kTilePitch + s;
                     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
                 }
             }
         } else {
             for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
                 const int c = e >> 6, s = e & 63;
-                if (s < q.nvalid) tile[c * kTilePitch + s] = ld_stream_f32(in + (size_t)c * nynx + s);
+                if (s < nv) buf[c * kTilePitch + s] = ld_stream_f32(tin + (size_t)c * nynx + s);
             }
         }
-    } else {                     // sparse: gather the few surviving rows, one sector per element
-        for (int i = w; i < npass; i += kWarps) {
-            const int r = S.list[i];
-            for (int c = lane; c < no; c += 32)
-                tile[c * kTilePitch + r] = __ldg(in + (size_t)c * nynx + r);
-        }
+        const int n_items = plan_dense_items(S, k, row0);
+        __syncthreads();
+        LogitTile T{buf, geom, s0 + k * kTileS};
+        filter_items(S, T, A, b, n_items);
+        write_dense_segment(S, A, b, seg0 + k);
+        __syncthreads();
     }
-    __syncthreads();
-
-    LogitTile T{tile, H.variant, H.nx[q.l], q.s0, H.stride[q.l], H.anchors[q.l][2 * q.a],
-                H.anchors[q.l][2 * q.a + 1]};
-    filter_backend(S, T, A, b, seg, q.row0);
 }
 
 __global__ void __launch_bounds__(kDecThreads)
 filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
-    extern __shared__ float tile[];  // [kTileS][no]
+    extern __shared__ float buf[];  // [64][no]: a dense tile or the gathered rows
     __shared__ FilterSmem S;
-    const int b = blockIdx.y, seg = blockIdx.x;
-    const int row0 = seg * kTileS;
-    const int nvalid = min(kTileS, A.rows - row0);
+    const int b = blockIdx.y;
+    const int G = A.group;
+    const int seg0 = blockIdx.x * G;
+    const int ntiles = min(G, A.segs - seg0);
+    const int row0 = seg0 * kTileS;
+    const int nrows = min(ntiles * kTileS, A.rows - row0);
     const float* __restrict__ in = pred + ((size_t)b * A.rows + row0) * no;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    auto tile_nvalid = [&](int k) { return min(kTileS, nrows - k * kTileS); };
 
-    bool pass = false;
-    if (threadIdx.x < kTileS) {
-        float obj = 0.f;
-        if (threadIdx.x < nvalid) {
-            obj = __ldg(in + (size_t)threadIdx.x * no + 4);
-            pass = obj > A.conf;                                   // image_proc.py:99
-        }
-        S.obj[threadIdx.x] = obj;
-    }
-    const int npass = __syncthreads_count(pass);
-    if (npass == 0) {
-        if (threadIdx.x == 0) {
-            A.seg_base[(size_t)b * A.segs + seg] = 0;
-            A.seg_count[(size_t)b * A.segs + seg] = 0;
-        }
-        return;
-    }
-    if (threadIdx.x == 0) S.npass = npass;
-    build_pass_list(S, pass);
-
-    if (npass * 4 > nvalid) {  // dense: the tile is one contiguous chunk of nvalid*no floats
-        const int n = nvalid * no;
-        if (((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((n & 3) == 0)) {
-            for (int e = threadIdx.x; e < (n >> 2); e += kDecThreads)
-                reinterpret_cast<float4*>(tile)[e] = ld_stream_f4(in + 4 * (size_t)e);
-        } else {
-            for (int e = threadIdx.x; e < n; e += kDecThreads) tile[e] = ld_stream_f32(in + e);
-        }
-    } else {
-        for (int i = w; i < npass; i += kWarps) {
-            const int r = S.list[i];
-            for (int c = lane; c < no; c += 32) tile[r * no + c] = __ldg(in + (size_t)r * no + c);
-        }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = threadIdx.x + h * kDecThreads;
+        S.obj[r] = (r < nrows) ? __ldg(in + (size_t)r * no + 4) : -1.0f;
     }
     __syncthreads();
-    PredTile T{tile, no};
-    filter_backend(S, T, A, b, seg, row0);
+    if (survivors(S, A.conf, ntiles) == 0) {
+        write_empty_segments(A, b, seg0, ntiles);
+        return;
+    }
+    const int n_sparse = plan_sparse_items(S, ntiles, row0, tile_nvalid);
+    if (n_sparse > 0) {
+        for (int i = w; i < n_sparse; i += kWarps) {
+            const float* src = in + (size_t)(S.it_row[i] - row0) * no;
+            for (int c = lane; c < no; c += 32) buf[i * no + c] = __ldg(src + c);
+        }
+        __syncthreads();
+        PredRows T{buf, no};
+        filter_items(S, T, A, b, n_sparse);
+    }
+    write_sparse_segments(S, A, b, seg0, ntiles, n_sparse, tile_nvalid);
+    __syncthreads();
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int np = S.tile_np[k], nv = tile_nvalid(k);
+        if (np == 0 || tile_is_sparse(np, nv)) continue;
+        const float* __restrict__ tin = in + (size_t)k * kTileS * no;   // nv*no contiguous floats
+        const int n = nv * no;
+        if (((reinterpret_cast<uintptr_t>(tin) & 15) == 0) && ((n & 3) == 0)) {
+            for (int e = threadIdx.x; e < (n >> 2); e += kDecThreads)
+                reinterpret_cast<float4*>(buf)[e] = ld_stream_f4(tin + 4 * (size_t)e);
+        } else {
+            for (int e = threadIdx.x; e < n; e += kDecThreads) buf[e] = ld_stream_f32(tin + e);
+        }
+        const int n_items = plan_dense_items(S, k, row0);
+        __syncthreads();
+        PredRows T{buf, no};
+        filter_items(S, T, A, b, n_items);
+        write_dense_segment(S, A, b, seg0 + k);
+        __syncthreads();
+    }
 }
 
 static int make_head(const VkHeadCfg* cfg, HeadDev* H, const char* who) {
@@ -432,7 +567,17 @@ static FilterArgs make_filter_args(const VkCandBuf* o, float conf, int multi_lab
     A.boxes = reinterpret_cast<float4*>(o->boxes);
     A.counts = o->counts; A.seg_base = o->seg_base; A.seg_count = o->seg_count;
     A.cap = o->cap; A.rows = o->rows; A.segs = o->segs; A.nc = o->nc;
+    A.group = 1;
     return A;
+}
+
+// Tiles per block: enough blocks for ~2 full waves of 8 resident blocks per SM, at most 8.
+static int choose_group(int batch, int tiles) {
+    const long blocks = (long)batch * tiles;
+    long g = blocks / (2L * kNumSMs * 8);
+    if (g < 1) g = 1;
+    if (g > kGroupMax) g = kGroupMax;
+    return (int)g;
 }
 
 }  // namespace vk
@@ -480,6 +625,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels
     if (int rc = make_head(cfg, &H, "vk_decode_filter")) return rc;
     if (batch == 0) return VK_OK;
     if (!levels || batch < 0) return fail_arg("vk_decode_filter: null/negative argument");
+    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_decode_filter: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_decode_filter: batch %d > 65535", batch);
     if (int rc = check_cand(out, H.rows, H.tiles, H.nc, "vk_decode_filter")) return rc;
     for (int l = 0; l < H.nl; ++l) {
@@ -492,8 +638,15 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels
     const size_t smem = (size_t)H.no * kTilePitch * sizeof(float);
     if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_decode_filter: nc=%d needs %zu B of shared memory", H.nc, smem);
     cudaFuncSetAttribute(decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
-    decode_filter_kernel<<<dim3(H.tiles, batch), kDecThreads, smem, stream>>>(H, A);
+    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
+    A.group = choose_group(batch, H.tiles);
+    int groups = 0;
+    for (int l = 0; l < H.nl; ++l) {
+        H.group_start[l] = groups;
+        groups += H.na * ceil_div(H.tpa[l], A.group);
+    }
+    for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) H.group_start[l] = groups;
+    decode_filter_kernel<<<dim3(groups, batch), kDecThreads, smem, stream>>>(H, A);
     count_launch();
     return check_launch("decode_filter_kernel");
 }
@@ -503,6 +656,7 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
                               vk_stream_t stream_) {
     if (batch == 0) return VK_OK;
     if (!pred || batch < 0 || rows <= 0 || nc < 1) return fail_arg("vk_filter_pred: null/negative argument");
+    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_filter_pred: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_filter_pred: batch %d > 65535", batch);
     const int segs = ceil_div(rows, kTileS);
     if (segs > VK_MAX_SEGMENTS) return fail_code(VK_E_LIMIT, "vk_filter_pred: %d rows > %d", rows, VK_MAX_SEGMENTS * kTileS);
@@ -514,8 +668,9 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
     const size_t smem = (size_t)no * kTileS * sizeof(float);
     if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_filter_pred: nc=%d needs %zu B of shared memory", nc, smem);
     cudaFuncSetAttribute(filter_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
-    filter_pred_kernel<<<dim3(segs, batch), kDecThreads, smem, stream>>>(pred, no, A);
+    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
+    A.group = choose_group(batch, segs);
+    filter_pred_kernel<<<dim3(ceil_div(segs, A.group), batch), kDecThreads, smem, stream>>>(pred, no, A);
     count_launch();
     return check_launch("filter_pred_kernel");
 }

@@ -7,11 +7,20 @@
 //   A2  n > max_nms only: exact radix select (11/11/10 bits) of the max_nms-th score; ties at
 //       the cut are resolved by canonical position (= the stable argsort the contract fixes)
 //   A3  ordered compaction of the selected candidates into shared (score, pos) arrays
-//   A4  bitonic sort on (score desc, pos asc)
-//   A5  greedy NMS over the sorted list in chunks of 256: each chunk is tested against the
-//       kept list (<= max_det boxes in shared memory), then against itself through a 256x256
-//       bit matrix resolved by one warp; stops as soon as max_det boxes are kept, which is
-//       exact because greedy NMS visits boxes in descending score order (image_proc.py:170).
+//   A4  bitonic sort on (score desc, pos asc); up to 1024 elements in registers + shuffles
+//   A5  greedy NMS over the sorted list in chunks of 256:
+//         1. each chunk box against the kept boxes of earlier chunks
+//         2. predecessor bit matrix pred[i] = { j < i in the chunk : IoU(j, i) > thr }
+//         3. fixed-point resolve: an undecided box with a kept predecessor is removed, one
+//            whose predecessors are all removed is kept.  The lowest undecided box is always
+//            decidable, so this ends with exactly the sequential greedy result after as many
+//            rounds as the longest suppression chain -- not after 256 dependent steps.
+//       Stops as soon as max_det boxes are kept, which is exact because greedy NMS visits
+//       boxes in descending score order (image_proc.py:170 truncates afterwards).
+//       Class-aware mode walks per-class hash lists (kept boxes and chunk boxes) so that only
+//       same-class pairs are ever tested.  That is exact while every coordinate seen so far
+//       lies within +-max_wh/2 (offset boxes of different classes are then disjoint); the
+//       first box outside that range switches the image to testing all pairs.
 //
 // IoU arithmetic: separate fp32 sub/mul/add/div (no FMA), strict '>' against the python-float
 // threshold promoted to double -- implemented as '>' against the largest float32 <= threshold.
@@ -26,6 +35,9 @@ constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kChunk = 256;
 constexpr int kChunkWords = kChunk / 32;
 constexpr int kHistBins = 2048;
+constexpr int kHash = 256;          // class hash buckets
+constexpr uint32_t kNil = 0xffffu;  // end of a hash list
+constexpr size_t kSmemLimit = 232448 - 256;  // 227 KB per CTA minus this kernel's static part
 
 struct NmsArgs {
     const uint64_t* cand;
@@ -41,9 +53,70 @@ struct NmsArgs {
     int32_t* det_counts;
     int64_t* keep_idx;
     int32_t* status;
-    uint32_t* sel;  // [batch][P]: compacted position -> physical candidate slot
+    uint32_t* sel;  // [batch][P]: compacted position -> row*nc + cls
     int P;          // sort capacity, power of two
 };
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Scratch after the sort arrays.  Phase A (A1-A3) and phase B (A5) alias; A4 uses `xchg`.
+struct ScratchA {
+    int* segoff;   // [segs + 1]
+    int* segbase;  // [segs]
+    int* hist;     // [kHistBins]        (A2)
+    int* gt;       // [segs]             (A3, aliases hist)
+    int* eq;       // [segs]
+    __host__ __device__ static size_t bytes(int segs) {
+        const size_t u = (size_t)kHistBins * 4 > (size_t)segs * 8 ? (size_t)kHistBins * 4 : (size_t)segs * 8;
+        return align16((size_t)(2 * segs + 1) * 4) + u;
+    }
+    __device__ ScratchA(unsigned char* p, int segs) {
+        segoff = reinterpret_cast<int*>(p);
+        segbase = segoff + segs + 1;
+        hist = reinterpret_cast<int*>(p + align16((size_t)(2 * segs + 1) * 4));
+        gt = hist;
+        eq = hist + segs;
+    }
+};
+struct ScratchB {
+    float4* kbox;      // [max_det] kept boxes (class-offset)
+    float4* cbox;      // [kChunk]
+    uint32_t* pred;    // [kChunk][kChunkWords]
+    uint32_t* kmeta;   // [max_det] cls << 16 | next kept slot of the bucket
+    int* khead;        // [kHash] newest kept slot per class bucket
+    uint32_t* ccnt2;   // [kHash / 2] chunk members per class bucket, two 16-bit counts per word
+    uint16_t* cstart;  // [kHash + 2] first member slot of each bucket (+ end)
+    uint16_t* members; // [kChunk] chunk rows grouped by class bucket
+    uint16_t* ccls;    // [kChunk]
+    uint32_t* kw;      // [2][3][kChunkWords] ping-pong kept | removed | undecided bits
+    uint32_t* kfinal;  // [kChunkWords] kept bits of the resolved chunk
+    uint8_t* state;    // [kChunk] 0 undecided, 1 kept, 2 removed
+    __host__ __device__ static size_t bytes(int max_det) {
+        return (size_t)max_det * 16 + kChunk * 16 + kChunk * kChunkWords * 4 + (size_t)max_det * 4 +
+               kHash * 4 + kHash * 2 + (kHash + 2) * 2 + kChunk * 2 * 2 + kChunkWords * 4 * 7 + kChunk;
+    }
+    __device__ ScratchB(unsigned char* p, int max_det) {
+        kbox = reinterpret_cast<float4*>(p);
+        cbox = kbox + max_det;
+        pred = reinterpret_cast<uint32_t*>(cbox + kChunk);
+        kmeta = pred + kChunk * kChunkWords;
+        khead = reinterpret_cast<int*>(kmeta + max_det);
+        ccnt2 = reinterpret_cast<uint32_t*>(khead + kHash);
+        cstart = reinterpret_cast<uint16_t*>(ccnt2 + kHash / 2);
+        members = cstart + kHash + 2;
+        ccls = members + kChunk;
+        kw = reinterpret_cast<uint32_t*>(ccls + kChunk);
+        kfinal = kw + 6 * kChunkWords;
+        state = reinterpret_cast<uint8_t*>(kfinal + kChunkWords);
+    }
+};
+
+static size_t nms_smem_bytes(int P, int segs, int max_det) {
+    size_t s = ScratchA::bytes(segs);
+    if (ScratchB::bytes(max_det) > s) s = ScratchB::bytes(max_det);
+    if ((size_t)kNmsThreads * 16 > s) s = (size_t)kNmsThreads * 16;   // A4 ping-pong exchange
+    return (size_t)P * 6 + align16(s);
+}
 
 __device__ __forceinline__ uint32_t order_key(uint32_t fbits) {  // float order -> unsigned order
     return fbits ^ ((fbits >> 31) ? 0xffffffffu : 0x80000000u);
@@ -51,51 +124,46 @@ __device__ __forceinline__ uint32_t order_key(uint32_t fbits) {  // float order 
 __device__ __forceinline__ uint32_t unorder_key(uint32_t k) {
     return k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu);
 }
+__device__ __forceinline__ float box_area(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
 
 // torchvision/csrc/ops/cpu/nms_kernel.cpp: suppress j when inter/(area_i+area_j-inter) > thr.
+// The division is only evaluated when a 1e-6-wide guard band around the threshold cannot
+// decide: fl(inter/den) > thr is implied by inter > fl(den*thr)*(1+1e-6) and excluded by
+// inter < fl(den*thr)*(1-1e-6) (each product/quotient is within 2^-24 relative of exact).
 __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b,
                                             const float ab, const float thr) {
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
     if (!(inter > 0.f)) return false;  // 0/x is 0, -0 or NaN: never > thr (thr >= 0)
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
-    return ovr > thr;
+    const float den = __fsub_rn(__fadd_rn(aa, ab), inter);
+    const float t = __fmul_rn(den, thr);
+    if (t > 1e-30f && den < 1e30f) {   // den > 0 and no under/overflow in the products
+        if (inter > __fmul_rn(t, 1.000001f)) return true;
+        if (inter < __fmul_rn(t, 0.999999f)) return false;
+    }
+    return __fdiv_rn(inter, den) > thr;
 }
 
-struct NmsScratch {              // lives after the sort arrays in dynamic shared memory
-    union {
-        struct {                 // A1-A3
-            int segoff[VK_MAX_SEGMENTS + 1];
-            int segbase[VK_MAX_SEGMENTS];
-            union {
-                int hist[kHistBins];
-                struct { int gt[VK_MAX_SEGMENTS]; int eq[VK_MAX_SEGMENTS]; } c;
-            } u;
-        } a;
-        struct {                 // A5
-            float4 kbox[VK_MAX_DET];
-            float karea[VK_MAX_DET];
-            float4 cbox[kChunk];
-            float carea[kChunk];
-            uint32_t mask[kChunk][kChunkWords];
-            uint8_t csup[kChunk];
-            uint8_t newk[kChunk];
-        } b;
-        unsigned long long xchg[kNmsThreads];  // A4 (small sorts): cross-warp exchange
-    };
-};
+// Optional phase timestamps (clock64) for profiling: [batch][32] written by thread 0 when set.
+__device__ long long* g_nms_timing = nullptr;
+#define VK_STAMP(k) do { if (timing && tid == 0) timing[(size_t)blockIdx.x * 32 + (k)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_image_kernel(const NmsArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wsum[33];
-    __shared__ int s_found_bin, s_found_above, s_kept, s_newcount;
+    __shared__ int s_found_bin, s_found_above;
 
     const int P = A.P;
     uint32_t* skey = reinterpret_cast<uint32_t*>(smem_raw);
     uint16_t* spos = reinterpret_cast<uint16_t*>(smem_raw + (size_t)P * 4);
-    NmsScratch& X = *reinterpret_cast<NmsScratch*>(smem_raw + (size_t)P * 6);
+    unsigned char* scratch = smem_raw + (size_t)P * 6;
+    ScratchA XA(scratch, A.segs);
+    ScratchB XB(scratch, A.max_det);
+    unsigned long long* xchg = reinterpret_cast<unsigned long long*>(scratch);
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,18 +175,11 @@ nms_image_kernel(const NmsArgs A) {
     float* dets = A.dets + (size_t)b * A.max_det * 6;
     int64_t* keep_out = A.keep_idx ? A.keep_idx + (size_t)b * A.max_det : nullptr;
 
-    // outputs start zeroed / -1 padded (the reference returns exactly k rows; the host slices)
-    for (int i = tid; i < A.max_det * 6; i += kNmsThreads) dets[i] = 0.f;
-    if (keep_out)
-        for (int i = tid; i < A.max_det; i += kNmsThreads) keep_out[i] = -1;
-
+    long long* timing = g_nms_timing;
+    VK_STAMP(0);
     const int n_total = A.counts[b];
     const int n = min(n_total, A.cap);
     if (tid == 0 && A.status) A.status[b] = (n_total > A.cap) ? 1 : 0;
-    if (n == 0) {
-        if (tid == 0) A.det_counts[b] = 0;
-        return;
-    }
 
     // ---------------- A1: canonical offsets of the segments
     {
@@ -129,18 +190,19 @@ nms_image_kernel(const NmsArgs A) {
             if (t < A.segs) {
                 c = seg_count[t];
                 const int sb = seg_base[t];
-                X.a.segbase[t] = sb;
-                if (c > 0) c = max(0, min(c, A.cap - sb));  // overflowed tail was never written
+                XA.segbase[t] = sb;
+                if (c > 0) c = max(0, min(c, A.cap - sb));  // an overflowed tail was never written
             }
             int total;
             const int ex = block_excl_scan(c, wsum, &total);
-            if (t < A.segs) X.a.segoff[t] = carry + ex;
+            if (t < A.segs) XA.segoff[t] = carry + ex;
             carry += total;
         }
-        if (tid == 0) X.a.segoff[A.segs] = carry;
+        if (tid == 0) XA.segoff[A.segs] = carry;
         __syncthreads();
     }
 
+    VK_STAMP(1);
     // ---------------- A2: exact selection of the max_nms-th best score (image_proc.py:161-163)
     const int K = A.max_nms;
     const bool cut = n > K;
@@ -149,22 +211,21 @@ nms_image_kernel(const NmsArgs A) {
     if (cut) {
         uint32_t prefix = 0, pmask = 0;
         int remaining = K;
-        const int shifts[3] = {21, 10, 0};
-        const int widths[3] = {11, 11, 10};
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
-            const int shift = shifts[pass], nb = 1 << widths[pass];
-            for (int i = tid; i < kHistBins; i += kNmsThreads) X.a.u.hist[i] = 0;
+            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+            const int nb = pass == 2 ? 1024 : 2048;
+            for (int i = tid; i < kHistBins; i += kNmsThreads) XA.hist[i] = 0;
             __syncthreads();
             for (int i = tid; i < n; i += kNmsThreads) {
                 const uint32_t key = order_key((uint32_t)cand[i]);
-                if ((key & pmask) == prefix) atomicAdd(&X.a.u.hist[(key >> shift) & (nb - 1)], 1);
+                if ((key & pmask) == prefix) atomicAdd(&XA.hist[(key >> shift) & (nb - 1)], 1);
             }
             __syncthreads();
             // bins from the top: thread t owns bins nb-1-2t and nb-2-2t
             const int b0 = nb - 1 - 2 * tid, b1 = nb - 2 - 2 * tid;
-            const int v0 = (b0 >= 0) ? X.a.u.hist[b0] : 0;
-            const int v1 = (b1 >= 0) ? X.a.u.hist[b1] : 0;
+            const int v0 = (b0 >= 0) ? XA.hist[b0] : 0;
+            const int v1 = (b1 >= 0) ? XA.hist[b1] : 0;
             int total;
             const int above = block_excl_scan(v0 + v1, wsum, &total);
             if (above < remaining && remaining <= above + v0) {
@@ -182,6 +243,7 @@ nms_image_kernel(const NmsArgs A) {
         need_eq = remaining;  // how many candidates equal to it make the cut (lowest position first)
     }
 
+    VK_STAMP(2);
     // ---------------- A3: ordered compaction into shared memory
     // sel[pos] = row*nc + cls of the candidate at compacted position pos
     const int M = cut ? K : n;
@@ -191,17 +253,17 @@ nms_image_kernel(const NmsArgs A) {
             int lo = 0, hi = A.segs;            // last t with segoff[t] <= p
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (X.a.segoff[mid] <= p) lo = mid; else hi = mid;
+                if (XA.segoff[mid] <= p) lo = mid; else hi = mid;
             }
-            const uint64_t cd = cand[X.a.segbase[lo] + (p - X.a.segoff[lo])];
+            const uint64_t cd = cand[XA.segbase[lo] + (p - XA.segoff[lo])];
             skey[p] = order_key((uint32_t)cd);
             spos[p] = (uint16_t)p;
             sel[p] = (uint32_t)(cd >> 32);
         }
     } else {
         for (int t = warp; t < A.segs; t += kNmsWarps) {
-            const int cnt = X.a.segoff[t + 1] - X.a.segoff[t];
-            const int base = X.a.segbase[t];
+            const int cnt = XA.segoff[t + 1] - XA.segoff[t];
+            const int base = XA.segbase[t];
             int gt = 0, eq = 0;
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 const int j = j0 + lane;
@@ -211,27 +273,27 @@ nms_image_kernel(const NmsArgs A) {
                 gt += __popc(__ballot_sync(0xffffffffu, ok && key > tval));
                 eq += __popc(__ballot_sync(0xffffffffu, ok && key == tval));
             }
-            if (lane == 0) { X.a.u.c.gt[t] = gt; X.a.u.c.eq[t] = eq; }
+            if (lane == 0) { XA.gt[t] = gt; XA.eq[t] = eq; }
         }
         __syncthreads();
         int carry_gt = 0, carry_eq = 0;
         for (int t0 = 0; t0 < A.segs; t0 += kNmsThreads) {
             const int t = t0 + tid;
-            const int g = (t < A.segs) ? X.a.u.c.gt[t] : 0;
-            const int e = (t < A.segs) ? X.a.u.c.eq[t] : 0;
+            const int g = (t < A.segs) ? XA.gt[t] : 0;
+            const int e = (t < A.segs) ? XA.eq[t] : 0;
             int tg, te;
             const int xg = block_excl_scan(g, wsum, &tg);
             const int xe = block_excl_scan(e, wsum, &te);
-            if (t < A.segs) { X.a.u.c.gt[t] = carry_gt + xg; X.a.u.c.eq[t] = carry_eq + xe; }
+            if (t < A.segs) { XA.gt[t] = carry_gt + xg; XA.eq[t] = carry_eq + xe; }
             carry_gt += tg; carry_eq += te;
         }
         __syncthreads();
         for (int t = warp; t < A.segs; t += kNmsWarps) {
-            const int cnt = X.a.segoff[t + 1] - X.a.segoff[t];
+            const int cnt = XA.segoff[t + 1] - XA.segoff[t];
             if (cnt == 0) continue;
-            const int base = X.a.segbase[t];
-            int eq_before = X.a.u.c.eq[t];
-            int pos0 = X.a.u.c.gt[t] + min(eq_before, need_eq);
+            const int base = XA.segbase[t];
+            int eq_before = XA.eq[t];
+            int pos0 = XA.gt[t] + min(eq_before, need_eq);
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 const int j = j0 + lane;
                 const bool ok = j < cnt;
@@ -259,34 +321,36 @@ nms_image_kernel(const NmsArgs A) {
     for (int i = M + tid; i < Ps; i += kNmsThreads) { skey[i] = 0u; spos[i] = 0xffffu; }
     __syncthreads();
 
+    VK_STAMP(3);
     // ---------------- A4: bitonic sort, "before" = higher score, then lower position
-    if (Ps <= kNmsThreads) {
+    if (M > 1 && Ps <= kNmsThreads) {
         // one element per thread in a register: composite = score<<16 | (0xffff - pos), sorted
-        // descending; strides below 32 exchange by shuffle, the rest through shared memory
-        unsigned long long v = 0ull;
-        if (tid < Ps) v = ((unsigned long long)skey[tid] << 16) | (unsigned long long)(0xffffu - spos[tid]);
-        __syncthreads();   // skey/spos read before the scratch is reused as exchange buffer
-        for (int k = 2; k <= Ps; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                unsigned long long o;
-                if (j >= 32) {
-                    X.xchg[tid] = v;
-                    __syncthreads();
-                    o = X.xchg[tid ^ j];
-                    __syncthreads();
-                } else {
-                    o = __shfl_xor_sync(0xffffffffu, v, j);
-                }
-                const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
-                v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
-            }
-        }
+        // descending; strides below 32 exchange by shuffle, the rest through shared memory.
+        // Only the Ps/32 warps that hold elements take part (named barrier 1).
         if (tid < Ps) {
+            unsigned long long v = ((unsigned long long)skey[tid] << 16) | (unsigned long long)(0xffffu - spos[tid]);
+            int pp = 0;   // ping-pong: a buffer is rewritten only two barriers after it was read
+            for (int k = 2; k <= Ps; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    unsigned long long o;
+                    if (j >= 32) {
+                        unsigned long long* xb = xchg + pp * kNmsThreads;
+                        xb[tid] = v;
+                        asm volatile("bar.sync 1, %0;" :: "r"(Ps) : "memory");
+                        o = xb[tid ^ j];
+                        pp ^= 1;
+                    } else {
+                        o = __shfl_xor_sync(0xffffffffu, v, j);
+                    }
+                    const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
+                    v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+                }
+            }
             skey[tid] = (uint32_t)(v >> 16);
             spos[tid] = (uint16_t)(0xffffu - (uint32_t)(v & 0xffffull));
         }
         __syncthreads();
-    } else {
+    } else if (M > 1) {
         for (int k = 2; k <= Ps; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int i = tid; i < (Ps >> 1); i += kNmsThreads) {
@@ -306,118 +370,216 @@ nms_image_kernel(const NmsArgs A) {
         }
     }
 
+    VK_STAMP(4);
     // ---------------- A5: greedy NMS with a kept list, early exit at max_det
-    if (tid == 0) s_kept = 0;
-    __syncthreads();
+    for (int i = tid; i < kHash; i += kNmsThreads) XB.khead[i] = (int)kNil;
+    int kept0 = 0;
+    bool safe = A.nc <= 65535;
     const float thr = A.iou_thr;
-    for (int chunk0 = 0; chunk0 < M; chunk0 += kChunk) {
-        const int kept0 = s_kept;
-        if (kept0 >= A.max_det) break;
+    const float half_wh = 0.5f * A.max_wh;
+    __syncthreads();
+    for (int chunk0 = 0; chunk0 < M && kept0 < A.max_det; chunk0 += kChunk) {
         const int cn = min(kChunk, M - chunk0);
+        bool ok = true;
+        if (tid < kHash / 2) XB.ccnt2[tid] = 0u;
         if (tid < kChunk) {
+            XB.state[tid] = 2;                               // rows past the end never matter
+#pragma unroll
+            for (int wd = 0; wd < kChunkWords; ++wd) XB.pred[tid * kChunkWords + wd] = 0u;
+        }
+        __syncthreads();
+        if (tid < cn) {
+            const uint32_t idx = sel[spos[chunk0 + tid]];
+            const uint32_t row = idx / (uint32_t)A.nc;
+            const uint32_t cls = idx - row * (uint32_t)A.nc;
+            const float4 bx = boxes[row];
+            ok = fabsf(bx.x) <= half_wh && fabsf(bx.y) <= half_wh && fabsf(bx.z) <= half_wh &&
+                 fabsf(bx.w) <= half_wh;
+            const float off = A.agnostic ? 0.f : __fmul_rn((float)cls, A.max_wh);  // image_proc.py:166
+            XB.cbox[tid] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off),
+                                       __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // :168
+            XB.ccls[tid] = (uint16_t)cls;
+            XB.state[tid] = 0;
+            atomicAdd(&XB.ccnt2[(cls & (kHash - 1)) >> 1], 1u << (16 * (cls & 1)));
+        }
+        safe = __syncthreads_and(ok) && safe;
+        const bool by_class = safe && !A.agnostic;
+        if (chunk0 == 0) VK_STAMP(5);
+        if (by_class) {
+            // group the chunk's rows by class bucket: counts -> starts -> member slots
+            if (warp == 0) {
+                int c[8], sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int bk = lane * 8 + k;
+                    c[k] = (int)((XB.ccnt2[bk >> 1] >> (16 * (bk & 1))) & 0xffffu);
+                    sum += c[k];
+                }
+                int base = warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { XB.cstart[lane * 8 + k] = (uint16_t)base; base += c[k]; }
+                if (lane == 31) XB.cstart[kHash] = (uint16_t)base;
+            }
+            __syncthreads();
             if (tid < cn) {
+                const uint32_t bk = XB.ccls[tid] & (kHash - 1);
+                const uint32_t old = atomicSub(&XB.ccnt2[bk >> 1], 1u << (16 * (bk & 1)));
+                const uint32_t v = (old >> (16 * (bk & 1))) & 0xffffu;      // 1..count: a unique slot
+                XB.members[XB.cstart[bk] + v - 1] = (uint16_t)tid;
+            }
+            // (the barrier after step 1 below also orders these writes before step 2 reads them)
+        }
+
+        if (by_class) {
+            // 1: same-class kept boxes only (hash list of the kept set)
+            if (tid < cn) {
+                const float4 cb = XB.cbox[tid];
+                const float ca = box_area(cb);
+                const uint32_t cc = XB.ccls[tid];
+                bool sup = false;
+                for (uint32_t k = (uint32_t)XB.khead[cc & (kHash - 1)]; k != kNil && !sup;) {
+                    const uint32_t meta = XB.kmeta[k];
+                    if ((meta >> 16) == cc) {
+                        const float4 kb = XB.kbox[k];
+                        sup = iou_exceeds(kb, box_area(kb), cb, ca, thr);
+                    }
+                    k = meta & 0xffffu;
+                }
+                if (sup) XB.state[tid] = 2;
+            }
+            __syncthreads();
+            if (chunk0 == 0) VK_STAMP(13);
+            // 2: same-class predecessors inside the chunk.  One warp per row, lanes over the
+            //    members of the row's class bucket (rows of a crowded class would otherwise walk
+            //    a long list one dependent step at a time).
+            for (int i = warp; i < cn; i += kNmsWarps) {
+                if (XB.state[i] != 0) continue;
+                const uint32_t ic = XB.ccls[i];
+                const uint32_t bk = ic & (kHash - 1);
+                const int e = XB.cstart[bk + 1];
+                const float4 ib = XB.cbox[i];
+                const float ia = box_area(ib);
+                for (int m = XB.cstart[bk] + lane; m < e; m += 32) {
+                    const int j = XB.members[m];
+                    if (j >= i || XB.ccls[j] != ic || XB.state[j] != 0) continue;
+                    const float4 jb = XB.cbox[j];
+                    if (iou_exceeds(jb, box_area(jb), ib, ia, thr))
+                        atomicOr(&XB.pred[i * kChunkWords + (j >> 5)], 1u << (j & 31));
+                }
+            }
+        } else {
+            // 1: all kept boxes.  Warp = (32-row block, quarter of the kept list); the kept box
+            //    is a shared-memory broadcast, every lane tests its own row against it.
+            {
+                const int i = (warp >> 2) * 32 + lane, part = warp & 3;
+                if (i < cn) {
+                    const float4 cb = XB.cbox[i];
+                    const float ca = box_area(cb);
+                    bool sup = false;
+                    for (int k = part; k < kept0 && !sup; k += 4) {
+                        const float4 kb = XB.kbox[k];
+                        sup = iou_exceeds(kb, box_area(kb), cb, ca, thr);
+                    }
+                    if (sup) XB.state[i] = 2;
+                }
+            }
+            __syncthreads();
+            // 2: warp tile = (32-row block rb, 32-column word wd <= rb): 36 tiles
+            for (int t = warp; t < 36; t += kNmsWarps) {
+                int rb = 0, wd = t;
+                while (wd > rb) { wd -= rb + 1; ++rb; }
+                const int i = rb * 32 + lane;
+                uint32_t m = 0;
+                if (i < cn && XB.state[i] == 0) {
+                    const float4 ib = XB.cbox[i];
+                    const float ia = box_area(ib);
+                    const int jn = min(32, i - wd * 32);       // columns j < i only
+                    for (int bit = 0; bit < jn; ++bit) {
+                        const int j = wd * 32 + bit;
+                        if (XB.state[j] != 0) continue;        // already removed: cannot suppress
+                        const float4 jb = XB.cbox[j];
+                        if (iou_exceeds(jb, box_area(jb), ib, ia, thr)) m |= 1u << bit;
+                    }
+                }
+                if (i < kChunk) XB.pred[i * kChunkWords + wd] = m;
+            }
+        }
+        __syncthreads();
+
+        if (chunk0 == 0) VK_STAMP(6);
+        // 3: fixed-point resolve; thread i < 256 owns row i.  Only those 8 warps iterate (named
+        //    barrier 2, one per round; the word buffers ping-pong so a buffer is rewritten only
+        //    after everyone has passed the next barrier).
+        int st = 2;
+        if (tid < kChunk) {
+            uint32_t p[kChunkWords];
+            st = XB.state[tid];
+#pragma unroll
+            for (int wd = 0; wd < kChunkWords; ++wd) p[wd] = XB.pred[tid * kChunkWords + wd];
+            if (chunk0 == 0) VK_STAMP(15);
+            for (int round = 0;; ++round) {
+                uint32_t* kwb = XB.kw + (round & 1) * 3 * kChunkWords;   // [kept | removed | undecided]
+                const unsigned km = __ballot_sync(0xffffffffu, st == 1);
+                const unsigned rm = __ballot_sync(0xffffffffu, st == 2);
+                const unsigned um = __ballot_sync(0xffffffffu, st == 0);
+                if (lane == 0) { kwb[warp] = km; kwb[kChunkWords + warp] = rm; kwb[2 * kChunkWords + warp] = um; }
+                asm volatile("bar.sync 2, %0;" :: "n"(kChunk) : "memory");
+                uint32_t hit = 0, pend = 0, und = 0;
+#pragma unroll
+                for (int wd = 0; wd < kChunkWords; ++wd) {
+                    const uint32_t kw = kwb[wd], rw = kwb[kChunkWords + wd];
+                    und |= kwb[2 * kChunkWords + wd];
+                    hit |= p[wd] & kw;
+                    pend |= p[wd] & ~(kw | rw);
+                }
+                if (und == 0) {                       // everyone sees the same words: uniform exit
+                    if (tid < kChunkWords) XB.kfinal[tid] = kwb[tid];
+                    if (timing && tid == 0 && chunk0 == 0) { timing[(size_t)blockIdx.x * 32 + 14] = round; timing[(size_t)blockIdx.x * 32 + 16] = clock64(); }
+                    break;
+                }
+                if (st == 0) {
+                    if (hit) st = 2;
+                    else if (!pend) st = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (chunk0 == 0) VK_STAMP(7);
+        // 4: kept boxes, in order, join the kept list and the output (image_proc.py:170-182)
+        int total = 0;
+#pragma unroll
+        for (int wd = 0; wd < kChunkWords; ++wd) total += __popc(XB.kfinal[wd]);
+        if (tid < kChunk && st == 1) {
+            int rank = __popc(XB.kfinal[warp] & ((1u << lane) - 1u));
+            for (int wd = 0; wd < warp; ++wd) rank += __popc(XB.kfinal[wd]);
+            const int slot = kept0 + rank;
+            if (slot < A.max_det) {
+                const uint32_t cls16 = XB.ccls[tid];
+                XB.kbox[slot] = XB.cbox[tid];
+                const uint32_t old = (uint32_t)atomicExch(&XB.khead[cls16 & (kHash - 1)], slot);
+                XB.kmeta[slot] = (cls16 << 16) | (old & 0xffffu);
                 const uint32_t idx = sel[spos[chunk0 + tid]];
                 const uint32_t row = idx / (uint32_t)A.nc;
-                const float cls = (float)(idx - row * (uint32_t)A.nc);
                 const float4 bx = boxes[row];
-                const float off = A.agnostic ? 0.f : __fmul_rn(cls, A.max_wh);     // image_proc.py:166
-                const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off),
-                                              __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // :168
-                X.b.cbox[tid] = ob;
-                X.b.carea[tid] = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
-            }
-            X.b.csup[tid] = 0;
-        }
-        __syncthreads();
-        {   // phase 1: chunk box t vs the kept list, 4 threads per box
-            const int t = tid >> 2, q = tid & 3;
-            bool sup = false;
-            if (t < cn) {
-                const float4 cb = X.b.cbox[t];
-                const float ca = X.b.carea[t];
-                for (int k = q; k < kept0 && !sup; k += 4)
-                    sup = iou_exceeds(X.b.kbox[k], X.b.karea[k], cb, ca, thr);
-            }
-            sup |= __shfl_xor_sync(0xffffffffu, sup, 1);
-            sup |= __shfl_xor_sync(0xffffffffu, sup, 2);
-            if (q == 0 && t < cn && sup) X.b.csup[t] = 1;
-        }
-        __syncthreads();
-        {   // phase 2: upper-triangular bit matrix of the chunk
-            const int i = tid >> 2, q = tid & 3;
-            if (i < cn) {
-                const bool live = !X.b.csup[i];
-                const float4 ib = X.b.cbox[i];
-                const float ia = X.b.carea[i];
-#pragma unroll
-                for (int ww = 0; ww < 2; ++ww) {
-                    const int wd = q * 2 + ww;
-                    uint32_t m = 0;
-                    if (live && wd * 32 + 31 > i) {
-                        for (int bit = 0; bit < 32; ++bit) {
-                            const int j = wd * 32 + bit;
-                            if (j > i && j < cn && iou_exceeds(ib, ia, X.b.cbox[j], X.b.carea[j], thr))
-                                m |= 1u << bit;
-                        }
-                    }
-                    X.b.mask[i][wd] = m;
-                }
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {  // phase 3: sequential resolve; every lane carries all 256 alive bits
-            uint32_t alive[kChunkWords];
-#pragma unroll
-            for (int wd = 0; wd < kChunkWords; ++wd) {
-                // lane `bit` of each ballot = "box wd*32+bit is a live candidate"
-                const int j = wd * 32 + lane;
-                alive[wd] = __ballot_sync(0xffffffffu, j < cn && !X.b.csup[j]);
-            }
-            int kept = kept0, newc = 0;
-            bool done = false;
-            const uint4* mrow = reinterpret_cast<const uint4*>(&X.b.mask[0][0]);
-            uint4 n0 = mrow[0], n1 = mrow[1];
-#pragma unroll
-            for (int wd = 0; wd < kChunkWords; ++wd) {
-                if (done || wd * 32 >= cn) break;
-                const int lim = min(32, cn - wd * 32);
-                for (int bit = 0; bit < lim; ++bit) {
-                    const int i = wd * 32 + bit;
-                    const uint4 m0 = n0, m1 = n1;
-                    const int nx = min(i + 1, kChunk - 1);   // prefetch the next row
-                    n0 = mrow[2 * nx]; n1 = mrow[2 * nx + 1];
-                    if ((alive[wd] >> bit) & 1u) {
-                        if (lane == 0) X.b.newk[newc] = (uint8_t)i;
-                        ++newc; ++kept;
-                        alive[0] &= ~m0.x; alive[1] &= ~m0.y; alive[2] &= ~m0.z; alive[3] &= ~m0.w;
-                        alive[4] &= ~m1.x; alive[5] &= ~m1.y; alive[6] &= ~m1.z; alive[7] &= ~m1.w;
-                        if (kept >= A.max_det) { done = true; break; }
-                    }
-                }
-            }
-            if (lane == 0) { s_kept = kept; s_newcount = newc; }
-        }
-        __syncthreads();
-        {   // phase 4: append to the kept list and emit the detections
-            const int newc = s_newcount;
-            if (tid < newc) {
-                const int i = X.b.newk[tid];
-                const int slot = kept0 + tid;
-                X.b.kbox[slot] = X.b.cbox[i];
-                X.b.karea[slot] = X.b.carea[i];
-                const uint32_t idx = sel[spos[chunk0 + i]];
-                const uint32_t row = idx / (uint32_t)A.nc;
-                const float4 bx = boxes[row];
-                float* o = dets + (size_t)slot * 6;     // image_proc.py:182 output[xi] = x[i]
+                float* o = dets + (size_t)slot * 6;
                 o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-                o[4] = __uint_as_float(unorder_key(skey[chunk0 + i]));
+                o[4] = __uint_as_float(unorder_key(skey[chunk0 + tid]));
                 o[5] = (float)(idx - row * (uint32_t)A.nc);
-                if (keep_out) keep_out[slot] = cut ? (int64_t)(chunk0 + i) : (int64_t)spos[chunk0 + i];
+                if (keep_out) keep_out[slot] = cut ? (int64_t)(chunk0 + tid) : (int64_t)spos[chunk0 + tid];
             }
         }
+        kept0 = min(A.max_det, kept0 + total);
         __syncthreads();
+        if (chunk0 == 0) VK_STAMP(8);
     }
-    if (tid == 0) A.det_counts[b] = s_kept;
+    VK_STAMP(9);
+    // rows past the count are zero / -1 (the reference returns exactly k rows; the host slices)
+    for (int i = kept0 * 6 + tid; i < A.max_det * 6; i += kNmsThreads) dets[i] = 0.f;
+    if (keep_out)
+        for (int i = kept0 + tid; i < A.max_det; i += kNmsThreads) keep_out[i] = -1;
+    if (tid == 0) A.det_counts[b] = kept0;
+    VK_STAMP(10);
+    if (timing && tid == 0) { timing[(size_t)blockIdx.x * 32 + 11] = n; timing[(size_t)blockIdx.x * 32 + 12] = kept0; }
 }
 
 static int next_pow2(int v) {
@@ -431,6 +593,14 @@ static int sort_capacity(int max_nms, int cap) { return next_pow2(max_nms < cap 
 }  // namespace vk
 
 using namespace vk;
+
+// Profiling hook (not part of the product ABI in include/vk_b200.h): dev buffer of
+// [batch][32] int64 receiving clock64() phase stamps of the next launches, or NULL.
+extern "C" int vkdbg_nms_timing(void* dev_buf) {
+    long long* p = static_cast<long long*>(dev_buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_nms_timing, &p, sizeof(p));
+    return e == cudaSuccess ? VK_OK : (int)e;
+}
 
 extern "C" size_t vk_nms_workspace_bytes(int batch, int max_nms) {
     if (batch <= 0 || max_nms <= 0 || max_nms > VK_MAX_NMS) return 0;
@@ -453,6 +623,10 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, float conf_unused, 
     const int P = sort_capacity(max_nms, c->cap);
     if (!ws || ws_bytes < (size_t)batch * P * sizeof(uint32_t))
         return fail_code(VK_E_WORKSPACE, "vk_nms_batched: workspace %zu < %zu", ws_bytes, (size_t)batch * P * sizeof(uint32_t));
+    const size_t smem = nms_smem_bytes(P, c->segs, max_det);
+    if (smem > kSmemLimit)
+        return fail_code(VK_E_LIMIT, "vk_nms_batched: max_nms=%d max_det=%d segs=%d need %zu B of shared memory (> %zu)",
+                         max_nms, max_det, c->segs, smem, kSmemLimit);
     NmsArgs A;
     A.cand = c->cand; A.boxes = reinterpret_cast<const float4*>(c->boxes); A.counts = c->counts;
     A.seg_base = c->seg_base; A.seg_count = c->seg_count;
@@ -463,7 +637,6 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, float conf_unused, 
     A.agnostic = agnostic ? 1 : 0; A.max_nms = max_nms; A.max_det = max_det; A.max_wh = max_wh;
     A.dets = dets; A.det_counts = det_counts; A.keep_idx = keep_idx; A.status = status;
     A.sel = static_cast<uint32_t*>(ws); A.P = P;
-    const size_t smem = (size_t)P * 6 + sizeof(NmsScratch);
     cudaError_t e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail_code((int)e, "vk_nms_batched: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     nms_image_kernel<<<batch, kNmsThreads, smem, as_stream(stream)>>>(A);

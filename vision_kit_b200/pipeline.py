@@ -24,7 +24,8 @@ class DetectPipeline:
                  conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None, agnostic: bool = False,
                  multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                  anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
-                 swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False):
+                 swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False,
+                 overlap: bool = False):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
@@ -40,14 +41,25 @@ class DetectPipeline:
         segs = _lib.lib().vk_decode_filter_segments(C.byref(self.cfg))
         ml = bool(multi_label) and nc > 1
         cap = cand_cap or ops.default_cap(self.rows, nc, ml)
-        self.cand = ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device)
-        self.out = ops.NmsOut(
+        # two sets of candidate / output buffers: with overlap=True the NMS of batch k runs on a
+        # side stream while the letterbox and filter kernels of batch k+1 run on the main one
+        self.overlap = bool(overlap)
+        nsets = 2 if self.overlap else 1
+        self._cands = [ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device) for _ in range(nsets)]
+        self._outs = [ops.NmsOut(
             torch.empty((batch, max_det, 6), dtype=torch.float32, device=self.device),
             torch.empty((batch,), dtype=torch.int32, device=self.device),
             torch.empty((batch, max_det), dtype=torch.int64, device=self.device) if want_keep else None,
-            torch.empty((batch,), dtype=torch.int32, device=self.device))
-        self.nms_ws = torch.empty(_lib.lib().vk_nms_workspace_bytes(batch, max_nms), dtype=torch.uint8,
-                                  device=self.device)
+            torch.empty((batch,), dtype=torch.int32, device=self.device)) for _ in range(nsets)]
+        self._nms_ws = [torch.empty(_lib.lib().vk_nms_workspace_bytes(batch, max_nms), dtype=torch.uint8,
+                                    device=self.device) for _ in range(nsets)]
+        self._set = 0
+        self.cand, self.out, self.nms_ws = self._cands[0], self._outs[0], self._nms_ws[0]
+        if self.overlap:
+            self.side = torch.cuda.Stream(device=self.device)
+            self._ev_filter = [torch.cuda.Event() for _ in range(2)]
+            self._ev_nms = [torch.cuda.Event() for _ in range(2)]
+            self._nms_pending = [False, False]
         self.input = torch.empty((batch, 3, img_sz[0], img_sz[1]), dtype=dtype, device=self.device)
         self.plan: Optional[ops.LetterboxPlan] = None
 
@@ -71,16 +83,44 @@ class DetectPipeline:
 
     # -- fused Detect decode + confidence filter + NMS
     def filter(self, feats: Sequence[torch.Tensor]) -> ops.CandBuf:
+        if self.overlap:
+            self._set ^= 1
+            self.cand, self.out, self.nms_ws = (self._cands[self._set], self._outs[self._set],
+                                                self._nms_ws[self._set])
+            if self._nms_pending[self._set]:        # the NMS that last read this buffer set
+                torch.cuda.current_stream().wait_event(self._ev_nms[self._set])
         return ops.decode_filter(self.cfg, feats, self.conf_thres, self.multi_label, self.classes,
                                  buf=self.cand)
 
     def nms(self) -> ops.NmsOut:
-        return ops.nms_batched(self.cand, self.iou_thres, self.agnostic, self.max_nms, self.max_det,
-                               out=self.out, ws=self.nms_ws)
+        if not self.overlap:
+            return ops.nms_batched(self.cand, self.iou_thres, self.agnostic, self.max_nms, self.max_det,
+                                   out=self.out, ws=self.nms_ws)
+        k = self._set
+        self._ev_filter[k].record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self._ev_filter[k])
+            out = ops.nms_batched(self.cand, self.iou_thres, self.agnostic, self.max_nms, self.max_det,
+                                  out=self.out, ws=self.nms_ws)
+            self._ev_nms[k].record()
+        self._nms_pending[k] = True
+        return out
 
-    def postprocess(self, feats: Sequence[torch.Tensor]) -> ops.NmsOut:
+    def join(self) -> None:
+        """Makes the current stream wait for every NMS issued on the side stream."""
+        if self.overlap:
+            for k in range(2):
+                if self._nms_pending[k]:
+                    torch.cuda.current_stream().wait_event(self._ev_nms[k])
+
+    def postprocess(self, feats: Sequence[torch.Tensor], join: bool = True) -> ops.NmsOut:
+        """join=False leaves the NMS running on the side stream (overlap=True): the caller must
+        call join() (or wait on the side stream) before reading the returned tensors."""
         self.filter(feats)
-        return self.nms()
+        out = self.nms()
+        if join:
+            self.join()
+        return out
 
     # -- drop-in layout: decode to the (B, rows, no) tensor, then filter + NMS from it
     def postprocess_materialised(self, feats: Sequence[torch.Tensor]):
