@@ -1,0 +1,160 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the host-only geometry entry point equals the oracle, argument validation, the
+division-free /255, and the world_size-2 sharding + all-gather logic over gloo."""
+import ctypes as C
+import os
+import socket
+from fractions import Fraction
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import restate
+
+
+def test_library_exports_every_declared_symbol(vk_lib):
+    from vision_kit_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 17 and set(_lib._PROTOS) <= set(names)
+    for n in names:
+        assert hasattr(vk_lib, n), n
+    assert vk_lib.vk_version() >= 100 and vk_lib.vk_build_arch() == 100
+    assert vk_lib.vk_last_error() is not None
+
+
+def test_struct_layouts_match_header():
+    from vision_kit_b200 import _lib
+    assert C.sizeof(_lib.VkLbDesc) == 48
+    assert C.sizeof(_lib.VkLbGeom) == 64
+    assert C.sizeof(_lib.VkHeadCfg) == 4 * 4 + 4 * 4 * 2 + 4 * 4 + 4 * 16 * 4
+    assert C.sizeof(_lib.VkCandBuf) == 5 * 8 + 4 * 4
+
+
+def test_geometry_equals_oracle(vk_lib):
+    from vision_kit_b200 import ops
+    rng = np.random.Generator(np.random.PCG64(3))
+    cases = [(1080, 810, (640, 640)), (375, 500, (640, 640)), (720, 1280, (640, 640)), (640, 640, 640),
+             (1, 1, (32, 32)), (3000, 17, (640, 640)), (45, 80, (64, 64))]
+    for _ in range(3000):
+        cases.append((int(rng.integers(1, 2500)), int(rng.integers(1, 2500)),
+                      (int(rng.integers(16, 1500)), int(rng.integers(16, 1500)))))
+    for h, w, sz in cases:
+        for lb in (True, False):
+            for su in (True, False):
+                for au in (True, False):
+                    e = restate.letterbox_geometry(h, w, sz, 32, lb, su, au)
+                    if e["new_w"] < 1 or e["new_h"] < 1:
+                        continue
+                    g = ops.letterbox_geometry(h, w, sz, 32, lb, su, au)
+                    got = (g.ratio, g.pad_w, g.pad_h, g.new_w, g.new_h, g.top, g.bottom, g.left, g.right,
+                           g.out_h, g.out_w)
+                    exp = (e["ratio"], float(e["pad"][0]), float(e["pad"][1]), e["new_w"], e["new_h"], e["top"],
+                           e["bottom"], e["left"], e["right"], e["out_h"], e["out_w"])
+                    assert got == exp, (h, w, sz, lb, su, au)
+
+
+def test_argument_validation_without_gpu(vk_lib):
+    from vision_kit_b200 import _lib, ops
+    g = _lib.VkLbGeom()
+    assert vk_lib.vk_letterbox_geometry(0, 5, 64, 64, 32, 1, 1, 0, C.byref(g)) == -1
+    assert b"bad size" in vk_lib.vk_last_error()
+    cfg = ops.head_cfg("v5", 80, [[1, 2, 3, 4, 5, 6]] * 3, (8, 16, 32), [(80, 80), (40, 40), (20, 20)])
+    assert ops.head_rows(cfg) == 25200
+    assert vk_lib.vk_decode_filter_segments(C.byref(cfg)) == 3 * (100 + 25 + 7)
+    assert vk_lib.vk_filter_segments(25200) == 394
+    cfg.nl = 9
+    with pytest.raises(_lib.VkError):
+        ops.head_rows(cfg)
+    assert vk_lib.vk_letterbox_workspace_bytes(64, 640, 640) == 3072 + 64 * 1280 * 16
+    assert vk_lib.vk_nms_workspace_bytes(4, 30000) == 4 * 32768 * 4
+    assert vk_lib.vk_nms_workspace_bytes(4, 40000) == 0          # > VK_MAX_NMS
+    # null pointers / out-of-range thresholds are rejected before any launch
+    assert vk_lib.vk_nms_batched(None, 1, 0.0, 0.5, 0, 30000, 300, 7680.0, None, None, None, None, None, 0, None) == -1
+    assert vk_lib.vk_filter_pred(None, 1, 100, 80, 0.25, 0, None, None, None) == -1
+    assert vk_lib.vk_scale_coords(None, 0, 4, 0.0, 0.0, 1.0, 1, -1.0, -1.0, None) == 0   # n = 0 is a no-op
+
+
+def test_shims_refuse_cpu_tensors(vk_lib):
+    from vision_kit_b200 import bboxes, image_proc
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        image_proc.nms(torch.zeros(1, 10, 85))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        bboxes.cxcywh_to_xyxy(torch.zeros(4, 4))
+    with pytest.raises(AssertionError):
+        image_proc.nms(torch.zeros(1, 10, 85), iou_thres=2.0)
+
+
+def test_norm255_two_fma_division_is_correctly_rounded():
+    # lb_kernel's norm255(): q = v*r; e = fma(-q, 255, v); q' = fma(e, r, q) with r = RN(1/255).
+    # Exact rational arithmetic, each step rounded to float32 -> equals RN(v/255) for all 256 inputs.
+    def rn(x: Fraction) -> Fraction:
+        return Fraction(float(np.float32(float(x)))) if x != 0 else Fraction(0)
+
+    def rn_exact(x: Fraction) -> Fraction:   # round-to-nearest-even of an exact rational to float32
+        if x == 0:
+            return Fraction(0)
+        f = np.float32(float(x))             # float(x) is the correctly rounded double; doubles of these
+        lo, hi = np.nextafter(f, np.float32(-np.inf)), np.nextafter(f, np.float32(np.inf))
+        best = min((abs(Fraction(float(c)) - x), i, c) for i, c in enumerate((f, lo, hi)))
+        return Fraction(float(best[2]))
+
+    r = Fraction(float(np.float32(1.0) / np.float32(255.0)))
+    assert float(r) == float(np.float32(0.003921568859368563))
+    for v in range(256):
+        q = rn_exact(Fraction(v) * r)
+        e = rn_exact(Fraction(v) - q * 255)
+        q2 = rn_exact(q + e * r)
+        assert float(q2) == float(np.float32(v) / np.float32(255.0)), v
+
+
+def test_iou_threshold_rounding_rule():
+    # vk_nms_batched compares against the largest float32 <= the double threshold
+    for thr in (0.6, 0.45, 0.5, 0.0, 1.0, float(np.float32(0.6))):
+        f = np.float32(thr)
+        if float(f) > thr:
+            f = np.nextafter(f, np.float32(-np.inf))
+        for x in (np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))):
+            assert (float(x) > thr) == (x > f)
+
+
+# ------------------------------------------------------------------ world_size-2 over gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_images, ret):
+    import torch.distributed as dist
+    from vision_kit_b200 import dist as vkd
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = vkd.shard_range(n_images, rank, world)
+    g = torch.Generator().manual_seed(0)
+    all_d = torch.rand((n_images, 7, 6), generator=g)
+    all_c = torch.randint(0, 8, (n_images,), generator=g, dtype=torch.int32)
+    d, c = vkd.allgather_detections(all_d[lo:hi].clone(), all_c[lo:hi].clone(), n_images)
+    ok = torch.equal(d, all_d) and torch.equal(c, all_c)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [8, 7])
+def test_shard_and_allgather_world2(n_images):
+    from vision_kit_b200 import dist as vkd
+    assert vkd.shard_sizes(7, 2) == [4, 3] and vkd.shard_range(7, 1, 2) == (4, 7)
+    assert sum(vkd.shard_sizes(512, 8)) == 512 and vkd.shard_range(256, 3, 8) == (96, 128)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_images, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
