@@ -116,13 +116,15 @@ int vk_detect_decode(const VkHeadCfg* cfg, const float* const* levels, int batch
  * `nonzero` or best-class `max`, optional class filter.
  *
  * A candidate set lives in caller-owned device buffers described by VkCandBuf.  Candidates
- * are written in segments (one per kernel tile); the canonical order of the reference
- * (row ascending, class ascending) is segment order x in-segment order.
+ * are written in segments: every 64-row tile owns a fixed slot range of vk_cand_tile_slots()
+ * entries, so the buffer needs cap >= segs * vk_cand_tile_slots(nc, multi_label) and can
+ * never overflow.  The canonical order of the reference (row ascending, class ascending)
+ * is segment order x in-segment order.
  */
 typedef struct VkCandBuf {
     uint64_t* cand;      /* dev [batch][cap]: low 32 = score bits, high 32 = row*nc + cls */
     float* boxes;        /* dev [batch][rows][4] xyxy of rows that produced candidates */
-    int32_t* counts;     /* dev [batch] candidates per image (may exceed cap => overflow) */
+    int32_t* counts;     /* dev [batch] candidates per image (informational; zeroed by the filter call) */
     int32_t* seg_base;   /* dev [batch][segs] first slot of each segment */
     int32_t* seg_count;  /* dev [batch][segs] */
     int32_t cap;         /* candidate slots per image */
@@ -131,6 +133,7 @@ typedef struct VkCandBuf {
     int32_t nc;
 } VkCandBuf;
 
+int vk_cand_tile_slots(int nc, int multi_label);     /* 64 * nc (multi-label, nc > 1) or 64 */
 int vk_filter_segments(int rows);                    /* for vk_filter_pred */
 int vk_decode_filter_segments(const VkHeadCfg* cfg); /* for vk_decode_filter */
 
@@ -154,7 +157,8 @@ int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch
  * dets: dev float32 (B, max_det, 6) [x1,y1,x2,y2,conf,cls], rows >= det_counts[b] zeroed.
  * keep_idx: dev int64 (B, max_det) or NULL -- indices torchvision.ops.nms returned
  *   (into the candidate list the reference handed it), -1 padded.
- * status: dev int32[batch] or NULL; bit0 = candidate buffer overflowed (results invalid).
+ * status: dev int32[batch] or NULL; bit0 = a segment reached past cap (results invalid;
+ *   cannot happen with buffers sized as above).
  */
 size_t vk_nms_workspace_bytes(int batch, int max_nms);
 

@@ -71,6 +71,7 @@ _PROTOS = {
                                      C.c_int, _P, _P, C.c_size_t, _P]),
     "vk_head_rows": (C.c_int, [C.POINTER(VkHeadCfg)]),
     "vk_detect_decode": (C.c_int, [C.POINTER(VkHeadCfg), _P, C.c_int, _P, _P, _P]),
+    "vk_cand_tile_slots": (C.c_int, [C.c_int, C.c_int]),
     "vk_filter_segments": (C.c_int, [C.c_int]),
     "vk_decode_filter_segments": (C.c_int, [C.POINTER(VkHeadCfg)]),
     "vk_filter_pred": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P,

@@ -10,9 +10,10 @@
 //
 // Candidate order: the reference's candidate list is ordered (row asc, class asc)
 // (`nonzero`, utils/image_proc.py:141-143).  Here every tile writes its candidates, in that
-// order, into a slot range claimed with one atomicAdd, and records (base, count) in a
-// segment table indexed by tile; canonical order = segment order x in-segment order.  The
-// consumer (nms.cu) walks the table, so results do not depend on which tile won the atomic.
+// order, into the fixed slot range its tile owns (64 rows x nc slots, or 64 in best-class
+// mode) and records (base, count) in a segment table indexed by tile; canonical order =
+// segment order x in-segment order.  No tile ever waits for an atomic, the buffer cannot
+// overflow, and the consumer (nms.cu) walks the table.
 #include "vk_common.cuh"
 
 namespace vk {
@@ -55,6 +56,39 @@ __device__ __forceinline__ TileLoc locate_tile(const HeadDev& H, int t) {
 // ---------------------------------------------------------------------------------------
 // materialised decode
 // ---------------------------------------------------------------------------------------
+// Coalesced load of one tile's logits into shared memory [no][kTilePitch].  Loads are issued in
+// batches of four 128-bit requests per thread before the first shared store, so that a block
+// keeps ~16 KB in flight instead of one request per thread.
+__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ in, int no, int nynx,
+                                          int nvalid, bool vec) {
+    if (vec) {
+        const int total = no * (kTileS / 4);
+        for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kDecThreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * kDecThreads;
+                const int c = e >> 4, sq = (e & 15) << 2;
+                v[u] = (e < total && sq < nvalid) ? ld_stream_f4(in + (size_t)c * nynx + sq)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * kDecThreads;
+                if (e < total) {
+                    float* d = tile + (e >> 4) * kTilePitch + ((e & 15) << 2);
+                    d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                }
+            }
+        }
+    } else {
+        for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
+            const int c = e >> 6, sq = e & 63;
+            if (sq < nvalid) tile[c * kTilePitch + sq] = ld_stream_f32(in + (size_t)c * nynx + sq);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kDecThreads)
 detect_decode_kernel(const HeadDev H, float* __restrict__ pred) {
     extern __shared__ float tile[];  // [no][kTilePitch] logits
@@ -62,45 +96,39 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred) {
     const TileLoc q = locate_tile(H, blockIdx.x);
     const int no = H.no, nynx = H.nynx[q.l];
     const float* __restrict__ in = H.lv[q.l] + ((size_t)(b * H.na + q.a) * no) * nynx + q.s0;
-
     const bool vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[q.l]) & 15) == 0);
-    if (vec) {
-        for (int e = threadIdx.x; e < no * (kTileS / 4); e += kDecThreads) {
-            const int c = e >> 4, s = (e & 15) << 2;
-            if (s < q.nvalid) {
-                const float4 v = ld_stream_f4(in + (size_t)c * nynx + s);
-                float* d = tile + c * kTilePitch + s;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
-        }
-    } else {
-        for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
-            const int c = e >> 6, s = e & 63;
-            if (s < q.nvalid) tile[c * kTilePitch + s] = ld_stream_f32(in + (size_t)c * nynx + s);
-        }
-    }
+    load_tile(tile, in, no, nynx, q.nvalid, vec);
     __syncthreads();
 
-    const int nx = H.nx[q.l];
-    const float stride = H.stride[q.l];
-    const float aw = H.anchors[q.l][2 * q.a], ah = H.anchors[q.l][2 * q.a + 1];
     const int nout = q.nvalid * no;
     float* __restrict__ out = pred + ((size_t)b * H.rows + q.row0) * no;
     float* __restrict__ raw = H.raw[q.l]
                                   ? H.raw[q.l] + (((size_t)b * H.na + q.a) * nynx + q.s0) * no
                                   : nullptr;
+    // Probabilities: element o of the contiguous output chunk is (row s = o / no, channel
+    // c = o % no).  (s, c) advance incrementally (kDecThreads = ds*no + dc): no division in the
+    // loop.  The four box channels of each row are skipped here and written below.
+    const int ds = kDecThreads / no, dc = kDecThreads - ds * no;
+    int s = 0, c = threadIdx.x;
+    while (c >= no) { c -= no; ++s; }
+#pragma unroll 4
     for (int o = threadIdx.x; o < nout; o += kDecThreads) {
-        const int s = o / no, c = o - s * no;
         const float logit = tile[c * kTilePitch + s];
-        float g = 0.f, anc = 0.f;
-        if (c < 4) {
-            const int sp = q.s0 + s;
-            const int gy = sp / nx, gx = sp - gy * nx;
-            g = (float)((c & 1) ? gy : gx);
-            anc = (c & 1) ? ah : aw;
-        }
-        st_stream_f32(out + o, decode_elem(logit, c, g, stride, anc, H.variant));
+        if (c >= 4) st_stream_f32(out + o, sigmoidf_vk(logit));
         if (raw) st_stream_f32(raw + o, logit);
+        s += ds; c += dc;
+        if (c >= no) { c -= no; ++s; }
+    }
+    // Boxes: 64 rows x 4 channels = one element per thread.
+    {
+        const int r = threadIdx.x >> 2, cb = threadIdx.x & 3;
+        if (r < q.nvalid) {
+            const int sp = q.s0 + r;
+            const int gy = sp / H.nx[q.l], gx = sp - gy * H.nx[q.l];
+            const float g = (float)((cb & 1) ? gy : gx);
+            const float anc = H.anchors[q.l][2 * q.a + (cb & 1)];
+            st_stream_f32(out + r * no + cb, decode_elem(tile[cb * kTilePitch + r], cb, g, H.stride[q.l], anc, H.variant));
+        }
     }
 }
 
@@ -111,9 +139,9 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred) {
 //            ordered list of surviving rows per tile
 //   stage B  tiles with <= 8 survivors are "sparse": their rows (<= 64 for the group) are
 //            gathered into one staging buffer in a single round trip, evaluated, and their
-//            candidates claimed with ONE atomicAdd for the group
+//            candidates written into the slot range of the group's first sparse tile
 //   stage C  the remaining "dense" tiles are loaded whole (coalesced planes / rows), one tile
-//            at a time, each with its own atomicAdd
+//            at a time, each into its own slot range
 //
 // At demo thresholds (0.7 % of rows survive) a group costs ~3 dependent memory round trips
 // instead of 3 per tile; at eval thresholds every tile is dense and HBM-bound.
@@ -132,6 +160,7 @@ struct FilterArgs {
     int32_t* seg_count;
     int cap, rows, segs, nc;
     int group;                   // tiles per block, 1..kGroupMax
+    int tile_cap;                // candidate slots each tile owns
 };
 
 struct FilterSmem {
@@ -147,6 +176,10 @@ struct FilterSmem {
     int it_excl[kItems + 1];
     float it_bv[kItems];
     int it_bj[kItems];
+    int part[kDecThreads + 1];           // per (item, class part): count, then exclusive offset
+    float part_bv[kDecThreads];          // best-class partial maxima
+    int part_bj[kDecThreads];
+    int wsum[33];
     int base;
 };
 
@@ -201,83 +234,111 @@ struct PredRows {        // decoded prediction rows [ai][no] (dense tile or gath
     }
 };
 
-// Evaluates S.it_*[0..n_items): class products, per-item candidate counts, one atomicAdd for
-// the lot, then the ordered candidate writes.  Ends with S.it_excl[0..n_items] valid and
-// S.base = first claimed slot.  All threads of the block must call it.
+// Evaluates S.it_*[0..n_items): class products, per-item candidate counts, then the ordered
+// candidate writes starting at slot `base` (a range the caller's tile owns).  Ends with
+// S.it_excl[0..n_items] valid and S.base = base.  All threads of the block must call it.
+//
+// Thread = (class part q, item i): lanes run over items, every thread walks its own consecutive
+// class range, so counting needs no ballot and the class order inside a row is the part order.
+// One exclusive scan over the 256 (item, part) counts gives every thread its first slot.
 template <class Acc>
-__device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const FilterArgs& A, int b, int n_items) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const FilterArgs& A, int b, int n_items,
+                                             int base) {
+    const int tid = threadIdx.x;
     const int nc = A.nc;
-    for (int i = w; i < n_items; i += kWarps) {
-        const int ai = S.it_ai[i];
-        const float obj = S.it_obj[i];
+    const int lgq = (n_items <= 32) ? 3 : 2;           // 8 parts x 32 items or 4 parts x 64 items
+    const int Q = 1 << lgq, ipq = kDecThreads >> lgq;
+    const int i = tid & (ipq - 1), qd = tid / ipq;
+    const int cpp = (nc + Q - 1) >> lgq;
+    const int c_lo = min(nc, qd * cpp), c_hi = min(nc, c_lo + cpp);
+    const bool act = i < n_items;
+    const int ai = act ? S.it_ai[i] : 0;
+    const int slot = (i << lgq) + qd;                   // item-major, part-minor: canonical order
+    {
         int count = 0;
-        if (A.multi_label) {
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-                const int c = c0 + lane;
-                bool flag = false;
-                if (c < nc) {
-                    const float prod = __fmul_rn(T.prob(ai, c), obj);               // image_proc.py:135
-                    flag = (prod > A.conf) && class_allowed(A.class_mask, c);       // :141,151
-                    T.put(ai, c, flag ? prod : -1.0f);
+        float bv = -INFINITY;
+        int bj = 0x7fffffff;
+        if (act) {
+            const float obj = S.it_obj[i];
+            if (A.multi_label) {
+                if (A.class_mask == nullptr) {
+#pragma unroll 4
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        const float prod = __fmul_rn(T.prob(ai, c), obj);              // image_proc.py:135
+                        const bool flag = prod > A.conf;                               // :141
+                        T.put(ai, c, flag ? prod : -1.0f);
+                        count += flag;
+                    }
+                } else {
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        const float prod = __fmul_rn(T.prob(ai, c), obj);
+                        const bool flag = (prod > A.conf) && class_allowed(A.class_mask, c);   // :141,151
+                        T.put(ai, c, flag ? prod : -1.0f);
+                        count += flag;
+                    }
                 }
-                count += __popc(__ballot_sync(0xffffffffu, flag));
-            }
-        } else {
-            float bv = -INFINITY;
-            int bj = 0x7fffffff;
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-                const int c = c0 + lane;
-                if (c < nc) {
+            } else {
+#pragma unroll 4
+                for (int c = c_lo; c < c_hi; ++c) {
                     const float prod = __fmul_rn(T.prob(ai, c), obj);
-                    if (prod > bv) { bv = prod; bj = c; }      // first max within the lane
+                    if (prod > bv) { bv = prod; bj = c; }      // first max within the part (:145)
                 }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {                      // first max across lanes (:145)
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
-            }
+        }
+        S.part[slot] = count;
+        S.part_bv[slot] = bv;
+        S.part_bj[slot] = bj;
+    }
+    __syncthreads();
+    if (!A.multi_label) {
+        if (act && qd == 0) {                                   // first max across the parts
+            float bv = S.part_bv[slot];
+            int bj = S.part_bj[slot];
+            for (int q2 = 1; q2 < Q; ++q2)
+                if (S.part_bv[slot + q2] > bv) { bv = S.part_bv[slot + q2]; bj = S.part_bj[slot + q2]; }
             const bool sel = (bj != 0x7fffffff) && (bv > A.conf) && class_allowed(A.class_mask, bj);  // :147,151
-            count = sel ? 1 : 0;
-            if (lane == 0) { S.it_bv[i] = bv; S.it_bj[i] = bj; }
+            S.it_bv[i] = bv;
+            S.it_bj[i] = bj;
+            S.part[slot] = sel ? 1 : 0;
         }
-        if (lane == 0) S.it_cnt[i] = count;
+        __syncthreads();
+    }
+    {   // exclusive scan of the 256 part counts in slot order
+        int total;
+        const int v = S.part[tid];
+        const int ex = block_excl_scan(v, S.wsum, &total);
+        S.part[tid] = ex;
+        if (tid == 0) {
+            S.part[kDecThreads] = total;
+            S.base = base;
+            if (total) atomicAdd(A.counts + b, total);         // result unused: fire-and-forget
+        }
     }
     __syncthreads();
-    if (w == 0) {   // exclusive scan of <= 64 counts, one atomic
-        const int i0 = 2 * lane, i1 = 2 * lane + 1;
-        const int a = (i0 < n_items) ? S.it_cnt[i0] : 0, c = (i1 < n_items) ? S.it_cnt[i1] : 0;
-        const int inc = warp_incl_scan(a + c, lane);
-        S.it_excl[i0] = inc - a - c;
-        S.it_excl[i1] = inc - c;
-        if (lane == 31) {
-            S.it_excl[kItems] = inc;
-            S.base = inc ? atomicAdd(A.counts + b, inc) : 0;
-        }
+    if (tid <= kItems) {
+        const int t = tid;
+        S.it_excl[t] = (t < n_items) ? S.part[t << lgq] : S.part[kDecThreads];
     }
-    __syncthreads();
+    if (tid < kItems) S.it_cnt[tid] = (tid < n_items) ? S.part[(tid + 1) << lgq] - S.part[tid << lgq] : 0;
     uint64_t* cand = A.cand + (size_t)b * A.cap;
-    for (int i = w; i < n_items; i += kWarps) {
-        if (S.it_cnt[i] == 0) continue;
-        const int ai = S.it_ai[i], row = S.it_row[i];
-        int pos = S.base + S.it_excl[i];
+    if (act) {
+        const int row = S.it_row[i];
+        int pos = base + S.part[slot];
         if (A.multi_label) {
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-                const int c = c0 + lane;
-                const float v = (c < nc) ? T.get(ai, c) : -1.0f;
-                const bool flag = v >= 0.0f;
-                const unsigned m = __ballot_sync(0xffffffffu, flag);
-                const int p = pos + __popc(m & ((1u << lane) - 1u));
-                if (flag && p < A.cap)
-                    cand[p] = ((uint64_t)(uint32_t)(row * nc + c) << 32) | __float_as_uint(v);
-                pos += __popc(m);
+            const int end = base + S.part[slot + 1];
+            if (pos < end) {
+                for (int c = c_lo; c < c_hi; ++c) {
+                    const float v = T.get(ai, c);
+                    if (v >= 0.0f) {
+                        if (pos < A.cap) cand[pos] = ((uint64_t)(uint32_t)(row * nc + c) << 32) | __float_as_uint(v);
+                        ++pos;
+                    }
+                }
             }
-        } else if (lane == 0 && pos < A.cap) {
+        } else if (qd == 0 && S.part[slot + 1] > S.part[slot] && pos < A.cap) {
             cand[pos] = ((uint64_t)(uint32_t)(row * nc + S.it_bj[i]) << 32) | __float_as_uint(S.it_bv[i]);
         }
-        if (lane == 0) A.boxes[(size_t)b * A.rows + row] = T.box(ai);
+        if (qd == 0 && S.part[(i + 1) << lgq] > S.part[slot]) A.boxes[(size_t)b * A.rows + row] = T.box(ai);
     }
     __syncthreads();
 }
@@ -332,6 +393,14 @@ __device__ __forceinline__ int plan_sparse_items(FilterSmem& S, int ntiles, int 
     return run;
 }
 
+// All sparse survivors of a group (<= 64 rows) fit the slot range of its first sparse tile.
+template <class NV>
+__device__ __forceinline__ int first_sparse_tile(const FilterSmem& S, int ntiles, NV tile_nvalid) {
+    for (int k = 0; k < ntiles; ++k)
+        if (tile_is_sparse(S.tile_np[k], tile_nvalid(k))) return k;
+    return 0;
+}
+
 // Items of one dense tile: its survivors, accessor index = row inside the tile.
 __device__ __forceinline__ int plan_dense_items(FilterSmem& S, int k, int row0_group) {
     const int np = S.tile_np[k];
@@ -381,7 +450,7 @@ __device__ __forceinline__ void write_dense_segment(FilterSmem& S, const FilterA
     }
 }
 
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, 5)
 decode_filter_kernel(const HeadDev H, const FilterArgs A) {
     extern __shared__ float buf[];  // dense tile [no][kTilePitch] or staging [64][no]
     __shared__ FilterSmem S;
@@ -430,7 +499,7 @@ decode_filter_kernel(const HeadDev H, const FilterArgs A) {
         }
         __syncthreads();
         LogitStage T{buf, no, geom, s_sp};
-        filter_items(S, T, A, b, n_sparse);
+        filter_items(S, T, A, b, n_sparse, (seg0 + first_sparse_tile(S, ntiles, tile_nvalid)) * A.tile_cap);
     }
     write_sparse_segments(S, A, b, seg0, ntiles, n_sparse, tile_nvalid);
     __syncthreads();
@@ -440,32 +509,17 @@ decode_filter_kernel(const HeadDev H, const FilterArgs A) {
     for (int k = 0; k < ntiles; ++k) {
         const int np = S.tile_np[k], nv = tile_nvalid(k);
         if (np == 0 || tile_is_sparse(np, nv)) continue;
-        const float* __restrict__ tin = in + k * kTileS;
-        if (vec) {
-            for (int e = threadIdx.x; e < no * (kTileS / 4); e += kDecThreads) {
-                const int c = e >> 4, s = (e & 15) << 2;
-                if (s < nv) {
-                    const float4 v = ld_stream_f4(tin + (size_t)c * nynx + s);
-                    float* d = buf + c * kTilePitch + s;
-                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                }
-            }
-        } else {
-            for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
-                const int c = e >> 6, s = e & 63;
-                if (s < nv) buf[c * kTilePitch + s] = ld_stream_f32(tin + (size_t)c * nynx + s);
-            }
-        }
+        load_tile(buf, in + k * kTileS, no, nynx, nv, vec);
         const int n_items = plan_dense_items(S, k, row0);
         __syncthreads();
         LogitTile T{buf, geom, s0 + k * kTileS};
-        filter_items(S, T, A, b, n_items);
+        filter_items(S, T, A, b, n_items, (seg0 + k) * A.tile_cap);
         write_dense_segment(S, A, b, seg0 + k);
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, 5)
 filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
     extern __shared__ float buf[];  // [64][no]: a dense tile or the gathered rows
     __shared__ FilterSmem S;
@@ -497,7 +551,7 @@ filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
         }
         __syncthreads();
         PredRows T{buf, no};
-        filter_items(S, T, A, b, n_sparse);
+        filter_items(S, T, A, b, n_sparse, (seg0 + first_sparse_tile(S, ntiles, tile_nvalid)) * A.tile_cap);
     }
     write_sparse_segments(S, A, b, seg0, ntiles, n_sparse, tile_nvalid);
     __syncthreads();
@@ -516,7 +570,7 @@ filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
         const int n_items = plan_dense_items(S, k, row0);
         __syncthreads();
         PredRows T{buf, no};
-        filter_items(S, T, A, b, n_items);
+        filter_items(S, T, A, b, n_items, (seg0 + k) * A.tile_cap);
         write_dense_segment(S, A, b, seg0 + k);
         __syncthreads();
     }
@@ -547,13 +601,17 @@ static int make_head(const VkHeadCfg* cfg, HeadDev* H, const char* who) {
     return VK_OK;
 }
 
-static int check_cand(const VkCandBuf* o, int rows, int segs, int nc, const char* who) {
+static int check_cand(const VkCandBuf* o, int rows, int segs, int nc, int multi_label, const char* who) {
     if (!o || !o->cand || !o->boxes || !o->counts || !o->seg_base || !o->seg_count)
         return fail_arg("%s: candidate buffer has a NULL member", who);
     if (o->cap <= 0 || o->rows != rows || o->segs != segs || o->nc != nc)
         return fail_arg("%s: candidate buffer shape (cap=%d rows=%d segs=%d nc=%d) != (rows=%d segs=%d nc=%d)",
                         who, o->cap, o->rows, o->segs, o->nc, rows, segs, nc);
-    if ((uint64_t)rows * (uint64_t)nc > 0xffffffffull) return fail_code(VK_E_LIMIT, "%s: rows*nc overflows 32 bits", who);
+    if ((uint64_t)rows * (uint64_t)nc > 0x7fffffffull) return fail_code(VK_E_LIMIT, "%s: rows*nc overflows 31 bits", who);
+    const long need = (long)segs * kTileS * ((multi_label && nc > 1) ? nc : 1);
+    if (o->cap < need)
+        return fail_arg("%s: cap %d < %ld (= segs * 64 * %s): every tile owns a fixed slot range", who, o->cap, need,
+                        (multi_label && nc > 1) ? "nc" : "1");
     if (reinterpret_cast<uintptr_t>(o->boxes) & 15) return fail_arg("%s: boxes must be 16-byte aligned", who);
     return VK_OK;
 }
@@ -568,6 +626,7 @@ static FilterArgs make_filter_args(const VkCandBuf* o, float conf, int multi_lab
     A.counts = o->counts; A.seg_base = o->seg_base; A.seg_count = o->seg_count;
     A.cap = o->cap; A.rows = o->rows; A.segs = o->segs; A.nc = o->nc;
     A.group = 1;
+    A.tile_cap = kTileS * (A.multi_label ? o->nc : 1);
     return A;
 }
 
@@ -595,6 +654,8 @@ extern "C" int vk_decode_filter_segments(const VkHeadCfg* cfg) {
     if (int rc = make_head(cfg, &H, "vk_decode_filter_segments")) return rc;
     return H.tiles;
 }
+
+extern "C" int vk_cand_tile_slots(int nc, int multi_label) { return kTileS * ((multi_label && nc > 1) ? nc : 1); }
 
 extern "C" int vk_filter_segments(int rows) { return rows > 0 ? ceil_div(rows, kTileS) : 0; }
 
@@ -627,7 +688,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels
     if (!levels || batch < 0) return fail_arg("vk_decode_filter: null/negative argument");
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_decode_filter: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_decode_filter: batch %d > 65535", batch);
-    if (int rc = check_cand(out, H.rows, H.tiles, H.nc, "vk_decode_filter")) return rc;
+    if (int rc = check_cand(out, H.rows, H.tiles, H.nc, multi_label, "vk_decode_filter")) return rc;
     for (int l = 0; l < H.nl; ++l) {
         if (!levels[l]) return fail_arg("vk_decode_filter: level %d is NULL", l);
         H.lv[l] = levels[l];
@@ -660,7 +721,7 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_filter_pred: batch %d > 65535", batch);
     const int segs = ceil_div(rows, kTileS);
     if (segs > VK_MAX_SEGMENTS) return fail_code(VK_E_LIMIT, "vk_filter_pred: %d rows > %d", rows, VK_MAX_SEGMENTS * kTileS);
-    if (int rc = check_cand(out, rows, segs, nc, "vk_filter_pred")) return rc;
+    if (int rc = check_cand(out, rows, segs, nc, multi_label, "vk_filter_pred")) return rc;
     cudaStream_t stream = as_stream(stream_);
     cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
     if (e != cudaSuccess) return fail_code((int)e, "vk_filter_pred: memset: %s", cudaGetErrorString(e));

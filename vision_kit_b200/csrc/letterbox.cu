@@ -37,7 +37,6 @@ lb_tables_kernel(const VkLbDesc* __restrict__ descs, int4* __restrict__ xtab,
                  int4* __restrict__ ytab, int out_h, int out_w) {
     const int b = blockIdx.x;
     const VkLbDesc d = descs[b];
-    if (d.new_h == d.src_h && d.new_w == d.src_w) return;  // image_proc.py:42
     int4* xt = xtab + (size_t)b * out_w;
     int4* yt = ytab + (size_t)b * out_h;
     for (int i = threadIdx.x; i < d.new_w + d.new_h; i += blockDim.x) {
@@ -86,18 +85,32 @@ __device__ __forceinline__ void store_px(typename OutT<FMT>::type* dst, size_t p
     }
 }
 
-constexpr int kLbRows = 8;      // canvas rows per block
-constexpr int kLbThreads = 320; // 640-wide canvas = 2 columns per thread, no idle lanes
+// Horizontal pass of one source row for one canvas column: h[c] = P0[c]*a0 + P1[c]*a1 where the
+// two source pixels are the 6 bytes starting `sh/8` bytes into the aligned words w0 w1 w2 and
+// a01 = a0 | a1 << 16.  PRMT pairs (P0[c], P1[c]) as adjacent bytes, DP2A does the two products.
+__device__ __forceinline__ void taps_dp2a(uint32_t w0, uint32_t w1, uint32_t w2, int sh, uint32_t a01, uint32_t h[3]) {
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    const uint32_t p01 = __byte_perm(lo, hi, 0x4130);   // [P0c0, P1c0, P0c1, P1c1]
+    const uint32_t p2 = __byte_perm(lo, hi, 0x0052);    // [P0c2, P1c2, -, -]
+    h[0] = __dp2a_lo(a01, p01, 0u);
+    h[1] = __dp2a_hi(a01, p01, 0u);
+    h[2] = __dp2a_lo(a01, p2, 0u);
+}
 
-// One block = kLbRows canvas rows of one image.  Block-uniform choice between
-//   (a) the vector copy path: no resize and everything 4-pixel aligned -> 3 x 32-bit
-//       loads (12 source bytes = 4 pixels) and one 128-bit store per plane;
-//   (b) the general path: one thread per canvas column, bilinear taps through L1.
+constexpr int kLbRows = 8;        // canvas rows per block
+constexpr int kLbThreads = 320;   // 640-wide canvas = 2 columns per thread, no idle lanes
+constexpr int kLbWarps = kLbThreads / 32;
+constexpr int kGenRows = 4;       // canvas rows per block of the general kernel
+constexpr int kLbMaxSrcRows = 2 * kGenRows + 4;  // staged source rows (down-scales up to ~2.2x)
+
+// ---------------------------------------------------------------------------------------
+// copy kernel: every image of the batch is a plain copy (no resize) with 4-pixel alignment.
+// 3 x 32-bit loads = 4 pixels, byte extract, /255, one 128-bit streaming store per plane.
+// ---------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(kLbThreads)
-lb_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ xtab,
-          const int4* __restrict__ ytab, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
-          typename OutT<FMT>::type* __restrict__ dst_all) {
+__global__ void __launch_bounds__(kLbThreads, 6)
+lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
+               typename OutT<FMT>::type* __restrict__ dst_all) {
     using T = typename OutT<FMT>::type;
     const int b = blockIdx.y;
     const int y_begin = blockIdx.x * kLbRows;
@@ -106,92 +119,244 @@ lb_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ xtab,
     const size_t plane = (size_t)out_h * out_w;
     T* dst = dst_all + (size_t)b * 3 * plane;
     const int p0 = pad_rgb & 255, p1 = (pad_rgb >> 8) & 255, p2 = (pad_rgb >> 16) & 255;
-    const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;  // source byte of output channel 0/2
-    const bool resize = !(d.new_h == d.src_h && d.new_w == d.src_w);
-
-    const bool vec_ok = (FMT != VK_LB_U8_NHWC) && !resize && ((d.left & 3) == 0) &&
-                        ((d.new_w & 3) == 0) && ((out_w & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(d.src) & 3) == 0) && ((d.pitch & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(dst_all) & 15) == 0);
-    if (vec_ok) {
-        const int gpr = out_w >> 2;  // 4-pixel groups per row
-        const int items = (y_end - y_begin) * gpr;
-        float fp[3];
-        fp[0] = norm255((float)p0); fp[1] = norm255((float)p1); fp[2] = norm255((float)p2);
-        for (int i = threadIdx.x; i < items; i += kLbThreads) {
-            const int ry = i / gpr;
-            const int x = (i - ry * gpr) << 2;
-            const int y = y_begin + ry;
-            const int sy = y - d.top, sx = x - d.left;
-            float4 o[3];
-            if (sy >= 0 && sy < d.new_h && sx >= 0 && sx < d.new_w) {
-                const uint8_t* p = d.src + (size_t)sy * d.pitch + (size_t)sx * 3;
-                const uint32_t w0 = ld_stream_u32(p), w1 = ld_stream_u32(p + 4),
-                               w2 = ld_stream_u32(p + 8);
-                // byte i of the 12-byte group: pixel k, source channel j sits at i = 3k + j
-                auto B = [&](int i) -> float {
-                    const uint32_t w = i < 4 ? w0 : (i < 8 ? w1 : w2);
-                    return norm255((float)((w >> (8 * (i & 3))) & 255u));
-                };
-                const float4 q0 = make_float4(B(0), B(3), B(6), B(9));
-                const float4 q1 = make_float4(B(1), B(4), B(7), B(10));
-                const float4 q2 = make_float4(B(2), B(5), B(8), B(11));
-                o[0] = swap_rb ? q2 : q0;
-                o[1] = q1;
-                o[2] = swap_rb ? q0 : q2;
-            } else {
-                o[0] = make_float4(fp[0], fp[0], fp[0], fp[0]);
-                o[1] = make_float4(fp[1], fp[1], fp[1], fp[1]);
-                o[2] = make_float4(fp[2], fp[2], fp[2], fp[2]);
-            }
-            const size_t off = (size_t)y * out_w + x;
+    const int gpr = out_w >> 2;  // 4-pixel groups per row
+    const int items = (y_end - y_begin) * gpr;
+    float fp[3];
+    fp[0] = norm255((float)p0); fp[1] = norm255((float)p1); fp[2] = norm255((float)p2);
+    for (int i = threadIdx.x; i < items; i += kLbThreads) {
+        const int ry = i / gpr;
+        const int x = (i - ry * gpr) << 2;
+        const int y = y_begin + ry;
+        const int sy = y - d.top, sx = x - d.left;
+        float4 o[3];
+        if (sy >= 0 && sy < d.new_h && sx >= 0 && sx < d.new_w) {
+            const uint8_t* p = d.src + (size_t)sy * d.pitch + (size_t)sx * 3;
+            const uint32_t w0 = ld_stream_u32(p), w1 = ld_stream_u32(p + 4), w2 = ld_stream_u32(p + 8);
+            // byte i of the 12-byte group: pixel k, source channel j sits at i = 3k + j
+            auto B = [&](int k) -> float {
+                const uint32_t w = k < 4 ? w0 : (k < 8 ? w1 : w2);
+                return norm255((float)((w >> (8 * (k & 3))) & 255u));
+            };
+            const float4 q0 = make_float4(B(0), B(3), B(6), B(9));
+            const float4 q1 = make_float4(B(1), B(4), B(7), B(10));
+            const float4 q2 = make_float4(B(2), B(5), B(8), B(11));
+            o[0] = swap_rb ? q2 : q0;
+            o[1] = q1;
+            o[2] = swap_rb ? q0 : q2;
+        } else {
+            o[0] = make_float4(fp[0], fp[0], fp[0], fp[0]);
+            o[1] = make_float4(fp[1], fp[1], fp[1], fp[1]);
+            o[2] = make_float4(fp[2], fp[2], fp[2], fp[2]);
+        }
+        const size_t off = (size_t)y * out_w + x;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 3; ++c) {
+            if constexpr (FMT == VK_LB_F32_NCHW) {
+                st_stream_f4(dst + off + c * plane, o[c]);
+            } else if constexpr (FMT == VK_LB_BF16_NCHW) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o[c].x, o[c].y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(o[c].z, o[c].w);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&lo);
+                u.y = *reinterpret_cast<uint32_t*>(&hi);
+                st_stream_u2(dst + off + c * plane, u);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// general kernel: one block = kLbRows canvas rows of one image (any size, any alignment).
+//
+//   1. the source rows the tile needs (a contiguous range, <= kLbMaxSrcRows) are staged in shared
+//      memory: one warp per row, 2 aligned 32-bit loads + a funnel shift per word, so that every
+//      staged row starts 4-byte aligned whatever the source pitch (3*w is rarely a multiple of 4).
+//      DRAM sees only coalesced word loads; nothing is read before the image's first aligned word
+//      or past its last byte.
+//   2. per canvas column the two horizontal taps are 6 consecutive bytes of a staged row: 2-3
+//      LDS.32, funnel shift, PRMT to pair the bytes, DP2A for P0*a0 + P1*a1.  Clamped taps at the
+//      right edge have weight 0 (OpenCV resets the fraction there), so every column takes this path.
+//   3. vertical pass with IMAD.HI on weights pre-shifted by 16, value/255 from a 256-entry
+//      table built with the correctly rounded two-FMA division.
+//
+// Images without resize use the same code with identity tables (weights 2048/0 reproduce the
+// source byte exactly).  Tiles whose source span exceeds the staging capacity (down-scales
+// beyond ~2x) fall back to byte taps through L1.
+// ---------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(kLbThreads)
+lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ xtab,
+                  const int4* __restrict__ ytab, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
+                  typename OutT<FMT>::type* __restrict__ dst_all, int row_words, int max_rows) {
+    using T = typename OutT<FMT>::type;
+    extern __shared__ uint32_t stage[];          // [max_rows][row_words]
+    __shared__ float s_lut[256];
+    __shared__ int4 s_y[kGenRows];                // {stage word offset of row r0, of row r1, b0<<16, b1<<16}
+    __shared__ int s_span[2];
+    const int b = blockIdx.y;
+    const int y_begin = blockIdx.x * kGenRows;
+    const int y_end = min(y_begin + kGenRows, out_h);
+    const int nrows = y_end - y_begin;
+    const VkLbDesc d = descs[b];
+    const size_t plane = (size_t)out_h * out_w;
+    T* dst = dst_all + (size_t)b * 3 * plane;
+    const int p0 = pad_rgb & 255, p1 = (pad_rgb >> 8) & 255, p2 = (pad_rgb >> 16) & 255;
+    const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;  // source byte of output channel 0/2
+    const int4* xt = xtab + (size_t)b * out_w;
+    const int4* yt = ytab + (size_t)b * out_h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // tile rows that intersect the image, and the source rows they touch
+    const int ys = max(y_begin, d.top), ye_ = min(y_end, d.top + d.new_h);   // [ys, ye_) valid canvas rows
+    for (int i = threadIdx.x; i < 256; i += kLbThreads) s_lut[i] = norm255((float)i);
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = -1;
+        if (ys < ye_) {
+            lo = __ldg(yt + (ys - d.top)).x;
+            hi = __ldg(yt + (ye_ - 1 - d.top)).y;
+        }
+        s_span[0] = lo; s_span[1] = hi;
+    }
+    __syncthreads();
+    const int rlo = s_span[0], nsrc = s_span[1] - s_span[0] + 1;
+    const bool staged = nsrc <= max_rows && 3 * d.src_w + 36 <= row_words * 4;
+
+    auto emit = [&](size_t off, int v0, int v1, int v2) {
+        if constexpr (FMT == VK_LB_F32_NCHW) {
+            st_stream_f32(dst + off, s_lut[v0]);
+            st_stream_f32(dst + off + plane, s_lut[v1]);
+            st_stream_f32(dst + off + 2 * plane, s_lut[v2]);
+        } else if constexpr (FMT == VK_LB_BF16_NCHW) {
+            dst[off] = __float2bfloat16_rn(s_lut[v0]);
+            dst[off + plane] = __float2bfloat16_rn(s_lut[v1]);
+            dst[off + 2 * plane] = __float2bfloat16_rn(s_lut[v2]);
+        } else {
+            dst[off * 3] = (uint8_t)v0; dst[off * 3 + 1] = (uint8_t)v1; dst[off * 3 + 2] = (uint8_t)v2;
+        }
+    };
+
+    if (staged) {
+        // ---- 1. stage: warp per source row, asynchronous copies (LDGSTS): every load of the tile
+        // is in flight before anyone waits.  A staged row keeps its source alignment: the aligned
+        // global word i of the row lands in staging word (k + i), k = its word index mod 4, so that
+        // 16-byte global chunks are 16-byte chunks in shared memory too and move with one copy.
+        const uint8_t* img_end = d.src + (size_t)(d.src_h - 1) * d.pitch + (size_t)3 * d.src_w;
+        for (int j = warp; j < nsrc; j += kLbWarps) {
+            const uint8_t* g = d.src + (size_t)(rlo + j) * d.pitch;
+            const int a = (int)(reinterpret_cast<uintptr_t>(g) & 3);
+            const uint8_t* ga = g - a;                                // first aligned word of the row
+            const int k = (int)((reinterpret_cast<uintptr_t>(ga) >> 2) & 3);
+            const int nwj = (a + 3 * d.src_w + 3) >> 2;              // aligned words holding the row
+            uint32_t* srow = stage + j * row_words;                  // 16-byte aligned (row_words % 4 == 0)
+            const bool last_row = (rlo + j == d.src_h - 1);          // only there a word can cross img_end
+            for (int c = lane; 4 * c < k + nwj; c += 32) {           // 16-byte chunk c = staging words 4c..4c+3
+                const int i0 = 4 * c - k;                            // row word of the chunk's first slot
+                const uint8_t* gp = ga + 4 * i0;
+                if (i0 >= 0 && i0 + 4 <= nwj && !(last_row && gp + 16 > img_end)) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(srow + 4 * c);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gp) : "memory");
+                } else {
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u;
+                        if (i < 0 || i >= nwj) continue;
+                        const uint8_t* wp = ga + 4 * i;
+                        if (!last_row || wp + 4 <= img_end) {
+                            const unsigned sa = (unsigned)__cvta_generic_to_shared(srow + 4 * c + u);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(wp) : "memory");
+                        } else {                                     // the image's very last word: no over-read
+                            uint32_t v = 0;
+                            for (int q = 0; q < 4 && wp + q < img_end; ++q) v |= (uint32_t)__ldg(wp + q) << (8 * q);
+                            srow[4 * c + u] = v;
+                        }
+                    }
+                }
+            }
+            if (lane < 3) srow[k + nwj + lane] = 0u;                 // taps may read past the row's words
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (threadIdx.x < kGenRows) {
+            const int y = y_begin + threadIdx.x;
+            int4 e = make_int4(-1, -1, 0, 0);
+            if (y >= ys && y < ye_) {
+                const int4 yc = __ldg(yt + (y - d.top));
+                // byte position of a row's first pixel inside its staging row: 4*k + a = address mod 16
+                const int a0 = (int)(reinterpret_cast<uintptr_t>(d.src + (size_t)yc.x * d.pitch) & 15);
+                const int a1 = (int)(reinterpret_cast<uintptr_t>(d.src + (size_t)yc.y * d.pitch) & 15);
+                // byte offsets into the staging buffer, source alignment included
+                e = make_int4((yc.x - rlo) * row_words * 4 + a0, (yc.y - rlo) * row_words * 4 + a1,
+                              yc.z << 16, yc.w << 16);
+            }
+            s_y[threadIdx.x] = e;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // ---- 2./3. taps from shared memory.  Index arithmetic is 32-bit relative to the image's
+        // block-uniform base pointers; BGR<->RGB is a swap of plane pointers, not of values.
+        T* const plane_a = dst + (FMT == VK_LB_U8_NHWC ? c0 : (size_t)c0 * plane);   // receives source byte 0
+        T* const plane_b = dst + (FMT == VK_LB_U8_NHWC ? 1 : plane);
+        T* const plane_c = dst + (FMT == VK_LB_U8_NHWC ? c2 : (size_t)c2 * plane);   // receives source byte 2
+        const int pa = swap_rb ? p2 : p0, pc = swap_rb ? p0 : p2;                    // pad value per pointer
+        for (int x = threadIdx.x; x < out_w; x += kLbThreads) {
+            const int sx = x - d.left;
+            const bool in_x = sx >= 0 && sx < d.new_w;
+            const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
+            const uint32_t a01 = (uint32_t)xc.z | ((uint32_t)xc.w << 16);
+            uint32_t idx = (uint32_t)(y_begin * out_w + x);
+#pragma unroll
+            for (int r = 0; r < kGenRows; ++r, idx += out_w) {
+                if (r >= nrows) break;
+                const int4 ye = s_y[r];
+                int va = pa, vb = p1, vc = pc;
+                if (in_x && ye.x >= 0) {
+                    const int t0 = ye.x + xc.x, t1 = ye.y + xc.x;       // byte offsets of the taps in `stage`
+                    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(stage) + (t0 & ~3));
+                    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(stage) + (t1 & ~3));
+                    uint32_t h0[3], h1[3];
+                    taps_dp2a(q0[0], q0[1], q0[2], (t0 & 3) * 8, a01, h0);
+                    taps_dp2a(q1[0], q1[1], q1[2], (t1 & 3) * 8, a01, h1);
+                    // ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
+                    va = (int)((__umulhi((uint32_t)ye.z, h0[0] >> 4) + __umulhi((uint32_t)ye.w, h1[0] >> 4) + 2u) >> 2);
+                    vb = (int)((__umulhi((uint32_t)ye.z, h0[1] >> 4) + __umulhi((uint32_t)ye.w, h1[1] >> 4) + 2u) >> 2);
+                    vc = (int)((__umulhi((uint32_t)ye.z, h0[2] >> 4) + __umulhi((uint32_t)ye.w, h1[2] >> 4) + 2u) >> 2);
+                }
                 if constexpr (FMT == VK_LB_F32_NCHW) {
-                    st_stream_f4(dst + off + c * plane, o[c]);
+                    st_stream_f32(plane_a + idx, s_lut[va]);
+                    st_stream_f32(plane_b + idx, s_lut[vb]);
+                    st_stream_f32(plane_c + idx, s_lut[vc]);
                 } else if constexpr (FMT == VK_LB_BF16_NCHW) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(o[c].x, o[c].y);
-                    __nv_bfloat162 hi = __floats2bfloat162_rn(o[c].z, o[c].w);
-                    uint2 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&lo);
-                    u.y = *reinterpret_cast<uint32_t*>(&hi);
-                    st_stream_u2(dst + off + c * plane, u);
+                    plane_a[idx] = __float2bfloat16_rn(s_lut[va]);
+                    plane_b[idx] = __float2bfloat16_rn(s_lut[vb]);
+                    plane_c[idx] = __float2bfloat16_rn(s_lut[vc]);
+                } else {
+                    plane_a[3 * idx] = (uint8_t)va; plane_b[3 * idx] = (uint8_t)vb; plane_c[3 * idx] = (uint8_t)vc;
                 }
             }
         }
         return;
     }
 
-    const int4* xt = xtab + (size_t)b * out_w;
-    const int4* yt = ytab + (size_t)b * out_h;
+    // ---- fallback: byte taps through L1 (source span larger than the staging buffer)
     for (int x = threadIdx.x; x < out_w; x += kLbThreads) {
         const int sx = x - d.left;
         const bool in_x = sx >= 0 && sx < d.new_w;
-        int4 xc = make_int4(3 * sx, 3 * sx, 2048, 0);
-        if (in_x && resize) xc = __ldg(xt + sx);
+        const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
         for (int y = y_begin; y < y_end; ++y) {
             const int sy = y - d.top;
             int v0 = p0, v1 = p1, v2 = p2;
             if (in_x && sy >= 0 && sy < d.new_h) {
-                if (resize) {
-                    const int4 yc = __ldg(yt + sy);
-                    const uint8_t* r0 = d.src + (size_t)yc.x * d.pitch;
-                    const uint8_t* r1 = d.src + (size_t)yc.y * d.pitch;
-                    int v[3];
+                const int4 yc = __ldg(yt + sy);
+                const uint8_t* r0 = d.src + (size_t)yc.x * d.pitch;
+                const uint8_t* r1 = d.src + (size_t)yc.y * d.pitch;
+                int v[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int h0 = (int)__ldg(r0 + xc.x + c) * xc.z + (int)__ldg(r0 + xc.y + c) * xc.w;
-                        const int h1 = (int)__ldg(r1 + xc.x + c) * xc.z + (int)__ldg(r1 + xc.y + c) * xc.w;
-                        v[c] = ((((yc.z * (h0 >> 4)) >> 16) + ((yc.w * (h1 >> 4)) >> 16) + 2) >> 2);
-                    }
-                    v0 = v[c0]; v1 = v[1]; v2 = v[c2];
-                } else {
-                    const uint8_t* p = d.src + (size_t)sy * d.pitch + xc.x;
-                    v0 = __ldg(p + c0); v1 = __ldg(p + 1); v2 = __ldg(p + c2);
+                for (int c = 0; c < 3; ++c) {
+                    const int h0 = (int)__ldg(r0 + xc.x + c) * xc.z + (int)__ldg(r0 + xc.y + c) * xc.w;
+                    const int h1 = (int)__ldg(r1 + xc.x + c) * xc.z + (int)__ldg(r1 + xc.y + c) * xc.w;
+                    v[c] = ((((yc.z * (h0 >> 4)) >> 16) + ((yc.w * (h1 >> 4)) >> 16) + 2) >> 2);
                 }
+                v0 = v[c0]; v1 = v[1]; v2 = v[c2];
             }
-            const size_t off = (size_t)y * out_w + x;
-            store_px<FMT>(dst, plane, off, off * 3, v0, v1, v2);
+            emit((size_t)y * out_w + x, v0, v1, v2);
         }
     }
 }
@@ -260,14 +425,24 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
     if (!ws || ws_bytes < vk_letterbox_workspace_bytes(batch, out_h, out_w))
         return fail_code(VK_E_WORKSPACE, "vk_letterbox_batch: workspace %zu < %zu", ws_bytes,
                          vk_letterbox_workspace_bytes(batch, out_h, out_w));
-    bool any_resize = false;
+    bool all_copy = (dst_fmt != VK_LB_U8_NHWC) && ((out_w & 3) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    int max_w = 1, max_rows = 3;
     for (int i = 0; i < batch; ++i) {
         const VkLbDesc& d = descs_host[i];
         if (!d.src || d.src_h <= 0 || d.src_w <= 0 || d.new_h <= 0 || d.new_w <= 0 ||
             d.pitch < (int64_t)d.src_w * 3 || d.top < 0 || d.left < 0 ||
             d.top + d.new_h > out_h || d.left + d.new_w > out_w)
             return fail_arg("vk_letterbox_batch: descriptor %d does not fit the %dx%d canvas", i, out_h, out_w);
-        any_resize |= !(d.new_h == d.src_h && d.new_w == d.src_w);
+        const bool rs = !(d.new_h == d.src_h && d.new_w == d.src_w);
+        all_copy &= !rs && ((d.left & 3) == 0) && ((d.new_w & 3) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(d.src) & 3) == 0) && ((d.pitch & 3) == 0);
+        // source rows one tile touches: kGenRows * (src_h / new_h) + 3, staged up to kLbMaxSrcRows
+        const int rows = (int)(((long long)kGenRows * d.src_h + d.new_h - 1) / d.new_h) + 3;
+        if (rows <= kLbMaxSrcRows) {
+            if (rows > max_rows) max_rows = rows;
+            if (d.src_w > max_w) max_w = d.src_w;
+        }
     }
     cudaStream_t stream = as_stream(stream_);
     char* w = static_cast<char*>(ws);
@@ -280,25 +455,36 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
     }
     int4* xtab = reinterpret_cast<int4*>(w + lb_desc_bytes(batch));
     int4* ytab = xtab + (size_t)batch * out_w;
-    if (any_resize) {
-        lb_tables_kernel<<<batch, 256, 0, stream>>>(dd, xtab, ytab, out_h, out_w);
-        count_launch();
-        if (int rc = check_launch("lb_tables_kernel")) return rc;
-    }
     dim3 grid(ceil_div(out_h, kLbRows), batch);
-    switch (dst_fmt) {
-        case VK_LB_F32_NCHW:
-            lb_kernel<VK_LB_F32_NCHW><<<grid, kLbThreads, 0, stream>>>(
-                dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, static_cast<float*>(dst));
-            break;
-        case VK_LB_BF16_NCHW:
-            lb_kernel<VK_LB_BF16_NCHW><<<grid, kLbThreads, 0, stream>>>(
-                dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, static_cast<__nv_bfloat16*>(dst));
-            break;
-        default:
-            lb_kernel<VK_LB_U8_NHWC><<<grid, kLbThreads, 0, stream>>>(
-                dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, static_cast<uint8_t*>(dst));
+    if (all_copy) {
+        if (dst_fmt == VK_LB_F32_NCHW)
+            lb_copy_kernel<VK_LB_F32_NCHW><<<grid, kLbThreads, 0, stream>>>(dd, out_h, out_w, swap_rb, pad_rgb, static_cast<float*>(dst));
+        else
+            lb_copy_kernel<VK_LB_BF16_NCHW><<<grid, kLbThreads, 0, stream>>>(dd, out_h, out_w, swap_rb, pad_rgb, static_cast<__nv_bfloat16*>(dst));
+        count_launch();
+        return check_launch("lb_copy_kernel");
     }
+    grid = dim3(ceil_div(out_h, kGenRows), batch);
+    lb_tables_kernel<<<batch, 256, 0, stream>>>(dd, xtab, ytab, out_h, out_w);
     count_launch();
-    return check_launch("lb_kernel");
+    if (int rc = check_launch("lb_tables_kernel")) return rc;
+    // staging buffer: rows x (words of the widest staged source + 2); kept under ~100 KB so that
+    // two blocks fit an SM -- wider sources take the L1 fallback inside the kernel
+    int row_words = ((((3 * max_w + 3) >> 2) + 10) + 3) & ~3;
+    if ((size_t)max_rows * row_words * 4 > 100 * 1024) row_words = ((100 * 1024 / 4) / max_rows) & ~3;
+    const size_t smem = (size_t)max_rows * row_words * 4;
+#define VK_LB_LAUNCH(FMT, T)                                                                              \
+    do {                                                                                                   \
+        cudaFuncSetAttribute(lb_general_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        lb_general_kernel<FMT><<<grid, kLbThreads, smem, stream>>>(dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, \
+                                                                    static_cast<T*>(dst), row_words, max_rows); \
+    } while (0)
+    switch (dst_fmt) {
+        case VK_LB_F32_NCHW: VK_LB_LAUNCH(VK_LB_F32_NCHW, float); break;
+        case VK_LB_BF16_NCHW: VK_LB_LAUNCH(VK_LB_BF16_NCHW, __nv_bfloat16); break;
+        default: VK_LB_LAUNCH(VK_LB_U8_NHWC, uint8_t);
+    }
+#undef VK_LB_LAUNCH
+    count_launch();
+    return check_launch("lb_general_kernel");
 }

@@ -177,13 +177,11 @@ nms_image_kernel(const NmsArgs A) {
 
     long long* timing = g_nms_timing;
     VK_STAMP(0);
-    const int n_total = A.counts[b];
-    const int n = min(n_total, A.cap);
-    if (tid == 0 && A.status) A.status[b] = (n_total > A.cap) ? 1 : 0;
 
     // ---------------- A1: canonical offsets of the segments
+    int n = 0;
     {
-        int carry = 0;
+        int carry = 0, clipped = 0;
         for (int t0 = 0; t0 < A.segs; t0 += kNmsThreads) {
             const int t = t0 + tid;
             int c = 0;
@@ -191,7 +189,8 @@ nms_image_kernel(const NmsArgs A) {
                 c = seg_count[t];
                 const int sb = seg_base[t];
                 XA.segbase[t] = sb;
-                if (c > 0) c = max(0, min(c, A.cap - sb));  // an overflowed tail was never written
+                if (c > 0 && sb + c > A.cap) { c = max(0, A.cap - sb); clipped = 1; }  // never happens with a
+                                                                                        // buffer sized per the header
             }
             int total;
             const int ex = block_excl_scan(c, wsum, &total);
@@ -199,7 +198,9 @@ nms_image_kernel(const NmsArgs A) {
             carry += total;
         }
         if (tid == 0) XA.segoff[A.segs] = carry;
-        __syncthreads();
+        n = carry;
+        clipped = __syncthreads_or(clipped);
+        if (tid == 0 && A.status) A.status[b] = clipped ? 1 : 0;
     }
 
     VK_STAMP(1);
@@ -217,9 +218,13 @@ nms_image_kernel(const NmsArgs A) {
             const int nb = pass == 2 ? 1024 : 2048;
             for (int i = tid; i < kHistBins; i += kNmsThreads) XA.hist[i] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += kNmsThreads) {
-                const uint32_t key = order_key((uint32_t)cand[i]);
-                if ((key & pmask) == prefix) atomicAdd(&XA.hist[(key >> shift) & (nb - 1)], 1);
+            for (int t = warp; t < A.segs; t += kNmsWarps) {       // candidates live in per-tile slot ranges
+                const int cnt = XA.segoff[t + 1] - XA.segoff[t];
+                const uint64_t* cp = cand + XA.segbase[t];
+                for (int j = lane; j < cnt; j += 32) {
+                    const uint32_t key = order_key((uint32_t)cp[j]);
+                    if ((key & pmask) == prefix) atomicAdd(&XA.hist[(key >> shift) & (nb - 1)], 1);
+                }
             }
             __syncthreads();
             // bins from the top: thread t owns bins nb-1-2t and nb-2-2t

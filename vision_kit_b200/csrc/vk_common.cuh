@@ -67,10 +67,14 @@ __device__ __forceinline__ void st_stream_u2(void* p, uint2 v) {
 }
 
 // The sigmoid every kernel of the path shares, so that the fused decode+filter and the
-// two-step decode -> filter paths produce identical bits.  ex2.approx + fast divide:
-// relative error < 2e-6 for |x| < 40, inside the 1e-5 decode tolerance.
+// two-step decode -> filter paths produce identical bits.  Four instructions: FMUL,
+// MUFU.EX2, FADD, MUFU.RCP (ex2.approx <= 2 ulp, rcp.approx <= 1 ulp: relative error below
+// 4e-7, inside the 1e-5 decode tolerance of SURVEY.md A.3; .ftz only touches results < 1.2e-38).
 __device__ __forceinline__ float sigmoidf_vk(float x) {
-    return __fdividef(1.0f, 1.0f + __expf(-x));
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
+    return r;
 }
 
 // Detect decode of one element; every product/sum rounded separately.

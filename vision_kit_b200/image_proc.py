@@ -83,15 +83,11 @@ def _run_nms(prediction: torch.Tensor, conf_thres: float, iou_thres: float, clas
     bs, rows, no = pred.shape
     nc = no - 5
     multi_label = bool(multi_label) and nc > 1                        # :111
-    cap = ops.default_cap(rows, nc, multi_label)
-    while True:
-        buf = ops.filter_pred(pred, conf_thres, multi_label, classes, cap=cap)
-        out = ops.nms_batched(buf, iou_thres, agnostic, max_nms, max_det, want_keep=want_keep)
-        counts, status = torch.stack((out.counts, out.status)).cpu().tolist()   # the one sync
-        if any(status) and cap < rows * nc:
-            cap = rows * nc                                            # candidate overflow: retry at worst case
-            continue
-        break
+    buf = ops.filter_pred(pred, conf_thres, multi_label, classes)
+    out = ops.nms_batched(buf, iou_thres, agnostic, max_nms, max_det, want_keep=want_keep)
+    counts, status = torch.stack((out.counts, out.status)).cpu().tolist()       # the one sync
+    if any(status):
+        raise RuntimeError("nms: candidate buffer overflow (internal sizing error)")
     dets = [out.dets[i, :k] for i, k in enumerate(counts)]
     if want_keep:
         return dets, [out.keep[i, :k] for i, k in enumerate(counts)]

@@ -18,7 +18,6 @@ from ._lib import (VK_HEAD_V5, VK_HEAD_V7, VK_LB_BF16_NCHW, VK_LB_F32_NCHW, VK_L
                    VK_MAX_ANCHORS, VK_MAX_LEVELS, VkCandBuf, VkHeadCfg, VkLbDesc, VkLbGeom)
 
 MAX_WH = 7680          # utils/image_proc.py:107
-DEFAULT_CAND_CAP = 1 << 19
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -223,8 +222,9 @@ def class_mask(classes, nc: int, device) -> Optional[torch.Tensor]:
     return torch.from_numpy(words.view(np.int32)).to(device)
 
 
-def default_cap(rows: int, nc: int, multi_label: bool) -> int:
-    return min(rows * nc, DEFAULT_CAND_CAP) if (multi_label and nc > 1) else rows
+def default_cap(segs: int, nc: int, multi_label: bool) -> int:
+    """Slots per image: every 64-row tile owns a fixed range (include/vk_b200.h)."""
+    return segs * _lib.lib().vk_cand_tile_slots(int(nc), int(bool(multi_label)))
 
 
 def filter_pred(pred: torch.Tensor, conf_thres: float, multi_label: bool = False, classes=None,
@@ -236,7 +236,7 @@ def filter_pred(pred: torch.Tensor, conf_thres: float, multi_label: bool = False
     nc = no - 5
     segs = _lib.lib().vk_filter_segments(rows)
     if buf is None:
-        buf = CandBuf.alloc(bs, rows, segs, nc, cap or default_cap(rows, nc, multi_label), pred.device)
+        buf = CandBuf.alloc(bs, rows, segs, nc, cap or default_cap(segs, nc, multi_label), pred.device)
     mask = class_mask(classes, nc, pred.device)
     cs = buf.c_struct()
     _lib.check("vk_filter_pred", _lib.lib().vk_filter_pred(
@@ -253,7 +253,7 @@ def decode_filter(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], conf_thres: fl
     rows = head_rows(cfg)
     segs = _lib.lib().vk_decode_filter_segments(C.byref(cfg))
     if buf is None:
-        buf = CandBuf.alloc(bs, rows, segs, cfg.nc, cap or default_cap(rows, cfg.nc, multi_label),
+        buf = CandBuf.alloc(bs, rows, segs, cfg.nc, cap or default_cap(segs, cfg.nc, multi_label),
                             levels[0].device)
     mask = class_mask(classes, cfg.nc, levels[0].device)
     cs = buf.c_struct()

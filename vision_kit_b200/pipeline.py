@@ -40,7 +40,7 @@ class DetectPipeline:
         import ctypes as C
         segs = _lib.lib().vk_decode_filter_segments(C.byref(self.cfg))
         ml = bool(multi_label) and nc > 1
-        cap = cand_cap or ops.default_cap(self.rows, nc, ml)
+        cap = cand_cap or ops.default_cap(segs, nc, ml)
         # two sets of candidate / output buffers: with overlap=True the NMS of batch k runs on a
         # side stream while the letterbox and filter kernels of batch k+1 run on the main one
         self.overlap = bool(overlap)
