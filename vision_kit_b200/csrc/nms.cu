@@ -147,12 +147,222 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, cons
     return __fdiv_rn(inter, den) > thr;
 }
 
+// Everything A5 needs besides the sorted candidates themselves.
+struct ChunkCtx {
+    ScratchB XB;
+    const float4* boxes;
+    float* dets;
+    int64_t* keep_out;
+    int nc, agnostic, max_det;
+    float max_wh, half_wh, thr;
+};
+
+// One chunk of <= 256 sorted candidates [chunk0, chunk0 + cn) of source S against the kept list.
+// S.idx(p) = row*nc + cls, S.okey(p) = ordered score bits, S.keep(p) = index torchvision would
+// report.  Returns the new kept count.  All 1024 threads call it; ends with a block barrier.
+template <class Src>
+__device__ __forceinline__ int nms_chunk(const ChunkCtx& C, const Src& S, int chunk0, int cn, int kept0, bool& safe) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool ok = true;
+    if (tid < kHash / 2) C.XB.ccnt2[tid] = 0u;
+    if (tid < kChunk) {
+        C.XB.state[tid] = 2;                               // rows past the end never matter
+#pragma unroll
+        for (int wd = 0; wd < kChunkWords; ++wd) C.XB.pred[tid * kChunkWords + wd] = 0u;
+    }
+    __syncthreads();
+    if (tid < cn) {
+        const uint32_t idx = S.idx(chunk0 + tid);
+        const uint32_t row = idx / (uint32_t)C.nc;
+        const uint32_t cls = idx - row * (uint32_t)C.nc;
+        const float4 bx = C.boxes[row];
+        ok = fabsf(bx.x) <= C.half_wh && fabsf(bx.y) <= C.half_wh && fabsf(bx.z) <= C.half_wh &&
+             fabsf(bx.w) <= C.half_wh;
+        const float off = C.agnostic ? 0.f : __fmul_rn((float)cls, C.max_wh);  // image_proc.py:166
+        C.XB.cbox[tid] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off),
+                                   __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // :168
+        C.XB.ccls[tid] = (uint16_t)cls;
+        C.XB.state[tid] = 0;
+        atomicAdd(&C.XB.ccnt2[(cls & (kHash - 1)) >> 1], 1u << (16 * (cls & 1)));
+    }
+    safe = __syncthreads_and(ok) && safe;
+    const bool by_class = safe && !C.agnostic;
+    if (by_class) {
+        // group the chunk's rows by class bucket: counts -> starts -> member slots
+        if (warp == 0) {
+            int c[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int bk = lane * 8 + k;
+                c[k] = (int)((C.XB.ccnt2[bk >> 1] >> (16 * (bk & 1))) & 0xffffu);
+                sum += c[k];
+            }
+            int base = warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { C.XB.cstart[lane * 8 + k] = (uint16_t)base; base += c[k]; }
+            if (lane == 31) C.XB.cstart[kHash] = (uint16_t)base;
+        }
+        __syncthreads();
+        if (tid < cn) {
+            const uint32_t bk = C.XB.ccls[tid] & (kHash - 1);
+            const uint32_t old = atomicSub(&C.XB.ccnt2[bk >> 1], 1u << (16 * (bk & 1)));
+            const uint32_t v = (old >> (16 * (bk & 1))) & 0xffffu;      // 1..count: a unique slot
+            C.XB.members[C.XB.cstart[bk] + v - 1] = (uint16_t)tid;
+        }
+        // (the barrier after step 1 below also orders these writes before step 2 reads them)
+    }
+
+    if (by_class) {
+        // 1: same-class kept boxes only (hash list of the kept set)
+        if (tid < cn) {
+            const float4 cb = C.XB.cbox[tid];
+            const float ca = box_area(cb);
+            const uint32_t cc = C.XB.ccls[tid];
+            bool sup = false;
+            for (uint32_t k = (uint32_t)C.XB.khead[cc & (kHash - 1)]; k != kNil && !sup;) {
+                const uint32_t meta = C.XB.kmeta[k];
+                if ((meta >> 16) == cc) {
+                    const float4 kb = C.XB.kbox[k];
+                    sup = iou_exceeds(kb, box_area(kb), cb, ca, C.thr);
+                }
+                k = meta & 0xffffu;
+            }
+            if (sup) C.XB.state[tid] = 2;
+        }
+        __syncthreads();
+        // 2: same-class predecessors inside the chunk.  One warp per row, lanes over the
+        //    members of the row's class bucket (rows of a crowded class would otherwise walk
+        //    a long list one dependent step at a time).
+        for (int i = warp; i < cn; i += kNmsWarps) {
+            if (C.XB.state[i] != 0) continue;
+            const uint32_t ic = C.XB.ccls[i];
+            const uint32_t bk = ic & (kHash - 1);
+            const int e = C.XB.cstart[bk + 1];
+            const float4 ib = C.XB.cbox[i];
+            const float ia = box_area(ib);
+            for (int m = C.XB.cstart[bk] + lane; m < e; m += 32) {
+                const int j = C.XB.members[m];
+                if (j >= i || C.XB.ccls[j] != ic || C.XB.state[j] != 0) continue;
+                const float4 jb = C.XB.cbox[j];
+                if (iou_exceeds(jb, box_area(jb), ib, ia, C.thr))
+                    atomicOr(&C.XB.pred[i * kChunkWords + (j >> 5)], 1u << (j & 31));
+            }
+        }
+    } else {
+        // 1: all kept boxes.  Warp = (32-row block, quarter of the kept list); the kept box
+        //    is a shared-memory broadcast, every lane tests its own row against it.
+        {
+            const int i = (warp >> 2) * 32 + lane, part = warp & 3;
+            if (i < cn) {
+                const float4 cb = C.XB.cbox[i];
+                const float ca = box_area(cb);
+                bool sup = false;
+                for (int k = part; k < kept0 && !sup; k += 4) {
+                    const float4 kb = C.XB.kbox[k];
+                    sup = iou_exceeds(kb, box_area(kb), cb, ca, C.thr);
+                }
+                if (sup) C.XB.state[i] = 2;
+            }
+        }
+        __syncthreads();
+        // 2: warp tile = (32-row block rb, 32-column word wd <= rb): 36 tiles
+        for (int t = warp; t < 36; t += kNmsWarps) {
+            int rb = 0, wd = t;
+            while (wd > rb) { wd -= rb + 1; ++rb; }
+            const int i = rb * 32 + lane;
+            uint32_t m = 0;
+            if (i < cn && C.XB.state[i] == 0) {
+                const float4 ib = C.XB.cbox[i];
+                const float ia = box_area(ib);
+                const int jn = min(32, i - wd * 32);       // columns j < i only
+                for (int bit = 0; bit < jn; ++bit) {
+                    const int j = wd * 32 + bit;
+                    if (C.XB.state[j] != 0) continue;        // already removed: cannot suppress
+                    const float4 jb = C.XB.cbox[j];
+                    if (iou_exceeds(jb, box_area(jb), ib, ia, C.thr)) m |= 1u << bit;
+                }
+            }
+            if (i < kChunk) C.XB.pred[i * kChunkWords + wd] = m;
+        }
+    }
+    __syncthreads();
+    // 3: fixed-point resolve; thread i < 256 owns row i.  Only those 8 warps iterate (named
+    //    barrier 2, one per round; the word buffers ping-pong so a buffer is rewritten only
+    //    after everyone has passed the next barrier).
+    int st = 2;
+    if (tid < kChunk) {
+        uint32_t p[kChunkWords];
+        st = C.XB.state[tid];
+#pragma unroll
+        for (int wd = 0; wd < kChunkWords; ++wd) p[wd] = C.XB.pred[tid * kChunkWords + wd];
+        for (int round = 0;; ++round) {
+            uint32_t* kwb = C.XB.kw + (round & 1) * 3 * kChunkWords;   // [kept | removed | undecided]
+            const unsigned km = __ballot_sync(0xffffffffu, st == 1);
+            const unsigned rm = __ballot_sync(0xffffffffu, st == 2);
+            const unsigned um = __ballot_sync(0xffffffffu, st == 0);
+            if (lane == 0) { kwb[warp] = km; kwb[kChunkWords + warp] = rm; kwb[2 * kChunkWords + warp] = um; }
+            asm volatile("bar.sync 2, %0;" :: "n"(kChunk) : "memory");
+            uint32_t hit = 0, pend = 0, und = 0;
+#pragma unroll
+            for (int wd = 0; wd < kChunkWords; ++wd) {
+                const uint32_t kw = kwb[wd], rw = kwb[kChunkWords + wd];
+                und |= kwb[2 * kChunkWords + wd];
+                hit |= p[wd] & kw;
+                pend |= p[wd] & ~(kw | rw);
+            }
+            if (und == 0) {                       // everyone sees the same words: uniform exit
+                if (tid < kChunkWords) C.XB.kfinal[tid] = kwb[tid];
+                break;
+            }
+            if (st == 0) {
+                if (hit) st = 2;
+                else if (!pend) st = 1;
+            }
+        }
+    }
+    __syncthreads();
+    // 4: kept boxes, in order, join the kept list and the output (image_proc.py:170-182)
+    int total = 0;
+#pragma unroll
+    for (int wd = 0; wd < kChunkWords; ++wd) total += __popc(C.XB.kfinal[wd]);
+    if (tid < kChunk && st == 1) {
+        int rank = __popc(C.XB.kfinal[warp] & ((1u << lane) - 1u));
+        for (int wd = 0; wd < warp; ++wd) rank += __popc(C.XB.kfinal[wd]);
+        const int slot = kept0 + rank;
+        if (slot < C.max_det) {
+            const uint32_t cls16 = C.XB.ccls[tid];
+            C.XB.kbox[slot] = C.XB.cbox[tid];
+            const uint32_t old = (uint32_t)atomicExch(&C.XB.khead[cls16 & (kHash - 1)], slot);
+            C.XB.kmeta[slot] = (cls16 << 16) | (old & 0xffffu);
+            const uint32_t idx = S.idx(chunk0 + tid);
+            const uint32_t row = idx / (uint32_t)C.nc;
+            const float4 bx = C.boxes[row];
+            float* o = C.dets + (size_t)slot * 6;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+            o[4] = __uint_as_float(unorder_key(S.okey(chunk0 + tid)));
+            o[5] = (float)(idx - row * (uint32_t)C.nc);
+            if (C.keep_out) C.keep_out[slot] = S.keep(chunk0 + tid);
+        }
+    }
+    const int kept = min(C.max_det, kept0 + total);
+    __syncthreads();
+    return kept;
+}
+
+struct SortedArrays {   // the big kernel's view of its sorted candidates
+    const uint32_t* skey; const uint16_t* spos; const uint32_t* sel; bool cut;
+    __device__ __forceinline__ uint32_t idx(int p) const { return sel[spos[p]]; }
+    __device__ __forceinline__ uint32_t okey(int p) const { return skey[p]; }
+    __device__ __forceinline__ int64_t keep(int p) const { return cut ? (int64_t)p : (int64_t)spos[p]; }
+};
+
 // Optional phase timestamps (clock64) for profiling: [batch][32] written by thread 0 when set.
 __device__ long long* g_nms_timing = nullptr;
 #define VK_STAMP(k) do { if (timing && tid == 0) timing[(size_t)blockIdx.x * 32 + (k)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kNmsThreads, 1)
-nms_image_kernel(const NmsArgs A) {
+nms_image_kernel(const NmsArgs A, const int32_t* __restrict__ only_flagged) {
+    if (only_flagged && !only_flagged[blockIdx.x]) return;   // the staged kernel already did this image
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wsum[33];
     __shared__ int s_found_bin, s_found_above;
@@ -380,201 +590,12 @@ nms_image_kernel(const NmsArgs A) {
     for (int i = tid; i < kHash; i += kNmsThreads) XB.khead[i] = (int)kNil;
     int kept0 = 0;
     bool safe = A.nc <= 65535;
-    const float thr = A.iou_thr;
-    const float half_wh = 0.5f * A.max_wh;
+    const ChunkCtx CC{XB, boxes, dets, keep_out, A.nc, A.agnostic, A.max_det, A.max_wh, 0.5f * A.max_wh, A.iou_thr};
+    const SortedArrays SRC{skey, spos, sel, cut};
     __syncthreads();
     for (int chunk0 = 0; chunk0 < M && kept0 < A.max_det; chunk0 += kChunk) {
         const int cn = min(kChunk, M - chunk0);
-        bool ok = true;
-        if (tid < kHash / 2) XB.ccnt2[tid] = 0u;
-        if (tid < kChunk) {
-            XB.state[tid] = 2;                               // rows past the end never matter
-#pragma unroll
-            for (int wd = 0; wd < kChunkWords; ++wd) XB.pred[tid * kChunkWords + wd] = 0u;
-        }
-        __syncthreads();
-        if (tid < cn) {
-            const uint32_t idx = sel[spos[chunk0 + tid]];
-            const uint32_t row = idx / (uint32_t)A.nc;
-            const uint32_t cls = idx - row * (uint32_t)A.nc;
-            const float4 bx = boxes[row];
-            ok = fabsf(bx.x) <= half_wh && fabsf(bx.y) <= half_wh && fabsf(bx.z) <= half_wh &&
-                 fabsf(bx.w) <= half_wh;
-            const float off = A.agnostic ? 0.f : __fmul_rn((float)cls, A.max_wh);  // image_proc.py:166
-            XB.cbox[tid] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off),
-                                       __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));  // :168
-            XB.ccls[tid] = (uint16_t)cls;
-            XB.state[tid] = 0;
-            atomicAdd(&XB.ccnt2[(cls & (kHash - 1)) >> 1], 1u << (16 * (cls & 1)));
-        }
-        safe = __syncthreads_and(ok) && safe;
-        const bool by_class = safe && !A.agnostic;
-        if (chunk0 == 0) VK_STAMP(5);
-        if (by_class) {
-            // group the chunk's rows by class bucket: counts -> starts -> member slots
-            if (warp == 0) {
-                int c[8], sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int bk = lane * 8 + k;
-                    c[k] = (int)((XB.ccnt2[bk >> 1] >> (16 * (bk & 1))) & 0xffffu);
-                    sum += c[k];
-                }
-                int base = warp_incl_scan(sum, lane) - sum;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { XB.cstart[lane * 8 + k] = (uint16_t)base; base += c[k]; }
-                if (lane == 31) XB.cstart[kHash] = (uint16_t)base;
-            }
-            __syncthreads();
-            if (tid < cn) {
-                const uint32_t bk = XB.ccls[tid] & (kHash - 1);
-                const uint32_t old = atomicSub(&XB.ccnt2[bk >> 1], 1u << (16 * (bk & 1)));
-                const uint32_t v = (old >> (16 * (bk & 1))) & 0xffffu;      // 1..count: a unique slot
-                XB.members[XB.cstart[bk] + v - 1] = (uint16_t)tid;
-            }
-            // (the barrier after step 1 below also orders these writes before step 2 reads them)
-        }
-
-        if (by_class) {
-            // 1: same-class kept boxes only (hash list of the kept set)
-            if (tid < cn) {
-                const float4 cb = XB.cbox[tid];
-                const float ca = box_area(cb);
-                const uint32_t cc = XB.ccls[tid];
-                bool sup = false;
-                for (uint32_t k = (uint32_t)XB.khead[cc & (kHash - 1)]; k != kNil && !sup;) {
-                    const uint32_t meta = XB.kmeta[k];
-                    if ((meta >> 16) == cc) {
-                        const float4 kb = XB.kbox[k];
-                        sup = iou_exceeds(kb, box_area(kb), cb, ca, thr);
-                    }
-                    k = meta & 0xffffu;
-                }
-                if (sup) XB.state[tid] = 2;
-            }
-            __syncthreads();
-            if (chunk0 == 0) VK_STAMP(13);
-            // 2: same-class predecessors inside the chunk.  One warp per row, lanes over the
-            //    members of the row's class bucket (rows of a crowded class would otherwise walk
-            //    a long list one dependent step at a time).
-            for (int i = warp; i < cn; i += kNmsWarps) {
-                if (XB.state[i] != 0) continue;
-                const uint32_t ic = XB.ccls[i];
-                const uint32_t bk = ic & (kHash - 1);
-                const int e = XB.cstart[bk + 1];
-                const float4 ib = XB.cbox[i];
-                const float ia = box_area(ib);
-                for (int m = XB.cstart[bk] + lane; m < e; m += 32) {
-                    const int j = XB.members[m];
-                    if (j >= i || XB.ccls[j] != ic || XB.state[j] != 0) continue;
-                    const float4 jb = XB.cbox[j];
-                    if (iou_exceeds(jb, box_area(jb), ib, ia, thr))
-                        atomicOr(&XB.pred[i * kChunkWords + (j >> 5)], 1u << (j & 31));
-                }
-            }
-        } else {
-            // 1: all kept boxes.  Warp = (32-row block, quarter of the kept list); the kept box
-            //    is a shared-memory broadcast, every lane tests its own row against it.
-            {
-                const int i = (warp >> 2) * 32 + lane, part = warp & 3;
-                if (i < cn) {
-                    const float4 cb = XB.cbox[i];
-                    const float ca = box_area(cb);
-                    bool sup = false;
-                    for (int k = part; k < kept0 && !sup; k += 4) {
-                        const float4 kb = XB.kbox[k];
-                        sup = iou_exceeds(kb, box_area(kb), cb, ca, thr);
-                    }
-                    if (sup) XB.state[i] = 2;
-                }
-            }
-            __syncthreads();
-            // 2: warp tile = (32-row block rb, 32-column word wd <= rb): 36 tiles
-            for (int t = warp; t < 36; t += kNmsWarps) {
-                int rb = 0, wd = t;
-                while (wd > rb) { wd -= rb + 1; ++rb; }
-                const int i = rb * 32 + lane;
-                uint32_t m = 0;
-                if (i < cn && XB.state[i] == 0) {
-                    const float4 ib = XB.cbox[i];
-                    const float ia = box_area(ib);
-                    const int jn = min(32, i - wd * 32);       // columns j < i only
-                    for (int bit = 0; bit < jn; ++bit) {
-                        const int j = wd * 32 + bit;
-                        if (XB.state[j] != 0) continue;        // already removed: cannot suppress
-                        const float4 jb = XB.cbox[j];
-                        if (iou_exceeds(jb, box_area(jb), ib, ia, thr)) m |= 1u << bit;
-                    }
-                }
-                if (i < kChunk) XB.pred[i * kChunkWords + wd] = m;
-            }
-        }
-        __syncthreads();
-
-        if (chunk0 == 0) VK_STAMP(6);
-        // 3: fixed-point resolve; thread i < 256 owns row i.  Only those 8 warps iterate (named
-        //    barrier 2, one per round; the word buffers ping-pong so a buffer is rewritten only
-        //    after everyone has passed the next barrier).
-        int st = 2;
-        if (tid < kChunk) {
-            uint32_t p[kChunkWords];
-            st = XB.state[tid];
-#pragma unroll
-            for (int wd = 0; wd < kChunkWords; ++wd) p[wd] = XB.pred[tid * kChunkWords + wd];
-            if (chunk0 == 0) VK_STAMP(15);
-            for (int round = 0;; ++round) {
-                uint32_t* kwb = XB.kw + (round & 1) * 3 * kChunkWords;   // [kept | removed | undecided]
-                const unsigned km = __ballot_sync(0xffffffffu, st == 1);
-                const unsigned rm = __ballot_sync(0xffffffffu, st == 2);
-                const unsigned um = __ballot_sync(0xffffffffu, st == 0);
-                if (lane == 0) { kwb[warp] = km; kwb[kChunkWords + warp] = rm; kwb[2 * kChunkWords + warp] = um; }
-                asm volatile("bar.sync 2, %0;" :: "n"(kChunk) : "memory");
-                uint32_t hit = 0, pend = 0, und = 0;
-#pragma unroll
-                for (int wd = 0; wd < kChunkWords; ++wd) {
-                    const uint32_t kw = kwb[wd], rw = kwb[kChunkWords + wd];
-                    und |= kwb[2 * kChunkWords + wd];
-                    hit |= p[wd] & kw;
-                    pend |= p[wd] & ~(kw | rw);
-                }
-                if (und == 0) {                       // everyone sees the same words: uniform exit
-                    if (tid < kChunkWords) XB.kfinal[tid] = kwb[tid];
-                    if (timing && tid == 0 && chunk0 == 0) { timing[(size_t)blockIdx.x * 32 + 14] = round; timing[(size_t)blockIdx.x * 32 + 16] = clock64(); }
-                    break;
-                }
-                if (st == 0) {
-                    if (hit) st = 2;
-                    else if (!pend) st = 1;
-                }
-            }
-        }
-        __syncthreads();
-        if (chunk0 == 0) VK_STAMP(7);
-        // 4: kept boxes, in order, join the kept list and the output (image_proc.py:170-182)
-        int total = 0;
-#pragma unroll
-        for (int wd = 0; wd < kChunkWords; ++wd) total += __popc(XB.kfinal[wd]);
-        if (tid < kChunk && st == 1) {
-            int rank = __popc(XB.kfinal[warp] & ((1u << lane) - 1u));
-            for (int wd = 0; wd < warp; ++wd) rank += __popc(XB.kfinal[wd]);
-            const int slot = kept0 + rank;
-            if (slot < A.max_det) {
-                const uint32_t cls16 = XB.ccls[tid];
-                XB.kbox[slot] = XB.cbox[tid];
-                const uint32_t old = (uint32_t)atomicExch(&XB.khead[cls16 & (kHash - 1)], slot);
-                XB.kmeta[slot] = (cls16 << 16) | (old & 0xffffu);
-                const uint32_t idx = sel[spos[chunk0 + tid]];
-                const uint32_t row = idx / (uint32_t)A.nc;
-                const float4 bx = boxes[row];
-                float* o = dets + (size_t)slot * 6;
-                o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-                o[4] = __uint_as_float(unorder_key(skey[chunk0 + tid]));
-                o[5] = (float)(idx - row * (uint32_t)A.nc);
-                if (keep_out) keep_out[slot] = cut ? (int64_t)(chunk0 + tid) : (int64_t)spos[chunk0 + tid];
-            }
-        }
-        kept0 = min(A.max_det, kept0 + total);
-        __syncthreads();
+        kept0 = nms_chunk(CC, SRC, chunk0, cn, kept0, safe);
         if (chunk0 == 0) VK_STAMP(8);
     }
     VK_STAMP(9);
@@ -585,6 +606,258 @@ nms_image_kernel(const NmsArgs A) {
     if (tid == 0) A.det_counts[b] = kept0;
     VK_STAMP(10);
     if (timing && tid == 0) { timing[(size_t)blockIdx.x * 32 + 11] = n; timing[(size_t)blockIdx.x * 32 + 12] = kept0; }
+}
+
+// ---------------------------------------------------------------------------------------
+// Staged kernel (the default): greedy NMS consumes candidates in descending score order and
+// stops at max_det, so the sorted order is only ever needed for a prefix.  Candidates are
+// therefore processed in stages of ~1024: a 2-3 pass radix histogram finds a score bound that
+// delimits the next stage (whole tie groups, at most kStageCap candidates), one streaming
+// pass compacts the stage into shared memory as 64-bit keys (ordered score << 32 | ~canonical
+// position), a bitonic sort orders it, and the chunk loop above runs on it.  At eval settings
+// (200 k candidates per image, cut at 30 000) one or two stages reach max_det; the 32 768-
+// element sort of the one-shot kernel never happens.  The exact cut at max_nms falls out of
+// the order: the stage that crosses rank max_nms is truncated there, ties already sorted by
+// canonical position.  A tie group larger than kStageCap (thousands of bit-identical scores)
+// is the one case this kernel hands to nms_image_kernel through the need_big flag.
+// ---------------------------------------------------------------------------------------
+constexpr int kStageCap = 2048;
+constexpr int kStageTarget = 1024;
+
+struct StagedSrc {
+    const unsigned long long* keys;
+    const int* segoff;
+    const int* segbase;
+    const uint64_t* cand;
+    int segs, rank_base;
+    bool cut;
+    __device__ __forceinline__ uint32_t canon(int p) const { return ~(uint32_t)keys[p]; }
+    __device__ __forceinline__ uint32_t idx(int p) const {
+        const int cp = (int)canon(p);
+        int lo = 0, hi = segs;                 // last t with segoff[t] <= cp
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (segoff[mid] <= cp) lo = mid; else hi = mid;
+        }
+        return (uint32_t)(cand[segbase[lo] + (cp - segoff[lo])] >> 32);
+    }
+    __device__ __forceinline__ uint32_t okey(int p) const { return (uint32_t)(keys[p] >> 32); }
+    __device__ __forceinline__ int64_t keep(int p) const { return cut ? (int64_t)(rank_base + p) : (int64_t)canon(p); }
+};
+
+static size_t staged_smem_bytes(int segs, int max_det) {
+    return (size_t)kStageCap * 8 + (size_t)kNmsThreads * 16 + align16((size_t)(2 * segs + 2) * 4) +
+           (size_t)kHistBins * 4 + align16(ScratchB::bytes(max_det));
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1)
+nms_staged_kernel(const NmsArgs A, int32_t* __restrict__ need_big) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int wsum[33];
+    __shared__ int s_bin, s_above, s_cnt;
+
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* xchg = keys + kStageCap;
+    int* segoff = reinterpret_cast<int*>(xchg + 2 * kNmsThreads);
+    int* segbase = segoff + A.segs + 1;
+    int* hist = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(segoff) + align16((size_t)(2 * A.segs + 2) * 4));
+    ScratchB XB(reinterpret_cast<unsigned char*>(hist + kHistBins), A.max_det);
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t* cand = A.cand + (size_t)b * A.cap;
+    const float4* boxes = A.boxes + (size_t)b * A.rows;
+    const int32_t* seg_base = A.seg_base + (size_t)b * A.segs;
+    const int32_t* seg_count = A.seg_count + (size_t)b * A.segs;
+    float* dets = A.dets + (size_t)b * A.max_det * 6;
+    int64_t* keep_out = A.keep_idx ? A.keep_idx + (size_t)b * A.max_det : nullptr;
+    if (tid == 0) need_big[b] = 0;
+
+    // ---- canonical offsets of the segments (as A1 of the one-shot kernel)
+    int n = 0;
+    {
+        int carry = 0, clipped = 0;
+        for (int t0 = 0; t0 < A.segs; t0 += kNmsThreads) {
+            const int t = t0 + tid;
+            int c = 0;
+            if (t < A.segs) {
+                c = seg_count[t];
+                const int sb = seg_base[t];
+                segbase[t] = sb;
+                if (c > 0 && sb + c > A.cap) { c = max(0, A.cap - sb); clipped = 1; }
+            }
+            int total;
+            const int ex = block_excl_scan(c, wsum, &total);
+            if (t < A.segs) segoff[t] = carry + ex;
+            carry += total;
+        }
+        if (tid == 0) segoff[A.segs] = carry;
+        n = carry;
+        clipped = __syncthreads_or(clipped);
+        if (tid == 0 && A.status) A.status[b] = clipped ? 1 : 0;
+    }
+    const int K = min(n, A.max_nms);
+    const bool cut = n > A.max_nms;
+
+    for (int i = tid; i < kHash; i += kNmsThreads) XB.khead[i] = (int)kNil;
+    int kept0 = 0;
+    bool safe = A.nc <= 65535;
+    const ChunkCtx CC{XB, boxes, dets, keep_out, A.nc, A.agnostic, A.max_det, A.max_wh, 0.5f * A.max_wh, A.iou_thr};
+    __syncthreads();
+
+    // streams every candidate of the image: f(ordered key, canonical position)
+    auto for_each_candidate = [&](auto&& f) {
+        for (int t = warp; t < A.segs; t += kNmsWarps) {
+            const int cnt = segoff[t + 1] - segoff[t];
+            if (cnt == 0) continue;
+            const uint64_t* cp = cand + segbase[t];
+            const int c0 = segoff[t];
+            for (int j0 = 0; j0 < cnt; j0 += 128) {        // 4 loads in flight per lane
+                uint64_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    v[u] = (j < cnt) ? cp[j] : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    f(j < cnt, order_key((uint32_t)v[u]), (uint32_t)(c0 + j));
+                }
+            }
+        }
+    };
+
+    unsigned long long U = 1ull << 32;       // exclusive upper bound of the scores not yet processed
+    int rank_base = 0;                       // candidates already processed (= those with key >= U)
+    while (rank_base < K && kept0 < A.max_det) {
+        const int remaining = n - rank_base;
+        uint32_t v = 0;                      // inclusive lower bound of this stage
+        if (remaining > kStageCap) {
+            const int tgt = min(kStageTarget, K - rank_base);
+            uint32_t prefix = 0, pmask = 0;
+            int rem_t = tgt, above_total = 0;
+            bool found = false;
+#pragma unroll 1
+            for (int pass = 0; pass < 3 && !found; ++pass) {
+                const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+                const int nb = pass == 2 ? 1024 : 2048;
+                for (int i = tid; i < kHistBins; i += kNmsThreads) hist[i] = 0;
+                __syncthreads();
+                for_each_candidate([&](bool ok, uint32_t key, uint32_t) {
+                    if (ok && (unsigned long long)key < U && (key & pmask) == prefix)
+                        atomicAdd(&hist[(key >> shift) & (nb - 1)], 1);
+                });
+                __syncthreads();
+                const int b0 = nb - 1 - 2 * tid, b1 = nb - 2 - 2 * tid;   // bins from the top
+                const int v0 = (b0 >= 0) ? hist[b0] : 0;
+                const int v1 = (b1 >= 0) ? hist[b1] : 0;
+                int total;
+                const int above = block_excl_scan(v0 + v1, wsum, &total);
+                if (above < rem_t && rem_t <= above + v0) { s_bin = b0; s_above = above; }
+                else if (above + v0 < rem_t && rem_t <= above + v0 + v1) { s_bin = b1; s_above = above + v0; }
+                __syncthreads();
+                const int bin = s_bin, ab = s_above;
+                prefix |= (uint32_t)bin << shift;
+                pmask |= (uint32_t)(nb - 1) << shift;
+                const int count_ge = above_total + ab + hist[bin];   // remaining candidates with key >= prefix
+                if (count_ge <= kStageCap) { v = prefix; found = true; }
+                above_total += ab;
+                rem_t -= ab;
+                __syncthreads();
+            }
+            if (!found) {                    // > kStageCap bit-identical scores: one-shot kernel takes over
+                if (tid == 0) need_big[b] = 1;
+                return;
+            }
+        }
+        // ---- compaction of the stage [v, U) into shared memory
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        if (remaining == n && n <= kNmsThreads) {
+            // small image, first (only) stage: one thread per canonical position
+            if (tid < n) {
+                int lo = 0, hi = A.segs;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (segoff[mid] <= tid) lo = mid; else hi = mid;
+                }
+                const uint64_t cd = cand[segbase[lo] + (tid - segoff[lo])];
+                keys[tid] = ((unsigned long long)order_key((uint32_t)cd) << 32) | (unsigned long long)(~(uint32_t)tid);
+            }
+            if (tid == 0) s_cnt = n;
+        } else {
+            for_each_candidate([&](bool ok, uint32_t key, uint32_t canon) {
+                const bool take = ok && key >= v && (unsigned long long)key < U;
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < kStageCap) keys[pos] = ((unsigned long long)key << 32) | (unsigned long long)(~canon);
+                    }
+                }
+            });
+        }
+        __syncthreads();
+        const int cnt = min(s_cnt, kStageCap);
+        int Ps = 32;
+        while (Ps < cnt) Ps <<= 1;
+        for (int i = cnt + tid; i < Ps; i += kNmsThreads) keys[i] = 0ull;
+        __syncthreads();
+        // ---- sort, descending
+        if (cnt > 1 && Ps <= kNmsThreads) {
+            if (tid < Ps) {
+                unsigned long long x = keys[tid];
+                int pp = 0;
+                for (int k = 2; k <= Ps; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        unsigned long long o;
+                        if (j >= 32) {
+                            unsigned long long* xb = xchg + pp * kNmsThreads;
+                            xb[tid] = x;
+                            asm volatile("bar.sync 1, %0;" :: "r"(Ps) : "memory");
+                            o = xb[tid ^ j];
+                            pp ^= 1;
+                        } else {
+                            o = __shfl_xor_sync(0xffffffffu, x, j);
+                        }
+                        const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
+                        x = keep_max ? (x > o ? x : o) : (x < o ? x : o);
+                    }
+                }
+                keys[tid] = x;
+            }
+            __syncthreads();
+        } else if (cnt > 1) {
+            for (int k = 2; k <= Ps; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < (Ps >> 1); i += kNmsThreads) {
+                        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                        const int hi = lo | j;
+                        const unsigned long long ka = keys[lo], kb = keys[hi];
+                        if ((kb > ka) == ((lo & k) == 0)) { keys[lo] = kb; keys[hi] = ka; }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        // ---- NMS over the stage, truncated at rank max_nms
+        const int M = min(cnt, K - rank_base);
+        const StagedSrc SRC{keys, segoff, segbase, cand, A.segs, rank_base, cut};
+        for (int chunk0 = 0; chunk0 < M && kept0 < A.max_det; chunk0 += kChunk)
+            kept0 = nms_chunk(CC, SRC, chunk0, min(kChunk, M - chunk0), kept0, safe);
+        rank_base += cnt;
+        U = v;
+        if (v == 0) break;                   // everything has been processed
+    }
+    // rows past the count are zero / -1 (the reference returns exactly k rows; the host slices)
+    for (int i = kept0 * 6 + tid; i < A.max_det * 6; i += kNmsThreads) dets[i] = 0.f;
+    if (keep_out)
+        for (int i = kept0 + tid; i < A.max_det; i += kNmsThreads) keep_out[i] = -1;
+    if (tid == 0) A.det_counts[b] = kept0;
 }
 
 static int next_pow2(int v) {
@@ -609,7 +882,7 @@ extern "C" int vkdbg_nms_timing(void* dev_buf) {
 
 extern "C" size_t vk_nms_workspace_bytes(int batch, int max_nms) {
     if (batch <= 0 || max_nms <= 0 || max_nms > VK_MAX_NMS) return 0;
-    return (size_t)batch * next_pow2(max_nms) * sizeof(uint32_t);
+    return (size_t)batch * next_pow2(max_nms) * sizeof(uint32_t) + (size_t)batch * sizeof(int32_t);
 }
 
 extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, float conf_unused, double iou_thres,
@@ -626,8 +899,9 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, float conf_unused, 
     if (c->cap < 1 || c->rows < 1 || c->nc < 1) return fail_arg("vk_nms_batched: bad candidate buffer shape");
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return fail_arg("vk_nms_batched: iou_thres %g outside [0,1]", iou_thres);
     const int P = sort_capacity(max_nms, c->cap);
-    if (!ws || ws_bytes < (size_t)batch * P * sizeof(uint32_t))
-        return fail_code(VK_E_WORKSPACE, "vk_nms_batched: workspace %zu < %zu", ws_bytes, (size_t)batch * P * sizeof(uint32_t));
+    const size_t ws_need = (size_t)batch * P * sizeof(uint32_t) + (size_t)batch * sizeof(int32_t);
+    if (!ws || ws_bytes < ws_need)
+        return fail_code(VK_E_WORKSPACE, "vk_nms_batched: workspace %zu < %zu", ws_bytes, ws_need);
     const size_t smem = nms_smem_bytes(P, c->segs, max_det);
     if (smem > kSmemLimit)
         return fail_code(VK_E_LIMIT, "vk_nms_batched: max_nms=%d max_det=%d segs=%d need %zu B of shared memory (> %zu)",
@@ -642,9 +916,17 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, float conf_unused, 
     A.agnostic = agnostic ? 1 : 0; A.max_nms = max_nms; A.max_det = max_det; A.max_wh = max_wh;
     A.dets = dets; A.det_counts = det_counts; A.keep_idx = keep_idx; A.status = status;
     A.sel = static_cast<uint32_t*>(ws); A.P = P;
-    cudaError_t e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int32_t* need_big = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + (size_t)batch * P * sizeof(uint32_t));
+    const size_t smem_st = staged_smem_bytes(c->segs, max_det);
+    cudaError_t e = cudaFuncSetAttribute(nms_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);
+    if (e != cudaSuccess) return fail_code((int)e, "vk_nms_batched: %zu B of shared memory: %s", smem_st, cudaGetErrorString(e));
+    nms_staged_kernel<<<batch, kNmsThreads, smem_st, as_stream(stream)>>>(A, need_big);
+    count_launch();
+    if (int rc = check_launch("nms_staged_kernel")) return rc;
+    // images with a tie group too large for a stage (need_big) are redone by the one-shot kernel
+    e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail_code((int)e, "vk_nms_batched: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    nms_image_kernel<<<batch, kNmsThreads, smem, as_stream(stream)>>>(A);
+    nms_image_kernel<<<batch, kNmsThreads, smem, as_stream(stream)>>>(A, need_big);
     count_launch();
     return check_launch("nms_image_kernel");
 }
