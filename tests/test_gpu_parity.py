@@ -379,3 +379,69 @@ def test_config3_eval_mode_properties(vk, cuda):
     k = int(r1.counts[0])
     assert np.array_equal(r1.keep[0, :k].cpu().numpy(), keeps[0].numpy())
     assert np.array_equal(r1.dets[0, :k].cpu().numpy(), outs[0].numpy())
+
+
+# --------------------------------------------------------------------------- staged NMS corner cases
+def test_nms_many_stages_heavy_suppression(vk, cuda):
+    # ~45 k candidates packed into 40 clusters: few boxes survive, so the staged kernel has to walk
+    # every stage down to the max_nms cut (rank 30000) instead of stopping after the first one
+    rng = np.random.Generator(np.random.PCG64(17))
+    rows, nc = 12000, 8
+    p = np.zeros((1, rows, 5 + nc), np.float32)
+    centers = rng.random((40, 2), dtype=np.float32) * np.float32(600) + np.float32(20)
+    k = rng.integers(0, 40, size=rows)
+    p[0, :, 0:2] = centers[k] + (rng.random((rows, 2), dtype=np.float32) - np.float32(0.5)) * np.float32(6)
+    p[0, :, 2:4] = np.float32(60) + rng.random((rows, 2), dtype=np.float32) * np.float32(6)
+    p[0, :, 4] = np.float32(0.5) + rng.random(rows, dtype=np.float32) * np.float32(0.5)
+    p[0, :, 5:] = rng.random((rows, nc), dtype=np.float32)
+    kw = dict(conf_thres=0.2, iou_thres=0.5, multi_label=True, agnostic=True)
+    outs, keeps = ref_port.nms(torch.from_numpy(p.copy()), return_keep=True, **kw)
+    dets, k2 = vk.image_proc._run_nms(torch.from_numpy(p).to(cuda), classes=None, labels=(),
+                                      max_det=300, max_nms=30000, want_keep=True, **kw)
+    assert outs[0].shape[0] < 300, "workload must not fill max_det"
+    assert np.array_equal(k2[0].cpu().numpy(), keeps[0].numpy())
+    assert np.array_equal(dets[0].cpu().numpy(), outs[0].numpy())
+
+
+def test_nms_oversized_tie_group_falls_back(vk, cuda):
+    # 5000 bit-identical scores: larger than a stage -> the one-shot kernel redoes the image
+    rng = np.random.Generator(np.random.PCG64(23))
+    rows, nc = 6000, 4
+    p = np.zeros((2, rows, 5 + nc), np.float32)
+    p[..., 0:2] = rng.random((2, rows, 2), dtype=np.float32) * np.float32(600)
+    p[..., 2:4] = np.float32(30)
+    p[..., 4] = 1.0
+    p[:, :5000, 5] = 0.5            # identical score 0.5 for 5000 rows of class 0
+    p[:, 5000:, 6] = rng.random((2, 1000), dtype=np.float32)
+    kw = dict(conf_thres=0.25, iou_thres=0.45)
+    outs, keeps = ref_port.nms(torch.from_numpy(p.copy()), return_keep=True, **kw)
+    dets, k2 = vk.image_proc._run_nms(torch.from_numpy(p).to(cuda), classes=None, agnostic=False, multi_label=False,
+                                      labels=(), max_det=300, max_nms=30000, want_keep=True, **kw)
+    for i in range(2):
+        assert np.array_equal(k2[i].cpu().numpy(), keeps[i].numpy())
+        assert np.array_equal(dets[i].cpu().numpy(), outs[i].numpy())
+
+
+def test_pipeline_overlap_equals_single_stream(vk, cuda):
+    from vision_kit_b200.pipeline import DetectPipeline
+    B = 8
+    batches = [[torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=40 + k, clusters=10)] for k in range(3)]
+    imgs = torch.from_numpy(synth.images_u8(B, 640, 640, seed=9)).to(cuda)
+    ref_pipe = DetectPipeline("v5", batch=B, device=cuda, overlap=False)
+    ovl_pipe = DetectPipeline("v5", batch=B, device=cuda, overlap=True)
+    x0 = ref_pipe.preprocess(list(imgs)).clone()
+    x1 = ovl_pipe.preprocess(list(imgs))
+    assert torch.equal(x0, x1)
+    expect = []
+    for lv in batches:
+        o = ref_pipe.postprocess(lv)
+        expect.append((o.dets.clone(), o.counts.clone()))
+    outs = [ovl_pipe.postprocess(lv, join=False) for lv in batches[:2]]       # two NMS in flight on the side stream
+    ovl_pipe.join()
+    got = [(o.dets.clone(), o.counts.clone()) for o in outs]
+    o = ovl_pipe.postprocess(batches[2])                                      # reuses buffer set 0 after its NMS finished
+    got.append((o.dets.clone(), o.counts.clone()))
+    torch.cuda.synchronize()
+    for (d0, c0), (d1, c1) in zip(expect, got):
+        assert torch.equal(c0, c1) and torch.equal(d0, d1)
+    assert DetectPipeline.to_list(o)[0].shape[1] == 6
