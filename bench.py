@@ -177,6 +177,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic workload, one shard of BATCH images per rank
@@ -238,6 +240,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * BATCH * K / (total_ms * 1e-3)
+    if world > 1:                                       # launches of the whole job
+        tl = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl.item())
 
     # ---- end to end through the public API with HOST buffers: H2D of the step's inputs
     # (uint8 images and the head's conv outputs), the three kernels, D2H of detections+counts
