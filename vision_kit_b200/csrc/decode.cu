@@ -19,7 +19,8 @@
 namespace vk {
 
 constexpr int kTileS = 64;        // spatial positions (= prediction rows) per tile
-constexpr int kTilePitch = kTileS + 1;
+constexpr int kTilePitch = kTileS + 1;   // decode: rows read with lanes over channels (odd pitch)
+constexpr int kFiltPitch = kTileS + 4;   // filters: rows read with lanes over rows; 16-byte aligned for STS.128
 constexpr int kDecThreads = 256;
 constexpr int kWarps = kDecThreads / 32;
 
@@ -59,6 +60,7 @@ __device__ __forceinline__ TileLoc locate_tile(const HeadDev& H, int t) {
 // Coalesced load of one tile's logits into shared memory [no][kTilePitch].  Loads are issued in
 // batches of four 128-bit requests per thread before the first shared store, so that a block
 // keeps ~16 KB in flight instead of one request per thread.
+template <int PITCH>
 __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ in, int no, int nynx,
                                           int nvalid, bool vec) {
     if (vec) {
@@ -76,15 +78,19 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
             for (int u = 0; u < 4; ++u) {
                 const int e = e0 + u * kDecThreads;
                 if (e < total) {
-                    float* d = tile + (e >> 4) * kTilePitch + ((e & 15) << 2);
-                    d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                    float* d = tile + (e >> 4) * PITCH + ((e & 15) << 2);
+                    if constexpr ((PITCH & 3) == 0) {          // rows 16-byte aligned: one STS.128
+                        *reinterpret_cast<float4*>(d) = v[u];
+                    } else {
+                        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                    }
                 }
             }
         }
     } else {
         for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
             const int c = e >> 6, sq = e & 63;
-            if (sq < nvalid) tile[c * kTilePitch + sq] = ld_stream_f32(in + (size_t)c * nynx + sq);
+            if (sq < nvalid) tile[c * PITCH + sq] = ld_stream_f32(in + (size_t)c * nynx + sq);
         }
     }
 }
@@ -97,7 +103,7 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred) {
     const int no = H.no, nynx = H.nynx[q.l];
     const float* __restrict__ in = H.lv[q.l] + ((size_t)(b * H.na + q.a) * no) * nynx + q.s0;
     const bool vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[q.l]) & 15) == 0);
-    load_tile(tile, in, no, nynx, q.nvalid, vec);
+    load_tile<kTilePitch>(tile, in, no, nynx, q.nvalid, vec);
     __syncthreads();
 
     const int nout = q.nvalid * no;
@@ -204,13 +210,13 @@ struct PlaneGeom {       // fused path: what is needed to decode a box from logi
                                 decode_elem(l3, 3, 0.f, stride, ah, variant));
     }
 };
-struct LogitTile {       // dense tile of logits [no][kTilePitch]; ai = row inside the tile
+struct LogitTile {       // dense tile of logits [no][kFiltPitch]; ai = row inside the tile
     float* t; PlaneGeom g; int tile_s0;
-    __device__ __forceinline__ float prob(int ai, int c) const { return sigmoidf_vk(t[(5 + c) * kTilePitch + ai]); }
-    __device__ __forceinline__ void put(int ai, int c, float v) { t[(5 + c) * kTilePitch + ai] = v; }
-    __device__ __forceinline__ float get(int ai, int c) const { return t[(5 + c) * kTilePitch + ai]; }
+    __device__ __forceinline__ float prob(int ai, int c) const { return sigmoidf_vk(t[(5 + c) * kFiltPitch + ai]); }
+    __device__ __forceinline__ void put(int ai, int c, float v) { t[(5 + c) * kFiltPitch + ai] = v; }
+    __device__ __forceinline__ float get(int ai, int c) const { return t[(5 + c) * kFiltPitch + ai]; }
     __device__ __forceinline__ float4 box(int ai) const {
-        return g.box(t[ai], t[kTilePitch + ai], t[2 * kTilePitch + ai], t[3 * kTilePitch + ai], tile_s0 + ai);
+        return g.box(t[ai], t[kFiltPitch + ai], t[2 * kFiltPitch + ai], t[3 * kFiltPitch + ai], tile_s0 + ai);
     }
 };
 struct LogitStage {      // gathered rows of logits [slot][no]; sp[slot] = spatial index in the plane
@@ -246,14 +252,17 @@ __device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const Filter
                                              int base) {
     const int tid = threadIdx.x;
     const int nc = A.nc;
-    const int lgq = (n_items <= 32) ? 3 : 2;           // 8 parts x 32 items or 4 parts x 64 items
-    const int Q = 1 << lgq, ipq = kDecThreads >> lgq;
-    const int i = tid & (ipq - 1), qd = tid / ipq;
-    const int cpp = (nc + Q - 1) >> lgq;
+    // Q class parts per item, as many as 256 threads allow (4..8): an eval-mode tile with ~43
+    // surviving rows runs 5 parts on 215 threads instead of 4 parts on 172
+    const int ni = max(n_items, 32);
+    const int Q = min(8, kDecThreads / ni);
+    const int qd = tid / ni, i = tid - qd * ni;
+    const int cpp = (nc + Q - 1) / Q;
     const int c_lo = min(nc, qd * cpp), c_hi = min(nc, c_lo + cpp);
-    const bool act = i < n_items;
+    const bool act = i < n_items && qd < Q;
     const int ai = act ? S.it_ai[i] : 0;
-    const int slot = (i << lgq) + qd;                   // item-major, part-minor: canonical order
+    const int slot = (qd < Q) ? i * Q + qd : tid;       // item-major, part-minor: canonical order; idle threads
+                                                        // own the unused tail slots
     {
         int count = 0;
         float bv = -INFINITY;
@@ -317,9 +326,9 @@ __device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const Filter
     __syncthreads();
     if (tid <= kItems) {
         const int t = tid;
-        S.it_excl[t] = (t < n_items) ? S.part[t << lgq] : S.part[kDecThreads];
+        S.it_excl[t] = (t < n_items) ? S.part[t * Q] : S.part[kDecThreads];
     }
-    if (tid < kItems) S.it_cnt[tid] = (tid < n_items) ? S.part[(tid + 1) << lgq] - S.part[tid << lgq] : 0;
+    if (tid < kItems) S.it_cnt[tid] = (tid < n_items) ? S.part[(tid + 1) * Q] - S.part[tid * Q] : 0;
     uint64_t* cand = A.cand + (size_t)b * A.cap;
     if (act) {
         const int row = S.it_row[i];
@@ -327,18 +336,27 @@ __device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const Filter
         if (A.multi_label) {
             const int end = base + S.part[slot + 1];
             if (pos < end) {
-                for (int c = c_lo; c < c_hi; ++c) {
-                    const float v = T.get(ai, c);
-                    if (v >= 0.0f) {
-                        if (pos < A.cap) cand[pos] = ((uint64_t)(uint32_t)(row * nc + c) << 32) | __float_as_uint(v);
-                        ++pos;
+                uint32_t idx = (uint32_t)(row * nc + c_lo);
+                if (end <= A.cap) {            // always, with a buffer sized per include/vk_b200.h
+                    uint2* wp = reinterpret_cast<uint2*>(cand) + pos;   // .x = score bits, .y = row*nc + cls
+                    for (int c = c_lo; c < c_hi; ++c, ++idx) {
+                        const float v = T.get(ai, c);
+                        if (v >= 0.0f) *wp++ = make_uint2(__float_as_uint(v), idx);
+                    }
+                } else {
+                    for (int c = c_lo; c < c_hi; ++c, ++idx) {
+                        const float v = T.get(ai, c);
+                        if (v >= 0.0f) {
+                            if (pos < A.cap) cand[pos] = ((uint64_t)idx << 32) | __float_as_uint(v);
+                            ++pos;
+                        }
                     }
                 }
             }
         } else if (qd == 0 && S.part[slot + 1] > S.part[slot] && pos < A.cap) {
             cand[pos] = ((uint64_t)(uint32_t)(row * nc + S.it_bj[i]) << 32) | __float_as_uint(S.it_bv[i]);
         }
-        if (qd == 0 && S.part[(i + 1) << lgq] > S.part[slot]) A.boxes[(size_t)b * A.rows + row] = T.box(ai);
+        if (qd == 0 && S.part[(i + 1) * Q] > S.part[slot]) A.boxes[(size_t)b * A.rows + row] = T.box(ai);
     }
     __syncthreads();
 }
@@ -452,7 +470,7 @@ __device__ __forceinline__ void write_dense_segment(FilterSmem& S, const FilterA
 
 __global__ void __launch_bounds__(kDecThreads, 5)
 decode_filter_kernel(const HeadDev H, const FilterArgs A) {
-    extern __shared__ float buf[];  // dense tile [no][kTilePitch] or staging [64][no]
+    extern __shared__ __align__(16) float buf[];  // dense tile [no][kFiltPitch] or staging [64][no]
     __shared__ FilterSmem S;
     __shared__ int s_sp[kItems];
     const int b = blockIdx.y;
@@ -509,7 +527,7 @@ decode_filter_kernel(const HeadDev H, const FilterArgs A) {
     for (int k = 0; k < ntiles; ++k) {
         const int np = S.tile_np[k], nv = tile_nvalid(k);
         if (np == 0 || tile_is_sparse(np, nv)) continue;
-        load_tile(buf, in + k * kTileS, no, nynx, nv, vec);
+        load_tile<kFiltPitch>(buf, in + k * kTileS, no, nynx, nv, vec);
         const int n_items = plan_dense_items(S, k, row0);
         __syncthreads();
         LogitTile T{buf, geom, s0 + k * kTileS};
@@ -696,7 +714,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels
     cudaStream_t stream = as_stream(stream_);
     cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
     if (e != cudaSuccess) return fail_code((int)e, "vk_decode_filter: memset: %s", cudaGetErrorString(e));
-    const size_t smem = (size_t)H.no * kTilePitch * sizeof(float);
+    const size_t smem = (size_t)H.no * kFiltPitch * sizeof(float);
     if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_decode_filter: nc=%d needs %zu B of shared memory", H.nc, smem);
     cudaFuncSetAttribute(decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
