@@ -176,9 +176,12 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: everything libraries print meanwhile (NCCL's version
+    # banner, warnings) is routed to stderr by pointing fd 1 at fd 2 until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic workload, one shard of BATCH images per rank
@@ -318,6 +321,8 @@ def main():
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"8 images of the batch x {passes} passes ({dt:.1f} s): cv2 letterbox+normalise, "
                          f"torch decode, torch+torchvision NMS", "os_cpu_count": os.cpu_count()}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps({
         "metric": baseline_metric(), "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -334,7 +339,7 @@ def main():
                 "steps": Ke, "note": "PCIe-bound: the head's conv outputs (548 MB/step) are copied from host "
                                      "memory too, as the contract asks; in deployment they are produced on the GPU"},
         "gpu_launches": int(launches), "clocks": clocks,
-    }))
+    }), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
