@@ -468,7 +468,7 @@ __device__ __forceinline__ void write_dense_segment(FilterSmem& S, const FilterA
     }
 }
 
-__global__ void __launch_bounds__(kDecThreads, 5)
+__global__ void __launch_bounds__(kDecThreads, 6)
 decode_filter_kernel(const HeadDev H, const FilterArgs A) {
     extern __shared__ __align__(16) float buf[];  // dense tile [no][kFiltPitch] or staging [64][no]
     __shared__ FilterSmem S;

@@ -108,10 +108,13 @@ constexpr int kLbMaxSrcRows = 2 * kGenRows + 4;  // staged source rows (down-sca
 // 3 x 32-bit loads = 4 pixels, byte extract, /255, one 128-bit streaming store per plane.
 // ---------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(kLbThreads, 6)
+__global__ void __launch_bounds__(kLbThreads, (FMT == VK_LB_BF16_NCHW) ? 4 : 5)
 lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
                typename OutT<FMT>::type* __restrict__ dst_all) {
     using T = typename OutT<FMT>::type;
+    // pixels per thread: every plane store is 128 bits (4 floats or 8 bfloat16)
+    constexpr int PX = (FMT == VK_LB_BF16_NCHW) ? 8 : 4;
+    constexpr int NW = PX * 3 / 4;               // source words per group
     const int b = blockIdx.y;
     const int y_begin = blockIdx.x * kLbRows;
     const int y_end = min(y_begin + kLbRows, out_h);
@@ -119,47 +122,49 @@ lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swa
     const size_t plane = (size_t)out_h * out_w;
     T* dst = dst_all + (size_t)b * 3 * plane;
     const int p0 = pad_rgb & 255, p1 = (pad_rgb >> 8) & 255, p2 = (pad_rgb >> 16) & 255;
-    const int gpr = out_w >> 2;  // 4-pixel groups per row
+    const int gpr = out_w / PX;                  // groups per row
     const int items = (y_end - y_begin) * gpr;
-    float fp[3];
-    fp[0] = norm255((float)p0); fp[1] = norm255((float)p1); fp[2] = norm255((float)p2);
+    // pad value per SOURCE channel slot (the store swaps planes for BGR input)
+    const float fq0 = norm255((float)(swap_rb ? p2 : p0)), fq1 = norm255((float)p1), fq2 = norm255((float)(swap_rb ? p0 : p2));
     for (int i = threadIdx.x; i < items; i += kLbThreads) {
         const int ry = i / gpr;
-        const int x = (i - ry * gpr) << 2;
+        const int x = (i - ry * gpr) * PX;
         const int y = y_begin + ry;
         const int sy = y - d.top, sx = x - d.left;
-        float4 o[3];
+        float o[3][PX];
         if (sy >= 0 && sy < d.new_h && sx >= 0 && sx < d.new_w) {
             const uint8_t* p = d.src + (size_t)sy * d.pitch + (size_t)sx * 3;
-            const uint32_t w0 = ld_stream_u32(p), w1 = ld_stream_u32(p + 4), w2 = ld_stream_u32(p + 8);
-            // byte i of the 12-byte group: pixel k, source channel j sits at i = 3k + j
-            auto B = [&](int k) -> float {
-                const uint32_t w = k < 4 ? w0 : (k < 8 ? w1 : w2);
-                return norm255((float)((w >> (8 * (k & 3))) & 255u));
-            };
-            const float4 q0 = make_float4(B(0), B(3), B(6), B(9));
-            const float4 q1 = make_float4(B(1), B(4), B(7), B(10));
-            const float4 q2 = make_float4(B(2), B(5), B(8), B(11));
-            o[0] = swap_rb ? q2 : q0;
-            o[1] = q1;
-            o[2] = swap_rb ? q0 : q2;
+            uint32_t w[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = ld_stream_u32(p + 4 * k);
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {       // byte 3k + j = pixel k, source channel j
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int bi = 3 * k + j;
+                    const float v = norm255((float)((w[bi >> 2] >> (8 * (bi & 3))) & 255u));
+                    o[j][k] = v;              // source channel order; the swap happens at the store
+                }
+            }
         } else {
-            o[0] = make_float4(fp[0], fp[0], fp[0], fp[0]);
-            o[1] = make_float4(fp[1], fp[1], fp[1], fp[1]);
-            o[2] = make_float4(fp[2], fp[2], fp[2], fp[2]);
+#pragma unroll
+            for (int k = 0; k < PX; ++k) { o[0][k] = fq0; o[1][k] = fq1; o[2][k] = fq2; }
         }
         const size_t off = (size_t)y * out_w + x;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+            T* const pl = dst + off + (size_t)((swap_rb && c != 1) ? 2 - c : c) * plane;   // BGR->RGB = plane swap
             if constexpr (FMT == VK_LB_F32_NCHW) {
-                st_stream_f4(dst + off + c * plane, o[c]);
+                st_stream_f4(pl, make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
             } else if constexpr (FMT == VK_LB_BF16_NCHW) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(o[c].x, o[c].y);
-                __nv_bfloat162 hi = __floats2bfloat162_rn(o[c].z, o[c].w);
-                uint2 u;
-                u.x = *reinterpret_cast<uint32_t*>(&lo);
-                u.y = *reinterpret_cast<uint32_t*>(&hi);
-                st_stream_u2(dst + off + c * plane, u);
+                uint32_t u[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[c][2 * k], o[c][2 * k + 1]);
+                    u[k] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+                             :: "l"(pl), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
             }
         }
     }
@@ -425,7 +430,8 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
     if (!ws || ws_bytes < vk_letterbox_workspace_bytes(batch, out_h, out_w))
         return fail_code(VK_E_WORKSPACE, "vk_letterbox_batch: workspace %zu < %zu", ws_bytes,
                          vk_letterbox_workspace_bytes(batch, out_h, out_w));
-    bool all_copy = (dst_fmt != VK_LB_U8_NHWC) && ((out_w & 3) == 0) &&
+    const int px = (dst_fmt == VK_LB_BF16_NCHW) ? 8 : 4;     // pixels per 128-bit plane store of the copy kernel
+    bool all_copy = (dst_fmt != VK_LB_U8_NHWC) && (out_w % px == 0) &&
                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     int max_w = 1, max_rows = 3;
     for (int i = 0; i < batch; ++i) {
@@ -435,7 +441,7 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
             d.top + d.new_h > out_h || d.left + d.new_w > out_w)
             return fail_arg("vk_letterbox_batch: descriptor %d does not fit the %dx%d canvas", i, out_h, out_w);
         const bool rs = !(d.new_h == d.src_h && d.new_w == d.src_w);
-        all_copy &= !rs && ((d.left & 3) == 0) && ((d.new_w & 3) == 0) &&
+        all_copy &= !rs && (d.left % px == 0) && (d.new_w % px == 0) &&
                     ((reinterpret_cast<uintptr_t>(d.src) & 3) == 0) && ((d.pitch & 3) == 0);
         // source rows one tile touches: kGenRows * (src_h / new_h) + 3, staged up to kLbMaxSrcRows
         const int rows = (int)(((long long)kGenRows * d.src_h + d.new_h - 1) / d.new_h) + 3;
