@@ -68,7 +68,7 @@ def test_argument_validation_without_gpu(vk_lib):
     with pytest.raises(_lib.VkError):
         ops.head_rows(cfg)
     assert vk_lib.vk_letterbox_workspace_bytes(64, 640, 640) == 3072 + 64 * 1280 * 16
-    assert vk_lib.vk_nms_workspace_bytes(4, 30000) == 4 * 32768 * 4
+    assert vk_lib.vk_nms_workspace_bytes(4, 30000) == 4 * 32768 * 4 + 4 * 4   # sel + need_big flags
     assert vk_lib.vk_nms_workspace_bytes(4, 40000) == 0          # > VK_MAX_NMS
     # null pointers / out-of-range thresholds are rejected before any launch
     assert vk_lib.vk_nms_batched(None, 1, 0.0, 0.5, 0, 30000, 300, 7680.0, None, None, None, None, None, 0, None) == -1

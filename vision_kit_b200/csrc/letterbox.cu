@@ -99,8 +99,9 @@ __device__ __forceinline__ void taps_dp2a(uint32_t w0, uint32_t w1, uint32_t w2,
 
 constexpr int kLbRows = 8;        // canvas rows per block
 constexpr int kLbThreads = 320;   // 640-wide canvas = 2 columns per thread, no idle lanes
-constexpr int kLbWarps = kLbThreads / 32;
 constexpr int kGenRows = 4;       // canvas rows per block of the general kernel
+constexpr int kGenThreads = 160;  // 640-wide canvas = one 4-column group per thread
+constexpr int kGenWarps = kGenThreads / 32;
 constexpr int kLbMaxSrcRows = 2 * kGenRows + 4;  // staged source rows (down-scales up to ~2.2x)
 
 // ---------------------------------------------------------------------------------------
@@ -189,7 +190,7 @@ lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swa
 // beyond ~2x) fall back to byte taps through L1.
 // ---------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(kLbThreads)
+__global__ void __launch_bounds__(kGenThreads)
 lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ xtab,
                   const int4* __restrict__ ytab, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
                   typename OutT<FMT>::type* __restrict__ dst_all, int row_words, int max_rows) {
@@ -213,7 +214,7 @@ lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ x
 
     // tile rows that intersect the image, and the source rows they touch
     const int ys = max(y_begin, d.top), ye_ = min(y_end, d.top + d.new_h);   // [ys, ye_) valid canvas rows
-    for (int i = threadIdx.x; i < 256; i += kLbThreads) s_lut[i] = norm255((float)i);
+    for (int i = threadIdx.x; i < 256; i += kGenThreads) s_lut[i] = norm255((float)i);
     if (threadIdx.x == 0) {
         int lo = 0, hi = -1;
         if (ys < ye_) {
@@ -246,7 +247,7 @@ lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ x
         // global word i of the row lands in staging word (k + i), k = its word index mod 4, so that
         // 16-byte global chunks are 16-byte chunks in shared memory too and move with one copy.
         const uint8_t* img_end = d.src + (size_t)(d.src_h - 1) * d.pitch + (size_t)3 * d.src_w;
-        for (int j = warp; j < nsrc; j += kLbWarps) {
+        for (int j = warp; j < nsrc; j += kGenWarps) {
             const uint8_t* g = d.src + (size_t)(rlo + j) * d.pitch;
             const int a = (int)(reinterpret_cast<uintptr_t>(g) & 3);
             const uint8_t* ga = g - a;                                // first aligned word of the row
@@ -295,45 +296,105 @@ lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ x
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // ---- 2./3. taps from shared memory.  Index arithmetic is 32-bit relative to the image's
-        // block-uniform base pointers; BGR<->RGB is a swap of plane pointers, not of values.
-        T* const plane_a = dst + (FMT == VK_LB_U8_NHWC ? c0 : (size_t)c0 * plane);   // receives source byte 0
-        T* const plane_b = dst + (FMT == VK_LB_U8_NHWC ? 1 : plane);
-        T* const plane_c = dst + (FMT == VK_LB_U8_NHWC ? c2 : (size_t)c2 * plane);   // receives source byte 2
+        // ---- 2./3. taps from shared memory.  A thread owns 4 adjacent canvas columns and walks the
+        // tile's rows: the three plane stores of a row are 128 bits each and their address
+        // arithmetic is shared by 4 pixels.  BGR<->RGB is a swap of plane pointers, not of values.
         const int pa = swap_rb ? p2 : p0, pc = swap_rb ? p0 : p2;                    // pad value per pointer
-        for (int x = threadIdx.x; x < out_w; x += kLbThreads) {
-            const int sx = x - d.left;
-            const bool in_x = sx >= 0 && sx < d.new_w;
-            const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
-            const uint32_t a01 = (uint32_t)xc.z | ((uint32_t)xc.w << 16);
-            uint32_t idx = (uint32_t)(y_begin * out_w + x);
+        const uint8_t* const stage_b = reinterpret_cast<const uint8_t*>(stage);
+        auto pixel = [&](const int4 ye, int tb, uint32_t a01, int& va, int& vb, int& vc) {
+            const int t0 = ye.x + tb, t1 = ye.y + tb;                 // byte offsets of the taps in `stage`
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(stage_b + (t0 & ~3));
+            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(stage_b + (t1 & ~3));
+            uint32_t h0[3], h1[3];
+            taps_dp2a(q0[0], q0[1], q0[2], (t0 & 3) * 8, a01, h0);
+            taps_dp2a(q1[0], q1[1], q1[2], (t1 & 3) * 8, a01, h1);
+            // ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
+            va = (int)((__umulhi((uint32_t)ye.z, h0[0] >> 4) + __umulhi((uint32_t)ye.w, h1[0] >> 4) + 2u) >> 2);
+            vb = (int)((__umulhi((uint32_t)ye.z, h0[1] >> 4) + __umulhi((uint32_t)ye.w, h1[1] >> 4) + 2u) >> 2);
+            vc = (int)((__umulhi((uint32_t)ye.z, h0[2] >> 4) + __umulhi((uint32_t)ye.w, h1[2] >> 4) + 2u) >> 2);
+        };
+        const bool vec4 = ((out_w & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst_all) & 15) == 0);
+        if (vec4) {
+            const size_t oa = (FMT == VK_LB_U8_NHWC) ? 0 : (size_t)c0 * plane;       // plane of source byte 0
+            const size_t ob = (FMT == VK_LB_U8_NHWC) ? 0 : plane;
+            const size_t oc = (FMT == VK_LB_U8_NHWC) ? 0 : (size_t)c2 * plane;
+            for (int x4 = threadIdx.x * 4; x4 < out_w; x4 += kGenThreads * 4) {
+                int tb[4];
+                uint32_t a01[4];
+                bool in_x[4];
 #pragma unroll
-            for (int r = 0; r < kGenRows; ++r, idx += out_w) {
-                if (r >= nrows) break;
-                const int4 ye = s_y[r];
-                int va = pa, vb = p1, vc = pc;
-                if (in_x && ye.x >= 0) {
-                    const int t0 = ye.x + xc.x, t1 = ye.y + xc.x;       // byte offsets of the taps in `stage`
-                    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(stage) + (t0 & ~3));
-                    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(stage) + (t1 & ~3));
-                    uint32_t h0[3], h1[3];
-                    taps_dp2a(q0[0], q0[1], q0[2], (t0 & 3) * 8, a01, h0);
-                    taps_dp2a(q1[0], q1[1], q1[2], (t1 & 3) * 8, a01, h1);
-                    // ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
-                    va = (int)((__umulhi((uint32_t)ye.z, h0[0] >> 4) + __umulhi((uint32_t)ye.w, h1[0] >> 4) + 2u) >> 2);
-                    vb = (int)((__umulhi((uint32_t)ye.z, h0[1] >> 4) + __umulhi((uint32_t)ye.w, h1[1] >> 4) + 2u) >> 2);
-                    vc = (int)((__umulhi((uint32_t)ye.z, h0[2] >> 4) + __umulhi((uint32_t)ye.w, h1[2] >> 4) + 2u) >> 2);
+                for (int j = 0; j < 4; ++j) {
+                    const int sx = x4 + j - d.left;
+                    in_x[j] = sx >= 0 && sx < d.new_w;
+                    const int4 xc = in_x[j] ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
+                    tb[j] = xc.x;
+                    a01[j] = (uint32_t)xc.z | ((uint32_t)xc.w << 16);
                 }
-                if constexpr (FMT == VK_LB_F32_NCHW) {
-                    st_stream_f32(plane_a + idx, s_lut[va]);
-                    st_stream_f32(plane_b + idx, s_lut[vb]);
-                    st_stream_f32(plane_c + idx, s_lut[vc]);
-                } else if constexpr (FMT == VK_LB_BF16_NCHW) {
-                    plane_a[idx] = __float2bfloat16_rn(s_lut[va]);
-                    plane_b[idx] = __float2bfloat16_rn(s_lut[vb]);
-                    plane_c[idx] = __float2bfloat16_rn(s_lut[vc]);
-                } else {
-                    plane_a[3 * idx] = (uint8_t)va; plane_b[3 * idx] = (uint8_t)vb; plane_c[3 * idx] = (uint8_t)vc;
+                uint32_t idx = (uint32_t)(y_begin * out_w + x4);
+                for (int r = 0; r < nrows; ++r, idx += out_w) {
+                    const int4 ye = s_y[r];
+                    int va[4], vb[4], vc[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        va[j] = pa; vb[j] = p1; vc[j] = pc;
+                        if (in_x[j] && ye.x >= 0) pixel(ye, tb[j], a01[j], va[j], vb[j], vc[j]);
+                    }
+                    if constexpr (FMT == VK_LB_F32_NCHW) {
+                        // value/255 by arithmetic here: the table would cost 12 more shared-memory
+                        // wavefronts per thread-row, and this loop is already shared-memory bound
+                        st_stream_f4(dst + oa + idx, make_float4(norm255((float)va[0]), norm255((float)va[1]), norm255((float)va[2]), norm255((float)va[3])));
+                        st_stream_f4(dst + ob + idx, make_float4(norm255((float)vb[0]), norm255((float)vb[1]), norm255((float)vb[2]), norm255((float)vb[3])));
+                        st_stream_f4(dst + oc + idx, make_float4(norm255((float)vc[0]), norm255((float)vc[1]), norm255((float)vc[2]), norm255((float)vc[3])));
+                    } else if constexpr (FMT == VK_LB_BF16_NCHW) {
+                        auto pack = [&](const int* v) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(s_lut[v[0]], s_lut[v[1]]);
+                            __nv_bfloat162 hi = __floats2bfloat162_rn(s_lut[v[2]], s_lut[v[3]]);
+                            uint2 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&lo);
+                            u.y = *reinterpret_cast<uint32_t*>(&hi);
+                            return u;
+                        };
+                        st_stream_u2(dst + oa + idx, pack(va));
+                        st_stream_u2(dst + ob + idx, pack(vb));
+                        st_stream_u2(dst + oc + idx, pack(vc));
+                    } else {
+                        // 4 pixels x 3 interleaved bytes = three aligned 32-bit words
+                        int v[12];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { v[3 * j + c0] = va[j]; v[3 * j + 1] = vb[j]; v[3 * j + c2] = vc[j]; }
+                        uint32_t* wp = reinterpret_cast<uint32_t*>(dst + (size_t)idx * 3);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            wp[k] = (uint32_t)v[4 * k] | ((uint32_t)v[4 * k + 1] << 8) | ((uint32_t)v[4 * k + 2] << 16) |
+                                    ((uint32_t)v[4 * k + 3] << 24);
+                    }
+                }
+            }
+        } else {
+            T* const plane_a = dst + (FMT == VK_LB_U8_NHWC ? c0 : (size_t)c0 * plane);   // receives source byte 0
+            T* const plane_b = dst + (FMT == VK_LB_U8_NHWC ? 1 : plane);
+            T* const plane_c = dst + (FMT == VK_LB_U8_NHWC ? c2 : (size_t)c2 * plane);   // receives source byte 2
+            for (int x = threadIdx.x; x < out_w; x += kGenThreads) {
+                const int sx = x - d.left;
+                const bool in_x = sx >= 0 && sx < d.new_w;
+                const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
+                const uint32_t a01 = (uint32_t)xc.z | ((uint32_t)xc.w << 16);
+                uint32_t idx = (uint32_t)(y_begin * out_w + x);
+                for (int r = 0; r < nrows; ++r, idx += out_w) {
+                    const int4 ye = s_y[r];
+                    int va = pa, vb = p1, vc = pc;
+                    if (in_x && ye.x >= 0) pixel(ye, xc.x, a01, va, vb, vc);
+                    if constexpr (FMT == VK_LB_F32_NCHW) {
+                        st_stream_f32(plane_a + idx, s_lut[va]);
+                        st_stream_f32(plane_b + idx, s_lut[vb]);
+                        st_stream_f32(plane_c + idx, s_lut[vc]);
+                    } else if constexpr (FMT == VK_LB_BF16_NCHW) {
+                        plane_a[idx] = __float2bfloat16_rn(s_lut[va]);
+                        plane_b[idx] = __float2bfloat16_rn(s_lut[vb]);
+                        plane_c[idx] = __float2bfloat16_rn(s_lut[vc]);
+                    } else {
+                        plane_a[3 * idx] = (uint8_t)va; plane_b[3 * idx] = (uint8_t)vb; plane_c[3 * idx] = (uint8_t)vc;
+                    }
                 }
             }
         }
@@ -341,7 +402,7 @@ lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ x
     }
 
     // ---- fallback: byte taps through L1 (source span larger than the staging buffer)
-    for (int x = threadIdx.x; x < out_w; x += kLbThreads) {
+    for (int x = threadIdx.x; x < out_w; x += kGenThreads) {
         const int sx = x - d.left;
         const bool in_x = sx >= 0 && sx < d.new_w;
         const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
@@ -482,7 +543,7 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
 #define VK_LB_LAUNCH(FMT, T)                                                                              \
     do {                                                                                                   \
         cudaFuncSetAttribute(lb_general_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        lb_general_kernel<FMT><<<grid, kLbThreads, smem, stream>>>(dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, \
+        lb_general_kernel<FMT><<<grid, kGenThreads, smem, stream>>>(dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, \
                                                                     static_cast<T*>(dst), row_words, max_rows); \
     } while (0)
     switch (dst_fmt) {
