@@ -19,7 +19,6 @@
 namespace vk {
 
 constexpr int kTileS = 64;        // spatial positions (= prediction rows) per tile
-constexpr int kTilePitch = kTileS + 1;   // decode: rows read with lanes over channels (odd pitch)
 constexpr int kFiltPitch = kTileS + 4;   // filters: rows read with lanes over rows; 16-byte aligned for STS.128
 constexpr int kDecThreads = 256;
 constexpr int kWarps = kDecThreads / 32;
@@ -57,7 +56,7 @@ __device__ __forceinline__ TileLoc locate_tile(const HeadDev& H, int t) {
 // ---------------------------------------------------------------------------------------
 // materialised decode
 // ---------------------------------------------------------------------------------------
-// Coalesced load of one tile's logits into shared memory [no][kTilePitch].  Loads are issued in
+// Coalesced load of one tile's logits into shared memory [no][PITCH] (the filter kernels).  Loads are issued in
 // batches of four 128-bit requests per thread before the first shared store, so that a block
 // keeps ~16 KB in flight instead of one request per thread.
 template <int PITCH>
@@ -95,47 +94,192 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(kDecThreads)
-detect_decode_kernel(const HeadDev H, float* __restrict__ pred) {
-    extern __shared__ float tile[];  // [no][kTilePitch] logits
-    const int b = blockIdx.y;
-    const TileLoc q = locate_tile(H, blockIdx.x);
-    const int no = H.no, nynx = H.nynx[q.l];
-    const float* __restrict__ in = H.lv[q.l] + ((size_t)(b * H.na + q.a) * no) * nynx + q.s0;
-    const bool vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[q.l]) & 15) == 0);
-    load_tile<kTilePitch>(tile, in, no, nynx, q.nvalid, vec);
-    __syncthreads();
+// Persistent blocks, each walking tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with a
+// two-deep shared-memory pipeline: while tile k is decoded and stored, the loads of tile k+1 are
+// already in flight, so every resident block keeps a full tile (64*no*4 B) of reads outstanding.
+//
+//  in   16-byte async copies (LDGSTS.128; 4-byte ones move only ~13 B/clk/SM on B200 and are
+//       kept for unaligned planes) of 4 consecutive rows of one channel plane into tile[c][64].
+//       The 16-byte chunk q of channel c sits at chunk position q ^ (c & 7), so that both the
+//       copies (8 lanes = 8 chunks of one channel) and the reads below (8 lanes = one chunk of 8
+//       consecutive channels) touch all 32 banks.
+//  out  a warp takes 4 rows x 32 channels: one LDS.128 per lane (its channel, 4 rows), 4 sigmoids,
+//       4 scalar stores -- each store instruction writes 128 contiguous bytes of one pred row.
+//       Lanes 0-3 of the first channel group hold the box channels and decode them instead.
+//  Tile descriptors (the integer divisions that locate a tile) are computed by one thread, two
+//  tiles ahead, and broadcast through shared memory.  profiles/micro/transpose_bw.cu is the design
+//  study behind these choices (6.4 TB/s for this structure vs 4.7 TB/s with 4-byte copies).
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
 
-    const int nout = q.nvalid * no;
-    float* __restrict__ out = pred + ((size_t)b * H.rows + q.row0) * no;
-    float* __restrict__ raw = H.raw[q.l]
-                                  ? H.raw[q.l] + (((size_t)b * H.na + q.a) * nynx + q.s0) * no
-                                  : nullptr;
-    // Probabilities: element o of the contiguous output chunk is (row s = o / no, channel
-    // c = o % no).  (s, c) advance incrementally (kDecThreads = ds*no + dc): no division in the
-    // loop.  The four box channels of each row are skipped here and written below.
-    const int ds = kDecThreads / no, dc = kDecThreads - ds * no;
-    int s = 0, c = threadIdx.x;
-    while (c >= no) { c -= no; ++s; }
-#pragma unroll 4
-    for (int o = threadIdx.x; o < nout; o += kDecThreads) {
-        const float logit = tile[c * kTilePitch + s];
-        if (c >= 4) st_stream_f32(out + o, sigmoidf_vk(logit));
-        if (raw) st_stream_f32(raw + o, logit);
-        s += ds; c += dc;
-        if (c >= no) { c -= no; ++s; }
-    }
-    // Boxes: 64 rows x 4 channels = one element per thread.
-    {
-        const int r = threadIdx.x >> 2, cb = threadIdx.x & 3;
-        if (r < q.nvalid) {
-            const int sp = q.s0 + r;
-            const int gy = sp / H.nx[q.l], gx = sp - gy * H.nx[q.l];
-            const float g = (float)((cb & 1) ? gy : gx);
-            const float anc = H.anchors[q.l][2 * q.a + (cb & 1)];
-            st_stream_f32(out + r * no + cb, decode_elem(tile[cb * kTilePitch + r], cb, g, H.stride[q.l], anc, H.variant));
+struct DecTile {
+    const float* src;     // first logit of the tile: channel 0, row s0 of plane (b, a)
+    float* out;           // pred chunk
+    float* raw;           // raw chunk or null
+    int nynx, nvalid, nx, gy0, gx0;   // (gy0, gx0): grid cell of the tile's first row
+    int vec;              // 16-byte copies allowed
+    int raw_bulk;         // raw chunk leaves as one bulk copy from shared memory (16-byte aligned, size % 16 == 0)
+    float stride, aw, ah;
+};
+
+__device__ __forceinline__ void decode_tile_of(const HeadDev& H, float* pred, int t, DecTile* d) {
+    const int b = t / H.tiles;
+    const TileLoc q = locate_tile(H, t - b * H.tiles);
+    const int no = H.no, nynx = H.nynx[q.l];
+    d->src = H.lv[q.l] + ((size_t)(b * H.na + q.a) * no) * nynx + q.s0;
+    d->out = pred + ((size_t)b * H.rows + q.row0) * no;
+    d->raw = H.raw[q.l] ? H.raw[q.l] + (((size_t)b * H.na + q.a) * nynx + q.s0) * no : nullptr;
+    d->nynx = nynx; d->nvalid = q.nvalid; d->nx = H.nx[q.l];
+    d->gy0 = q.s0 / H.nx[q.l]; d->gx0 = q.s0 - d->gy0 * H.nx[q.l];
+    d->raw_bulk = d->raw != nullptr && ((reinterpret_cast<uintptr_t>(d->raw) & 15) == 0) && (((q.nvalid * no) & 3) == 0);
+    d->vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[q.l]) & 15) == 0);
+    d->stride = H.stride[q.l]; d->aw = H.anchors[q.l][2 * q.a]; d->ah = H.anchors[q.l][2 * q.a + 1];
+}
+
+__device__ __forceinline__ int swz(int c, int s) { return c * kTileS + ((((s >> 2) ^ c) & 7) << 2 | (s & 32) | (s & 3)); }
+
+__device__ __forceinline__ void decode_prefetch(const DecTile& d, float* tile, int no) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
+    if (d.vec) {
+        const int q = threadIdx.x & 15, c0 = threadIdx.x >> 4;      // 16 chunks per channel, 16 channels per pass
+        if (4 * q < d.nvalid) {
+            const float* src = d.src + (size_t)c0 * d.nynx + 4 * q;
+            const size_t step = (size_t)(kDecThreads / 16) * d.nynx;
+            for (int c = c0; c < no; c += kDecThreads / 16, src += step)
+                cp_async_16(base + 4u * (uint32_t)swz(c, 4 * q), src);
+        }
+    } else {
+        const int r = threadIdx.x & (kTileS - 1), c0 = threadIdx.x >> 6;
+        if (r < d.nvalid) {
+            const float* src = d.src + (size_t)c0 * d.nynx + r;
+            const size_t step = (size_t)(kDecThreads / kTileS) * d.nynx;
+            for (int c = c0; c < no; c += kDecThreads / kTileS, src += step)
+                cp_async_4(base + 4u * (uint32_t)swz(c, r), src);
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// NCG > 0: no <= 32*NCG channels, item loop unrolled; NCG == 0: runtime loop over channel groups.
+template <int NCG>
+__global__ void __launch_bounds__(kDecThreads, 3)
+detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles, int have_lin) {
+    extern __shared__ __align__(16) float tiles_sm[];  // 2 x [no][kTileS] logits, chunk-swizzled (+ [kTileS][no] raw staging)
+    __shared__ DecTile s_dt[3];
+    const int no = H.no;
+    const int tile_floats = kTileS * no;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    if (t >= total_tiles) return;
+    if (threadIdx.x == 0) {
+        decode_tile_of(H, pred, t, &s_dt[0]);
+        if (t + (int)gridDim.x < total_tiles) decode_tile_of(H, pred, t + gridDim.x, &s_dt[1]);
+    }
+    __syncthreads();
+    decode_prefetch(s_dt[0], tiles_sm, no);
+    for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
+        const float* tile = tiles_sm + (k & 1) * tile_floats;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (have_lin && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();                      // tile k landed; everyone is done with the other buffer (and `lin`)
+        const int slot = k % 3;
+        if (t + (int)gridDim.x < total_tiles)
+            decode_prefetch(s_dt[slot == 2 ? 0 : slot + 1], tiles_sm + ((k + 1) & 1) * tile_floats, no);
+        if (threadIdx.x == 0 && t + 2 * (int)gridDim.x < total_tiles )      // slot (k+2)%3 was tile k-1's: free
+            decode_tile_of(H, pred, t + 2 * gridDim.x, &s_dt[slot == 0 ? 2 : slot - 1]);
+        const DecTile& d = s_dt[slot];
+        const int nvalid = d.nvalid;
+        float* __restrict__ out = d.out;
+        float* __restrict__ raw = d.raw;
+        float* const lin = tiles_sm + 2 * tile_floats;       // raw logits of the tile in output order
+        const bool raw_bulk = have_lin && d.raw_bulk;
+
+        // Box channels.  Warp w owns rows 4w..4w+3 and 4(w+8)..4(w+8)+3 in the first channel group:
+        // 8 rows x 4 box channels = one element per lane, decoded here and handed to lanes 0-3 of
+        // the two items by shuffles, so that a row's first 128 bytes leave in ONE store instruction
+        // (the sector holding channels 0-7 is never written in two pieces).
+        float boxv;
+        {
+            const int rl = lane >> 2, cb = lane & 3;
+            const int br = (rl < 4) ? 4 * w + rl : 4 * (w + 8) + rl - 4;
+            const int nx = d.nx;
+            int gx = d.gx0 + br, gy = d.gy0;
+            if (gx >= nx) { const int wq = gx / nx; gy += wq; gx -= wq * nx; }
+            const float anc = (cb & 1) ? d.ah : d.aw;
+            boxv = decode_elem(tile[swz(cb, br)], cb, (float)((cb & 1) ? gy : gx), d.stride, anc, H.variant);
+        }
+        auto item = [&](int cgp, int q, const float4 v) {
+            // rows 4q..4q+3 of channel c = 32*cgp + lane
+            const int c = 32 * cgp + lane;
+            const int r0 = 4 * q;
+            const int left = nvalid - r0;
+            float r[4] = {sigmoidf_vk(v.x), sigmoidf_vk(v.y), sigmoidf_vk(v.z), sigmoidf_vk(v.w)};
+            if (cgp == 0) {
+                const int src0 = (q >= 8 ? 16 : 0) + (lane & 3);
+#pragma unroll
+                for (int jr = 0; jr < 4; ++jr) {
+                    const float bx = __shfl_sync(0xffffffffu, boxv, src0 + 4 * jr);
+                    if (lane < 4) r[jr] = bx;
+                }
+            }
+            if (c < no) {
+                float* po = out + r0 * no + c;
+                if (left >= 4) {
+                    st_stream_f32(po, r[0]); st_stream_f32(po + no, r[1]);
+                    st_stream_f32(po + 2 * no, r[2]); st_stream_f32(po + 3 * no, r[3]);
+                } else {
+#pragma unroll
+                    for (int jr = 0; jr < 4; ++jr) if (jr < left) st_stream_f32(po + jr * no, r[jr]);
+                }
+                if (raw_bulk) {
+                    float* pl = lin + r0 * no + c;                   // rows past nvalid stay inside the buffer
+                    pl[0] = v.x; pl[no] = v.y; pl[2 * no] = v.z; pl[3 * no] = v.w;
+                } else if (raw) {
+                    float* pr = raw + r0 * no + c;
+                    const float l4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int jr = 0; jr < 4; ++jr) if (jr < left) st_stream_f32(pr + jr * no, l4[jr]);
+                }
+            }
+        };
+        // every lane of a warp enters item() together (shuffles inside): q is warp-uniform
+        if (NCG > 0) {
+            float4 v[2 * (NCG > 0 ? NCG : 1)];
+#pragma unroll
+            for (int j = 0; j < 2 * NCG; ++j) {
+                const int c = 32 * (j >> 1) + lane, q = w + 8 * (j & 1);
+                v[j] = (c < no) ? *reinterpret_cast<const float4*>(tile + swz(c, 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NCG; ++j) {
+                const int q = w + 8 * (j & 1);
+                if (4 * q < nvalid) item(j >> 1, q, v[j]);
+            }
+        } else {
+            for (int cgp = 0; 32 * cgp < no; ++cgp)
+                for (int q = w; q < 16; q += kWarps) {
+                    const int c = 32 * cgp + lane;
+                    if (4 * q < nvalid)
+                        item(cgp, q, (c < no) ? *reinterpret_cast<const float4*>(tile + swz(c, 4 * q))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+        }
+        if (raw_bulk) {
+            // generic-proxy writes of `lin` -> visible to the bulk-copy engine -> one 64*no*4-byte store
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(raw), "r"((uint32_t)__cvta_generic_to_shared(lin)), "r"(nvalid * no * 4) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (have_lin && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -689,10 +833,28 @@ extern "C" int vk_detect_decode(const VkHeadCfg* cfg, const float* const* levels
         H.lv[l] = levels[l];
         H.raw[l] = raw ? raw[l] : nullptr;
     }
-    const size_t smem = (size_t)H.no * kTilePitch * sizeof(float);
+    const int have_lin = raw != nullptr;
+    const size_t smem = (size_t)(have_lin ? 3 : 2) * kTileS * H.no * sizeof(float);
     if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_detect_decode: nc=%d needs %zu B of shared memory", H.nc, smem);
-    cudaFuncSetAttribute(detect_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    detect_decode_kernel<<<dim3(H.tiles, batch), kDecThreads, smem, as_stream(stream)>>>(H, pred);
+    if ((long)H.tiles * batch > 0x7fffffffL) return fail_code(VK_E_LIMIT, "vk_detect_decode: %d x %d tiles", H.tiles, batch);
+    const int total_tiles = H.tiles * batch;
+#define VK_DEC_LAUNCH(NCG)                                                                                  \
+    do {                                                                                                     \
+        cudaFuncSetAttribute(detect_decode_kernel<NCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        int per_sm = 0;                                                                                      \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, detect_decode_kernel<NCG>, kDecThreads, smem); \
+        if (per_sm > 3) per_sm = 3;               /* more concurrent tile streams cost DRAM locality */      \
+        if (per_sm < 1) per_sm = 1;                                                                          \
+        const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;                    \
+        detect_decode_kernel<NCG><<<grid, kDecThreads, smem, as_stream(stream)>>>(H, pred, total_tiles, have_lin); \
+    } while (0)
+    // persistent: every block is resident
+    if (H.no <= 32) VK_DEC_LAUNCH(1);
+    else if (H.no <= 64) VK_DEC_LAUNCH(2);
+    else if (H.no <= 96) VK_DEC_LAUNCH(3);
+    else if (H.no <= 128) VK_DEC_LAUNCH(4);
+    else VK_DEC_LAUNCH(0);
+#undef VK_DEC_LAUNCH
     count_launch();
     return check_launch("detect_decode_kernel");
 }
