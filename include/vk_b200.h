@@ -42,6 +42,14 @@ typedef void* vk_stream_t; /* a cudaStream_t (torch.cuda.current_stream().cuda_s
 int vk_version(void);                    /* 100*major + minor */
 const char* vk_last_error(void);         /* thread-local, never NULL */
 uint64_t vk_launch_count(void);          /* kernels launched by this library so far */
+
+/* Which kernel vk_decode_filter uses: VK_FILTER_AUTO picks from the threshold (conf < 0.05: the dense,
+ * persistent kernel; else the group kernel that gathers surviving rows).  Both produce identical bits;
+ * the setter exists for tuning and so that tests can run every case through both.  Returns the old mode. */
+#define VK_FILTER_AUTO 0
+#define VK_FILTER_SPARSE 1
+#define VK_FILTER_DENSE 2
+int vk_set_filter_kernel(int mode);
 int vk_build_arch(void);                 /* 100 => sm_100a */
 
 /* ---------------------------------------------------------------- letterbox

@@ -1,0 +1,15 @@
+#!/usr/bin/env python
+"""Launches the eval-mode fused filter a few times (for ncu captures): python profiles/run_eval.py [batch]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vision_kit_b200 import ops, synth
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+dev = torch.device("cuda:0")
+grids = [(640 // s, 640 // s) for s in synth.STRIDES]
+cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)
+lv = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
+for _ in range(3):
+    buf = ops.decode_filter(cfg, lv, 0.001, True)
+torch.cuda.synchronize()
+print("ok", int(buf.counts.sum()))

@@ -284,6 +284,54 @@ def test_fused_decode_filter_equals_two_step_and_oracle(variant, kw, vk, cuda):
             np.testing.assert_allclose(a.dets[i, :k].cpu().numpy(), outs2[i].numpy(), rtol=1e-5, atol=1e-4)
 
 
+def _canonical(buf):
+    """Candidate lists in canonical order + boxes of the candidate rows, per image (host copies)."""
+    cand, base, cnt, boxes = buf.cand.cpu().numpy(), buf.seg_base.cpu().numpy(), buf.seg_count.cpu().numpy(), buf.boxes.cpu().numpy()
+    out = []
+    for b in range(cand.shape[0]):
+        lst = np.concatenate([cand[b, base[b, s]: base[b, s] + cnt[b, s]] for s in range(buf.segs)] or [np.zeros(0, np.int64)])
+        rows = np.unique((lst >> 32) // buf.nc)
+        out.append((lst, rows, boxes[b, rows]))
+    return out
+
+
+@pytest.mark.parametrize("variant,nc,img,conf,ml,classes", [
+    ("v5", 80, 640, 0.001, True, None),
+    ("v7", 80, 640, 0.001, True, [0, 3, 17, 79]),
+    ("v5", 80, 640, 0.25, False, None),
+    ("v7", 80, 640, 0.001, False, [1, 2, 40]),
+    ("v5", 80, 672, 0.0, True, None),        # 84/42/21 grids: unaligned planes (4-byte copies), partial tiles
+    ("v5", 17, 672, 0.01, True, None),
+    ("v7", 3, 320, 0.001, True, None),
+    ("v5", 1, 320, 0.001, True, None),
+    ("v5", 40, 320, 0.3, True, None),
+    ("v7", 100, 320, 0.001, True, None),     # 4 channel groups
+])
+def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, conf, ml, classes, vk, cuda):
+    """vk_decode_filter picks one of two kernels from the threshold; both must give the same
+    candidates (order included), boxes, counts and therefore the same detections."""
+    cfg, _ = _cfg(vk, variant, img=img, nc=nc)
+    lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(3, seed=77 + nc, img=img, nc=nc, clusters=12)]
+    from vision_kit_b200 import _lib
+    L = _lib.lib()
+    res = {}
+    try:
+        for mode in (1, 2):       # VK_FILTER_SPARSE, VK_FILTER_DENSE
+            L.vk_set_filter_kernel(mode)
+            buf = vk.ops.decode_filter(cfg, lv, conf, ml, classes=classes)
+            out = vk.ops.nms_batched(buf, 0.6, want_keep=True)
+            torch.cuda.synchronize()
+            res[mode] = (_canonical(buf), buf.counts.cpu().numpy(), out)
+    finally:
+        L.vk_set_filter_kernel(0)
+    (ca, na, oa), (cb, nb, ob) = res[1], res[2]
+    assert np.array_equal(na, nb)
+    assert na.sum() > 0 or conf >= 0.25
+    for (la, ra, ba), (lb, rb, bb) in zip(ca, cb):
+        assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
+    assert torch.equal(oa.counts, ob.counts) and torch.equal(oa.dets, ob.dets) and torch.equal(oa.keep, ob.keep)
+
+
 def test_head_forward_nms(vk, cuda):
     torch.manual_seed(1)
     head = vk.heads.YoloV5Head(width=0.25).to(cuda).eval()

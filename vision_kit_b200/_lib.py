@@ -64,6 +64,7 @@ _PROTOS = {
     "vk_version": (C.c_int, []),
     "vk_last_error": (C.c_char_p, []),
     "vk_launch_count": (C.c_uint64, []),
+    "vk_set_filter_kernel": (C.c_int, [C.c_int]),
     "vk_build_arch": (C.c_int, []),
     "vk_letterbox_geometry": (C.c_int, [C.c_int] * 8 + [C.POINTER(VkLbGeom)]),
     "vk_letterbox_workspace_bytes": (C.c_size_t, [C.c_int] * 3),

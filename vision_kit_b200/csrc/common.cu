@@ -68,6 +68,12 @@ using namespace vk;
 
 extern "C" int vk_version(void) { return 100; }
 extern "C" const char* vk_last_error(void) { return g_err; }
+static std::atomic<int> g_filter_mode{VK_FILTER_AUTO};
+int vk::filter_mode() { return g_filter_mode.load(std::memory_order_relaxed); }
+extern "C" int vk_set_filter_kernel(int mode) {
+    if (mode < VK_FILTER_AUTO || mode > VK_FILTER_DENSE) return fail_arg("vk_set_filter_kernel: mode %d", mode);
+    return g_filter_mode.exchange(mode, std::memory_order_relaxed);
+}
 extern "C" uint64_t vk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int vk_build_arch(void) { return 100; }
 

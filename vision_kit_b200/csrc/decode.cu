@@ -126,18 +126,61 @@ struct DecTile {
     float stride, aw, ah;
 };
 
-__device__ __forceinline__ void decode_tile_of(const HeadDev& H, float* pred, int t, DecTile* d) {
-    const int b = t / H.tiles;
-    const TileLoc q = locate_tile(H, t - b * H.tiles);
-    const int no = H.no, nynx = H.nynx[q.l];
-    d->src = H.lv[q.l] + ((size_t)(b * H.na + q.a) * no) * nynx + q.s0;
-    d->out = pred + ((size_t)b * H.rows + q.row0) * no;
-    d->raw = H.raw[q.l] ? H.raw[q.l] + (((size_t)b * H.na + q.a) * nynx + q.s0) * no : nullptr;
-    d->nynx = nynx; d->nvalid = q.nvalid; d->nx = H.nx[q.l];
-    d->gy0 = q.s0 / H.nx[q.l]; d->gx0 = q.s0 - d->gy0 * H.nx[q.l];
-    d->raw_bulk = d->raw != nullptr && ((reinterpret_cast<uintptr_t>(d->raw) & 15) == 0) && (((q.nvalid * no) & 3) == 0);
-    d->vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[q.l]) & 15) == 0);
-    d->stride = H.stride[q.l]; d->aw = H.anchors[q.l][2 * q.a]; d->ah = H.anchors[q.l][2 * q.a + 1];
+// Tile descriptors are produced by ONE thread, two tiles ahead of their use; that thread's warp is
+// what the block waits for at the next barrier, so the arithmetic avoids integer division: the
+// (image, tile) cursor advances by a precomputed (quotient, remainder) step, the anchor comes
+// from at most na-1 subtractions and the grid row from a corrected float reciprocal.
+struct DecCursor {
+    int b, ti;            // image and tile inside the image of the NEXT descriptor to produce
+    int step_b, step_t;   // gridDim.x = step_b * tiles + step_t
+    int t;                // linear tile index of (b, ti)
+};
+
+__device__ __forceinline__ DecCursor cursor_begin(const HeadDev& H, int t0, int step) {
+    DecCursor c;
+    c.b = t0 / H.tiles; c.ti = t0 - c.b * H.tiles;
+    c.step_b = step / H.tiles; c.step_t = step - c.step_b * H.tiles;
+    c.t = t0;
+    return c;
+}
+
+__device__ __forceinline__ void cursor_next(const HeadDev& H, DecCursor& c) {
+    c.b += c.step_b; c.ti += c.step_t;
+    if (c.ti >= H.tiles) { c.ti -= H.tiles; ++c.b; }
+    c.t += c.step_b * H.tiles + c.step_t;
+}
+
+struct TilePos {          // what the filter kernel needs on top of DecTile
+    int b, seg, row0, s0; // image, tile index inside the image, first pred row, first row inside the plane
+};
+
+__device__ __forceinline__ void decode_tile_at(const HeadDev& H, float* pred, const DecCursor& cur, DecTile* d,
+                                               TilePos* loc = nullptr) {
+    const int b = cur.b;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < VK_MAX_LEVELS; ++i)
+        if (i < H.nl && cur.ti >= H.tile_start[i]) l = i;
+    int rel = cur.ti - H.tile_start[l], a = 0;
+    const int tpa = H.tpa[l];
+    while (rel >= tpa) { rel -= tpa; ++a; }
+    const int no = H.no, nynx = H.nynx[l], nx = H.nx[l];
+    const int s0 = rel * kTileS;
+    const int nvalid = min(kTileS, nynx - s0);
+    const int row0 = H.row_base[l] + a * nynx + s0;
+    int gy0 = (int)((float)s0 * __frcp_rn((float)nx));      // s0 < 2^24: off by at most one, fixed below
+    int gx0 = s0 - gy0 * nx;
+    if (gx0 < 0) { --gy0; gx0 += nx; }
+    if (gx0 >= nx) { ++gy0; gx0 -= nx; }
+    d->src = H.lv[l] + ((size_t)(b * H.na + a) * no) * nynx + s0;
+    d->out = pred ? pred + ((size_t)b * H.rows + row0) * no : nullptr;
+    d->raw = H.raw[l] ? H.raw[l] + (((size_t)b * H.na + a) * nynx + s0) * no : nullptr;
+    d->nynx = nynx; d->nvalid = nvalid; d->nx = nx;
+    d->gy0 = gy0; d->gx0 = gx0;
+    if (loc) { loc->b = b; loc->seg = cur.ti; loc->row0 = row0; loc->s0 = s0; }
+    d->raw_bulk = d->raw != nullptr && ((reinterpret_cast<uintptr_t>(d->raw) & 15) == 0) && (((nvalid * no) & 3) == 0);
+    d->vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[l]) & 15) == 0);
+    d->stride = H.stride[l]; d->aw = H.anchors[l][2 * a]; d->ah = H.anchors[l][2 * a + 1];
 }
 
 __device__ __forceinline__ int swz(int c, int s) { return c * kTileS + ((((s >> 2) ^ c) & 7) << 2 | (s & 32) | (s & 3)); }
@@ -149,8 +192,9 @@ __device__ __forceinline__ void decode_prefetch(const DecTile& d, float* tile, i
         if (4 * q < d.nvalid) {
             const float* src = d.src + (size_t)c0 * d.nynx + 4 * q;
             const size_t step = (size_t)(kDecThreads / 16) * d.nynx;
-            for (int c = c0; c < no; c += kDecThreads / 16, src += step)
-                cp_async_16(base + 4u * (uint32_t)swz(c, 4 * q), src);
+            // c advances by 16: (c & 7) and with it the chunk position stay the same, dst moves 16 channel rows
+            uint32_t dst = base + 4u * (uint32_t)swz(c0, 4 * q);
+            for (int c = c0; c < no; c += kDecThreads / 16, src += step, dst += 16 * kTileS * 4) cp_async_16(dst, src);
         }
     } else {
         const int r = threadIdx.x & (kTileS - 1), c0 = threadIdx.x >> 6;
@@ -175,9 +219,13 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int t = blockIdx.x;
     if (t >= total_tiles) return;
+    __shared__ DecCursor cur;                       // thread 0 only (shared: keeps it out of everyone's registers)
     if (threadIdx.x == 0) {
-        decode_tile_of(H, pred, t, &s_dt[0]);
-        if (t + (int)gridDim.x < total_tiles) decode_tile_of(H, pred, t + gridDim.x, &s_dt[1]);
+        cur = cursor_begin(H, t, gridDim.x);
+        decode_tile_at(H, pred, cur, &s_dt[0]);
+        cursor_next(H, cur);
+        if (cur.t < total_tiles) decode_tile_at(H, pred, cur, &s_dt[1]);
+        cursor_next(H, cur);
     }
     __syncthreads();
     decode_prefetch(s_dt[0], tiles_sm, no);
@@ -189,8 +237,10 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
         const int slot = k % 3;
         if (t + (int)gridDim.x < total_tiles)
             decode_prefetch(s_dt[slot == 2 ? 0 : slot + 1], tiles_sm + ((k + 1) & 1) * tile_floats, no);
-        if (threadIdx.x == 0 && t + 2 * (int)gridDim.x < total_tiles )      // slot (k+2)%3 was tile k-1's: free
-            decode_tile_of(H, pred, t + 2 * gridDim.x, &s_dt[slot == 0 ? 2 : slot - 1]);
+        if (threadIdx.x == 0) {                                            // slot (k+2)%3 was tile k-1's: free
+            if (cur.t < total_tiles) decode_tile_at(H, pred, cur, &s_dt[slot == 0 ? 2 : slot - 1]);
+            cursor_next(H, cur);
+        }
         const DecTile& d = s_dt[slot];
         const int nvalid = d.nvalid;
         float* __restrict__ out = d.out;
@@ -296,6 +346,9 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
 // At demo thresholds (0.7 % of rows survive) a group costs ~3 dependent memory round trips
 // instead of 3 per tile; at eval thresholds every tile is dense and HBM-bound.
 // ---------------------------------------------------------------------------------------
+#ifndef VK_DENSE_BPS
+#define VK_DENSE_BPS 4
+#endif
 constexpr int kGroupMax = 8;
 constexpr int kItems = kTileS;  // rows evaluated per back-end call (64)
 
@@ -681,6 +734,177 @@ decode_filter_kernel(const HeadDev H, const FilterArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Dense variant of the fused filter (eval thresholds: most rows survive, every tile is read
+// whole).  Same persistent two-deep pipeline and tile layout as detect_decode_kernel: 16-byte
+// async copies keep a full tile of reads in flight per block while the previous tile is
+// evaluated.  Thread = (class part qd = tid / 64, row = tid % 64): lanes run over rows
+// (conflict-free scalar reads of the chunk-swizzled tile), every thread walks its own CPP
+// consecutive classes and keeps the products in registers, so there is no second pass over
+// shared memory.  One scan over the 256 (row, part) counts in canonical order gives every
+// thread its first slot inside the range the tile owns.
+// ML = multi_label.  Results are bit-identical to decode_filter_kernel (same sigmoid, same
+// product, same order); the host picks the kernel from the threshold only (vk_decode_filter).
+// ---------------------------------------------------------------------------------------
+constexpr int kParts = kDecThreads / kTileS;   // 4 class parts per row
+
+// p[I] = sigmoid(logit of the thread's I-th class) * obj, the logit read with an immediate offset
+// from one of eight base addresses (compile-time recursion: the offset must be a constant).
+template <int I, int N>
+struct ClassProducts {
+    static __device__ __forceinline__ void run(float* p, const uint32_t* tq, float obj) {
+        float x;
+        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(tq[I & 7]), "n"(I * kTileS * 4));
+        p[I] = __fmul_rn(sigmoidf_vk(x), obj);                                                    // image_proc.py:135
+        ClassProducts<I + 1, N>::run(p, tq, obj);
+    }
+};
+template <int N>
+struct ClassProducts<N, N> {
+    static __device__ __forceinline__ void run(float*, const uint32_t*, float) {}
+};
+
+template <int CPP, bool ML>
+__global__ void __launch_bounds__(kDecThreads, VK_DENSE_BPS)
+decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
+    extern __shared__ __align__(16) float tiles_sm[];  // 2 x [no][kTileS] logits, chunk-swizzled
+    __shared__ DecTile s_dt[3];
+    __shared__ TilePos s_pos[3];
+    __shared__ int s_cnt[kDecThreads];      // counts, slot = row * kParts + part (canonical order)
+    __shared__ int s_off[kDecThreads + 1];  // exclusive offsets inside each warp's 32 slots
+    __shared__ int s_wsum[kWarps];
+    __shared__ float s_bv[kDecThreads];     // best-class partials
+    __shared__ int s_bj[kDecThreads];
+    const int no = H.no, nc = A.nc;
+    const int tile_floats = kTileS * no;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row = threadIdx.x & (kTileS - 1), qd = threadIdx.x >> 6;
+    const int cpp = (nc + kParts - 1) / kParts;            // <= CPP
+    const int c_lo = min(nc, qd * cpp), c_hi = min(nc, c_lo + cpp);
+    const int slot = row * kParts + qd;
+    // classes this thread may emit (class filter, :151): bit i <-> class c_lo + i
+    uint32_t allowed = 0;
+    for (int i = 0; i < c_hi - c_lo; ++i)
+        if (class_allowed(A.class_mask, c_lo + i)) allowed |= 1u << i;
+    int t = blockIdx.x;
+    if (t >= total_tiles) return;
+    __shared__ DecCursor cur;                       // thread 0 only (shared: keeps it out of everyone's registers)
+    if (threadIdx.x == 0) {
+        cur = cursor_begin(H, t, gridDim.x);
+        decode_tile_at(H, nullptr, cur, &s_dt[0], &s_pos[0]);
+        cursor_next(H, cur);
+        if (cur.t < total_tiles) decode_tile_at(H, nullptr, cur, &s_dt[1], &s_pos[1]);
+        cursor_next(H, cur);
+    }
+    __syncthreads();
+    decode_prefetch(s_dt[0], tiles_sm, no);
+    for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
+        const float* tile = tiles_sm + (k & 1) * tile_floats;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                      // tile k landed; everyone is done with the other buffer and the scratch arrays
+        const int slot3 = k % 3;
+        if (t + (int)gridDim.x < total_tiles)
+            decode_prefetch(s_dt[slot3 == 2 ? 0 : slot3 + 1], tiles_sm + ((k + 1) & 1) * tile_floats, no);
+        if (threadIdx.x == 0) {
+            if (cur.t < total_tiles) decode_tile_at(H, nullptr, cur, &s_dt[slot3 == 0 ? 2 : slot3 - 1], &s_pos[slot3 == 0 ? 2 : slot3 - 1]);
+            cursor_next(H, cur);
+        }
+        const DecTile& d = s_dt[slot3];
+        const TilePos& tp = s_pos[slot3];
+
+        // ---- products of this thread's classes (registers), flags as a bit mask.
+        // Element i of the thread is channel ch0 + i of its row; its 16-byte chunk sits at position
+        // (row/4 ^ channel) & 7, which repeats with period 8 in i: eight base pointers, immediate offsets.
+        const float* trow = tile + ((row & 32) | (row & 3));
+        const int rq = row >> 2;
+        const float o = sigmoidf_vk(trow[4 * kTileS + (((rq ^ 4) & 7) << 2)]);
+        const float obj = (row < d.nvalid && o > A.conf) ? o : 0.0f;  // image_proc.py:99 (dead rows: products 0)
+        const int ch0 = 5 + c_lo;
+        uint32_t tq[8];
+        {
+            const uint32_t trow_s = (uint32_t)__cvta_generic_to_shared(trow + ch0 * kTileS);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tq[j] = trow_s + ((((uint32_t)(rq ^ (ch0 + j))) & 7u) << 4);
+        }
+        float p[CPP];
+        ClassProducts<0, CPP>::run(p, tq, obj);   // reads past the thread's last class stay inside the (padded) buffer
+        uint32_t flags = 0;
+        float bv = -INFINITY;
+        int bj = 0x7fffffff;
+        if (ML) {
+#pragma unroll
+            for (int i = 0; i < CPP; ++i)
+                if (p[i] > A.conf) flags |= 1u << i;                                              // :141
+        } else {
+            const int ncls = c_hi - c_lo;
+#pragma unroll
+            for (int i = 0; i < CPP; ++i)
+                if (i < ncls && p[i] > bv) { bv = p[i]; bj = c_lo + i; }                          // first max (:145)
+        }
+        int count;
+        if (ML) {
+            flags &= allowed;
+            count = __popc(flags);
+        } else {
+            s_bv[slot] = bv; s_bj[slot] = bj;
+            __syncthreads();
+            count = 0;
+            if (qd == 0) {                                          // first max across the parts
+#pragma unroll
+                for (int q2 = 1; q2 < kParts; ++q2)
+                    if (s_bv[slot + q2] > bv) { bv = s_bv[slot + q2]; bj = s_bj[slot + q2]; }
+                count = (bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;   // :147,151
+            }
+        }
+        s_cnt[slot] = count;
+        __syncthreads();
+        {   // scan in slot order: thread tid owns slot tid
+            const int v = s_cnt[threadIdx.x];
+            const int inc = warp_incl_scan(v, lane);
+            s_off[threadIdx.x] = inc - v;
+            if (lane == 31) s_wsum[w] = inc;
+        }
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) {
+            const int x = s_wsum[i];
+            if (i < (slot >> 5)) wbase += x;
+            total += x;
+        }
+        const int tile_base = tp.seg * A.tile_cap;
+        if (count) {
+            uint2* const wp = reinterpret_cast<uint2*>(A.cand + (size_t)tp.b * A.cap) + tile_base + wbase + s_off[slot];
+            const uint32_t idx0 = (uint32_t)((tp.row0 + row) * nc + c_lo);
+            if (ML) {
+                uint32_t pos = 0;
+#pragma unroll
+                for (int i = 0; i < CPP; ++i) {
+                    const bool f = (flags & (1u << i)) != 0;
+                    if (f) wp[pos] = make_uint2(__float_as_uint(p[i]), idx0 + (uint32_t)i);
+                    pos += f;
+                }
+            } else {
+                *wp = make_uint2(__float_as_uint(bv), (uint32_t)((tp.row0 + row) * nc + bj));
+            }
+        }
+        // ---- box of the row if any of its parts produced a candidate
+        if (qd == 0) {
+            const int n = s_cnt[slot] + s_cnt[slot + 1] + s_cnt[slot + 2] + s_cnt[slot + 3];
+            if (n > 0) {
+                const PlaneGeom geom{H.variant, d.nx, tp.s0, d.stride, d.aw, d.ah};
+                A.boxes[(size_t)tp.b * A.rows + tp.row0 + row] =
+                    geom.box(tile[swz(0, row)], tile[swz(1, row)], tile[swz(2, row)], tile[swz(3, row)], tp.s0 + row);
+            }
+        }
+        if (threadIdx.x == 0) {
+            A.seg_base[(size_t)tp.b * A.segs + tp.seg] = total ? tile_base : 0;
+            A.seg_count[(size_t)tp.b * A.segs + tp.seg] = total;
+            if (total) atomicAdd(A.counts + tp.b, total);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kDecThreads, 5)
 filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
     extern __shared__ float buf[];  // [64][no]: a dense tile or the gathered rows
@@ -887,6 +1111,35 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels
         groups += H.na * ceil_div(H.tpa[l], A.group);
     }
     for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) H.group_start[l] = groups;
+    // Eval thresholds (most rows survive) -> the dense, persistent kernel; otherwise the group
+    // kernel that gathers only surviving rows.  Both give identical bits; vk_set_filter_kernel()
+    // overrides the choice (tests run every case through both).
+    const int mode = filter_mode();
+    const bool dense = mode == VK_FILTER_DENSE || (mode == VK_FILTER_AUTO && conf_thres < 0.05f);
+    if (dense && H.nc <= 128 && (long)H.tiles * batch <= 0x7fffffffL) {
+        const int cpp_max = H.nc <= 32 ? 8 : H.nc <= 80 ? 20 : 32;
+        // + one part's worth of rows: the unrolled class loop may read past channel no-1
+        const size_t dsmem = (2 * (size_t)kTileS * H.no + (size_t)kTileS * cpp_max) * sizeof(float);
+        const int total_tiles = H.tiles * batch;
+#define VK_DF_LAUNCH(CPP, ML)                                                                                      \
+        do {                                                                                                        \
+            cudaFuncSetAttribute(decode_filter_dense_kernel<CPP, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); \
+            int per_sm = 0;                                                                                         \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_filter_dense_kernel<CPP, ML>, kDecThreads, dsmem); \
+            if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;                                                       \
+            if (per_sm < 1) per_sm = 1;                                                                             \
+            const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;                       \
+            decode_filter_dense_kernel<CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(H, A, total_tiles);           \
+        } while (0)
+#define VK_DF_CPP(CPP) do { if (A.multi_label) VK_DF_LAUNCH(CPP, true); else VK_DF_LAUNCH(CPP, false); } while (0)
+        if (H.nc <= 32) VK_DF_CPP(8);                 // classes per part = ceil(nc / 4)
+        else if (H.nc <= 80) VK_DF_CPP(20);
+        else VK_DF_CPP(32);
+#undef VK_DF_CPP
+#undef VK_DF_LAUNCH
+        count_launch();
+        return check_launch("decode_filter_dense_kernel");
+    }
     decode_filter_kernel<<<dim3(groups, batch), kDecThreads, smem, stream>>>(H, A);
     count_launch();
     return check_launch("decode_filter_kernel");
