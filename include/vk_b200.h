@@ -186,6 +186,29 @@ int vk_scale_coords(float* coords, int n, int row_stride, float pad_w, float pad
 /* utils/bboxes.py:103-111 `cxcywh_to_xyxy` on n rows of 4 floats (out may alias in). */
 int vk_cxcywh_to_xyxy(const float* in, float* out, int n, vk_stream_t stream);
 
+/* ---------------------------------------------------------------- evaluator matching */
+/* The per-image body of `DetEvaluator.evaluate` (core/eval/det_evaluator.py:141-178) for a whole
+ * batch, one block per image: un-letterbox + clip of detections and labels (`scale_coords`,
+ * utils/image_proc.py:63-80), torchvision `box_iou`, and `process_batch` (:274-300) at every IoU
+ * threshold.
+ *   dets [batch][max_det][6], det_counts [batch]   the NMS output (canvas pixels)
+ *   labels [n][6] = image, cls, cx, cy, w, h       canvas pixels (after `targets[:, 2:] *= (w,h,w,h)`, :139),
+ *                                                  grouped by image: rows label_offsets[b] .. label_offsets[b+1]
+ *   max_labels                                     largest label count of one image (sizes shared memory)
+ *   img0_hw [batch][2]                             original (h, w) of every image; img1 = the canvas
+ *   prescaled                                      1 = `process_batch` alone (:274-300): dets and labels are already in
+ *                                                  one frame, labels carry x1, y1, x2, y2 instead of cx, cy, w, h, img0_hw unused
+ *   iouv [niou]                                    thresholds (reference: linspace(0.5, 0.95, 10)), niou <= 32
+ * Outputs: predn [batch][max_det][6] and labeln [n][5] = cls, x1, y1, x2, y2 in original pixels
+ * (either may be NULL), correct [batch][max_det][niou] (1 = true positive; rows >= count are 0).
+ * IoU ties between two labels of one detection go to the lower label index (the reference's order
+ * there comes from an unstable argsort). */
+size_t vk_eval_match_smem_bytes(int niou, int max_labels);
+int vk_eval_match(const float* dets, const int32_t* det_counts, int batch, int max_det,
+                  const float* labels, const int32_t* label_offsets, int max_labels,
+                  const int32_t* img0_hw, int img1_h, int img1_w, int prescaled, const float* iouv, int niou,
+                  float* predn, float* labeln, uint8_t* correct, vk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

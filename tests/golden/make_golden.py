@@ -167,6 +167,28 @@ def gen_scale_coords(ref):
     np.savez_compressed(os.path.join(OUT, "scale_coords.npz"), **blob)
 
 
+def gen_eval():
+    """``DetEvaluator.evaluate`` of the unmodified reference (core/eval/det_evaluator.py:129-182):
+    stats = (correct, conf, pred_cls, target_cls) per image, plus the vstacked predn / targetn."""
+    from vision_kit.core.eval.det_evaluator import DetEvaluator
+    blob = {}
+    for name, n_img, canvas, _, _ in synth.EVAL_CASES:
+        preds, targets, shapes, _ = synth.eval_inputs(name)
+        ev = DetEvaluator([str(i) for i in range(5)], img_size=canvas)
+        img = torch.zeros((n_img, 3, canvas[0], canvas[1]))
+        pn, tn = ev.evaluate(img, shapes, list(range(n_img)), [torch.from_numpy(p.copy()) for p in preds],
+                             torch.from_numpy(targets.copy()))
+        blob[f"{name}_predn"] = pn.numpy()
+        blob[f"{name}_targetn"] = tn.numpy()
+        blob[f"{name}_nstats"] = np.int64(len(ev.stats))
+        for j, st in enumerate(ev.stats):
+            blob[f"{name}_correct{j}"] = st[0].numpy()
+            blob[f"{name}_conf{j}"] = st[1].numpy()
+            blob[f"{name}_pcls{j}"] = st[2].numpy()
+            blob[f"{name}_tcls{j}"] = st[3].numpy()
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), **blob)
+
+
 if __name__ == "__main__":
     assert live.available(), "needs /root/reference"
     torch.manual_seed(0)
@@ -175,5 +197,6 @@ if __name__ == "__main__":
     gen_decode()
     gen_nms(ref)
     gen_scale_coords(ref)
+    gen_eval()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

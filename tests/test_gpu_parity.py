@@ -493,3 +493,85 @@ def test_pipeline_overlap_equals_single_stream(vk, cuda):
     for (d0, c0), (d1, c1) in zip(expect, got):
         assert torch.equal(c0, c1) and torch.equal(d0, d1)
     assert DetectPipeline.to_list(o)[0].shape[1] == 6
+
+
+# --------------------------------------------------------------------------- evaluator matching (§8f row 1)
+@pytest.mark.parametrize("name", [c[0] for c in synth.EVAL_CASES])
+def test_evaluator_golden(name, golden_dir, vk, cuda):
+    """vision_kit_b200.evaluator.DetEvaluator.evaluate against the live reference's stats
+    (tests/golden/eval.npz): TP matrices, conf, classes and un-letterboxed boxes bit-exact."""
+    from vision_kit_b200.evaluator import DetEvaluator
+    g = np.load(os.path.join(golden_dir, "eval.npz"))
+    _, n_img, canvas, _, _ = next(c for c in synth.EVAL_CASES if c[0] == name)
+    preds, targets, shapes, _ = synth.eval_inputs(name)
+    ev = DetEvaluator([str(i) for i in range(5)], img_size=canvas)
+    img = torch.zeros((n_img, 3, canvas[0], canvas[1]), device=cuda)
+    pn, tn = ev.evaluate(img, shapes, list(range(n_img)), [torch.from_numpy(p.copy()).to(cuda) for p in preds],
+                         torch.from_numpy(targets.copy()).to(cuda))
+    assert len(ev.stats) == int(g[f"{name}_nstats"])
+    for j, st in enumerate(ev.stats):
+        assert np.array_equal(st[0].cpu().numpy(), g[f"{name}_correct{j}"])
+        assert np.array_equal(st[1].cpu().numpy(), g[f"{name}_conf{j}"])
+        assert np.array_equal(st[2].cpu().numpy(), g[f"{name}_pcls{j}"])
+        assert np.array_equal(st[3].cpu().numpy(), g[f"{name}_tcls{j}"])
+    assert np.array_equal(pn.cpu().numpy(), g[f"{name}_predn"])
+    assert ev.seen == n_img
+
+
+def test_process_batch_vs_oracle_random(vk, cuda):
+    from vision_kit_b200.evaluator import DetEvaluator
+    rng = np.random.Generator(np.random.PCG64(19))
+    iouv = torch.linspace(0.5, 0.95, 10)
+    for trial in range(12):
+        m, n = int(rng.integers(0, 200)), int(rng.integers(1, 300))
+        lab = np.zeros((m, 5), np.float32)
+        lab[:, 0] = rng.integers(0, 4, m)
+        lab[:, 1:3] = rng.random((m, 2), dtype=np.float32) * 600
+        lab[:, 3:5] = lab[:, 1:3] + rng.random((m, 2), dtype=np.float32) * 120 + 8
+        pred = np.zeros((n, 6), np.float32)
+        if m:
+            src = rng.integers(0, m, n)
+            pred[:, :4] = lab[src, 1:] + (rng.random((n, 4), dtype=np.float32) - 0.5) * 40
+            pred[:, 5] = np.where(rng.random(n) < 0.8, lab[src, 0], rng.integers(0, 4, n))
+        else:
+            pred[:, :2] = rng.random((n, 2), dtype=np.float32) * 500
+            pred[:, 2:4] = pred[:, :2] + 50
+        pred[:, 4] = rng.random(n, dtype=np.float32)
+        got = DetEvaluator.process_batch(torch.from_numpy(pred).to(cuda), torch.from_numpy(lab).to(cuda), iouv.to(cuda))
+        exp = restate.process_batch(pred, lab, iouv.numpy())
+        assert np.array_equal(got.cpu().numpy(), exp), trial
+
+
+def test_eval_match_after_nms_full_batch(vk, cuda):
+    """Config-3-shaped use: eval-mode NMS output (padded, 300 per image) straight into the
+    matching kernel, B = 64, labels planted where the synthetic clusters are; per-image oracle."""
+    B = 16
+    cfg, _ = _cfg(vk, "v5")
+    lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=5, clusters=20)]
+    buf = vk.ops.decode_filter(cfg, lv, 0.001, True)
+    out = vk.ops.nms_batched(buf, 0.6)
+    rng = np.random.Generator(np.random.PCG64(3))
+    dets = out.dets.cpu().numpy()
+    cnt = out.counts.cpu().numpy()
+    labels, offs, shapes = [], [0], []
+    for b in range(B):
+        k = int(cnt[b])
+        pick = rng.choice(k, size=min(k, 25), replace=False) if k else np.zeros(0, int)
+        bx = dets[b, pick, :4] + (rng.random((len(pick), 4), dtype=np.float32) - 0.5) * 6
+        cxcywh = np.stack([(bx[:, 0] + bx[:, 2]) / 2, (bx[:, 1] + bx[:, 3]) / 2, bx[:, 2] - bx[:, 0], bx[:, 3] - bx[:, 1]], 1)
+        labels.append(np.concatenate([np.full((len(pick), 1), b, np.float32), dets[b, pick, 5:6], cxcywh], 1).astype(np.float32))
+        offs.append(offs[-1] + len(pick))
+        shapes.append((int(rng.integers(300, 1300)), int(rng.integers(300, 1300))))
+    lab = np.concatenate(labels, 0)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    m = vk.ops.eval_match(out.dets, out.counts, torch.from_numpy(lab).to(cuda),
+                          torch.tensor(offs, dtype=torch.int32, device=cuda), max(len(l) for l in labels),
+                          torch.tensor(shapes, dtype=torch.int32, device=cuda), (640, 640), iouv)
+    corr, predn, labeln = m.correct.cpu().numpy(), m.predn.cpu().numpy(), m.labeln.cpu().numpy()
+    for b in range(B):
+        k = int(cnt[b])
+        pn, ln, c = restate.evaluate_image(dets[b, :k], labels[b][:, 1:], (640, 640), shapes[b], iouv.numpy())
+        assert np.array_equal(corr[b, :k], c), b
+        assert not corr[b, k:].any()
+        assert np.array_equal(predn[b, :k], pn) and np.array_equal(labeln[offs[b]:offs[b + 1]], ln)
+    assert corr.sum() > 0

@@ -85,6 +85,9 @@ _PROTOS = {
     "vk_scale_coords": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                   C.c_float, C.c_float, _P]),
     "vk_cxcywh_to_xyxy": (C.c_int, [_P, _P, C.c_int, _P]),
+    "vk_eval_match_smem_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "vk_eval_match": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int,
+                                _P, _P, _P, _P]),
 }
 
 _lib = None

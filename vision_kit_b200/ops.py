@@ -315,3 +315,35 @@ def cxcywh_to_xyxy(b: torch.Tensor) -> torch.Tensor:
     _lib.check("vk_cxcywh_to_xyxy", _lib.lib().vk_cxcywh_to_xyxy(
         _ptr(src), _ptr(out), int(src.shape[0]), _lib.stream_ptr()))
     return out.view(b.shape)
+
+
+# ---------------------------------------------------------------------------- evaluator matching
+@dataclass
+class EvalMatch:
+    predn: torch.Tensor       # float32 (B, max_det, 6): detections in original-image pixels, clipped
+    labeln: torch.Tensor      # float32 (n_labels, 5): cls, x1, y1, x2, y2 in original-image pixels
+    correct: torch.Tensor     # bool (B, max_det, niou): true-positive matrix (rows >= count are False)
+
+
+def eval_match(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, label_offsets: torch.Tensor,
+               max_labels: int, img0_hw, img1_hw, iouv: torch.Tensor, prescaled: bool = False) -> EvalMatch:
+    """vk_eval_match: un-letterbox + box_iou + process_batch for a batch in one launch.
+    dets (B, max_det, 6) / counts (B,) = NMS output; labels (n, 6) = image, cls, cx, cy, w, h in canvas
+    pixels grouped by image; label_offsets int32 (B+1,); img0_hw int32 (B, 2).
+    prescaled: process_batch alone -- labels carry x1, y1, x2, y2, nothing is rescaled."""
+    _lib.require_cuda(dets, "dets")
+    B, max_det = int(dets.shape[0]), int(dets.shape[1])
+    dev = dets.device
+    dets = dets.contiguous().float()
+    labels = labels.contiguous().float().view(-1, 6)
+    iouv = iouv.to(device=dev, dtype=torch.float32).contiguous()
+    niou = int(iouv.numel())
+    predn = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    labeln = torch.empty((labels.shape[0], 5), dtype=torch.float32, device=dev)
+    correct = torch.empty((B, max_det, niou), dtype=torch.uint8, device=dev)
+    _lib.check("vk_eval_match", _lib.lib().vk_eval_match(
+        _ptr(dets), _ptr(counts), B, max_det, _ptr(labels) if labels.numel() else C.c_void_p(0),
+        _ptr(label_offsets), int(max_labels), _ptr(img0_hw) if img0_hw is not None else C.c_void_p(0),
+        int(img1_hw[0]), int(img1_hw[1]), int(bool(prescaled)), _ptr(iouv), niou, _ptr(predn), _ptr(labeln) if labels.numel() else C.c_void_p(0), _ptr(correct),
+        _lib.stream_ptr()))
+    return EvalMatch(predn, labeln, correct.bool())

@@ -138,3 +138,56 @@ def mixed_sizes(batch: int, seed: int = 0, lo: int = 480, hi: int = 1280):
     while len(out) < batch:
         out.append((int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))))
     return out
+
+
+# ---------------------------------------------------------------------------- evaluator inputs
+def _name_seed(name: str) -> int:
+    import hashlib
+    return int.from_bytes(hashlib.sha256(name.encode()).digest()[:4], "little")
+
+
+# (name, n_images, canvas, label count range, max dets)
+EVAL_CASES = [
+    ("e_small", 4, (640, 640), (0, 12), 40),
+    ("e_dense", 3, (640, 640), (30, 60), 300),
+    ("e_rect", 3, (512, 640), (1, 20), 100),
+]
+
+
+def eval_inputs(name):
+    """Seeded detections / targets for the evaluator cases (shared with the tests):
+    detections are jittered copies of the labels (so IoUs cover 0.3-1.0 and several detections
+    compete for one label) plus random boxes; classes are drawn from 5 values."""
+    _, n_img, canvas, (lo, hi), max_det = next(c for c in EVAL_CASES if c[0] == name)
+    rng = np.random.Generator(np.random.PCG64(_name_seed(name)))
+    H, W = canvas
+    preds, targets, shapes = [], [], []
+    for i in range(n_img):
+        h0, w0 = int(rng.integers(200, 1400)), int(rng.integers(200, 1400))
+        shapes.append((h0, w0))
+        m = int(rng.integers(lo, hi + 1))
+        cxy = rng.random((m, 2), dtype=np.float32) * np.float32([W, H])
+        wh = rng.random((m, 2), dtype=np.float32) * np.float32(150) + np.float32(20)
+        cls = rng.integers(0, 5, m).astype(np.float32)
+        lab = np.concatenate([cls[:, None], cxy / np.float32([W, H]), wh / np.float32([W, H])], 1).astype(np.float32)
+        targets.append(np.concatenate([np.full((m, 1), i, np.float32), lab], 1))
+        k = 0 if (i == 1 and lo == 0) else int(rng.integers(max_det // 2, max_det + 1))
+        rows = []
+        for j in range(k):
+            if m and rng.random() < 0.7:
+                l = int(rng.integers(0, m))
+                jit = (rng.random(4, dtype=np.float32) - np.float32(0.5)) * np.float32(0.5) * np.concatenate([wh[l], wh[l]])
+                x1, y1 = cxy[l] - wh[l] / 2 + jit[:2]
+                x2, y2 = cxy[l] + wh[l] / 2 + jit[2:]
+                c = cls[l] if rng.random() < 0.8 else np.float32(rng.integers(0, 5))
+            else:
+                x1, y1 = rng.random(2, dtype=np.float32) * np.float32([W - 60, H - 60])
+                x2, y2 = x1 + rng.random(dtype=np.float32) * 200 + 5, y1 + rng.random(dtype=np.float32) * 200 + 5
+                c = np.float32(rng.integers(0, 5))
+            rows.append([x1, y1, x2, y2, rng.random(dtype=np.float32), c])
+        p = np.asarray(rows, np.float32).reshape(-1, 6)
+        p = p[np.argsort(-p[:, 4], kind="stable")]
+        preds.append(p)
+    return preds, np.concatenate(targets, 0).astype(np.float32), shapes, canvas
+
+
