@@ -71,6 +71,13 @@ typedef struct VkLbGeom {
 int vk_letterbox_geometry(int src_h, int src_w, int img_h, int img_w, int stride,
                           int letterbox, int scaleup, int auto_, VkLbGeom* out);
 
+/* Eval-time dataset ingest: `YOLODataset.load_resized_image` (data/datasets/yolo.py:144-160:
+ * r = max(img_sz) / max(h, w), target (int(w*r), int(h*r)), INTER_LINEAR) + the validation
+ * pipeline's `A.PadIfNeeded` (data/augmentations.py:197-200: centred, before = int(diff / 2.0)).
+ * Fills the same VkLbGeom (ratio = r, pad = (left, top)); the result feeds vk_letterbox_batch,
+ * whose float32/bf16 NCHW output is `permute(0,3,1,2).float() / 255` of core/train/det_trainer.py:74-75. */
+int vk_dataset_geometry(int src_h, int src_w, int img_h, int img_w, VkLbGeom* out);
+
 typedef struct VkLbDesc {  /* one source image; 48 bytes */
     const uint8_t* src;    /* dev, HWC uint8, 3 channels */
     int64_t pitch;         /* bytes between source rows */

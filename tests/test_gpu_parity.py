@@ -575,3 +575,23 @@ def test_eval_match_after_nms_full_batch(vk, cuda):
         assert not corr[b, k:].any()
         assert np.array_equal(predn[b, :k], pn) and np.array_equal(labeln[offs[b]:offs[b + 1]], ln)
     assert corr.sum() > 0
+
+
+# --------------------------------------------------------------------------- eval ingest (§8f row 3)
+def test_dataset_ingest_batch_vs_oracle(vk, cuda):
+    """load_resized_image + PadIfNeeded + collate + permute/float//255 for a mixed-size batch:
+    uint8 canvas bit-exact against the oracle (cv2 arithmetic), float32 = value / 255 exactly."""
+    rng = np.random.Generator(np.random.PCG64(21))
+    sizes = [(480, 640), (640, 480), (1280, 720), (640, 640), (1279, 853), (333, 500), (97, 41), (2000, 3000)]
+    sizes += [(int(rng.integers(60, 1400)), int(rng.integers(60, 1400))) for _ in range(8)]
+    imgs = [synth.image_u8(h, w, 300 + i) for i, (h, w) in enumerate(sizes)]
+    srcs = [torch.from_numpy(im).to(cuda) for im in imgs]
+    u8, orig, resized = vk.ops.dataset_batch(srcs, (640, 640), dtype=torch.uint8)
+    f32, _, _ = vk.ops.dataset_batch(srcs, (640, 640), dtype=torch.float32)
+    u8, f32 = u8.cpu().numpy(), f32.cpu().numpy()
+    for i, im in enumerate(imgs):
+        exp = restate.dataset_ingest_u8(im, (640, 640))
+        assert np.array_equal(u8[i], exp), sizes[i]
+        assert np.array_equal(f32[i], (exp.transpose(2, 0, 1).astype(np.float32) / np.float32(255.0))), sizes[i]
+        assert orig[i] == sizes[i]
+        assert resized[i] == restate.dataset_geometry(sizes[i][0], sizes[i][1], (640, 640))[1]

@@ -158,3 +158,23 @@ def test_shard_and_allgather_world2(n_images):
         p.join(120)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def test_dataset_geometry_equals_oracle(vk_lib):
+    """vk_dataset_geometry (C, host) against oracle/restate.py::dataset_geometry on random sizes,
+    including r == 1 and the int() truncation cases."""
+    from vision_kit_b200 import ops
+    from oracle import restate
+    rng = np.random.Generator(np.random.PCG64(4))
+    cases = [(640, 640), (480, 640), (1280, 720), (333, 500), (1279, 853), (2000, 3000), (640, 1)]
+    cases += [(int(rng.integers(1, 3000)), int(rng.integers(1, 3000))) for _ in range(300)]
+    for h, w in cases:
+        r, (nh, nw), (top, bottom, left, right) = restate.dataset_geometry(h, w, (640, 640))
+        if nh <= 0 or nw <= 0:
+            continue
+        g = ops.dataset_geometry(h, w, (640, 640))
+        assert (g.new_h, g.new_w, g.top, g.bottom, g.left, g.right) == (nh, nw, top, bottom, left, right), (h, w)
+        assert g.ratio == r and (g.out_h, g.out_w) == (640, 640)
+    from vision_kit_b200 import _lib
+    g = _lib.VkLbGeom()
+    assert vk_lib.vk_dataset_geometry(1000, 500, 512, 640, C.byref(g)) == -1      # 640 tall on a 512 canvas

@@ -67,6 +67,7 @@ _PROTOS = {
     "vk_set_filter_kernel": (C.c_int, [C.c_int]),
     "vk_build_arch": (C.c_int, []),
     "vk_letterbox_geometry": (C.c_int, [C.c_int] * 8 + [C.POINTER(VkLbGeom)]),
+    "vk_dataset_geometry": (C.c_int, [C.c_int] * 4 + [C.POINTER(VkLbGeom)]),
     "vk_letterbox_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "vk_letterbox_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                      C.c_int, _P, _P, C.c_size_t, _P]),

@@ -473,6 +473,36 @@ extern "C" int vk_letterbox_geometry(int src_h, int src_w, int img_h, int img_w,
     return VK_OK;
 }
 
+// Eval-time ingest: data/datasets/yolo.py:144-160 `load_resized_image`
+// (longest side -> max(img_sz), int() truncation, INTER_LINEAR) followed by the validation
+// pipeline's albumentations PadIfNeeded (data/augmentations.py:197-200: centre position,
+// pad_before = int((min - size) / 2.0)).  Same VkLbGeom as the letterbox, so the same kernels run.
+extern "C" int vk_dataset_geometry(int src_h, int src_w, int img_h, int img_w, VkLbGeom* g) {
+    if (!g || src_h <= 0 || src_w <= 0 || img_h <= 0 || img_w <= 0)
+        return fail_arg("vk_dataset_geometry: bad size");
+    const int m_img = img_h > img_w ? img_h : img_w, m_src = src_h > src_w ? src_h : src_w;
+    const double r = (double)m_img / (double)m_src;                  // yolo.py:154
+    int new_w = src_w, new_h = src_h;
+    if (r != 1.0) {                                                  // :155-157
+        new_w = (int)((double)src_w * r);
+        new_h = (int)((double)src_h * r);
+    }
+    if (new_w <= 0 || new_h <= 0) return fail_arg("vk_dataset_geometry: degenerate target %dx%d", new_w, new_h);
+    if (new_h > img_h || new_w > img_w)
+        return fail_arg("vk_dataset_geometry: resized %dx%d exceeds the %dx%d canvas (PadIfNeeded never crops)",
+                        new_h, new_w, img_h, img_w);
+    const int top = (int)((double)(img_h - new_h) / 2.0), left = (int)((double)(img_w - new_w) / 2.0);
+    memset(g, 0, sizeof(*g));
+    g->ratio = r;
+    g->pad_w = (double)left;
+    g->pad_h = (double)top;
+    g->new_w = new_w; g->new_h = new_h;
+    g->top = top; g->bottom = img_h - new_h - top; g->left = left; g->right = img_w - new_w - left;
+    g->out_h = img_h; g->out_w = img_w;
+    g->needs_resize = !(new_w == src_w && new_h == src_h);
+    return VK_OK;
+}
+
 static size_t lb_desc_bytes(int batch) { return align_up((size_t)batch * sizeof(VkLbDesc), 256); }
 
 extern "C" size_t vk_letterbox_workspace_bytes(int batch, int out_h, int out_w) {

@@ -46,13 +46,27 @@ def pack_color(color: Sequence[int]) -> int:
 _FMT = {torch.float32: VK_LB_F32_NCHW, torch.bfloat16: VK_LB_BF16_NCHW, torch.uint8: VK_LB_U8_NHWC}
 
 
+def dataset_geometry(src_h: int, src_w: int, img_sz) -> VkLbGeom:
+    """load_resized_image + PadIfNeeded geometry (data/datasets/yolo.py:144-160, data/augmentations.py:197-200)."""
+    if isinstance(img_sz, int):
+        img_sz = (img_sz, img_sz)
+    g = VkLbGeom()
+    _lib.check("vk_dataset_geometry", _lib.lib().vk_dataset_geometry(
+        int(src_h), int(src_w), int(img_sz[0]), int(img_sz[1]), C.byref(g)))
+    return g
+
+
 class LetterboxPlan:
     """Host-side descriptors of one batch: geometry per source, the device descriptor array
     and the coefficient-table workspace.  Re-usable while the source pointers stay valid."""
 
     def __init__(self, srcs: Sequence[torch.Tensor], img_sz=(640, 640), stride: int = 32,
                  letterbox: bool = True, scaleup: bool = True, auto: bool = False,
-                 upload: bool = True):
+                 upload: bool = True, mode: str = "letterbox"):
+        """mode "letterbox": utils/image_proc.py `resize`; "dataset": the eval loader's
+        load_resized_image + PadIfNeeded (stride / letterbox / scaleup / auto unused)."""
+        if mode not in ("letterbox", "dataset"):
+            raise ValueError(f"mode {mode!r}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
         self.batch = len(srcs)
@@ -64,7 +78,8 @@ class LetterboxPlan:
             if s.dtype != torch.uint8 or s.dim() != 3 or s.shape[2] != 3 or s.stride(2) != 1 or s.stride(1) != 3:
                 raise ValueError("letterbox source must be a uint8 HWC tensor with packed pixels")
             h, w = int(s.shape[0]), int(s.shape[1])
-            g = letterbox_geometry(h, w, img_sz, stride, letterbox, scaleup, auto)
+            g = (letterbox_geometry(h, w, img_sz, stride, letterbox, scaleup, auto) if mode == "letterbox"
+                 else dataset_geometry(h, w, img_sz))
             if out_hw is None:
                 out_hw = (g.out_h, g.out_w)
             elif out_hw != (g.out_h, g.out_w):
@@ -99,6 +114,20 @@ class LetterboxPlan:
             int(bool(swap_rb)), pack_color(color), fmt, _ptr(out), _ptr(self.ws), self.ws.numel(),
             _lib.stream_ptr()))
         return out
+
+
+def dataset_batch(srcs: Sequence[torch.Tensor], img_sz=(640, 640), color=(114, 114, 114), dtype=torch.float32):
+    """Eval ingest of one batch: RGB uint8 HWC CUDA sources of any size ->
+    what `validation_step` feeds the model, `(B,3,H,W)` float32/bf16 in [0,1]
+    (load_resized_image -> PadIfNeeded -> collate -> permute/float//255, core/train/det_trainer.py:72-75),
+    or the (B,H,W,3) uint8 batch the collate produces for dtype=torch.uint8.
+    Returns (tensor, [(orig_h, orig_w)], [(resized_h, resized_w)]) like the loader's shapes."""
+    plan = LetterboxPlan(srcs, img_sz, upload=False, mode="dataset")
+    dev = srcs[0].device
+    shape = (plan.batch, plan.out_h, plan.out_w, 3) if dtype == torch.uint8 else (plan.batch, 3, plan.out_h, plan.out_w)
+    out = torch.empty(shape, dtype=dtype, device=dev)
+    plan.run(out, swap_rb=False, color=color)
+    return out, [(int(s.shape[0]), int(s.shape[1])) for s in srcs], [(g.new_h, g.new_w) for g in plan.geoms]
 
 
 def letterbox_batch(srcs: Sequence[torch.Tensor], img_sz=(640, 640), stride: int = 32,
