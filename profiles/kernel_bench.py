@@ -95,4 +95,29 @@ lv0 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, cluster
 buf3 = ops.decode_filter(cfg, lv0, 0.25, False)
 ms = timeit(lambda: ops.decode_filter(cfg, lv0, 0.25, False, buf=buf3))
 report("decode_filter demo (no clusters)", ms, in_bytes + 8 * int(buf3.counts.sum()), f"{int(buf3.counts.sum()) // B} candidates/img")
+# ---- evaluator matching after eval-mode NMS, and the eval loader's ingest
+buf4 = ops.decode_filter(cfg, lv, 0.001, True)
+nout = ops.nms_batched(buf4, 0.6)
+rng = np.random.Generator(np.random.PCG64(3))
+dets_h, cnt_h = nout.dets.cpu().numpy(), nout.counts.cpu().numpy()
+labs, offs, shp = [], [0], []
+for b in range(B):
+    k = int(cnt_h[b])
+    pick = rng.choice(k, size=min(k, 25), replace=False)
+    bx = dets_h[b, pick, :4]
+    labs.append(np.concatenate([np.full((len(pick), 1), b, np.float32), dets_h[b, pick, 5:6],
+                                np.stack([(bx[:, 0] + bx[:, 2]) / 2, (bx[:, 1] + bx[:, 3]) / 2, bx[:, 2] - bx[:, 0], bx[:, 3] - bx[:, 1]], 1)], 1))
+    offs.append(offs[-1] + len(pick))
+    shp.append((int(rng.integers(300, 1300)), int(rng.integers(300, 1300))))
+lab_d = torch.from_numpy(np.concatenate(labs).astype(np.float32)).to(dev)
+offs_d = torch.tensor(offs, dtype=torch.int32, device=dev)
+shp_d = torch.tensor(shp, dtype=torch.int32, device=dev)
+iouv = torch.linspace(0.5, 0.95, 10, device=dev)
+ms = timeit(lambda: ops.eval_match(nout.dets, nout.counts, lab_d, offs_d, 25, shp_d, (640, 640), iouv))
+report("eval_match (300 dets x 25 labels)", ms, B * (300 * 24 * 2 + 300 * 10 + 25 * 44), "latency-bound: one block per image")
+srcs = [torch.from_numpy(synth.image_u8(h, w, 50 + i)).to(dev) for i, (h, w) in enumerate(sizes)]
+plan = ops.LetterboxPlan(srcs, (640, 640), mode="dataset")
+out = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev)
+ms = timeit(lambda: plan.run(out))
+report("dataset ingest mixed 480-1280 f32", ms, src_bytes + B * 3 * 640 * 640 * 4, "load_resized_image + PadIfNeeded + /255")
 print(json.dumps({"batch": B, "peak_GBps": PEAK, "kernels": res}))
