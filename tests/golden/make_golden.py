@@ -186,6 +186,12 @@ def gen_eval():
             blob[f"{name}_conf{j}"] = st[1].numpy()
             blob[f"{name}_pcls{j}"] = st[2].numpy()
             blob[f"{name}_tcls{j}"] = st[3].numpy()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                      # np.trapz deprecation
+            m50, m95, _, _ = ev.summarize()
+        blob[f"{name}_map"] = np.asarray([m50, m95, ev.mp, ev.mr], np.float64)
+        blob[f"{name}_prf"] = np.stack([ev.precision, ev.recall, ev.f1]).astype(np.float64)
     np.savez_compressed(os.path.join(OUT, "eval.npz"), **blob)
 
 

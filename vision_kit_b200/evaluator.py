@@ -3,13 +3,15 @@
 reference's signatures, the per-image loop replaced by ONE kernel launch for the batch
 (``vk_eval_match``: un-letterbox + clip, torchvision box_iou, greedy unique matching at the ten
 IoU thresholds).  ``stats`` holds the same four tensors per image as the reference's, so the
-reference's own ``summarize`` / ``ap_per_class`` (host-side NumPy, out of scope here) consume it
-unchanged.
+reference's own ``summarize`` / ``ap_per_class`` consume it unchanged; ``summarize`` here restates
+that host-side NumPy arithmetic (:13-97, 184-195; SURVEY.md §8f row 4 -- float64, no kernel) so the
+class is usable on its own.
 """
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -27,6 +29,8 @@ class DetEvaluator:
         self.num_iou = self.iouv.numel()
         self.seen = 0
         self.stats: list = []
+        self.precision = self.recall = self.f1 = 0.0
+        self.mp = self.mr = self.map50 = self.map95 = 0.0
 
     # ------------------------------------------------------------------ batch entry
     def evaluate(self, img: torch.Tensor, img_infos: Sequence, idxs: Sequence, preds, targets: torch.Tensor):
@@ -94,3 +98,83 @@ class DetEvaluator:
                              lab6, torch.tensor([0, m], dtype=torch.int32, device=dev), m, None, (1, 1),
                              iouv.to(dev), prescaled=True)
         return out.correct[0, :n]
+
+
+# ---------------------------------------------------------------------------------------------
+# AP accumulation (host, float64): core/eval/det_evaluator.py:13-97 + utils/metrics.py:15-20
+# ---------------------------------------------------------------------------------------------
+_PR_GRID = np.linspace(0, 1, 1000)      # confidence grid of the P/R/F1 curves (:35)
+_AP_GRID = np.linspace(0, 1, 101)       # 101-point COCO interpolation (:87)
+
+
+def _envelope_ap(recall: np.ndarray, precision: np.ndarray) -> float:
+    """:70-97 ('interp' method): sentinels, monotone precision envelope from the right, trapezoid
+    over 101 recall points."""
+    r = np.concatenate(([0.0], recall, [1.0]))
+    p = np.concatenate(([1.0], precision, [0.0]))
+    p = np.maximum.accumulate(p[::-1])[::-1]
+    y = np.interp(_AP_GRID, r, p)
+    return float(np.sum((y[1:] + y[:-1]) * np.diff(_AP_GRID) / 2.0))     # == np.trapz(y, x)
+
+
+def _box_smooth(y: np.ndarray, frac: float) -> np.ndarray:
+    """utils/metrics.py:15-20: box filter over a fraction of the curve, edge-padded."""
+    n = round(len(y) * frac * 2) // 2 + 1
+    half = np.ones(n // 2)
+    return np.convolve(np.concatenate((half * y[0], y, half * y[-1])), np.ones(n) / n, mode="valid")
+
+
+def average_precision_per_class(tp, conf, pred_cls, target_cls, eps: float = 1e-16):
+    """``ap_per_class`` (:13-67).  tp (n, niou) bool/0-1, conf (n,), pred_cls (n,), target_cls (m,).
+    Returns (tp, fp, precision, recall, f1, ap (nc, niou), classes) at the max-F1 confidence."""
+    order = np.argsort(-conf)
+    tp, conf, pred_cls = tp[order], conf[order], pred_cls[order]
+    classes, n_labels = np.unique(target_cls, return_counts=True)
+    niou = tp.shape[1]
+    ap = np.zeros((len(classes), niou))
+    p_curve = np.zeros((len(classes), _PR_GRID.size))
+    r_curve = np.zeros_like(p_curve)
+    for k, (c, nl) in enumerate(zip(classes, n_labels)):
+        sel = pred_cls == c
+        if not sel.any() or nl == 0:
+            continue
+        hits = tp[sel].cumsum(0)
+        misses = (1 - tp[sel]).cumsum(0)
+        recall = hits / (nl + eps)
+        precision = hits / (hits + misses)
+        # curves over confidence at IoU 0.5; -x because np.interp wants increasing abscissae
+        r_curve[k] = np.interp(-_PR_GRID, -conf[sel], recall[:, 0], left=0)
+        p_curve[k] = np.interp(-_PR_GRID, -conf[sel], precision[:, 0], left=1)
+        for j in range(niou):
+            ap[k, j] = _envelope_ap(recall[:, j], precision[:, j])
+    f1_curve = 2 * p_curve * r_curve / (p_curve + r_curve + eps)
+    best = _box_smooth(f1_curve.mean(0), 0.1).argmax()
+    p, r, f1 = p_curve[:, best], r_curve[:, best], f1_curve[:, best]
+    tp_n = (r * n_labels).round()
+    fp_n = (tp_n / (p + eps) - tp_n).round()
+    return tp_n, fp_n, p, r, f1, ap, classes.astype(int)
+
+
+def _summarize(self, details_per_class: bool = False, do_coco_eval: bool = False):
+    """``DetEvaluator.summarize`` (:184-226) without the rich table / pycocotools parts: returns
+    (map50, map95, per_class rows or None, None) and resets the accumulators."""
+    stats = [torch.cat(x, 0).cpu().numpy() for x in zip(*self.stats)] if self.stats else []
+    rows = None
+    ap_class = np.zeros(0, int)
+    ap50 = ap = np.zeros(0)
+    if len(stats) and stats[0].any():
+        _, _, self.precision, self.recall, self.f1, ap_all, ap_class = average_precision_per_class(*stats)
+        ap50, ap = ap_all[:, 0], ap_all.mean(1)
+        self.mp, self.mr = self.precision.mean(), self.recall.mean()
+        self.map50, self.map95 = ap50.mean(), ap.mean()
+    if details_per_class and len(stats):
+        counts = np.bincount(stats[3].astype(int), minlength=len(self.class_labels))
+        rows = [[self.class_labels[int(c)], self.seen, int(counts[c]), round(float(self.precision[i]), 3),
+                 round(float(self.recall[i]), 3), round(float(ap50[i]), 3), round(float(ap[i]), 3)]
+                for i, c in enumerate(ap_class)]
+    self.seen = 0
+    self.stats.clear()
+    return self.map50, self.map95, rows, None
+
+
+DetEvaluator.summarize = _summarize
