@@ -314,14 +314,17 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
     lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(3, seed=77 + nc, img=img, nc=nc, clusters=12)]
     from vision_kit_b200 import _lib
     L = _lib.lib()
-    res = {}
+    res, resp = {}, {}
+    pred = vk.ops.detect_decode(cfg, lv)
     try:
         for mode in (1, 2):       # VK_FILTER_SPARSE, VK_FILTER_DENSE
             L.vk_set_filter_kernel(mode)
             buf = vk.ops.decode_filter(cfg, lv, conf, ml, classes=classes)
             out = vk.ops.nms_batched(buf, 0.6, want_keep=True)
+            bufp = vk.ops.filter_pred(pred, conf, ml, classes=classes)      # the nms(prediction) drop-in path
             torch.cuda.synchronize()
             res[mode] = (_canonical(buf), buf.counts.cpu().numpy(), out)
+            resp[mode] = (_canonical(bufp), bufp.counts.cpu().numpy())
     finally:
         L.vk_set_filter_kernel(0)
     (ca, na, oa), (cb, nb, ob) = res[1], res[2]
@@ -330,6 +333,11 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
     for (la, ra, ba), (lb, rb, bb) in zip(ca, cb):
         assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
     assert torch.equal(oa.counts, ob.counts) and torch.equal(oa.dets, ob.dets) and torch.equal(oa.keep, ob.keep)
+    # filter_pred: dense == sparse == the fused path (same sigmoid bits, same order)
+    for m in (1, 2):
+        assert np.array_equal(resp[m][1], na)
+        for (lp, rp, bp), (la, ra, ba) in zip(resp[m][0], ca):
+            assert np.array_equal(lp, la) and np.array_equal(rp, ra) and np.array_equal(bp, ba)
 
 
 def test_head_forward_nms(vk, cuda):

@@ -905,6 +905,157 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Dense variant of filter_pred (the `nms(prediction)` drop-in at eval thresholds): the same
+// persistent pipeline and (row, class part) mapping as decode_filter_dense_kernel, reading an
+// existing (B, rows, no) prediction tensor.  A tile is 64 consecutive rows = one contiguous run of
+// 64*no floats, copied as it is ([row][no], odd pitch: lanes over rows are conflict-free); the
+// values are probabilities already, boxes are cxcywh.
+// ---------------------------------------------------------------------------------------
+template <int I, int N>
+struct PredProducts {
+    static __device__ __forceinline__ void run(float* p, uint32_t base, float obj) {
+        float x;
+        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(base), "n"(I * 4));
+        p[I] = __fmul_rn(x, obj);                                                                 // image_proc.py:135
+        PredProducts<I + 1, N>::run(p, base, obj);
+    }
+};
+template <int N>
+struct PredProducts<N, N> {
+    static __device__ __forceinline__ void run(float*, uint32_t, float) {}
+};
+
+__device__ __forceinline__ void pred_prefetch(const float* __restrict__ src, int nfloats, float* tile) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((nfloats & 3) == 0)) {
+        for (int e = threadIdx.x; 4 * e < nfloats; e += kDecThreads) cp_async_16(base + 16u * e, src + 4 * e);
+    } else {
+        for (int e = threadIdx.x; e < nfloats; e += kDecThreads) cp_async_4(base + 4u * e, src + e);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int CPP, bool ML>
+__global__ void __launch_bounds__(kDecThreads, VK_DENSE_BPS)
+filter_pred_dense_kernel(const float* __restrict__ pred, int no, const FilterArgs A, int total_tiles) {
+    extern __shared__ __align__(16) float tiles_sm[];  // 2 x [kTileS][no] prediction rows
+    __shared__ int s_cnt[kDecThreads];
+    __shared__ int s_off[kDecThreads + 1];
+    __shared__ int s_wsum[kWarps];
+    __shared__ float s_bv[kDecThreads];
+    __shared__ int s_bj[kDecThreads];
+    const int nc = A.nc;
+    const int tile_floats = kTileS * no;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row = threadIdx.x & (kTileS - 1), qd = threadIdx.x >> 6;
+    const int cpp = (nc + kParts - 1) / kParts;
+    const int c_lo = min(nc, qd * cpp), c_hi = min(nc, c_lo + cpp);
+    const int slot = row * kParts + qd;
+    uint32_t allowed = 0;
+    for (int i = 0; i < c_hi - c_lo; ++i)
+        if (class_allowed(A.class_mask, c_lo + i)) allowed |= 1u << i;
+    int t = blockIdx.x;
+    if (t >= total_tiles) return;
+    // tile t = (image b, segment seg): rows seg*64 .. of image b
+    auto tile_src = [&](int tt, int& b, int& seg, int& nvalid) {
+        b = tt / A.segs; seg = tt - b * A.segs;
+        nvalid = min(kTileS, A.rows - seg * kTileS);
+        return pred + ((size_t)b * A.rows + (size_t)seg * kTileS) * no;
+    };
+    int b, seg, nvalid;
+    {
+        const float* src = tile_src(t, b, seg, nvalid);
+        pred_prefetch(src, nvalid * no, tiles_sm);
+    }
+    for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
+        const float* tile = tiles_sm + (k & 1) * tile_floats;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                      // tile k landed; everyone is done with the other buffer and the scratch arrays
+        if (t + (int)gridDim.x < total_tiles) {
+            int b2, seg2, nv2;
+            const float* src = tile_src(t + gridDim.x, b2, seg2, nv2);
+            pred_prefetch(src, nv2 * no, tiles_sm + ((k + 1) & 1) * tile_floats);
+        }
+        tile_src(t, b, seg, nvalid);
+        const float* prow = tile + row * no;
+        const float o = prow[4];
+        const float obj = (row < nvalid && o > A.conf) ? o : 0.0f;    // image_proc.py:99 (dead rows: products 0)
+        float p[CPP];
+        PredProducts<0, CPP>::run(p, (uint32_t)__cvta_generic_to_shared(prow + 5 + c_lo), obj);
+        uint32_t flags = 0;
+        float bv = -INFINITY;
+        int bj = 0x7fffffff;
+        if (ML) {
+#pragma unroll
+            for (int i = 0; i < CPP; ++i)
+                if (p[i] > A.conf) flags |= 1u << i;                                              // :141
+        } else {
+            const int ncls = c_hi - c_lo;
+#pragma unroll
+            for (int i = 0; i < CPP; ++i)
+                if (i < ncls && p[i] > bv) { bv = p[i]; bj = c_lo + i; }                          // first max (:145)
+        }
+        int count;
+        if (ML) {
+            flags &= allowed;
+            count = __popc(flags);
+        } else {
+            s_bv[slot] = bv; s_bj[slot] = bj;
+            __syncthreads();
+            count = 0;
+            if (qd == 0) {
+#pragma unroll
+                for (int q2 = 1; q2 < kParts; ++q2)
+                    if (s_bv[slot + q2] > bv) { bv = s_bv[slot + q2]; bj = s_bj[slot + q2]; }
+                count = (bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;   // :147,151
+            }
+        }
+        s_cnt[slot] = count;
+        __syncthreads();
+        {
+            const int v = s_cnt[threadIdx.x];
+            const int inc = warp_incl_scan(v, lane);
+            s_off[threadIdx.x] = inc - v;
+            if (lane == 31) s_wsum[w] = inc;
+        }
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) {
+            const int x = s_wsum[i];
+            if (i < (slot >> 5)) wbase += x;
+            total += x;
+        }
+        const int tile_base = seg * A.tile_cap;
+        const int grow = seg * kTileS + row;                                   // row inside the image
+        if (count) {
+            uint2* const wp = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + tile_base + wbase + s_off[slot];
+            const uint32_t idx0 = (uint32_t)(grow * nc + c_lo);
+            if (ML) {
+                uint32_t pos = 0;
+#pragma unroll
+                for (int i = 0; i < CPP; ++i) {
+                    const bool f = (flags & (1u << i)) != 0;
+                    if (f) wp[pos] = make_uint2(__float_as_uint(p[i]), idx0 + (uint32_t)i);
+                    pos += f;
+                }
+            } else {
+                *wp = make_uint2(__float_as_uint(bv), (uint32_t)(grow * nc + bj));
+            }
+        }
+        if (qd == 0) {
+            const int n = s_cnt[slot] + s_cnt[slot + 1] + s_cnt[slot + 2] + s_cnt[slot + 3];
+            if (n > 0) A.boxes[(size_t)b * A.rows + grow] = xyxy_from_cxcywh(prow[0], prow[1], prow[2], prow[3]);
+        }
+        if (threadIdx.x == 0) {
+            A.seg_base[(size_t)b * A.segs + seg] = total ? tile_base : 0;
+            A.seg_count[(size_t)b * A.segs + seg] = total;
+            if (total) atomicAdd(A.counts + b, total);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kDecThreads, 5)
 filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
     extern __shared__ float buf[];  // [64][no]: a dense tile or the gathered rows
@@ -1163,6 +1314,31 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
     if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_filter_pred: nc=%d needs %zu B of shared memory", nc, smem);
     cudaFuncSetAttribute(filter_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
+    const int mode = filter_mode();
+    const bool dense = mode == VK_FILTER_DENSE || (mode == VK_FILTER_AUTO && conf_thres < 0.05f);
+    if (dense && nc <= 128 && (long)segs * batch <= 0x7fffffffL) {
+        const int cpp_max = nc <= 32 ? 8 : nc <= 80 ? 20 : 32;
+        const size_t dsmem = (2 * (size_t)kTileS * no + (size_t)cpp_max + 8) * sizeof(float);   // + slack: unrolled class loop
+        const int total_tiles = segs * batch;
+#define VK_FP_LAUNCH(CPP, ML)                                                                                      \
+        do {                                                                                                        \
+            cudaFuncSetAttribute(filter_pred_dense_kernel<CPP, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); \
+            int per_sm = 0;                                                                                         \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pred_dense_kernel<CPP, ML>, kDecThreads, dsmem); \
+            if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;                                                       \
+            if (per_sm < 1) per_sm = 1;                                                                             \
+            const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;                       \
+            filter_pred_dense_kernel<CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(pred, no, A, total_tiles);      \
+        } while (0)
+#define VK_FP_CPP(CPP) do { if (A.multi_label) VK_FP_LAUNCH(CPP, true); else VK_FP_LAUNCH(CPP, false); } while (0)
+        if (nc <= 32) VK_FP_CPP(8);
+        else if (nc <= 80) VK_FP_CPP(20);
+        else VK_FP_CPP(32);
+#undef VK_FP_CPP
+#undef VK_FP_LAUNCH
+        count_launch();
+        return check_launch("filter_pred_dense_kernel");
+    }
     A.group = choose_group(batch, segs);
     filter_pred_kernel<<<dim3(ceil_div(segs, A.group), batch), kDecThreads, smem, stream>>>(pred, no, A);
     count_launch();
