@@ -99,7 +99,10 @@ __device__ __forceinline__ void taps_dp2a(uint32_t w0, uint32_t w1, uint32_t w2,
 
 constexpr int kLbRows = 8;        // canvas rows per block
 constexpr int kLbThreads = 320;   // 640-wide canvas = 2 columns per thread, no idle lanes
-constexpr int kGenRows = 4;       // canvas rows per block of the general kernel
+#ifndef VK_GEN_ROWS
+#define VK_GEN_ROWS 4
+#endif
+constexpr int kGenRows = VK_GEN_ROWS;       // canvas rows per block of the general kernel
 constexpr int kGenThreads = 160;  // 640-wide canvas = one 4-column group per thread
 constexpr int kGenWarps = kGenThreads / 32;
 constexpr int kLbMaxSrcRows = 2 * kGenRows + 4;  // staged source rows (down-scales up to ~2.2x)
