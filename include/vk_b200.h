@@ -163,6 +163,21 @@ int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch
                      float conf_thres, int multi_label, const uint32_t* class_mask,
                      const VkCandBuf* out, vk_stream_t stream);
 
+/* Fused Detect head: the 1x1 conv of models/heads/yolov5.py:58 / yolov7.py:67-71
+ * (implicit layers already folded into weights/biases), the decode and nms()'s candidate selection in one
+ * kernel -- D[s][co] = X^T W^T on the tensor cores (tcgen05, TF32 inputs, fp32 accumulation in TMEM), the
+ * filter straight from TMEM.  The (B, na*no, ny, nx) conv output is never written.
+ *   feats[l]   dev (B, cin[l], ny, nx) float32, 16-byte aligned, ny*nx % 4 == 0, cin[l] % 32 == 0
+ *   weights[l] dev (na*no, cin[l]) float32 (the conv weight with its trailing 1x1 dropped); biases[l] (na*no) or NULL
+ *   out        the candidate buffer of vk_decode_filter (same sizes), consumed by vk_nms_batched
+ *   fault      dev int32, set to 1 if a tensor-core completion wait timed out (never observed; the
+ *              kernel then terminates instead of hanging)
+ * Logits differ from an fp32 conv by TF32 input rounding (~1e-3 relative). */
+int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const int32_t* cin,
+                          const float* const* weights, const float* const* biases, int batch,
+                          float conf_thres, int multi_label, const uint32_t* class_mask,
+                          const VkCandBuf* out, int32_t* fault, vk_stream_t stream);
+
 /* ---------------------------------------------------------------- NMS
  * utils/image_proc.py:154-182: top-max_nms cut by score (stable), class offset
  * cls*max_wh, torchvision.ops.nms greedy suppression, [:max_det].

@@ -603,3 +603,59 @@ def test_dataset_ingest_batch_vs_oracle(vk, cuda):
         assert np.array_equal(f32[i], (exp.transpose(2, 0, 1).astype(np.float32) / np.float32(255.0))), sizes[i]
         assert orig[i] == sizes[i]
         assert resized[i] == restate.dataset_geometry(sizes[i][0], sizes[i][1], (640, 640))[1]
+
+
+# --------------------------------------------------------------------------- fused conv head (§8f row 2)
+def _tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1fff).view(torch.float32)
+
+
+@pytest.mark.parametrize("variant,conf,ml,cins", [
+    ("v5", 0.25, False, (64, 96, 128)),
+    ("v7", 0.001, True, (32, 64, 160)),
+    ("v5", 0.05, True, (128, 256, 512)),       # YOLOv5s head widths
+])
+def test_conv_head_matches_conv_then_filter(variant, conf, ml, cins, vk, cuda):
+    """vk_conv_decode_filter (tcgen05, TF32 inputs, fp32 accumulate) against an fp32 conv of the
+    TF32-truncated operands followed by vk_decode_filter: the same candidates up to threshold
+    flips within 1e-4 of conf_thres, scores and boxes within 1e-4 relative (accumulation order)."""
+    cfg, _ = _cfg(vk, variant)
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(123 + len(cins) + cins[0])
+    feats, ws, bs = [], [], []
+    for l, s in enumerate(synth.STRIDES):
+        n = 640 // s
+        feats.append((torch.randn(B, cins[l], n, n, generator=g) * 1.0).to(cuda))
+        ws.append((torch.randn(255, cins[l], 1, 1, generator=g) * (1.2 / cins[l] ** 0.5)).to(cuda))
+        bias = torch.randn(255, generator=g) * 0.5
+        bias.view(3, 85)[:, 4] -= 3.0          # objectness prior: few rows survive
+        bias.view(3, 85)[:, 5:] -= 1.5
+        bs.append(bias.to(cuda))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        logits = [torch.nn.functional.conv2d(_tf32_trunc(f), _tf32_trunc(w), b).contiguous() for f, w, b in zip(feats, ws, bs)]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = vk.ops.decode_filter(cfg, logits, conf, ml)
+    got = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
+    torch.cuda.synchronize()
+    assert int(got.fault.item()) == 0
+    assert int(ref.counts.sum()) > 20
+    for (la, ra, ba), (lb, rb, bb) in zip(_canonical(ref), _canonical(got)):
+        sa = {int(v >> 32): np.uint32(v & 0xffffffff).view(np.float32) for v in la}
+        sb = {int(v >> 32): np.uint32(v & 0xffffffff).view(np.float32) for v in lb}
+        for k in set(sa) ^ set(sb):            # threshold flips only
+            assert abs(float(sa.get(k, sb.get(k))) - conf) < 1e-4 * max(conf, 1e-2), k
+        common = sorted(set(sa) & set(sb))
+        assert len(common) > 5
+        np.testing.assert_allclose([sb[k] for k in common], [sa[k] for k in common], rtol=2e-4, atol=1e-6)
+        assert [k for k in (int(v >> 32) for v in lb)] == sorted(sb)       # canonical (row, class) order
+        rows = sorted(set(ra) & set(rb))
+        ia = {r: i for i, r in enumerate(ra)}
+        ib = {r: i for i, r in enumerate(rb)}
+        np.testing.assert_allclose(bb[[ib[r] for r in rows]], ba[[ia[r] for r in rows]], rtol=2e-4, atol=2e-3)
+    # and through NMS: same number of detections up to flips
+    a = vk.ops.nms_batched(ref, 0.5)
+    b = vk.ops.nms_batched(got, 0.5)
+    assert (a.counts - b.counts).abs().max().item() <= 2

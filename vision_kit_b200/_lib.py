@@ -80,6 +80,8 @@ _PROTOS = {
                                  C.POINTER(VkCandBuf), _P]),
     "vk_decode_filter": (C.c_int, [C.POINTER(VkHeadCfg), _P, C.c_int, C.c_float, C.c_int, _P,
                                    C.POINTER(VkCandBuf), _P]),
+    "vk_conv_decode_filter": (C.c_int, [C.POINTER(VkHeadCfg), _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P,
+                                        C.POINTER(VkCandBuf), _P, _P]),
     "vk_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vk_nms_batched": (C.c_int, [C.POINTER(VkCandBuf), C.c_int, C.c_float, C.c_double, C.c_int,
                                  C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -1344,3 +1344,304 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
     count_launch();
     return check_launch("filter_pred_kernel");
 }
+
+// =======================================================================================
+// Fused Detect head: 1x1 conv (tensor cores) + decode + confidence filter  
+//
+//   models/heads/yolov5.py:58-69 / yolov7.py:67-81: x[i] = m[i](x[i]) (a 1x1 conv, Cout = na*no),
+//   then sigmoid / grid / anchors, then nms()'s candidate selection (utils/image_proc.py:99-151).
+//   Here the (B, 255, ny, nx) conv output never exists: one CTA computes
+//       D[s][co] = sum_ci X[b][ci][s] * W[co][ci]        s: 128 spatial positions, co: 256 (padded)
+//   with tcgen05.mma (kind::tf32, fp32 bits of X and W used as TF32, fp32 accumulate in TMEM).
+//   With D transposed like this a TMEM lane is a spatial position, so every epilogue thread owns
+//   whole prediction rows (one per anchor) and runs the dense filter's per-row logic straight
+//   from tcgen05.ld -- no shared-memory round trip of the logits.
+//
+//   Operands: both K-major, 128-byte swizzled (rows of 32 tf32 = 128 B, 8-row atoms of 1024 B).
+//   W[co][ci] is K-major as stored: 16-byte cp.async copies land directly in the swizzled tile.
+//   X is [ci][s] (s contiguous = MN-major; tcgen05 returned zeros for MN-major TF32 operands on
+//   this part -- profiles/micro/umma_tf32.cu -- so X is transposed on chip): 16-byte cp.async into
+//   a raw [k][128] staging tile, then thread s reads its column (conflict-free LDS.32) and writes
+//   row s of the A tile with 128-bit stores (the swizzle makes them conflict-free).
+//   Pipeline per 32-channel block: copies of block k+1 in flight while block k is transposed and
+//   multiplied; the A tile is single-buffered behind the MMA-completion mbarrier.
+//   128 threads, 256 TMEM columns, 112 KB shared memory -> 2 CTAs per SM overlap each other.
+//
+//   Candidates, boxes, segment table: exactly vk_decode_filter's format (same VkCandBuf), so
+//   vk_nms_batched consumes it unchanged.  Results equal conv-then-vk_decode_filter up to TF32
+//   rounding of the logits (tests/test_gpu_parity.py::test_conv_head_*).
+// =======================================================================================
+namespace vk {
+
+constexpr int kChM = 128, kChN = 256, kChKB = 32, kChThreads = 128;
+constexpr int kChStageBytes = kChKB * kChM * 4;       // 16 KB raw X block [k][m]
+constexpr int kChABytes = kChM * 128;                 // 16 KB
+constexpr int kChBBytes = kChN * 128;                 // 32 KB
+constexpr int kChSmem = 2 * kChStageBytes + kChABytes + 2 * kChBBytes + 1024;   // + alignment slack
+
+struct ConvHead {
+    const float* x[VK_MAX_LEVELS];      // (B, cin, ny, nx)
+    const float* w[VK_MAX_LEVELS];      // (na*no, cin)
+    const float* bias[VK_MAX_LEVELS];   // (na*no) or null
+    int cin[VK_MAX_LEVELS];
+    int mtile_start[VK_MAX_LEVELS + 1]; // first 128-row tile of each level inside an image
+    int mtiles;                         // per image
+};
+
+__device__ __forceinline__ uint32_t ch_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major SW128 tile: row r = 128 B (32 tf32), 16-byte chunk c of row r at position c ^ (r & 7)
+__device__ __forceinline__ uint32_t ch_koff(int r, int chunk) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint64_t ch_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;              // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset: 8-row atoms 1024 B apart
+    d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void ch_cp16(uint32_t dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;        // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+}
+// bounded wait on an mbarrier phase; returns false on time-out (never hangs the GPU)
+__device__ __forceinline__ bool ch_wait(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
+#define VK_TMEM_LD16(r, taddr)                                                                                     \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+                 : "r"(taddr));                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
+__global__ void __launch_bounds__(kChThreads, 2)
+conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int* __restrict__ fault) {
+    extern __shared__ uint8_t ch_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bias[kChN];
+    __shared__ int s_wtot[4];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ch_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sStage = smem;                                  // 2 x 16 KB
+    uint8_t* sA = smem + 2 * kChStageBytes;                  // 16 KB
+    uint8_t* sB = sA + kChABytes;                            // 2 x 32 KB
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < VK_MAX_LEVELS; ++i)
+        if (i < H.nl && (int)blockIdx.x >= C.mtile_start[i]) l = i;
+    const int s0 = ((int)blockIdx.x - C.mtile_start[l]) * kChM;
+    const int nynx = H.nynx[l], cin = C.cin[l], no = H.no, cout = H.na * no;
+    const int nvalid = min(kChM, nynx - s0);
+    const float* __restrict__ X = C.x[l] + (size_t)b * cin * nynx + s0;
+    const float* __restrict__ W = C.w[l];
+    const int nkb = cin / kChKB;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(&s_tmem)), "n"(kChN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ch_smem(&s_bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < kChN; i += kChThreads) s_bias[i] = (C.bias[l] && i < cout) ? __ldg(C.bias[l] + i) : 0.0f;
+
+    auto issue_copies = [&](int kb) {
+        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes), sb = ch_smem(sB + (kb & 1) * kChBBytes);
+        // X block: 32 channels x 32 chunks of 4 positions (raw [k][128]); positions past the plane are zeros
+        for (int e = tid; e < kChKB * 32; e += kChThreads) {
+            const int k = e >> 5, m4 = (e & 31) << 2;
+            ch_cp16(st + (uint32_t)(k * kChM + m4) * 4, X + (size_t)(kb * kChKB + k) * nynx + (m4 < nvalid ? m4 : 0), m4 < nvalid);
+        }
+        // W block: 256 rows x 8 chunks of 4 channels, straight into the swizzled K-major tile
+        for (int e = tid; e < kChN * 8; e += kChThreads) {
+            const int n = e >> 3, c = e & 7;
+            ch_cp16(sb + ch_koff(n, c), W + (size_t)(n < cout ? n : 0) * cin + kb * kChKB + 4 * c, n < cout);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_copies(0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
+    bool ok = true;
+    for (int kb = 0; kb < nkb; ++kb) {
+        // the MMAs of block kb-1 read the A tile (single-buffered) and the W buffer that block kb+1 reuses
+        if (kb > 0) ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((kb - 1) & 1));
+        if (kb + 1 < nkb) {
+            issue_copies(kb + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                      // block kb landed (staging + W tile)
+        {   // transpose: thread = spatial position; 8 chunks of 4 channels -> row `tid` of the A tile
+            const float* st = reinterpret_cast<const float*>(sStage + (kb & 1) * kChStageBytes) + tid;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
+                *reinterpret_cast<float4*>(sA + ch_koff(tid, c)) = v;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes (cp.async W, stores A) -> async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = ch_smem(sA), b0 = ch_smem(sB + (kb & 1) * kChBBytes);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {                  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte row
+                const uint32_t acc = (kb | ks) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                             :: "r"(tmem), "l"(ch_desc(a0 + ks * 32)), "l"(ch_desc(b0 + ks * 32)), "r"(idesc), "r"(acc) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
+        }
+    }
+    ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((nkb - 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok && tid == 0) atomicExch(fault, 1);
+
+    // ---------------- epilogue: thread = spatial position s0 + tid = TMEM lane; one prediction row per anchor
+    const int nc = A.nc;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int sp = s0 + tid;
+    const int half = tid >> 6;                                 // 64-row segment of the thread inside the tile
+    const bool seg_exists = s0 + 64 * half < nynx;
+    struct { int variant, nx; float stride; } const gbase{H.variant, H.nx[l], H.stride[l]};
+    for (int a = 0; a < H.na; ++a) {
+        const int cb = a * no;
+        uint32_t r[16];
+        VK_TMEM_LD16(r, trow + cb);                            // x, y, w, h, obj, first 11 classes
+        float box_l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) box_l[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[cb + j]);
+        const float o = sigmoidf_vk(__fadd_rn(__uint_as_float(r[4]), s_bias[cb + 4]));
+        const bool alive = ok && tid < nvalid && o > A.conf;       // image_proc.py:99
+        const float obj = alive ? o : 0.0f;
+        // pass 1: count (multi-label) or best class
+        int count = 0;
+        float bv = -INFINITY;
+        int bj = 0x7fffffff;
+        const bool any_alive = __any_sync(0xffffffffu, alive);
+        if (any_alive) {
+            for (int c0 = 0; c0 < nc; c0 += 16) {
+                uint32_t q[16];
+                VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + j;
+                    if (c < nc) {
+                        const float p = __fmul_rn(sigmoidf_vk(__fadd_rn(__uint_as_float(q[j]), s_bias[cb + 5 + c])), obj);   // :135
+                        if (A.multi_label) count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;               // :141,151
+                        else if (p > bv) { bv = p; bj = c; }                                                              // :145
+                    }
+                }
+            }
+            if (!A.multi_label) count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
+        }
+        // offsets inside the 64-row segment (warps 2*half, 2*half+1), canonical order = row order
+        const int incl = warp_incl_scan(count, lane);
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        const int base = (warp & 1) ? s_wtot[warp - 1] : 0;
+        const int seg_total = s_wtot[2 * half] + s_wtot[2 * half + 1];
+        const int seg = H.tile_start[l] + a * H.tpa[l] + (s0 >> 6) + half;
+        const int row = H.row_base[l] + a * nynx + sp;             // prediction row inside the image
+        // pass 2 (warp-uniform: tcgen05.ld is a warp-collective): recompute the products and store
+        uint2* wp = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + (size_t)seg * A.tile_cap + base + (incl - count);
+        const uint32_t idx0 = (uint32_t)(row * nc);
+        if (A.multi_label) {
+            if (__any_sync(0xffffffffu, count > 0)) {
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        if (c < nc && count > 0) {
+                            const float p = __fmul_rn(sigmoidf_vk(__fadd_rn(__uint_as_float(q[j]), s_bias[cb + 5 + c])), obj);
+                            if (p > A.conf && class_allowed(A.class_mask, c)) *wp++ = make_uint2(__float_as_uint(p), idx0 + (uint32_t)c);
+                        }
+                    }
+                }
+            }
+        } else if (count > 0) {
+            *wp = make_uint2(__float_as_uint(bv), idx0 + (uint32_t)bj);
+        }
+        if (count > 0) {
+            const int gy = sp / gbase.nx, gx = sp - gy * gbase.nx;
+            const float aw = H.anchors[l][2 * a], ah = H.anchors[l][2 * a + 1];
+            A.boxes[(size_t)b * A.rows + row] =
+                xyxy_from_cxcywh(decode_elem(box_l[0], 0, (float)gx, gbase.stride, aw, gbase.variant),
+                                 decode_elem(box_l[1], 1, (float)gy, gbase.stride, ah, gbase.variant),
+                                 decode_elem(box_l[2], 2, 0.f, gbase.stride, aw, gbase.variant),
+                                 decode_elem(box_l[3], 3, 0.f, gbase.stride, ah, gbase.variant));
+        }
+        if ((tid & 63) == 0 && seg_exists) {
+            A.seg_base[(size_t)b * A.segs + seg] = seg_total ? seg * A.tile_cap : 0;
+            A.seg_count[(size_t)b * A.segs + seg] = seg_total;
+            if (seg_total) atomicAdd(A.counts + b, seg_total);
+        }
+        __syncthreads();                                       // s_wtot is reused by the next anchor
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kChN));
+}
+
+}  // namespace vk
+
+extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const int32_t* cin,
+                                     const float* const* weights, const float* const* biases, int batch,
+                                     float conf_thres, int multi_label, const uint32_t* class_mask,
+                                     const VkCandBuf* out, int32_t* fault, vk_stream_t stream_) {
+    HeadDev H;
+    if (int rc = make_head(cfg, &H, "vk_conv_decode_filter")) return rc;
+    if (batch == 0) return VK_OK;
+    if (!feats || !cin || !weights || !fault || batch < 0) return fail_arg("vk_conv_decode_filter: null/negative argument");
+    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_conv_decode_filter: conf_thres %g outside [0,1]", conf_thres);
+    if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: batch %d > 65535", batch);
+    if (H.na * H.no > kChN || (H.na - 1) * H.no + 5 + 16 * ceil_div(H.nc, 16) > kChN)
+        return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: %d output channels do not fit %d TMEM columns", H.na * H.no, kChN);
+    if (int rc = check_cand(out, H.rows, H.tiles, H.nc, multi_label, "vk_conv_decode_filter")) return rc;
+    ConvHead C;
+    memset(&C, 0, sizeof(C));
+    int mt = 0;
+    for (int l = 0; l < H.nl; ++l) {
+        if (!feats[l] || !weights[l]) return fail_arg("vk_conv_decode_filter: level %d is NULL", l);
+        if (cin[l] <= 0 || cin[l] % kChKB) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: cin[%d] = %d is not a multiple of %d", l, cin[l], kChKB);
+        if (H.nynx[l] % 4 || (reinterpret_cast<uintptr_t>(feats[l]) & 15) || (reinterpret_cast<uintptr_t>(weights[l]) & 15))
+            return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: level %d needs ny*nx %% 4 == 0 and 16-byte aligned tensors", l);
+        C.x[l] = feats[l]; C.w[l] = weights[l]; C.bias[l] = biases ? biases[l] : nullptr; C.cin[l] = cin[l];
+        C.mtile_start[l] = mt;
+        mt += ceil_div(H.nynx[l], kChM);
+    }
+    for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) C.mtile_start[l] = mt;
+    C.mtiles = mt;
+    cudaStream_t stream = as_stream(stream_);
+    cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fault, 0, sizeof(int32_t), stream);
+    if (e != cudaSuccess) return fail_code((int)e, "vk_conv_decode_filter: memset: %s", cudaGetErrorString(e));
+    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
+    cudaFuncSetAttribute(conv_decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem);
+    conv_decode_filter_kernel<<<dim3(mt, batch), kChThreads, kChSmem, stream>>>(H, C, A, fault);
+    count_launch();
+    return check_launch("conv_decode_filter_kernel");
+}

@@ -293,6 +293,43 @@ def decode_filter(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], conf_thres: fl
     return buf
 
 
+def conv_decode_filter(cfg: VkHeadCfg, feats: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+                       biases: Optional[Sequence[Optional[torch.Tensor]]], conf_thres: float,
+                       multi_label: bool = False, classes=None, buf: Optional[CandBuf] = None) -> CandBuf:
+    """vk_conv_decode_filter: Detect 1x1 conv (tcgen05, TF32) + decode + filter in one kernel.
+    feats[l] (B, cin, ny, nx) float32; weights[l] (na*no, cin) or (na*no, cin, 1, 1); biases[l] (na*no) or None."""
+    nl = cfg.nl
+    bs = int(feats[0].shape[0])
+    dev = feats[0].device
+    keep = []
+    fp = (C.c_void_p * VK_MAX_LEVELS)(); wp = (C.c_void_p * VK_MAX_LEVELS)(); bp = (C.c_void_p * VK_MAX_LEVELS)()
+    cin = (C.c_int32 * VK_MAX_LEVELS)()
+    for l in range(nl):
+        f = feats[l]
+        _lib.require_cuda(f, "features")
+        if f.dtype != torch.float32 or not f.is_contiguous() or f.dim() != 4 or int(f.shape[0]) != bs or \
+                (int(f.shape[2]), int(f.shape[3])) != (cfg.ny[l], cfg.nx[l]):
+            raise ValueError(f"feats[{l}] must be a contiguous float32 (B, cin, {cfg.ny[l]}, {cfg.nx[l]}) tensor")
+        w = weights[l].detach().reshape(weights[l].shape[0], -1).contiguous().float()
+        if tuple(w.shape) != (cfg.na * (cfg.nc + 5), int(f.shape[1])):
+            raise ValueError(f"weights[{l}] must have shape ({cfg.na * (cfg.nc + 5)}, {int(f.shape[1])})")
+        bb = None if biases is None or biases[l] is None else biases[l].detach().contiguous().float()
+        keep += [w, bb]
+        fp[l], wp[l], bp[l], cin[l] = f.data_ptr(), w.data_ptr(), (bb.data_ptr() if bb is not None else None), int(f.shape[1])
+    rows = head_rows(cfg)
+    segs = _lib.lib().vk_decode_filter_segments(C.byref(cfg))
+    if buf is None:
+        buf = CandBuf.alloc(bs, rows, segs, cfg.nc, default_cap(segs, cfg.nc, multi_label), dev)
+    mask = class_mask(classes, cfg.nc, dev)
+    fault = torch.zeros(1, dtype=torch.int32, device=dev)
+    cs = buf.c_struct()
+    _lib.check("vk_conv_decode_filter", _lib.lib().vk_conv_decode_filter(
+        C.byref(cfg), C.cast(fp, C.c_void_p), C.cast(cin, C.c_void_p), C.cast(wp, C.c_void_p), C.cast(bp, C.c_void_p),
+        bs, float(conf_thres), int(bool(multi_label)), _ptr(mask), C.byref(cs), _ptr(fault), _lib.stream_ptr()))
+    buf._mask, buf._keep, buf.fault = mask, keep, fault
+    return buf
+
+
 @dataclass
 class NmsOut:
     dets: torch.Tensor        # float32 (B, max_det, 6), rows >= count zero
