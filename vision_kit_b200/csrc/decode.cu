@@ -1365,7 +1365,7 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
 //   row s of the A tile with 128-bit stores (the swizzle makes them conflict-free).
 //   Pipeline per 32-channel block: copies of block k+1 in flight while block k is transposed and
 //   multiplied; the A tile is single-buffered behind the MMA-completion mbarrier.
-//   128 threads, 256 TMEM columns, 112 KB shared memory -> 2 CTAs per SM overlap each other.
+//   128 threads, 256 TMEM columns, 97 KB shared memory -> 2 CTAs per SM overlap each other.
 //
 //   Candidates, boxes, segment table: exactly vk_decode_filter's format (same VkCandBuf), so
 //   vk_nms_batched consumes it unchanged.  Results equal conv-then-vk_decode_filter up to TF32
@@ -1377,7 +1377,7 @@ constexpr int kChM = 128, kChN = 256, kChKB = 32, kChThreads = 128;
 constexpr int kChStageBytes = kChKB * kChM * 4;       // 16 KB raw X block [k][m]
 constexpr int kChABytes = kChM * 128;                 // 16 KB
 constexpr int kChBBytes = kChN * 128;                 // 32 KB
-constexpr int kChSmem = 2 * kChStageBytes + kChABytes + 2 * kChBBytes + 1024;   // + alignment slack
+constexpr int kChSmem = kChStageBytes + kChABytes + 2 * kChBBytes + 1024;   // 97 KB (+ alignment slack): 2 CTAs per SM
 
 struct ConvHead {
     const float* x[VK_MAX_LEVELS];      // (B, cin, ny, nx)
@@ -1432,8 +1432,8 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     __shared__ float s_bias[kChN];
     __shared__ int s_wtot[4];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ch_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sStage = smem;                                  // 2 x 16 KB
-    uint8_t* sA = smem + 2 * kChStageBytes;                  // 16 KB
+    uint8_t* sStage = smem;                                  // 16 KB
+    uint8_t* sA = smem + kChStageBytes;                      // 16 KB
     uint8_t* sB = sA + kChABytes;                            // 2 x 32 KB
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -1458,21 +1458,26 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     }
     for (int i = tid; i < kChN; i += kChThreads) s_bias[i] = (C.bias[l] && i < cout) ? __ldg(C.bias[l] + i) : 0.0f;
 
-    auto issue_copies = [&](int kb) {
-        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes), sb = ch_smem(sB + (kb & 1) * kChBBytes);
+    auto issue_x = [&](int kb) {
         // X block: 32 channels x 32 chunks of 4 positions (raw [k][128]); positions past the plane are zeros
+        const uint32_t st = ch_smem(sStage);
         for (int e = tid; e < kChKB * 32; e += kChThreads) {
             const int k = e >> 5, m4 = (e & 31) << 2;
             ch_cp16(st + (uint32_t)(k * kChM + m4) * 4, X + (size_t)(kb * kChKB + k) * nynx + (m4 < nvalid ? m4 : 0), m4 < nvalid);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue_w = [&](int kb) {
         // W block: 256 rows x 8 chunks of 4 channels, straight into the swizzled K-major tile
+        const uint32_t sb = ch_smem(sB + (kb & 1) * kChBBytes);
         for (int e = tid; e < kChN * 8; e += kChThreads) {
             const int n = e >> 3, c = e & 7;
             ch_cp16(sb + ch_koff(n, c), W + (size_t)(n < cout ? n : 0) * cin + kb * kChKB + 4 * c, n < cout);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue_copies(0);
+    issue_x(0);
+    issue_w(0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1480,18 +1485,20 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
     bool ok = true;
+    // copy groups are committed in the order X0 W0 W1 X1 W2 X2 ...: at block kb everything but the
+    // newest group (W of block kb+1) must have landed
     for (int kb = 0; kb < nkb; ++kb) {
         // the MMAs of block kb-1 read the A tile (single-buffered) and the W buffer that block kb+1 reuses
         if (kb > 0) ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((kb - 1) & 1));
         if (kb + 1 < nkb) {
-            issue_copies(kb + 1);
+            issue_w(kb + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();                                      // block kb landed (staging + W tile)
         {   // transpose: thread = spatial position; 8 chunks of 4 channels -> row `tid` of the A tile
-            const float* st = reinterpret_cast<const float*>(sStage + (kb & 1) * kChStageBytes) + tid;
+            const float* st = reinterpret_cast<const float*>(sStage) + tid;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
@@ -1501,6 +1508,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes (cp.async W, stores A) -> async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        if (kb + 1 < nkb) issue_x(kb + 1);                    // the staging tile is free again
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = ch_smem(sA), b0 = ch_smem(sB + (kb & 1) * kChBBytes);
