@@ -49,6 +49,7 @@ for name, cins in (("yolov5s", (128, 256, 512)), ("yolov5x", (320, 640, 1280))):
             conv = lambda: [torch.nn.functional.conv2d(f, w, b) for f, w, b in zip(feats, ws, bs)]
             lv = conv()
             buf2 = ops.decode_filter(cfg, lv, conf, ml)
+            row["cudnn_%s_candidates_per_img" % ("tf32" if tf32 else "fp32")] = int(buf2.counts.sum()) // B
             t_conv = timeit(conv)
             t_both = timeit(lambda: ops.decode_filter(cfg, conv(), conf, ml, buf=buf2))
             row["cudnn_%s_conv_us" % ("tf32" if tf32 else "fp32")] = round(t_conv, 1)

@@ -1363,9 +1363,9 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
 //   this part -- profiles/micro/umma_tf32.cu -- so X is transposed on chip): 16-byte cp.async into
 //   a raw [k][128] staging tile, then thread s reads its column (conflict-free LDS.32) and writes
 //   row s of the A tile with 128-bit stores (the swizzle makes them conflict-free).
-//   Pipeline per 32-channel block: copies of block k+1 in flight while block k is transposed and
-//   multiplied; the A tile is single-buffered behind the MMA-completion mbarrier.
-//   128 threads, 256 TMEM columns, 97 KB shared memory -> 2 CTAs per SM overlap each other.
+//   Pipeline per 32-channel block: the copies of block k+1 (X and W) are in flight while block k is
+//   transposed and multiplied; the A tile is single-buffered behind the MMA-completion mbarrier.
+//   128 threads, 256 TMEM columns, 112 KB shared memory and no static allocation -> 2 CTAs per SM.
 //
 //   Candidates, boxes, segment table: exactly vk_decode_filter's format (same VkCandBuf), so
 //   vk_nms_batched consumes it unchanged.  Results equal conv-then-vk_decode_filter up to TF32
@@ -1377,7 +1377,8 @@ constexpr int kChM = 128, kChN = 256, kChKB = 32, kChThreads = 128;
 constexpr int kChStageBytes = kChKB * kChM * 4;       // 16 KB raw X block [k][m]
 constexpr int kChABytes = kChM * 128;                 // 16 KB
 constexpr int kChBBytes = kChN * 128;                 // 32 KB
-constexpr int kChSmem = kChStageBytes + kChABytes + 2 * kChBBytes + 1024;   // 97 KB (+ alignment slack): 2 CTAs per SM
+constexpr int kChTail = 64;                           // mbarrier, TMEM base, warp totals
+constexpr int kChSmem = 2 * kChStageBytes + kChABytes + 2 * kChBBytes + kChTail;   // 112 KB + 64 B, no static shared memory: 2 CTAs per SM
 
 struct ConvHead {
     const float* x[VK_MAX_LEVELS];      // (B, cin, ny, nx)
@@ -1426,15 +1427,15 @@ __device__ __forceinline__ bool ch_wait(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(kChThreads, 2)
 conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int* __restrict__ fault) {
-    extern __shared__ uint8_t ch_raw[];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_tmem;
-    __shared__ float s_bias[kChN];
-    __shared__ int s_wtot[4];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ch_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sStage = smem;                                  // 16 KB
-    uint8_t* sA = smem + kChStageBytes;                      // 16 KB
+    // no static shared memory: the dynamic window then starts 1024-byte aligned (the swizzled tiles need it)
+    // and 2 x (112 KB + 64 B + 1 KB reserved) fits one SM
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sStage = smem;                                  // 2 x 16 KB
+    uint8_t* sA = smem + 2 * kChStageBytes;                  // 16 KB
     uint8_t* sB = sA + kChABytes;                            // 2 x 32 KB
+    uint64_t& s_bar = *reinterpret_cast<uint64_t*>(sB + 2 * kChBBytes);
+    uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(sB + 2 * kChBBytes + 8);
+    int* s_wtot = reinterpret_cast<int*>(sB + 2 * kChBBytes + 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     int l = 0;
@@ -1456,16 +1457,15 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ch_smem(&s_bar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < kChN; i += kChThreads) s_bias[i] = (C.bias[l] && i < cout) ? __ldg(C.bias[l] + i) : 0.0f;
+    const float* __restrict__ bias = C.bias[l];
 
     auto issue_x = [&](int kb) {
         // X block: 32 channels x 32 chunks of 4 positions (raw [k][128]); positions past the plane are zeros
-        const uint32_t st = ch_smem(sStage);
+        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes);
         for (int e = tid; e < kChKB * 32; e += kChThreads) {
             const int k = e >> 5, m4 = (e & 31) << 2;
             ch_cp16(st + (uint32_t)(k * kChM + m4) * 4, X + (size_t)(kb * kChKB + k) * nynx + (m4 < nvalid ? m4 : 0), m4 < nvalid);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto issue_w = [&](int kb) {
         // W block: 256 rows x 8 chunks of 4 channels, straight into the swizzled K-major tile
@@ -1485,12 +1485,13 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
     bool ok = true;
-    // copy groups are committed in the order X0 W0 W1 X1 W2 X2 ...: at block kb everything but the
-    // newest group (W of block kb+1) must have landed
+    // one copy group per block (X then W): at block kb everything but the newest group must have landed
     for (int kb = 0; kb < nkb; ++kb) {
-        // the MMAs of block kb-1 read the A tile (single-buffered) and the W buffer that block kb+1 reuses
+        // the MMAs of block kb-1 read the A tile (single-buffered) and the W buffer that block kb+1 reuses;
+        // the staging buffer of block kb+1 was drained by the transposition of block kb-1
         if (kb > 0) ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((kb - 1) & 1));
         if (kb + 1 < nkb) {
+            issue_x(kb + 1);
             issue_w(kb + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
@@ -1498,7 +1499,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         }
         __syncthreads();                                      // block kb landed (staging + W tile)
         {   // transpose: thread = spatial position; 8 chunks of 4 channels -> row `tid` of the A tile
-            const float* st = reinterpret_cast<const float*>(sStage) + tid;
+            const float* st = reinterpret_cast<const float*>(sStage + (kb & 1) * kChStageBytes) + tid;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
@@ -1508,7 +1509,6 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes (cp.async W, stores A) -> async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (kb + 1 < nkb) issue_x(kb + 1);                    // the staging tile is free again
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = ch_smem(sA), b0 = ch_smem(sB + (kb & 1) * kChBBytes);
@@ -1522,7 +1522,37 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
         }
     }
-    ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((nkb - 1) & 1));
+    // The bias rides on the tensor cores as one more K = 8 step: A gets the columns [1, 1, 0, ...], W the
+    // columns [hi, lo, 0, ...] with bias = hi + lo split into two TF32 values (fp32-accurate sum), built in
+    // the staging / W buffers that block nkb would use (both free: their last readers have completed).
+    int last_phase = (nkb - 1) & 1;
+    if (bias != nullptr) {
+        // a parity wait only distinguishes adjacent phases: pass the last block's phase before the
+        // bias step can complete the next one
+        ok &= ch_wait(ch_smem(&s_bar), (uint32_t)last_phase);
+        uint8_t* ea = sStage + (nkb & 1) * kChStageBytes;
+        uint8_t* eb = sB + (nkb & 1) * kChBBytes;
+        *reinterpret_cast<float4*>(ea + ch_koff(tid, 0)) = make_float4(1.f, 1.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(ea + ch_koff(tid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n = tid; n < kChN; n += kChThreads) {
+            const float v = n < cout ? __ldg(bias + n) : 0.0f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            *reinterpret_cast<float4*>(eb + ch_koff(n, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
+            *reinterpret_cast<float4*>(eb + ch_koff(n, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                         :: "r"(tmem), "l"(ch_desc(ch_smem(ea))), "l"(ch_desc(ch_smem(eb))), "r"(idesc), "r"(1u) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
+        }
+        last_phase = nkb & 1;
+    }
+    ok &= ch_wait(ch_smem(&s_bar), (uint32_t)last_phase);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (!ok && tid == 0) atomicExch(fault, 1);
 
@@ -1539,8 +1569,8 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         VK_TMEM_LD16(r, trow + cb);                            // x, y, w, h, obj, first 11 classes
         float box_l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) box_l[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[cb + j]);
-        const float o = sigmoidf_vk(__fadd_rn(__uint_as_float(r[4]), s_bias[cb + 4]));
+        for (int j = 0; j < 4; ++j) box_l[j] = __uint_as_float(r[j]);
+        const float o = sigmoidf_vk(__uint_as_float(r[4]));
         const bool alive = ok && tid < nvalid && o > A.conf;       // image_proc.py:99
         const float obj = alive ? o : 0.0f;
         // pass 1: count (multi-label) or best class
@@ -1556,7 +1586,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
                 for (int j = 0; j < 16; ++j) {
                     const int c = c0 + j;
                     if (c < nc) {
-                        const float p = __fmul_rn(sigmoidf_vk(__fadd_rn(__uint_as_float(q[j]), s_bias[cb + 5 + c])), obj);   // :135
+                        const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);   // :135
                         if (A.multi_label) count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;               // :141,151
                         else if (p > bv) { bv = p; bj = c; }                                                              // :145
                     }
@@ -1584,7 +1614,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
                     for (int j = 0; j < 16; ++j) {
                         const int c = c0 + j;
                         if (c < nc && count > 0) {
-                            const float p = __fmul_rn(sigmoidf_vk(__fadd_rn(__uint_as_float(q[j]), s_bias[cb + 5 + c])), obj);
+                            const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);
                             if (p > A.conf && class_allowed(A.class_mask, c)) *wp++ = make_uint2(__float_as_uint(p), idx0 + (uint32_t)c);
                         }
                     }
