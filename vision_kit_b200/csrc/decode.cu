@@ -1459,20 +1459,28 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     }
     const float* __restrict__ bias = C.bias[l];
 
+    // copy loops: thread-constant parts of the addresses hoisted (element e = tid + i * 128)
+    const int xk0 = tid >> 5, xm4 = (tid & 31) << 2;                       // X: channel xk0 + 4 i, positions xm4..+3
+    const bool xvalid = xm4 < nvalid;
+    const float* const xsrc0 = X + (size_t)xk0 * nynx + (xvalid ? xm4 : 0);
+    const uint32_t xdst0 = (uint32_t)(xk0 * kChM + xm4) * 4;
+    const int wn0 = tid >> 3, wc = tid & 7;                                // W: row wn0 + 16 i, chunk wc
+    const uint32_t wdst0 = ch_koff(wn0, wc);                               // (n & 7) does not change with i: + i * 2048
     auto issue_x = [&](int kb) {
         // X block: 32 channels x 32 chunks of 4 positions (raw [k][128]); positions past the plane are zeros
-        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes);
-        for (int e = tid; e < kChKB * 32; e += kChThreads) {
-            const int k = e >> 5, m4 = (e & 31) << 2;
-            ch_cp16(st + (uint32_t)(k * kChM + m4) * 4, X + (size_t)(kb * kChKB + k) * nynx + (m4 < nvalid ? m4 : 0), m4 < nvalid);
-        }
+        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes) + xdst0;
+        const float* src = xsrc0 + (size_t)kb * kChKB * nynx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ch_cp16(st + i * (4 * kChM * 4), src + (size_t)(4 * i) * nynx, xvalid);
     };
     auto issue_w = [&](int kb) {
         // W block: 256 rows x 8 chunks of 4 channels, straight into the swizzled K-major tile
-        const uint32_t sb = ch_smem(sB + (kb & 1) * kChBBytes);
-        for (int e = tid; e < kChN * 8; e += kChThreads) {
-            const int n = e >> 3, c = e & 7;
-            ch_cp16(sb + ch_koff(n, c), W + (size_t)(n < cout ? n : 0) * cin + kb * kChKB + 4 * c, n < cout);
+        const uint32_t sb = ch_smem(sB + (kb & 1) * kChBBytes) + wdst0;
+        const float* src = W + kb * kChKB + 4 * wc;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = wn0 + 16 * i;
+            ch_cp16(sb + i * 2048, src + (size_t)(n < cout ? n : 0) * cin, n < cout);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -1573,26 +1581,60 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         const float o = sigmoidf_vk(__uint_as_float(r[4]));
         const bool alive = ok && tid < nvalid && o > A.conf;       // image_proc.py:99
         const float obj = alive ? o : 0.0f;
-        // pass 1: count (multi-label) or best class
+        // pass 1: count (multi-label) or best class.  The sigmoid is monotone, so the 2 MUFU + 4 FP32
+        // instructions per class are spent only where the outcome is open: multi-label evaluates
+        // p = sigmoid(x) * obj exactly only for logits above logit(conf / obj) - 0.05 (everything below
+        // cannot pass p > conf); best-class finds the largest logit first and evaluates the products
+        // only within 1e-3 of it (first maximum of the PRODUCTS, as the reference takes it).
         int count = 0;
         float bv = -INFINITY;
         int bj = 0x7fffffff;
         const bool any_alive = __any_sync(0xffffffffu, alive);
+        // logit(conf / obj): conf/obj in (0,1) for alive rows; log via MUFU, generous margin below
+        float tau = INFINITY;
+        if (alive) {
+            const float rr = __fdividef(A.conf, obj);
+            tau = (rr > 0.f) ? __logf(__fdividef(rr, 1.0f - rr)) - 0.05f : -INFINITY;
+        }
         if (any_alive) {
-            for (int c0 = 0; c0 < nc; c0 += 16) {
-                uint32_t q[16];
-                VK_TMEM_LD16(q, trow + cb + 5 + c0);
+            if (A.multi_label) {
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = c0 + j;
-                    if (c < nc) {
-                        const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);   // :135
-                        if (A.multi_label) count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;               // :141,151
-                        else if (p > bv) { bv = p; bj = c; }                                                              // :145
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        const float x = __uint_as_float(q[j]);
+                        if (c < nc && x > tau) {
+                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
+                            count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;            // :141,151
+                        }
                     }
                 }
+            } else {
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < nc) mx = fmaxf(mx, __uint_as_float(q[j]));
+                }
+                const float near = mx - 1e-3f;
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = __uint_as_float(q[j]);
+                        if (c0 + j < nc && x >= near) {
+                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
+                            if (p > bv) { bv = p; bj = c0 + j; }                                        // :145
+                        }
+                    }
+                }
+                count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
             }
-            if (!A.multi_label) count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
         }
         // offsets inside the 64-row segment (warps 2*half, 2*half+1), canonical order = row order
         const int incl = warp_incl_scan(count, lane);
@@ -1613,7 +1655,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = c0 + j;
-                        if (c < nc && count > 0) {
+                        if (c < nc && count > 0 && __uint_as_float(q[j]) > tau) {
                             const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);
                             if (p > A.conf && class_allowed(A.class_mask, c)) *wp++ = make_uint2(__float_as_uint(p), idx0 + (uint32_t)c);
                         }
