@@ -659,3 +659,23 @@ def test_conv_head_matches_conv_then_filter(variant, conf, ml, cins, B, vk, cuda
     a = vk.ops.nms_batched(ref, 0.5)
     b = vk.ops.nms_batched(got, 0.5)
     assert (a.counts - b.counts).abs().max().item() <= 2
+
+
+def test_head_forward_nms_fused_conv(vk, cuda):
+    """heads.forward_nms(fused_conv=True) (implicit layers folded, tensor-core conv) against the
+    module's own convs + the unfused path: same detections up to TF32 input rounding."""
+    torch.manual_seed(3)
+    for head in (vk.heads.YoloV5Head(width=0.5).to(cuda).eval(), vk.heads.YoloV7Head("base").to(cuda).eval()):
+        x = [torch.randn(2, m.in_channels, 640 // s, 640 // s, device=cuda) for m, s in zip(head.m, (8, 16, 32))]
+        with torch.no_grad():
+            for m in head.m:                       # lift the objectness prior so that boxes survive
+                m.bias.view(3, -1)[:, 4] += 3.5
+                m.bias.view(3, -1)[:, 5:] += 3.0
+            a = head.forward_nms(x, conf_thres=0.3, iou_thres=0.5)
+            b = head.forward_nms(x, conf_thres=0.3, iou_thres=0.5, fused_conv=True)
+        assert int(a.counts.sum()) > 10
+        assert (a.counts - b.counts).abs().max().item() <= 3
+        for i in range(2):
+            k = min(int(a.counts[i]), int(b.counts[i]), 20)
+            # the highest-scoring detections agree within TF32 tolerance
+            np.testing.assert_allclose(b.dets[i, :k, 4].cpu().numpy(), a.dets[i, :k, 4].cpu().numpy(), rtol=5e-3, atol=1e-3)

@@ -88,15 +88,40 @@ class _DetectBase(nn.Module):
         pred, raws = ops.detect_decode(cfg, feats, want_raw=True)
         return pred, raws
 
+    def _fused_conv_params(self):
+        """(weights, biases) of the 1x1 convs as plain matrices, implicit layers folded in
+        (heads/yolov7.py:67-71: im * (W (x + ia) + b) = (im * W) x + im * (W ia + b))."""
+        ws, bs = [], []
+        for i in range(self.num_det_layers):
+            w = self.m[i].weight.detach().reshape(self.m[i].out_channels, -1).float()
+            b = self.m[i].bias.detach().float() if self.m[i].bias is not None else torch.zeros(w.shape[0], device=w.device)
+            if hasattr(self, "ia"):
+                ia = self.ia[i].implicit.detach().reshape(-1).float()
+                im = self.im[i].implicit.detach().reshape(-1).float()
+                b = im * (w @ ia + b)
+                w = im[:, None] * w
+            ws.append(w.contiguous())
+            bs.append(b.contiguous())
+        return ws, bs
+
     @torch.no_grad()
     def forward_nms(self, x, conf_thres: float = 0.25, iou_thres: float = 0.45, classes=None,
                     agnostic: bool = False, multi_label: bool = False, max_det: int = 300,
-                    max_nms: int = 30000):
+                    max_nms: int = 30000, fused_conv: bool = False):
         """Fused eval path: conv outputs -> candidates -> NMS, no prediction tensor.
+        ``fused_conv=True`` also folds the Detect 1x1 convs in (``vk_conv_decode_filter``: tcgen05,
+        TF32 inputs -- what cuDNN does by default for fp32 convs -- fp32 accumulation): the neck
+        outputs go in, the (B, 255, ny, nx) conv outputs are never written.
         Returns an ``ops.NmsOut`` (device tensors; no synchronisation)."""
-        feats = self._conv_all(list(x))
-        cfg = self._cfg(feats)
-        buf = ops.decode_filter(cfg, feats, conf_thres, multi_label, classes)
+        if fused_conv:
+            feats = [f.float().contiguous() for f in x]
+            cfg = self._cfg(feats)
+            ws, bs = self._fused_conv_params()
+            buf = ops.conv_decode_filter(cfg, feats, ws, bs, conf_thres, multi_label, classes)
+        else:
+            feats = self._conv_all(list(x))
+            cfg = self._cfg(feats)
+            buf = ops.decode_filter(cfg, feats, conf_thres, multi_label, classes)
         return ops.nms_batched(buf, iou_thres, agnostic, max_nms, max_det)
 
 
