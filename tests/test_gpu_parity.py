@@ -437,6 +437,57 @@ def test_config3_eval_mode_properties(vk, cuda):
     assert np.array_equal(r1.dets[0, :k].cpu().numpy(), outs[0].numpy())
 
 
+def test_config4_v7_agnostic_vs_class_aware(vk, cuda):
+    # BASELINE config 4 on one GPU's shard (256 images / 8 GPUs = 32): YOLOv7 decode order, nc = 80,
+    # eval-mode NMS, agnostic vs class-aware
+    B = 32
+    lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=4, clusters=20)]
+    cfg, _ = _cfg(vk, "v7")
+    buf = vk.ops.decode_filter(cfg, lv, 0.001, True)
+    res = {}
+    for agn in (False, True):
+        r1 = vk.ops.nms_batched(buf, 0.6, agn, want_keep=True)
+        r2 = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.001, True), 0.6, agn, want_keep=True)
+        assert torch.equal(r1.dets, r2.dets) and torch.equal(r1.keep, r2.keep) and int(r1.status.sum()) == 0
+        _check_nms_properties(r1.dets, r1.counts, 0.6, agn, 300)
+        res[agn] = r1
+    # both runs start from the same best candidate; images 0 and 1 against the oracle in both modes
+    assert torch.equal(res[False].dets[:, 0], res[True].dets[:, 0])
+    pred = vk.ops.detect_decode(cfg, [t[:2] for t in lv])
+    for agn in (False, True):
+        outs, keeps = ref_port.nms(pred.cpu(), conf_thres=0.001, iou_thres=0.6, multi_label=True, agnostic=agn,
+                                   return_keep=True)
+        for i in range(2):
+            k = int(res[agn].counts[i])
+            assert np.array_equal(res[agn].keep[i, :k].cpu().numpy(), keeps[i].numpy())
+            assert np.array_equal(res[agn].dets[i, :k].cpu().numpy(), outs[i].numpy())
+
+
+def test_config5_shard_mixed_letterbox_pipeline(vk, cuda):
+    # BASELINE config 5 on one GPU's shard (512 images / 8 GPUs = 64): mixed 480-1280 sources -> 640
+    # letterbox (fp32 and bf16), YOLOv7 decode, eval NMS; letterbox of every image against the oracle
+    B = 64
+    sizes = synth.mixed_sizes(B, seed=5)
+    imgs = [synth.image_u8(h, w, 50 + i) for i, (h, w) in enumerate(sizes)]
+    srcs = [torch.from_numpy(im).to(cuda) for im in imgs]
+    u8, rps = vk.ops.letterbox_batch(srcs, (640, 640), swap_rb=True, dtype=torch.uint8)
+    f32, _ = vk.ops.letterbox_batch(srcs, (640, 640), swap_rb=True, dtype=torch.float32)
+    bf16, _ = vk.ops.letterbox_batch(srcs, (640, 640), swap_rb=True, dtype=torch.bfloat16)
+    u8h = u8.cpu().numpy()
+    for i, im in enumerate(imgs):
+        exp, (ratio, pad) = restate.letterbox_u8(im[:, :, ::-1], (640, 640))
+        assert np.array_equal(u8h[i], exp), sizes[i]
+        assert rps[i][0] == ratio and tuple(rps[i][1]) == tuple(pad)
+    expf = u8.permute(0, 3, 1, 2).float().cpu() / 255
+    assert torch.equal(f32.cpu(), expf)
+    assert torch.equal(bf16.cpu(), expf.to(torch.bfloat16))
+    lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(B, seed=6, clusters=20)]
+    cfg, _ = _cfg(vk, "v7")
+    r = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.001, True), 0.6)
+    assert int(r.status.sum()) == 0 and int(r.counts.min()) > 0
+    _check_nms_properties(r.dets, r.counts, 0.6, False, 300)
+
+
 # --------------------------------------------------------------------------- staged NMS corner cases
 def test_nms_many_stages_heavy_suppression(vk, cuda):
     # ~45 k candidates packed into 40 clusters: few boxes survive, so the staged kernel has to walk
