@@ -1425,6 +1425,133 @@ __device__ __forceinline__ bool ch_wait(uint32_t bar, uint32_t parity) {
                  : "r"(taddr));                                                                                    \
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
+// Epilogue of one 128-position tile whose accumulator sits in 256 TMEM columns at `trow` (lane
+// offset of the calling warp included): thread `tid` (0..127) = spatial position s0 + tid = TMEM
+// lane, one prediction row per anchor.  `bar_id` names a 128-thread barrier shared by the 4 warps
+// that run it, `s_wtot` 4 ints of their scratch.
+__device__ __forceinline__ void ch_bar_sync(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
+
+__device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs& A, uint32_t trow, int l, int b, int s0,
+                                              int nvalid, int tid, int* s_wtot, int bar_id, bool ok) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nynx = H.nynx[l], no = H.no;
+    const int nc = A.nc;
+    const int sp = s0 + tid;
+    const int half = tid >> 6;                                 // 64-row segment of the thread inside the tile
+    const bool seg_exists = s0 + 64 * half < nynx;
+    struct { int variant, nx; float stride; } const gbase{H.variant, H.nx[l], H.stride[l]};
+    for (int a = 0; a < H.na; ++a) {
+        const int cb = a * no;
+        uint32_t r[16];
+        VK_TMEM_LD16(r, trow + cb);                            // x, y, w, h, obj, first 11 classes
+        float box_l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) box_l[j] = __uint_as_float(r[j]);
+        const float o = sigmoidf_vk(__uint_as_float(r[4]));
+        const bool alive = ok && tid < nvalid && o > A.conf;       // image_proc.py:99
+        const float obj = alive ? o : 0.0f;
+        // pass 1: count (multi-label) or best class.  The sigmoid is monotone, so the 2 MUFU + 4 FP32
+        // instructions per class are spent only where the outcome is open: multi-label evaluates
+        // p = sigmoid(x) * obj exactly only for logits above logit(conf / obj) - 0.05 (everything below
+        // cannot pass p > conf); best-class finds the largest logit first and evaluates the products
+        // only within 1e-3 of it (first maximum of the PRODUCTS, as the reference takes it).
+        int count = 0;
+        float bv = -INFINITY;
+        int bj = 0x7fffffff;
+        const bool any_alive = __any_sync(0xffffffffu, alive);
+        // logit(conf / obj): conf/obj in (0,1) for alive rows; log via MUFU, generous margin below
+        float tau = INFINITY;
+        if (alive) {
+            const float rr = __fdividef(A.conf, obj);
+            tau = (rr > 0.f) ? __logf(__fdividef(rr, 1.0f - rr)) - 0.05f : -INFINITY;
+        }
+        if (any_alive) {
+            if (A.multi_label) {
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        const float x = __uint_as_float(q[j]);
+                        if (c < nc && x > tau) {
+                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
+                            count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;            // :141,151
+                        }
+                    }
+                }
+            } else {
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < nc) mx = fmaxf(mx, __uint_as_float(q[j]));
+                }
+                const float near = mx - 1e-3f;
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = __uint_as_float(q[j]);
+                        if (c0 + j < nc && x >= near) {
+                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
+                            if (p > bv) { bv = p; bj = c0 + j; }                                        // :145
+                        }
+                    }
+                }
+                count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
+            }
+        }
+        // offsets inside the 64-row segment (warps 2*half, 2*half+1), canonical order = row order
+        const int incl = warp_incl_scan(count, lane);
+        if (lane == 31) s_wtot[warp] = incl;
+        ch_bar_sync(bar_id);
+        const int base = (warp & 1) ? s_wtot[warp - 1] : 0;
+        const int seg_total = s_wtot[2 * half] + s_wtot[2 * half + 1];
+        const int seg = H.tile_start[l] + a * H.tpa[l] + (s0 >> 6) + half;
+        const int row = H.row_base[l] + a * nynx + sp;             // prediction row inside the image
+        // pass 2 (warp-uniform: tcgen05.ld is a warp-collective): recompute the products and store
+        uint2* wp = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + (size_t)seg * A.tile_cap + base + (incl - count);
+        const uint32_t idx0 = (uint32_t)(row * nc);
+        if (A.multi_label) {
+            if (__any_sync(0xffffffffu, count > 0)) {
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    uint32_t q[16];
+                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        if (c < nc && count > 0 && __uint_as_float(q[j]) > tau) {
+                            const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);
+                            if (p > A.conf && class_allowed(A.class_mask, c)) *wp++ = make_uint2(__float_as_uint(p), idx0 + (uint32_t)c);
+                        }
+                    }
+                }
+            }
+        } else if (count > 0) {
+            *wp = make_uint2(__float_as_uint(bv), idx0 + (uint32_t)bj);
+        }
+        if (count > 0) {
+            const int gy = sp / gbase.nx, gx = sp - gy * gbase.nx;
+            const float aw = H.anchors[l][2 * a], ah = H.anchors[l][2 * a + 1];
+            A.boxes[(size_t)b * A.rows + row] =
+                xyxy_from_cxcywh(decode_elem(box_l[0], 0, (float)gx, gbase.stride, aw, gbase.variant),
+                                 decode_elem(box_l[1], 1, (float)gy, gbase.stride, ah, gbase.variant),
+                                 decode_elem(box_l[2], 2, 0.f, gbase.stride, aw, gbase.variant),
+                                 decode_elem(box_l[3], 3, 0.f, gbase.stride, ah, gbase.variant));
+        }
+        if ((tid & 63) == 0 && seg_exists) {
+            A.seg_base[(size_t)b * A.segs + seg] = seg_total ? seg * A.tile_cap : 0;
+            A.seg_count[(size_t)b * A.segs + seg] = seg_total;
+            if (seg_total) atomicAdd(A.counts + b, seg_total);
+        }
+        ch_bar_sync(bar_id);                                       // s_wtot is reused by the next anchor
+    }
+}
+
 __global__ void __launch_bounds__(kChThreads, 2)
 conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int* __restrict__ fault) {
     // no static shared memory: the dynamic window then starts 1024-byte aligned (the swizzled tiles need it)
@@ -1565,122 +1692,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     if (!ok && tid == 0) atomicExch(fault, 1);
 
     // ---------------- epilogue: thread = spatial position s0 + tid = TMEM lane; one prediction row per anchor
-    const int nc = A.nc;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const int sp = s0 + tid;
-    const int half = tid >> 6;                                 // 64-row segment of the thread inside the tile
-    const bool seg_exists = s0 + 64 * half < nynx;
-    struct { int variant, nx; float stride; } const gbase{H.variant, H.nx[l], H.stride[l]};
-    for (int a = 0; a < H.na; ++a) {
-        const int cb = a * no;
-        uint32_t r[16];
-        VK_TMEM_LD16(r, trow + cb);                            // x, y, w, h, obj, first 11 classes
-        float box_l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) box_l[j] = __uint_as_float(r[j]);
-        const float o = sigmoidf_vk(__uint_as_float(r[4]));
-        const bool alive = ok && tid < nvalid && o > A.conf;       // image_proc.py:99
-        const float obj = alive ? o : 0.0f;
-        // pass 1: count (multi-label) or best class.  The sigmoid is monotone, so the 2 MUFU + 4 FP32
-        // instructions per class are spent only where the outcome is open: multi-label evaluates
-        // p = sigmoid(x) * obj exactly only for logits above logit(conf / obj) - 0.05 (everything below
-        // cannot pass p > conf); best-class finds the largest logit first and evaluates the products
-        // only within 1e-3 of it (first maximum of the PRODUCTS, as the reference takes it).
-        int count = 0;
-        float bv = -INFINITY;
-        int bj = 0x7fffffff;
-        const bool any_alive = __any_sync(0xffffffffu, alive);
-        // logit(conf / obj): conf/obj in (0,1) for alive rows; log via MUFU, generous margin below
-        float tau = INFINITY;
-        if (alive) {
-            const float rr = __fdividef(A.conf, obj);
-            tau = (rr > 0.f) ? __logf(__fdividef(rr, 1.0f - rr)) - 0.05f : -INFINITY;
-        }
-        if (any_alive) {
-            if (A.multi_label) {
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = c0 + j;
-                        const float x = __uint_as_float(q[j]);
-                        if (c < nc && x > tau) {
-                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
-                            count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;            // :141,151
-                        }
-                    }
-                }
-            } else {
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < nc) mx = fmaxf(mx, __uint_as_float(q[j]));
-                }
-                const float near = mx - 1e-3f;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float x = __uint_as_float(q[j]);
-                        if (c0 + j < nc && x >= near) {
-                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
-                            if (p > bv) { bv = p; bj = c0 + j; }                                        // :145
-                        }
-                    }
-                }
-                count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
-            }
-        }
-        // offsets inside the 64-row segment (warps 2*half, 2*half+1), canonical order = row order
-        const int incl = warp_incl_scan(count, lane);
-        if (lane == 31) s_wtot[warp] = incl;
-        __syncthreads();
-        const int base = (warp & 1) ? s_wtot[warp - 1] : 0;
-        const int seg_total = s_wtot[2 * half] + s_wtot[2 * half + 1];
-        const int seg = H.tile_start[l] + a * H.tpa[l] + (s0 >> 6) + half;
-        const int row = H.row_base[l] + a * nynx + sp;             // prediction row inside the image
-        // pass 2 (warp-uniform: tcgen05.ld is a warp-collective): recompute the products and store
-        uint2* wp = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + (size_t)seg * A.tile_cap + base + (incl - count);
-        const uint32_t idx0 = (uint32_t)(row * nc);
-        if (A.multi_label) {
-            if (__any_sync(0xffffffffu, count > 0)) {
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = c0 + j;
-                        if (c < nc && count > 0 && __uint_as_float(q[j]) > tau) {
-                            const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);
-                            if (p > A.conf && class_allowed(A.class_mask, c)) *wp++ = make_uint2(__float_as_uint(p), idx0 + (uint32_t)c);
-                        }
-                    }
-                }
-            }
-        } else if (count > 0) {
-            *wp = make_uint2(__float_as_uint(bv), idx0 + (uint32_t)bj);
-        }
-        if (count > 0) {
-            const int gy = sp / gbase.nx, gx = sp - gy * gbase.nx;
-            const float aw = H.anchors[l][2 * a], ah = H.anchors[l][2 * a + 1];
-            A.boxes[(size_t)b * A.rows + row] =
-                xyxy_from_cxcywh(decode_elem(box_l[0], 0, (float)gx, gbase.stride, aw, gbase.variant),
-                                 decode_elem(box_l[1], 1, (float)gy, gbase.stride, ah, gbase.variant),
-                                 decode_elem(box_l[2], 2, 0.f, gbase.stride, aw, gbase.variant),
-                                 decode_elem(box_l[3], 3, 0.f, gbase.stride, ah, gbase.variant));
-        }
-        if ((tid & 63) == 0 && seg_exists) {
-            A.seg_base[(size_t)b * A.segs + seg] = seg_total ? seg * A.tile_cap : 0;
-            A.seg_count[(size_t)b * A.segs + seg] = seg_total;
-            if (seg_total) atomicAdd(A.counts + b, seg_total);
-        }
-        __syncthreads();                                       // s_wtot is reused by the next anchor
-    }
+    conv_epilogue(H, A, tmem + ((uint32_t)(warp * 32) << 16), l, b, s0, nvalid, tid, s_wtot, 0, ok);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kChN));
