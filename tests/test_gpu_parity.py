@@ -690,8 +690,18 @@ def test_conv_head_matches_conv_then_filter(variant, conf, ml, cins, B, vk, cuda
         torch.backends.cudnn.allow_tf32 = old
     ref = vk.ops.decode_filter(cfg, logits, conf, ml)
     got = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
-    torch.cuda.synchronize()
-    assert int(got.fault.item()) == 0
+    # the persistent warp-specialised variant must produce the very same bits
+    from vision_kit_b200 import _lib
+    _lib.lib().vk_set_conv_kernel(1)
+    try:
+        got2 = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().vk_set_conv_kernel(0)
+    assert int(got.fault.item()) == 0 and int(got2.fault.item()) == 0
+    assert torch.equal(got.counts, got2.counts)
+    for (la, ra, ba), (lb, rb, bb) in zip(_canonical(got), _canonical(got2)):
+        assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
     assert int(ref.counts.sum()) > 20
     for (la, ra, ba), (lb, rb, bb) in zip(_canonical(ref), _canonical(got)):
         sa = {int(v >> 32): np.uint32(v & 0xffffffff).view(np.float32) for v in la}

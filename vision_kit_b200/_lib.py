@@ -65,6 +65,7 @@ _PROTOS = {
     "vk_last_error": (C.c_char_p, []),
     "vk_launch_count": (C.c_uint64, []),
     "vk_set_filter_kernel": (C.c_int, [C.c_int]),
+    "vk_set_conv_kernel": (C.c_int, [C.c_int]),
     "vk_build_arch": (C.c_int, []),
     "vk_letterbox_geometry": (C.c_int, [C.c_int] * 8 + [C.POINTER(VkLbGeom)]),
     "vk_dataset_geometry": (C.c_int, [C.c_int] * 4 + [C.POINTER(VkLbGeom)]),

@@ -25,6 +25,7 @@ int fail_code(int code, const char* fmt, ...);
 int check_launch(const char* what);        // cudaGetLastError -> return code
 void count_launch(int n = 1);
 int filter_mode();                         // VK_FILTER_AUTO / _SPARSE / _DENSE
+int conv_mode();                           // VK_CONV_TILE / _PERSISTENT
 
 inline cudaStream_t as_stream(vk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
