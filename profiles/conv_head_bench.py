@@ -7,6 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vision_kit_b200 import ops, synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+from vision_kit_b200 import _lib
+_lib.lib().vk_set_conv_kernel(int(os.environ.get("VK_CONV_MODE", "0")))   # 1 = persistent warp-specialised variant
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]
 res = {}

@@ -95,6 +95,27 @@ __global__ void __launch_bounds__(128) umma_tile(const float* __restrict__ X, in
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     if (tid == 0 && (dbg & 4)) printf("tmem_base = 0x%08x sA=0x%x sB=0x%x\n", tmem, smem_u32(sA), smem_u32(sB));
+    if (tid == 0 && (dbg & 64)) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const long long t0 = clock64();
+        const int REP = 256;
+        for (int rep = 0; rep < REP; ++rep)
+            for (int kb = 0; kb < KT; ++kb)
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t da = make_desc(smem_u32(sA + kb * 16384) + ks * 32, 16, 1024);
+                    const uint64_t db = make_desc(smem_u32(sB + kb * 32768) + ks * 32, 16, 1024);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+        const long long t1 = clock64();
+        printf("%d MMAs (M128 N256 K8 tf32): %lld cycles = %.1f cycles per MMA\n", REP * KT * 4, t1 - t0, (double)(t1 - t0) / (REP * KT * 4));
+    } else
     if (tid == 0 && !(dbg & 2)) {
         // idesc: D = F32, A = B = TF32, A MN-major, B K-major, N = 256, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((dbg & 8) ? 0u : (1u << 15)) | ((dbg & 32) ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

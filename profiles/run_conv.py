@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Launches the fused conv head a few times (for ncu captures): python profiles/run_conv.py [batch] [conf]"""
+"""Launches the fused conv head a few times (for ncu captures): python profiles/run_conv.py [batch] [conf] [mode]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from vision_kit_b200 import ops, synth
+from vision_kit_b200 import _lib, ops, synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 conf = float(sys.argv[2]) if len(sys.argv) > 2 else 0.25
+_lib.lib().vk_set_conv_kernel(int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]
 cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)

@@ -1699,21 +1699,22 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-specialised persistent variant: one CTA per SM, 13 warps.
-//   warps 8-11  producers: cp.async of the X and W blocks two blocks ahead (4 staging slots,
-//               3 operand slots), transposition of X into the A tile, bias block at the end of a tile
-//   warp 12     MMA issuer (one lane): tcgen05.mma into one of TWO 256-column accumulators,
+// Warp-specialised persistent variant: one CTA per SM, 17 warps.
+//   warps 8-15  two producer teams taking alternate k-blocks: cp.async of the X and W blocks two blocks
+//               ahead (4 staging slots, 2 A slots, 4 W slots), transposition of X into the A tile, bias
+//               block at the end of a tile
+//   warp 16     MMA issuer (one lane): tcgen05.mma into one of TWO 256-column accumulators,
 //               tcgen05.commit -> "slot free" and "accumulator full" mbarriers
 //   warps 0-7   two epilogue groups (one per accumulator) draining tile i while the mainloop
 //               of tile i+1 runs
 // Every mbarrier phase is waited in order by its consumer (a parity wait cannot tell phase n from
 // n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
 // ---------------------------------------------------------------------------------------
-constexpr int kWsThreads = 13 * 32;
-constexpr int kWsStage = 4, kWsSlots = 3;
+constexpr int kWsThreads = 17 * 32;
+constexpr int kWsStage = 4, kWsASlots = 2, kWsBSlots = 4;            // staging / A tile / W tile ring depths
 constexpr int kWsOffA = kWsStage * kChStageBytes;                    // 64 KB
-constexpr int kWsOffB = kWsOffA + kWsSlots * kChABytes;              // 112 KB
-constexpr int kWsOffBar = kWsOffB + kWsSlots * kChBBytes;            // 208 KB
+constexpr int kWsOffB = kWsOffA + kWsASlots * kChABytes;             // 96 KB
+constexpr int kWsOffBar = kWsOffB + kWsBSlots * kChBBytes;           // 224 KB
 constexpr int kWsSmem = kWsOffBar + 256;
 
 struct WsTile {
@@ -1740,11 +1741,18 @@ __device__ __forceinline__ WsTile ws_tile(const HeadDev& H, const ConvHead& C, i
 __device__ __forceinline__ void ws_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+// POLL = true: mbarrier.test_wait in a tight loop (the single MMA-issuing lane: its hand-offs happen once
+// per 0.3 us k-block); false: try_wait, which lets the hardware suspend the (many) waiting threads.
+template <bool POLL>
 __device__ __forceinline__ bool ws_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-    for (int spin = 0; spin < (1 << 22); ++spin) {
+    for (int spin = 0; spin < (POLL ? (1 << 26) : (1 << 22)); ++spin) {
         uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (POLL)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return true;
         if ((spin & 1023) == 1023 && *abort_flag) return false;
     }
@@ -1758,24 +1766,24 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     uint8_t* sStage = smem;
     uint8_t* sA = smem + kWsOffA;
     uint8_t* sB = smem + kWsOffB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[3] done[3] tfull[2] tempty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 96);
-    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 100);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[4] done[4] tfull[2] tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 112);
+    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 116);
     int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 128);     // [2][4]
     const uint32_t bar0 = ch_smem(bars);
     auto READY = [&](int s) { return bar0 + 8u * s; };
-    auto DONE = [&](int s) { return bar0 + 8u * (3 + s); };
-    auto TFULL = [&](int g) { return bar0 + 8u * (6 + g); };
-    auto TEMPTY = [&](int g) { return bar0 + 8u * (8 + g); };
+    auto DONE = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto TFULL = [&](int g) { return bar0 + 8u * (8 + g); };
+    auto TEMPTY = [&](int g) { return bar0 + 8u * (10 + g); };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int no = H.no, cout = H.na * no;
 
-    if (warp == 12) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(s_tmem)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar0 + 8u * i), "r"(1));
+        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar0 + 8u * i), "r"(1));
         for (int g = 0; g < 2; ++g) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TFULL(g)), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TEMPTY(g)), "r"(4));
@@ -1789,28 +1797,32 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     const uint32_t tmem = *s_tmem;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
 
-    if (warp >= 8 && warp < 12) {
-        // ------------------------------------------------------------------ producers
-        const int ptid = tid - 256;
+    if (warp >= 8 && warp < 16) {
+        // ------------------------------------------------------------------ producers: two teams of 4 warps,
+        // team T owns the blocks j = T, T+2, T+4, ... (copies of block j+2 in flight while block j is transposed)
+        const int team = (warp - 8) >> 2;
+        const int ptid = (tid - 256) & 127;
         const int xk0 = ptid >> 5, xm4 = (ptid & 31) << 2;
         const int wn0 = ptid >> 3, wc = ptid & 7;
         const uint32_t wdst0 = ch_koff(wn0, wc);
-        // issue cursor (two blocks ahead) and process cursor over the CTA's tiles; a tile has nkb data
-        // blocks + one bias block
-        int it_i = 0, it_kb = 0;                       // issue cursor: tile index (local), block inside the tile
-        WsTile it = ws_tile(H, C, blockIdx.x, total_tiles);
-        int pr_i = 0, pr_kb = 0;
-        WsTile pr = it;
-        auto issue_block = [&](int j) {                // copies of the block at the issue cursor into slot j
-            if (it.valid && it_kb < it.nkb) {
-                const int nynx = H.nynx[it.l], cin = C.cin[it.l];
-                const bool xvalid = xm4 < it.nvalid;
-                const float* xsrc = C.x[it.l] + (size_t)it.b * cin * nynx + it.s0 + (size_t)(it_kb * kChKB + xk0) * nynx + (xvalid ? xm4 : 0);
+        // cursors over the CTA's tiles; a tile has nkb data blocks + one bias block
+        struct Cursor { int i, kb; WsTile q; };
+        auto advance = [&](Cursor& c) {                // one block forward
+            if (c.q.valid && ++c.kb > c.q.nkb) { c.kb = 0; ++c.i; c.q = ws_tile(H, C, blockIdx.x + c.i * gridDim.x, total_tiles); }
+        };
+        Cursor it{0, 0, ws_tile(H, C, blockIdx.x, total_tiles)};
+        if (team) advance(it);
+        Cursor pr = it;
+        auto issue_block = [&](int j) {                // copies of the block at the issue cursor into the rings at j
+            if (it.q.valid && it.kb < it.q.nkb) {
+                const int nynx = H.nynx[it.q.l], cin = C.cin[it.q.l];
+                const bool xvalid = xm4 < it.q.nvalid;
+                const float* xsrc = C.x[it.q.l] + (size_t)it.q.b * cin * nynx + it.q.s0 + (size_t)(it.kb * kChKB + xk0) * nynx + (xvalid ? xm4 : 0);
                 const uint32_t st = ch_smem(sStage + (j % kWsStage) * kChStageBytes) + (uint32_t)(xk0 * kChM + xm4) * 4;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ch_cp16(st + i * (4 * kChM * 4), xsrc + (size_t)(4 * i) * nynx, xvalid);
-                const float* wsrc = C.w[it.l] + it_kb * kChKB + 4 * wc;
-                const uint32_t sb = ch_smem(sB + (j % kWsSlots) * kChBBytes) + wdst0;
+                const float* wsrc = C.w[it.q.l] + it.kb * kChKB + 4 * wc;
+                const uint32_t sb = ch_smem(sB + (j % kWsBSlots) * kChBBytes) + wdst0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int n = wn0 + 16 * i;
@@ -1818,21 +1830,19 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            if (it.valid) {                            // advance the issue cursor
-                if (++it_kb > it.nkb) { it_kb = 0; ++it_i; it = ws_tile(H, C, blockIdx.x + it_i * gridDim.x, total_tiles); }
-            }
+            advance(it); advance(it);
         };
         bool ok = true;
-        issue_block(0);
-        issue_block(1);
-        for (int j = 0; pr.valid && ok; ++j) {
-            // slot (j+2) % 3 was read by the MMAs of block j-1
-            if (j >= 1) ok &= ws_wait(DONE((j + 2) % kWsSlots), (uint32_t)(((j - 1) / kWsSlots) & 1), s_abort);
+        issue_block(team);
+        for (int j = team; pr.q.valid && ok; j += 2) {
+            // ring slots of block j+2 (staging, W) and of block j (A) were last used by block j-2: its MMAs
+            // are two blocks behind the newest, so this wait rarely stalls
+            if (j >= 2) ok &= ws_wait<false>(DONE((j - 2) % kWsBSlots), (uint32_t)(((j - 2) / kWsBSlots) & 1), s_abort);
             issue_block(j + 2);
-            asm volatile("cp.async.wait_group 2;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");                    // block j landed for every producer
-            uint8_t* a_tile = sA + (j % kWsSlots) * kChABytes;
-            if (pr_kb < pr.nkb) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");    // block j landed for the whole team
+            uint8_t* a_tile = sA + (j % kWsASlots) * kChABytes;
+            if (pr.kb < pr.q.nkb) {
                 const float* st = reinterpret_cast<const float*>(sStage + (j % kWsStage) * kChStageBytes) + ptid;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -1840,8 +1850,8 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                     *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, c)) = v;
                 }
             } else {                                   // bias block: A = [1, 1, 0...], W = [hi, lo, 0...]
-                uint8_t* b_tile = sB + (j % kWsSlots) * kChBBytes;
-                const float* bias = C.bias[pr.l];
+                uint8_t* b_tile = sB + (j % kWsBSlots) * kChBBytes;
+                const float* bias = C.bias[pr.q.l];
                 *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, 0)) = make_float4(1.f, 1.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int n = ptid; n < kChN; n += 128) {
@@ -1852,12 +1862,12 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (ptid == 0) ws_arrive(READY(j % kWsSlots));
-            if (++pr_kb > pr.nkb) { pr_kb = 0; ++pr_i; pr = ws_tile(H, C, blockIdx.x + pr_i * gridDim.x, total_tiles); }
+            asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");
+            if (ptid == 0) ws_arrive(READY(j % kWsBSlots));
+            advance(pr); advance(pr);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == 12) {
+    } else if (warp == 16) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             bool ok = true;
@@ -1866,14 +1876,14 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 const WsTile q = ws_tile(H, C, blockIdx.x + i * gridDim.x, total_tiles);
                 if (!q.valid) break;
                 const int g = i & 1;
-                if (i >= 2) ok &= ws_wait(TEMPTY(g), (uint32_t)(((i - 2) >> 1) & 1), s_abort);   // epilogue drained tile i-2
+                if (i >= 2) ok &= ws_wait<true>(TEMPTY(g), (uint32_t)(((i - 2) >> 1) & 1), s_abort);   // epilogue drained tile i-2
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_addr = tmem + (uint32_t)(g * kChN);
                 for (int kb = 0; kb <= q.nkb && ok; ++kb, ++j) {
-                    const int s = j % kWsSlots;
-                    ok &= ws_wait(READY(s), (uint32_t)((j / kWsSlots) & 1), s_abort);
+                    const int s = j % kWsBSlots;
+                    ok &= ws_wait<true>(READY(s), (uint32_t)((j / kWsBSlots) & 1), s_abort);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a0 = ch_smem(sA + s * kChABytes), b0 = ch_smem(sB + s * kChBBytes);
+                    const uint32_t a0 = ch_smem(sA + (j % kWsASlots) * kChABytes), b0 = ch_smem(sB + s * kChBBytes);
                     const int nks = (kb < q.nkb) ? 4 : 1;                      // the bias block is one K = 8 step
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t acc = (kb | ks) ? 1u : 0u;
@@ -1893,10 +1903,10 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
         for (int i = g; ; i += 2) {
             const WsTile q = ws_tile(H, C, blockIdx.x + i * gridDim.x, total_tiles);
             if (!q.valid) break;
-            ok &= ws_wait(TFULL(g), (uint32_t)((i >> 1) & 1), s_abort);
+            ok &= ws_wait<false>(TFULL(g), (uint32_t)((i >> 1) & 1), s_abort);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             conv_epilogue(H, A, tmem + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(g * kChN), q.l, q.b, q.s0, q.nvalid,
-                          etid, s_wtot + 4 * g, 2 + g, ok);
+                          etid, s_wtot + 4 * g, 3 + g, ok);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) ws_arrive(TEMPTY(g));
@@ -1905,7 +1915,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0 && *s_abort) atomicExch(fault, 1);
-    if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
+    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
 }
 
 }  // namespace vk
