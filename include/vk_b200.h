@@ -173,10 +173,10 @@ int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch
  *   fault      dev int32, set to 1 if a tensor-core completion wait timed out (never observed; the
  *              kernel then terminates instead of hanging)
  * Logits differ from an fp32 conv by TF32 input rounding (~1e-3 relative). */
-/* Two implementations with identical results: VK_CONV_TILE (default; one tile per CTA, 2 CTAs per SM) and
- * VK_CONV_PERSISTENT (one CTA per SM: producer / MMA / epilogue warps, double-buffered TMEM accumulator).
- * The tile kernel is the faster one today (281 vs 301 us per 64 images at YOLOv5s widths); the setter
- * exists for tuning and so that the tests cover both.  Returns the old mode. */
+/* Two implementations with identical results: VK_CONV_PERSISTENT (default; one CTA per SM: two producer
+ * teams, one MMA-issuing lane, two epilogue groups over a double-buffered TMEM accumulator) and
+ * VK_CONV_TILE (one tile per CTA, 2 CTAs per SM; 281 vs 239 us per 64 images at YOLOv5s widths).
+ * The setter exists for tuning and so that the tests cover both.  Returns the old mode. */
 #define VK_CONV_TILE 0
 #define VK_CONV_PERSISTENT 1
 int vk_set_conv_kernel(int mode);

@@ -8,7 +8,7 @@ import torch
 from vision_kit_b200 import ops, synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 from vision_kit_b200 import _lib
-_lib.lib().vk_set_conv_kernel(int(os.environ.get("VK_CONV_MODE", "0")))   # 1 = persistent warp-specialised variant
+_lib.lib().vk_set_conv_kernel(int(os.environ.get("VK_CONV_MODE", "1")))   # 1 = persistent warp-specialised kernel (default), 0 = tile kernel
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]
 res = {}

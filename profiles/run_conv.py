@@ -6,7 +6,7 @@ import torch
 from vision_kit_b200 import _lib, ops, synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 conf = float(sys.argv[2]) if len(sys.argv) > 2 else 0.25
-_lib.lib().vk_set_conv_kernel(int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+_lib.lib().vk_set_conv_kernel(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]
 cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)

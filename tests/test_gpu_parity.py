@@ -690,14 +690,14 @@ def test_conv_head_matches_conv_then_filter(variant, conf, ml, cins, B, vk, cuda
         torch.backends.cudnn.allow_tf32 = old
     ref = vk.ops.decode_filter(cfg, logits, conf, ml)
     got = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
-    # the persistent warp-specialised variant must produce the very same bits
+    # the one-tile-per-CTA variant must produce the very same bits as the (default) persistent kernel
     from vision_kit_b200 import _lib
-    _lib.lib().vk_set_conv_kernel(1)
+    _lib.lib().vk_set_conv_kernel(0)
     try:
         got2 = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
         torch.cuda.synchronize()
     finally:
-        _lib.lib().vk_set_conv_kernel(0)
+        _lib.lib().vk_set_conv_kernel(1)
     assert int(got.fault.item()) == 0 and int(got2.fault.item()) == 0
     assert torch.equal(got.counts, got2.counts)
     for (la, ra, ba), (lb, rb, bb) in zip(_canonical(got), _canonical(got2)):

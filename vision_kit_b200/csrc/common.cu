@@ -74,7 +74,7 @@ extern "C" int vk_set_filter_kernel(int mode) {
     if (mode < VK_FILTER_AUTO || mode > VK_FILTER_DENSE) return fail_arg("vk_set_filter_kernel: mode %d", mode);
     return g_filter_mode.exchange(mode, std::memory_order_relaxed);
 }
-static std::atomic<int> g_conv_mode{VK_CONV_TILE};
+static std::atomic<int> g_conv_mode{VK_CONV_PERSISTENT};
 int vk::conv_mode() { return g_conv_mode.load(std::memory_order_relaxed); }
 extern "C" int vk_set_conv_kernel(int mode) {
     if (mode != VK_CONV_TILE && mode != VK_CONV_PERSISTENT) return fail_arg("vk_set_conv_kernel: mode %d", mode);
