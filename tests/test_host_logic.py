@@ -178,3 +178,13 @@ def test_dataset_geometry_equals_oracle(vk_lib):
     from vision_kit_b200 import _lib
     g = _lib.VkLbGeom()
     assert vk_lib.vk_dataset_geometry(1000, 500, 512, 640, C.byref(g)) == -1      # 640 tall on a 512 canvas
+
+
+def test_kernel_selectors_validate_and_restore(vk_lib):
+    """vk_set_filter_kernel / vk_set_conv_kernel: return the previous mode, reject unknown ones."""
+    assert vk_lib.vk_set_filter_kernel(2) == 0 and vk_lib.vk_set_filter_kernel(0) == 2
+    assert vk_lib.vk_set_filter_kernel(7) == -1 and b"mode 7" in vk_lib.vk_last_error()
+    assert vk_lib.vk_set_conv_kernel(0) == 1 and vk_lib.vk_set_conv_kernel(1) == 0     # default: persistent
+    assert vk_lib.vk_set_conv_kernel(5) == -1
+    assert vk_lib.vk_eval_match_smem_bytes(10, 100) == 100 * 6 * 4 + 10 * 100 * 4
+    assert vk_lib.vk_eval_match_smem_bytes(0, 100) == 0
