@@ -14,25 +14,10 @@
 // mode) and records (base, count) in a segment table indexed by tile; canonical order =
 // segment order x in-segment order.  No tile ever waits for an atomic, the buffer cannot
 // overflow, and the consumer (nms.cu) walks the table.
-#include "vk_common.cuh"
+#include "decode_common.cuh"
 
 namespace vk {
 
-constexpr int kTileS = 64;        // spatial positions (= prediction rows) per tile
-constexpr int kFiltPitch = kTileS + 4;   // filters: rows read with lanes over rows; 16-byte aligned for STS.128
-constexpr int kDecThreads = 256;
-constexpr int kWarps = kDecThreads / 32;
-
-struct HeadDev {
-    int variant, nl, na, nc, no, rows, tiles;
-    int ny[VK_MAX_LEVELS], nx[VK_MAX_LEVELS], nynx[VK_MAX_LEVELS];
-    int row_base[VK_MAX_LEVELS], tile_start[VK_MAX_LEVELS + 1], tpa[VK_MAX_LEVELS];
-    int group_start[VK_MAX_LEVELS + 1];  // first block of each level for the chosen group size
-    float stride[VK_MAX_LEVELS];
-    float anchors[VK_MAX_LEVELS][2 * VK_MAX_ANCHORS];
-    const float* lv[VK_MAX_LEVELS];
-    float* raw[VK_MAX_LEVELS];
-};
 
 struct TileLoc {
     int l, a, s0, nvalid, row0;
@@ -352,19 +337,6 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
 constexpr int kGroupMax = 8;
 constexpr int kItems = kTileS;  // rows evaluated per back-end call (64)
 
-struct FilterArgs {
-    float conf;
-    int multi_label;
-    const uint32_t* class_mask;  // dev or null
-    uint64_t* cand;
-    float4* boxes;
-    int32_t* counts;
-    int32_t* seg_base;
-    int32_t* seg_count;
-    int cap, rows, segs, nc;
-    int group;                   // tiles per block, 1..kGroupMax
-    int tile_cap;                // candidate slots each tile owns
-};
 
 struct FilterSmem {
     float obj[kGroupMax * kTileS];
@@ -386,14 +358,6 @@ struct FilterSmem {
     int base;
 };
 
-__device__ __forceinline__ bool class_allowed(const uint32_t* m, int c) {
-    return m == nullptr || ((__ldg(m + (c >> 5)) >> (c & 31)) & 1u);
-}
-
-__device__ __forceinline__ float4 xyxy_from_cxcywh(float cx, float cy, float w, float h) {
-    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // utils/bboxes.py:103-111
-    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-}
 
 // ---- accessors: where the 5+nc values of item `ai` live and how they turn into numbers
 struct PlaneGeom {       // fused path: what is needed to decode a box from logits
@@ -1113,60 +1077,6 @@ filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
     }
 }
 
-static int make_head(const VkHeadCfg* cfg, HeadDev* H, const char* who) {
-    if (!cfg) return fail_arg("%s: cfg is NULL", who);
-    if (cfg->nl < 1 || cfg->nl > VK_MAX_LEVELS || cfg->na < 1 || cfg->na > VK_MAX_ANCHORS || cfg->nc < 1)
-        return fail_code(VK_E_LIMIT, "%s: nl=%d na=%d nc=%d outside limits", who, cfg->nl, cfg->na, cfg->nc);
-    if (cfg->variant != VK_HEAD_V5 && cfg->variant != VK_HEAD_V7) return fail_arg("%s: variant %d", who, cfg->variant);
-    memset(H, 0, sizeof(*H));
-    H->variant = cfg->variant; H->nl = cfg->nl; H->na = cfg->na; H->nc = cfg->nc; H->no = cfg->nc + 5;
-    int rows = 0, tiles = 0;
-    for (int l = 0; l < cfg->nl; ++l) {
-        if (cfg->ny[l] <= 0 || cfg->nx[l] <= 0) return fail_arg("%s: level %d grid %dx%d", who, l, cfg->ny[l], cfg->nx[l]);
-        H->ny[l] = cfg->ny[l]; H->nx[l] = cfg->nx[l]; H->nynx[l] = cfg->ny[l] * cfg->nx[l];
-        H->stride[l] = cfg->stride[l];
-        for (int k = 0; k < 2 * cfg->na; ++k) H->anchors[l][k] = cfg->anchors[l][k];
-        H->row_base[l] = rows;
-        H->tile_start[l] = tiles;
-        H->tpa[l] = ceil_div(H->nynx[l], kTileS);
-        rows += cfg->na * H->nynx[l];
-        tiles += cfg->na * H->tpa[l];
-    }
-    for (int l = cfg->nl; l <= VK_MAX_LEVELS; ++l) H->tile_start[l] = tiles;
-    H->rows = rows; H->tiles = tiles;
-    if (tiles > VK_MAX_SEGMENTS) return fail_code(VK_E_LIMIT, "%s: %d tiles per image > %d", who, tiles, VK_MAX_SEGMENTS);
-    return VK_OK;
-}
-
-static int check_cand(const VkCandBuf* o, int rows, int segs, int nc, int multi_label, const char* who) {
-    if (!o || !o->cand || !o->boxes || !o->counts || !o->seg_base || !o->seg_count)
-        return fail_arg("%s: candidate buffer has a NULL member", who);
-    if (o->cap <= 0 || o->rows != rows || o->segs != segs || o->nc != nc)
-        return fail_arg("%s: candidate buffer shape (cap=%d rows=%d segs=%d nc=%d) != (rows=%d segs=%d nc=%d)",
-                        who, o->cap, o->rows, o->segs, o->nc, rows, segs, nc);
-    if ((uint64_t)rows * (uint64_t)nc > 0x7fffffffull) return fail_code(VK_E_LIMIT, "%s: rows*nc overflows 31 bits", who);
-    const long need = (long)segs * kTileS * ((multi_label && nc > 1) ? nc : 1);
-    if (o->cap < need)
-        return fail_arg("%s: cap %d < %ld (= segs * 64 * %s): every tile owns a fixed slot range", who, o->cap, need,
-                        (multi_label && nc > 1) ? "nc" : "1");
-    if (reinterpret_cast<uintptr_t>(o->boxes) & 15) return fail_arg("%s: boxes must be 16-byte aligned", who);
-    return VK_OK;
-}
-
-static FilterArgs make_filter_args(const VkCandBuf* o, float conf, int multi_label, const uint32_t* mask) {
-    FilterArgs A;
-    A.conf = conf;
-    A.multi_label = (multi_label && o->nc > 1) ? 1 : 0;   // image_proc.py:111
-    A.class_mask = mask;
-    A.cand = o->cand;
-    A.boxes = reinterpret_cast<float4*>(o->boxes);
-    A.counts = o->counts; A.seg_base = o->seg_base; A.seg_count = o->seg_count;
-    A.cap = o->cap; A.rows = o->rows; A.segs = o->segs; A.nc = o->nc;
-    A.group = 1;
-    A.tile_cap = kTileS * (A.multi_label ? o->nc : 1);
-    return A;
-}
-
 // Tiles per block: enough blocks for ~2 full waves of 8 resident blocks per SM, at most 8.
 static int choose_group(int batch, int tiles) {
     const long blocks = (long)batch * tiles;
@@ -1343,624 +1253,4 @@ extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, fl
     filter_pred_kernel<<<dim3(ceil_div(segs, A.group), batch), kDecThreads, smem, stream>>>(pred, no, A);
     count_launch();
     return check_launch("filter_pred_kernel");
-}
-
-// =======================================================================================
-// Fused Detect head: 1x1 conv (tensor cores) + decode + confidence filter  
-//
-//   models/heads/yolov5.py:58-69 / yolov7.py:67-81: x[i] = m[i](x[i]) (a 1x1 conv, Cout = na*no),
-//   then sigmoid / grid / anchors, then nms()'s candidate selection (utils/image_proc.py:99-151).
-//   Here the (B, 255, ny, nx) conv output never exists: one CTA computes
-//       D[s][co] = sum_ci X[b][ci][s] * W[co][ci]        s: 128 spatial positions, co: 256 (padded)
-//   with tcgen05.mma (kind::tf32, fp32 bits of X and W used as TF32, fp32 accumulate in TMEM).
-//   With D transposed like this a TMEM lane is a spatial position, so every epilogue thread owns
-//   whole prediction rows (one per anchor) and runs the dense filter's per-row logic straight
-//   from tcgen05.ld -- no shared-memory round trip of the logits.
-//
-//   Operands: both K-major, 128-byte swizzled (rows of 32 tf32 = 128 B, 8-row atoms of 1024 B).
-//   W[co][ci] is K-major as stored: 16-byte cp.async copies land directly in the swizzled tile.
-//   X is [ci][s] (s contiguous = MN-major; tcgen05 returned zeros for MN-major TF32 operands on
-//   this part -- profiles/micro/umma_tf32.cu -- so X is transposed on chip): 16-byte cp.async into
-//   a raw [k][128] staging tile, then thread s reads its column (conflict-free LDS.32) and writes
-//   row s of the A tile with 128-bit stores (the swizzle makes them conflict-free).
-//   Pipeline per 32-channel block: the copies of block k+1 (X and W) are in flight while block k is
-//   transposed and multiplied; the A tile is single-buffered behind the MMA-completion mbarrier.
-//   128 threads, 256 TMEM columns, 112 KB shared memory and no static allocation -> 2 CTAs per SM.
-//
-//   Candidates, boxes, segment table: exactly vk_decode_filter's format (same VkCandBuf), so
-//   vk_nms_batched consumes it unchanged.  Results equal conv-then-vk_decode_filter up to TF32
-//   rounding of the logits (tests/test_gpu_parity.py::test_conv_head_*).
-// =======================================================================================
-namespace vk {
-
-constexpr int kChM = 128, kChN = 256, kChKB = 32, kChThreads = 128;
-constexpr int kChStageBytes = kChKB * kChM * 4;       // 16 KB raw X block [k][m]
-constexpr int kChABytes = kChM * 128;                 // 16 KB
-constexpr int kChBBytes = kChN * 128;                 // 32 KB
-constexpr int kChTail = 64;                           // mbarrier, TMEM base, warp totals
-constexpr int kChSmem = 2 * kChStageBytes + kChABytes + 2 * kChBBytes + kChTail;   // 112 KB + 64 B, no static shared memory: 2 CTAs per SM
-
-struct ConvHead {
-    const float* x[VK_MAX_LEVELS];      // (B, cin, ny, nx)
-    const float* w[VK_MAX_LEVELS];      // (na*no, cin)
-    const float* bias[VK_MAX_LEVELS];   // (na*no) or null
-    int cin[VK_MAX_LEVELS];
-    int mtile_start[VK_MAX_LEVELS + 1]; // first 128-row tile of each level inside an image
-    int mtiles;                         // per image
-};
-
-__device__ __forceinline__ uint32_t ch_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// K-major SW128 tile: row r = 128 B (32 tf32), 16-byte chunk c of row r at position c ^ (r & 7)
-__device__ __forceinline__ uint32_t ch_koff(int r, int chunk) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-}
-__device__ __forceinline__ uint64_t ch_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)1 << 16;              // leading byte offset: unused for swizzled K-major
-    d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset: 8-row atoms 1024 B apart
-    d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void ch_cp16(uint32_t dst, const void* src, bool valid) {
-    const int n = valid ? 16 : 0;        // src-size 0: the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
-}
-// bounded wait on an mbarrier phase; returns false on time-out (never hangs the GPU)
-__device__ __forceinline__ bool ch_wait(uint32_t bar, uint32_t parity) {
-    for (int spin = 0; spin < (1 << 24); ++spin) {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return true;
-    }
-    return false;
-}
-
-#define VK_TMEM_LD16(r, taddr)                                                                                     \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
-                 : "r"(taddr));                                                                                    \
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
-
-// Epilogue of one 128-position tile whose accumulator sits in 256 TMEM columns at `trow` (lane
-// offset of the calling warp included): thread `tid` (0..127) = spatial position s0 + tid = TMEM
-// lane, one prediction row per anchor.  `bar_id` names a 128-thread barrier shared by the 4 warps
-// that run it, `s_wtot` 4 ints of their scratch.
-__device__ __forceinline__ void ch_bar_sync(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
-
-__device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs& A, uint32_t trow, int l, int b, int s0,
-                                              int nvalid, int tid, int* s_wtot, int bar_id, bool ok) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nynx = H.nynx[l], no = H.no;
-    const int nc = A.nc;
-    const int sp = s0 + tid;
-    const int half = tid >> 6;                                 // 64-row segment of the thread inside the tile
-    const bool seg_exists = s0 + 64 * half < nynx;
-    struct { int variant, nx; float stride; } const gbase{H.variant, H.nx[l], H.stride[l]};
-    for (int a = 0; a < H.na; ++a) {
-        const int cb = a * no;
-        uint32_t r[16];
-        VK_TMEM_LD16(r, trow + cb);                            // x, y, w, h, obj, first 11 classes
-        float box_l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) box_l[j] = __uint_as_float(r[j]);
-        const float o = sigmoidf_vk(__uint_as_float(r[4]));
-        const bool alive = ok && tid < nvalid && o > A.conf;       // image_proc.py:99
-        const float obj = alive ? o : 0.0f;
-        // pass 1: count (multi-label) or best class.  The sigmoid is monotone, so the 2 MUFU + 4 FP32
-        // instructions per class are spent only where the outcome is open: multi-label evaluates
-        // p = sigmoid(x) * obj exactly only for logits above logit(conf / obj) - 0.05 (everything below
-        // cannot pass p > conf); best-class finds the largest logit first and evaluates the products
-        // only within 1e-3 of it (first maximum of the PRODUCTS, as the reference takes it).
-        int count = 0;
-        float bv = -INFINITY;
-        int bj = 0x7fffffff;
-        const bool any_alive = __any_sync(0xffffffffu, alive);
-        // logit(conf / obj): conf/obj in (0,1) for alive rows; log via MUFU, generous margin below
-        float tau = INFINITY;
-        if (alive) {
-            const float rr = __fdividef(A.conf, obj);
-            tau = (rr > 0.f) ? __logf(__fdividef(rr, 1.0f - rr)) - 0.05f : -INFINITY;
-        }
-        if (any_alive) {
-            if (A.multi_label) {
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = c0 + j;
-                        const float x = __uint_as_float(q[j]);
-                        if (c < nc && x > tau) {
-                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
-                            count += (p > A.conf && class_allowed(A.class_mask, c)) ? 1 : 0;            // :141,151
-                        }
-                    }
-                }
-            } else {
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < nc) mx = fmaxf(mx, __uint_as_float(q[j]));
-                }
-                const float near = mx - 1e-3f;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float x = __uint_as_float(q[j]);
-                        if (c0 + j < nc && x >= near) {
-                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
-                            if (p > bv) { bv = p; bj = c0 + j; }                                        // :145
-                        }
-                    }
-                }
-                count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
-            }
-        }
-        // offsets inside the 64-row segment (warps 2*half, 2*half+1), canonical order = row order
-        const int incl = warp_incl_scan(count, lane);
-        if (lane == 31) s_wtot[warp] = incl;
-        ch_bar_sync(bar_id);
-        const int base = (warp & 1) ? s_wtot[warp - 1] : 0;
-        const int seg_total = s_wtot[2 * half] + s_wtot[2 * half + 1];
-        const int seg = H.tile_start[l] + a * H.tpa[l] + (s0 >> 6) + half;
-        const int row = H.row_base[l] + a * nynx + sp;             // prediction row inside the image
-        // pass 2 (warp-uniform: tcgen05.ld is a warp-collective): recompute the products and store
-        uint2* wp = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + (size_t)seg * A.tile_cap + base + (incl - count);
-        const uint32_t idx0 = (uint32_t)(row * nc);
-        if (A.multi_label) {
-            if (__any_sync(0xffffffffu, count > 0)) {
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = c0 + j;
-                        if (c < nc && count > 0 && __uint_as_float(q[j]) > tau) {
-                            const float p = __fmul_rn(sigmoidf_vk(__uint_as_float(q[j])), obj);
-                            if (p > A.conf && class_allowed(A.class_mask, c)) *wp++ = make_uint2(__float_as_uint(p), idx0 + (uint32_t)c);
-                        }
-                    }
-                }
-            }
-        } else if (count > 0) {
-            *wp = make_uint2(__float_as_uint(bv), idx0 + (uint32_t)bj);
-        }
-        if (count > 0) {
-            const int gy = sp / gbase.nx, gx = sp - gy * gbase.nx;
-            const float aw = H.anchors[l][2 * a], ah = H.anchors[l][2 * a + 1];
-            A.boxes[(size_t)b * A.rows + row] =
-                xyxy_from_cxcywh(decode_elem(box_l[0], 0, (float)gx, gbase.stride, aw, gbase.variant),
-                                 decode_elem(box_l[1], 1, (float)gy, gbase.stride, ah, gbase.variant),
-                                 decode_elem(box_l[2], 2, 0.f, gbase.stride, aw, gbase.variant),
-                                 decode_elem(box_l[3], 3, 0.f, gbase.stride, ah, gbase.variant));
-        }
-        if ((tid & 63) == 0 && seg_exists) {
-            A.seg_base[(size_t)b * A.segs + seg] = seg_total ? seg * A.tile_cap : 0;
-            A.seg_count[(size_t)b * A.segs + seg] = seg_total;
-            if (seg_total) atomicAdd(A.counts + b, seg_total);
-        }
-        ch_bar_sync(bar_id);                                       // s_wtot is reused by the next anchor
-    }
-}
-
-__global__ void __launch_bounds__(kChThreads, 2)
-conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int* __restrict__ fault) {
-    // no static shared memory: the dynamic window then starts 1024-byte aligned (the swizzled tiles need it)
-    // and 2 x (112 KB + 64 B + 1 KB reserved) fits one SM
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sStage = smem;                                  // 2 x 16 KB
-    uint8_t* sA = smem + 2 * kChStageBytes;                  // 16 KB
-    uint8_t* sB = sA + kChABytes;                            // 2 x 32 KB
-    uint64_t& s_bar = *reinterpret_cast<uint64_t*>(sB + 2 * kChBBytes);
-    uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(sB + 2 * kChBBytes + 8);
-    int* s_wtot = reinterpret_cast<int*>(sB + 2 * kChBBytes + 16);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < VK_MAX_LEVELS; ++i)
-        if (i < H.nl && (int)blockIdx.x >= C.mtile_start[i]) l = i;
-    const int s0 = ((int)blockIdx.x - C.mtile_start[l]) * kChM;
-    const int nynx = H.nynx[l], cin = C.cin[l], no = H.no, cout = H.na * no;
-    const int nvalid = min(kChM, nynx - s0);
-    const float* __restrict__ X = C.x[l] + (size_t)b * cin * nynx + s0;
-    const float* __restrict__ W = C.w[l];
-    const int nkb = cin / kChKB;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(&s_tmem)), "n"(kChN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ch_smem(&s_bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const float* __restrict__ bias = C.bias[l];
-
-    // copy loops: thread-constant parts of the addresses hoisted (element e = tid + i * 128)
-    const int xk0 = tid >> 5, xm4 = (tid & 31) << 2;                       // X: channel xk0 + 4 i, positions xm4..+3
-    const bool xvalid = xm4 < nvalid;
-    const float* const xsrc0 = X + (size_t)xk0 * nynx + (xvalid ? xm4 : 0);
-    const uint32_t xdst0 = (uint32_t)(xk0 * kChM + xm4) * 4;
-    const int wn0 = tid >> 3, wc = tid & 7;                                // W: row wn0 + 16 i, chunk wc
-    const uint32_t wdst0 = ch_koff(wn0, wc);                               // (n & 7) does not change with i: + i * 2048
-    auto issue_x = [&](int kb) {
-        // X block: 32 channels x 32 chunks of 4 positions (raw [k][128]); positions past the plane are zeros
-        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes) + xdst0;
-        const float* src = xsrc0 + (size_t)kb * kChKB * nynx;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ch_cp16(st + i * (4 * kChM * 4), src + (size_t)(4 * i) * nynx, xvalid);
-    };
-    auto issue_w = [&](int kb) {
-        // W block: 256 rows x 8 chunks of 4 channels, straight into the swizzled K-major tile
-        const uint32_t sb = ch_smem(sB + (kb & 1) * kChBBytes) + wdst0;
-        const float* src = W + kb * kChKB + 4 * wc;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int n = wn0 + 16 * i;
-            ch_cp16(sb + i * 2048, src + (size_t)(n < cout ? n : 0) * cin, n < cout);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    issue_x(0);
-    issue_w(0);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
-    bool ok = true;
-    // one copy group per block (X then W): at block kb everything but the newest group must have landed
-    for (int kb = 0; kb < nkb; ++kb) {
-        // the MMAs of block kb-1 read the A tile (single-buffered) and the W buffer that block kb+1 reuses;
-        // the staging buffer of block kb+1 was drained by the transposition of block kb-1
-        if (kb > 0) ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((kb - 1) & 1));
-        if (kb + 1 < nkb) {
-            issue_x(kb + 1);
-            issue_w(kb + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();                                      // block kb landed (staging + W tile)
-        {   // transpose: thread = spatial position; 8 chunks of 4 channels -> row `tid` of the A tile
-            const float* st = reinterpret_cast<const float*>(sStage + (kb & 1) * kChStageBytes) + tid;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
-                *reinterpret_cast<float4*>(sA + ch_koff(tid, c)) = v;
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes (cp.async W, stores A) -> async proxy
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = ch_smem(sA), b0 = ch_smem(sB + (kb & 1) * kChBBytes);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte row
-                const uint32_t acc = (kb | ks) ? 1u : 0u;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             :: "r"(tmem), "l"(ch_desc(a0 + ks * 32)), "l"(ch_desc(b0 + ks * 32)), "r"(idesc), "r"(acc) : "memory");
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
-        }
-    }
-    // The bias rides on the tensor cores as one more K = 8 step: A gets the columns [1, 1, 0, ...], W the
-    // columns [hi, lo, 0, ...] with bias = hi + lo split into two TF32 values (fp32-accurate sum), built in
-    // the staging / W buffers that block nkb would use (both free: their last readers have completed).
-    int last_phase = (nkb - 1) & 1;
-    if (bias != nullptr) {
-        // a parity wait only distinguishes adjacent phases: pass the last block's phase before the
-        // bias step can complete the next one
-        ok &= ch_wait(ch_smem(&s_bar), (uint32_t)last_phase);
-        uint8_t* ea = sStage + (nkb & 1) * kChStageBytes;
-        uint8_t* eb = sB + (nkb & 1) * kChBBytes;
-        *reinterpret_cast<float4*>(ea + ch_koff(tid, 0)) = make_float4(1.f, 1.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(ea + ch_koff(tid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int n = tid; n < kChN; n += kChThreads) {
-            const float v = n < cout ? __ldg(bias + n) : 0.0f;
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            *reinterpret_cast<float4*>(eb + ch_koff(n, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
-            *reinterpret_cast<float4*>(eb + ch_koff(n, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                         :: "r"(tmem), "l"(ch_desc(ch_smem(ea))), "l"(ch_desc(ch_smem(eb))), "r"(idesc), "r"(1u) : "memory");
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
-        }
-        last_phase = nkb & 1;
-    }
-    ok &= ch_wait(ch_smem(&s_bar), (uint32_t)last_phase);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (!ok && tid == 0) atomicExch(fault, 1);
-
-    // ---------------- epilogue: thread = spatial position s0 + tid = TMEM lane; one prediction row per anchor
-    conv_epilogue(H, A, tmem + ((uint32_t)(warp * 32) << 16), l, b, s0, nvalid, tid, s_wtot, 0, ok);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kChN));
-}
-
-// ---------------------------------------------------------------------------------------
-// Warp-specialised persistent variant: one CTA per SM, 17 warps.
-//   warps 8-15  two producer teams taking alternate k-blocks: cp.async of the X and W blocks two blocks
-//               ahead (4 staging slots, 2 A slots, 4 W slots), transposition of X into the A tile, bias
-//               block at the end of a tile
-//   warp 16     MMA issuer (one lane): tcgen05.mma into one of TWO 256-column accumulators,
-//               tcgen05.commit -> "slot free" and "accumulator full" mbarriers
-//   warps 0-7   two epilogue groups (one per accumulator) draining tile i while the mainloop
-//               of tile i+1 runs
-// Every mbarrier phase is waited in order by its consumer (a parity wait cannot tell phase n from
-// n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
-// ---------------------------------------------------------------------------------------
-constexpr int kWsThreads = 17 * 32;
-constexpr int kWsStage = 4, kWsASlots = 2, kWsBSlots = 4;            // staging / A tile / W tile ring depths
-constexpr int kWsOffA = kWsStage * kChStageBytes;                    // 64 KB
-constexpr int kWsOffB = kWsOffA + kWsASlots * kChABytes;             // 96 KB
-constexpr int kWsOffBar = kWsOffB + kWsBSlots * kChBBytes;           // 224 KB
-constexpr int kWsSmem = kWsOffBar + 256;
-
-struct WsTile {
-    int valid, b, l, s0, nvalid, nkb;
-};
-
-__device__ __forceinline__ WsTile ws_tile(const HeadDev& H, const ConvHead& C, int t, int total) {
-    WsTile q;
-    q.valid = t < total;
-    if (!q.valid) { q.b = q.l = q.s0 = q.nvalid = q.nkb = 0; return q; }
-    q.b = t / C.mtiles;
-    const int mt = t - q.b * C.mtiles;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < VK_MAX_LEVELS; ++i)
-        if (i < H.nl && mt >= C.mtile_start[i]) l = i;
-    q.l = l;
-    q.s0 = (mt - C.mtile_start[l]) * kChM;
-    q.nvalid = min(kChM, H.nynx[l] - q.s0);
-    q.nkb = C.cin[l] / kChKB;
-    return q;
-}
-
-__device__ __forceinline__ void ws_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
-// POLL = true: mbarrier.test_wait in a tight loop (the single MMA-issuing lane: its hand-offs happen once
-// per 0.3 us k-block); false: try_wait, which lets the hardware suspend the (many) waiting threads.
-template <bool POLL>
-__device__ __forceinline__ bool ws_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-    for (int spin = 0; spin < (POLL ? (1 << 26) : (1 << 22)); ++spin) {
-        uint32_t done;
-        if (POLL)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        else
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return true;
-        if ((spin & 1023) == 1023 && *abort_flag) return false;
-    }
-    *abort_flag = 1;
-    return false;
-}
-
-__global__ void __launch_bounds__(kWsThreads, 1)
-conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int total_tiles, int* __restrict__ fault) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sStage = smem;
-    uint8_t* sA = smem + kWsOffA;
-    uint8_t* sB = smem + kWsOffB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[4] done[4] tfull[2] tempty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 112);
-    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 116);
-    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 128);     // [2][4]
-    const uint32_t bar0 = ch_smem(bars);
-    auto READY = [&](int s) { return bar0 + 8u * s; };
-    auto DONE = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto TFULL = [&](int g) { return bar0 + 8u * (8 + g); };
-    auto TEMPTY = [&](int g) { return bar0 + 8u * (10 + g); };
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int no = H.no, cout = H.na * no;
-
-    if (warp == 16) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(s_tmem)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar0 + 8u * i), "r"(1));
-        for (int g = 0; g < 2; ++g) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TFULL(g)), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TEMPTY(g)), "r"(4));
-        }
-        *s_abort = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *s_tmem;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
-
-    if (warp >= 8 && warp < 16) {
-        // ------------------------------------------------------------------ producers: two teams of 4 warps,
-        // team T owns the blocks j = T, T+2, T+4, ... (copies of block j+2 in flight while block j is transposed)
-        const int team = (warp - 8) >> 2;
-        const int ptid = (tid - 256) & 127;
-        const int xk0 = ptid >> 5, xm4 = (ptid & 31) << 2;
-        const int wn0 = ptid >> 3, wc = ptid & 7;
-        const uint32_t wdst0 = ch_koff(wn0, wc);
-        // cursors over the CTA's tiles; a tile has nkb data blocks + one bias block
-        struct Cursor { int i, kb; WsTile q; };
-        auto advance = [&](Cursor& c) {                // one block forward
-            if (c.q.valid && ++c.kb > c.q.nkb) { c.kb = 0; ++c.i; c.q = ws_tile(H, C, blockIdx.x + c.i * gridDim.x, total_tiles); }
-        };
-        Cursor it{0, 0, ws_tile(H, C, blockIdx.x, total_tiles)};
-        if (team) advance(it);
-        Cursor pr = it;
-        auto issue_block = [&](int j) {                // copies of the block at the issue cursor into the rings at j
-            if (it.q.valid && it.kb < it.q.nkb) {
-                const int nynx = H.nynx[it.q.l], cin = C.cin[it.q.l];
-                const bool xvalid = xm4 < it.q.nvalid;
-                const float* xsrc = C.x[it.q.l] + (size_t)it.q.b * cin * nynx + it.q.s0 + (size_t)(it.kb * kChKB + xk0) * nynx + (xvalid ? xm4 : 0);
-                const uint32_t st = ch_smem(sStage + (j % kWsStage) * kChStageBytes) + (uint32_t)(xk0 * kChM + xm4) * 4;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ch_cp16(st + i * (4 * kChM * 4), xsrc + (size_t)(4 * i) * nynx, xvalid);
-                const float* wsrc = C.w[it.q.l] + it.kb * kChKB + 4 * wc;
-                const uint32_t sb = ch_smem(sB + (j % kWsBSlots) * kChBBytes) + wdst0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int n = wn0 + 16 * i;
-                    ch_cp16(sb + i * 2048, wsrc + (size_t)(n < cout ? n : 0) * cin, n < cout);
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            advance(it); advance(it);
-        };
-        bool ok = true;
-        issue_block(team);
-        for (int j = team; pr.q.valid && ok; j += 2) {
-            // ring slots of block j+2 (staging, W) and of block j (A) were last used by block j-2: its MMAs
-            // are two blocks behind the newest, so this wait rarely stalls
-            if (j >= 2) ok &= ws_wait<false>(DONE((j - 2) % kWsBSlots), (uint32_t)(((j - 2) / kWsBSlots) & 1), s_abort);
-            issue_block(j + 2);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");    // block j landed for the whole team
-            uint8_t* a_tile = sA + (j % kWsASlots) * kChABytes;
-            if (pr.kb < pr.q.nkb) {
-                const float* st = reinterpret_cast<const float*>(sStage + (j % kWsStage) * kChStageBytes) + ptid;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
-                    *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, c)) = v;
-                }
-            } else {                                   // bias block: A = [1, 1, 0...], W = [hi, lo, 0...]
-                uint8_t* b_tile = sB + (j % kWsBSlots) * kChBBytes;
-                const float* bias = C.bias[pr.q.l];
-                *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, 0)) = make_float4(1.f, 1.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int n = ptid; n < kChN; n += 128) {
-                    const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
-                    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                    *reinterpret_cast<float4*>(b_tile + ch_koff(n, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
-                    *reinterpret_cast<float4*>(b_tile + ch_koff(n, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");
-            if (ptid == 0) ws_arrive(READY(j % kWsBSlots));
-            advance(pr); advance(pr);
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == 16) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            bool ok = true;
-            int j = 0;
-            for (int i = 0; ok; ++i) {
-                const WsTile q = ws_tile(H, C, blockIdx.x + i * gridDim.x, total_tiles);
-                if (!q.valid) break;
-                const int g = i & 1;
-                if (i >= 2) ok &= ws_wait<true>(TEMPTY(g), (uint32_t)(((i - 2) >> 1) & 1), s_abort);   // epilogue drained tile i-2
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc_addr = tmem + (uint32_t)(g * kChN);
-                for (int kb = 0; kb <= q.nkb && ok; ++kb, ++j) {
-                    const int s = j % kWsBSlots;
-                    ok &= ws_wait<true>(READY(s), (uint32_t)((j / kWsBSlots) & 1), s_abort);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a0 = ch_smem(sA + (j % kWsASlots) * kChABytes), b0 = ch_smem(sB + s * kChBBytes);
-                    const int nks = (kb < q.nkb) ? 4 : 1;                      // the bias block is one K = 8 step
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t acc = (kb | ks) ? 1u : 0u;
-                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                     :: "r"(acc_addr), "l"(ch_desc(a0 + ks * 32)), "l"(ch_desc(b0 + ks * 32)), "r"(idesc), "r"(acc) : "memory");
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(DONE(s)) : "memory");
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(TFULL(g)) : "memory");
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue groups
-        const int g = warp >> 2, etid = tid & 127, ewarp = warp & 3;
-        bool ok = true;
-        for (int i = g; ; i += 2) {
-            const WsTile q = ws_tile(H, C, blockIdx.x + i * gridDim.x, total_tiles);
-            if (!q.valid) break;
-            ok &= ws_wait<false>(TFULL(g), (uint32_t)((i >> 1) & 1), s_abort);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            conv_epilogue(H, A, tmem + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(g * kChN), q.l, q.b, q.s0, q.nvalid,
-                          etid, s_wtot + 4 * g, 3 + g, ok);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) ws_arrive(TEMPTY(g));
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0 && *s_abort) atomicExch(fault, 1);
-    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
-}
-
-}  // namespace vk
-
-extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const int32_t* cin,
-                                     const float* const* weights, const float* const* biases, int batch,
-                                     float conf_thres, int multi_label, const uint32_t* class_mask,
-                                     const VkCandBuf* out, int32_t* fault, vk_stream_t stream_) {
-    HeadDev H;
-    if (int rc = make_head(cfg, &H, "vk_conv_decode_filter")) return rc;
-    if (batch == 0) return VK_OK;
-    if (!feats || !cin || !weights || !fault || batch < 0) return fail_arg("vk_conv_decode_filter: null/negative argument");
-    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_conv_decode_filter: conf_thres %g outside [0,1]", conf_thres);
-    if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: batch %d > 65535", batch);
-    if (H.na * H.no > kChN || (H.na - 1) * H.no + 5 + 16 * ceil_div(H.nc, 16) > kChN)
-        return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: %d output channels do not fit %d TMEM columns", H.na * H.no, kChN);
-    if (int rc = check_cand(out, H.rows, H.tiles, H.nc, multi_label, "vk_conv_decode_filter")) return rc;
-    ConvHead C;
-    memset(&C, 0, sizeof(C));
-    int mt = 0;
-    for (int l = 0; l < H.nl; ++l) {
-        if (!feats[l] || !weights[l]) return fail_arg("vk_conv_decode_filter: level %d is NULL", l);
-        if (cin[l] <= 0 || cin[l] % kChKB) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: cin[%d] = %d is not a multiple of %d", l, cin[l], kChKB);
-        if (H.nynx[l] % 4 || (reinterpret_cast<uintptr_t>(feats[l]) & 15) || (reinterpret_cast<uintptr_t>(weights[l]) & 15))
-            return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: level %d needs ny*nx %% 4 == 0 and 16-byte aligned tensors", l);
-        C.x[l] = feats[l]; C.w[l] = weights[l]; C.bias[l] = biases ? biases[l] : nullptr; C.cin[l] = cin[l];
-        C.mtile_start[l] = mt;
-        mt += ceil_div(H.nynx[l], kChM);
-    }
-    for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) C.mtile_start[l] = mt;
-    C.mtiles = mt;
-    cudaStream_t stream = as_stream(stream_);
-    cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(fault, 0, sizeof(int32_t), stream);
-    if (e != cudaSuccess) return fail_code((int)e, "vk_conv_decode_filter: memset: %s", cudaGetErrorString(e));
-    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
-    if (conv_mode() == VK_CONV_PERSISTENT) {
-        const int total = mt * batch;
-        cudaFuncSetAttribute(conv_decode_filter_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem);
-        conv_decode_filter_ws_kernel<<<total < kNumSMs ? total : kNumSMs, kWsThreads, kWsSmem, stream>>>(H, C, A, total, fault);
-        count_launch();
-        return check_launch("conv_decode_filter_ws_kernel");
-    }
-    cudaFuncSetAttribute(conv_decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem);
-    conv_decode_filter_kernel<<<dim3(mt, batch), kChThreads, kChSmem, stream>>>(H, C, A, fault);
-    count_launch();
-    return check_launch("conv_decode_filter_kernel");
 }
