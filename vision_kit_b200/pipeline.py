@@ -12,6 +12,7 @@ utils/image_proc.py:83-187, with no host synchronisation between the three kerne
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional, Sequence
 
 import torch
@@ -62,6 +63,23 @@ class DetectPipeline:
             self._nms_pending = [False, False]
         self.input = torch.empty((batch, 3, img_sz[0], img_sz[1]), dtype=dtype, device=self.device)
         self.plan: Optional[ops.LetterboxPlan] = None
+        # Pre-marshalled ctypes arguments: a step of the loop is three C calls with constant arguments,
+        # and at ~150 us of GPU work per step the Python around them decides whether 8 ranks on one host
+        # stay GPU-bound (host time to enqueue a step: 113 -> see profiles/).
+        self._lib = _lib.lib()
+        self._mask = ops.class_mask(classes, nc, self.device)
+        self._mask_p = ops._ptr(self._mask)
+        self._cs = [c.c_struct() for c in self._cands]
+        self._cfg_ref = C.byref(self.cfg)
+        self._ml = int(ml)
+        self._conf = C.c_float(float(conf_thres))
+        self._nms_args = [(C.byref(cs), batch, C.c_float(0.0), C.c_double(float(iou_thres)), int(bool(agnostic)),
+                           int(max_nms), int(max_det), C.c_float(ops.MAX_WH), ops._ptr(o.dets), ops._ptr(o.counts),
+                           ops._ptr(o.keep), ops._ptr(o.status), ops._ptr(w), C.c_size_t(w.numel()))
+                          for cs, o, w in zip(self._cs, self._outs, self._nms_ws)]
+        self._lv_key = None
+        self._lv_arr = None
+        self._lb_args = None
 
     # -- letterbox + normalise
     def plan_sources(self, srcs: Sequence[torch.Tensor]) -> ops.LetterboxPlan:
@@ -70,12 +88,20 @@ class DetectPipeline:
         if len(srcs) != self.batch:
             raise ValueError(f"expected {self.batch} sources, got {len(srcs)}")
         self.plan = ops.LetterboxPlan(srcs, self.img_sz, upload=True)
+        pl = self.plan
+        if (pl.out_h, pl.out_w) != self.img_sz:
+            raise ValueError(f"letterbox canvas {(pl.out_h, pl.out_w)} != pipeline image size {self.img_sz}")
+        self._lb_args = (C.cast(pl.descs, C.c_void_p), ops._ptr(pl.descs_dev), pl.batch, pl.out_h, pl.out_w,
+                         int(bool(self.swap_rb)), ops.pack_color(self.color), ops._FMT[self.input.dtype],
+                         ops._ptr(self.input), ops._ptr(pl.ws), C.c_size_t(pl.ws.numel()))
         return self.plan
 
     def preprocess(self, srcs: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
         if srcs is not None:
             self.plan_sources(srcs)
-        self.plan.run(self.input, swap_rb=self.swap_rb, color=self.color)
+        rc = self._lib.vk_letterbox_batch(*self._lb_args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            _lib.check("vk_letterbox_batch", rc)
         return self.input
 
     def ratio_pads(self):
@@ -89,22 +115,35 @@ class DetectPipeline:
                                                 self._nms_ws[self._set])
             if self._nms_pending[self._set]:        # the NMS that last read this buffer set
                 torch.cuda.current_stream().wait_event(self._ev_nms[self._set])
-        return ops.decode_filter(self.cfg, feats, self.conf_thres, self.multi_label, self.classes,
-                                 buf=self.cand)
+        key = tuple(t.data_ptr() for t in feats)
+        if key != self._lv_key:                     # new tensors: validate and marshal once
+            self._lv_arr, bs = ops._level_ptrs(feats, self.cfg)
+            if bs != self.batch:
+                raise ValueError(f"expected a batch of {self.batch}, got {bs}")
+            self._lv_key = key
+        rc = self._lib.vk_decode_filter(self._cfg_ref, C.cast(self._lv_arr, C.c_void_p), self.batch, self._conf,
+                                        self._ml, self._mask_p, C.byref(self._cs[self._set]),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            _lib.check("vk_decode_filter", rc)
+        return self.cand
 
     def nms(self) -> ops.NmsOut:
-        if not self.overlap:
-            return ops.nms_batched(self.cand, self.iou_thres, self.agnostic, self.max_nms, self.max_det,
-                                   out=self.out, ws=self.nms_ws)
         k = self._set
+        if not self.overlap:
+            rc = self._lib.vk_nms_batched(*self._nms_args[k], C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc:
+                _lib.check("vk_nms_batched", rc)
+            return self.out
+        # the kernels take the stream as an argument: no need to switch torch's current stream
         self._ev_filter[k].record()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(self._ev_filter[k])
-            out = ops.nms_batched(self.cand, self.iou_thres, self.agnostic, self.max_nms, self.max_det,
-                                  out=self.out, ws=self.nms_ws)
-            self._ev_nms[k].record()
+        self.side.wait_event(self._ev_filter[k])
+        rc = self._lib.vk_nms_batched(*self._nms_args[k], C.c_void_p(self.side.cuda_stream))
+        if rc:
+            _lib.check("vk_nms_batched", rc)
+        self._ev_nms[k].record(self.side)
         self._nms_pending[k] = True
-        return out
+        return self.out
 
     def join(self) -> None:
         """Makes the current stream wait for every NMS issued on the side stream."""
