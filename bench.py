@@ -324,7 +324,7 @@ def main():
                          "surviving rows, so its DRAM traffic is below the algorithmic bytes and frac can exceed 1"
                          if dom == "decode_filter_kernel" else
                          ("duration measured while the NMS of the previous batch runs concurrently on the side stream "
-                          "(it shares the SMs); the same kernel alone: 68 us = 0.88 of peak, profiles/r1z_kernels.txt"
+                          "(it shares the SMs); the same kernel alone: 64 us = 0.94 of peak, profiles/r1z_kernels.txt"
                           if pipe.overlap else ""))}
 
     if rank != 0:

@@ -97,6 +97,12 @@ __device__ __forceinline__ void taps_dp2a(uint32_t w0, uint32_t w1, uint32_t w2,
     h[2] = __dp2a_lo(a01, p2, 0u);
 }
 
+#ifndef VK_LB_UNR
+#define VK_LB_UNR 2
+#endif
+#ifndef VK_LB_MINB
+#define VK_LB_MINB 3
+#endif
 constexpr int kLbRows = 8;        // canvas rows per block
 constexpr int kLbThreads = 320;   // 640-wide canvas = 2 columns per thread, no idle lanes
 #ifndef VK_GEN_ROWS
@@ -112,7 +118,7 @@ constexpr int kLbMaxSrcRows = 2 * kGenRows + 4;  // staged source rows (down-sca
 // 3 x 32-bit loads = 4 pixels, byte extract, /255, one 128-bit streaming store per plane.
 // ---------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(kLbThreads, (FMT == VK_LB_BF16_NCHW) ? 4 : 5)
+__global__ void __launch_bounds__(kLbThreads, (FMT == VK_LB_BF16_NCHW) ? (VK_LB_MINB > 4 ? 4 : VK_LB_MINB) : VK_LB_MINB)
 lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
                typename OutT<FMT>::type* __restrict__ dst_all) {
     using T = typename OutT<FMT>::type;
@@ -130,45 +136,60 @@ lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swa
     const int items = (y_end - y_begin) * gpr;
     // pad value per SOURCE channel slot (the store swaps planes for BGR input)
     const float fq0 = norm255((float)(swap_rb ? p2 : p0)), fq1 = norm255((float)p1), fq2 = norm255((float)(swap_rb ? p0 : p2));
-    for (int i = threadIdx.x; i < items; i += kLbThreads) {
-        const int ry = i / gpr;
-        const int x = (i - ry * gpr) * PX;
-        const int y = y_begin + ry;
-        const int sy = y - d.top, sx = x - d.left;
-        float o[3][PX];
-        if (sy >= 0 && sy < d.new_h && sx >= 0 && sx < d.new_w) {
-            const uint8_t* p = d.src + (size_t)sy * d.pitch + (size_t)sx * 3;
-            uint32_t w[NW];
+    // UNR items per pass: all their loads are issued before the first conversion, so a thread keeps
+    // UNR x 12 (24) bytes of reads and UNR x 3 plane stores in flight
+    constexpr int UNR = VK_LB_UNR;
+    for (int i0 = threadIdx.x; i0 < items; i0 += UNR * kLbThreads) {
+        uint32_t w[UNR][NW];
+        bool in[UNR];
+        size_t off[UNR];
 #pragma unroll
-            for (int k = 0; k < NW; ++k) w[k] = ld_stream_u32(p + 4 * k);
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * kLbThreads;
+            const int ry = i / gpr;
+            const int x = (i - ry * gpr) * PX;
+            const int y = y_begin + ry;
+            const int sy = y - d.top, sx = x - d.left;
+            off[u] = (size_t)y * out_w + x;
+            in[u] = i < items && sy >= 0 && sy < d.new_h && sx >= 0 && sx < d.new_w;
+            if (in[u]) {
+                const uint8_t* p = d.src + (size_t)sy * d.pitch + (size_t)sx * 3;
 #pragma unroll
-            for (int k = 0; k < PX; ++k) {       // byte 3k + j = pixel k, source channel j
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int bi = 3 * k + j;
-                    const float v = norm255((float)((w[bi >> 2] >> (8 * (bi & 3))) & 255u));
-                    o[j][k] = v;              // source channel order; the swap happens at the store
-                }
+                for (int k = 0; k < NW; ++k) w[u][k] = ld_stream_u32(p + 4 * k);
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < PX; ++k) { o[0][k] = fq0; o[1][k] = fq1; o[2][k] = fq2; }
         }
-        const size_t off = (size_t)y * out_w + x;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            T* const pl = dst + off + (size_t)((swap_rb && c != 1) ? 2 - c : c) * plane;   // BGR->RGB = plane swap
-            if constexpr (FMT == VK_LB_F32_NCHW) {
-                st_stream_f4(pl, make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
-            } else if constexpr (FMT == VK_LB_BF16_NCHW) {
-                uint32_t u[4];
+        for (int u = 0; u < UNR; ++u) {
+            if (i0 + u * kLbThreads >= items) break;
+            float o[3][PX];
+            if (in[u]) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[c][2 * k], o[c][2 * k + 1]);
-                    u[k] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int k = 0; k < PX; ++k) {       // byte 3k + j = pixel k, source channel j
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int bi = 3 * k + j;
+                        o[j][k] = norm255((float)((w[u][bi >> 2] >> (8 * (bi & 3))) & 255u));   // source channel order; the swap happens at the store
+                    }
                 }
-                asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
-                             :: "l"(pl), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+            } else {
+#pragma unroll
+                for (int k = 0; k < PX; ++k) { o[0][k] = fq0; o[1][k] = fq1; o[2][k] = fq2; }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T* const pl = dst + off[u] + (size_t)((swap_rb && c != 1) ? 2 - c : c) * plane;   // BGR->RGB = plane swap
+                if constexpr (FMT == VK_LB_F32_NCHW) {
+                    st_stream_f4(pl, make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
+                } else if constexpr (FMT == VK_LB_BF16_NCHW) {
+                    uint32_t uu[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o[c][2 * k], o[c][2 * k + 1]);
+                        uu[k] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+                                 :: "l"(pl), "r"(uu[0]), "r"(uu[1]), "r"(uu[2]), "r"(uu[3]) : "memory");
+                }
             }
         }
     }
