@@ -94,7 +94,7 @@ def cpu_reference_pass(imgs, levels):
     Detect decode, torch + torchvision.ops.nms (oracle/ref_port.py, pinned to the live
     reference by tests/test_oracle_golden.py)."""
     from oracle import ref_port
-    from vision_kit_b200 import synth
+    from tests import synth
     xs = [ref_port.preprocess(im, (IMG, IMG), is_bgr=True)[0] for im in imgs]
     pred, _ = ref_port.detect_decode(levels, synth.V5_ANCHORS, synth.STRIDES, "v5")
     dets = ref_port.nms(pred, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
@@ -102,7 +102,7 @@ def cpu_reference_pass(imgs, levels):
 
 
 def cpu_sample(n: int, seed: int = 0):
-    from vision_kit_b200 import synth
+    from tests import synth
     imgs = list(synth.images_u8(n, IMG, IMG, seed=seed))
     levels = [torch.from_numpy(x) for x in synth.head_logits(n, seed=2 + seed, clusters=20)]
     return imgs, levels
@@ -170,7 +170,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
-    from vision_kit_b200 import _lib, synth
+    from vision_kit_b200 import _lib
+    from tests import synth
     from vision_kit_b200.pipeline import DetectPipeline
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")

@@ -34,7 +34,6 @@ typedef void* vk_stream_t; /* a cudaStream_t (torch.cuda.current_stream().cuda_s
 
 #define VK_MAX_LEVELS 4
 #define VK_MAX_ANCHORS 8     /* anchors per level */
-#define VK_MAX_NMS 32768     /* largest max_nms (reference: 30000 / 10000) */
 #define VK_MAX_DET 1024      /* largest max_det (reference default 300) */
 #define VK_MAX_SEGMENTS 2048 /* candidate segments per image (64 rows each) */
 
@@ -43,13 +42,6 @@ int vk_version(void);                    /* 100*major + minor */
 const char* vk_last_error(void);         /* thread-local, never NULL */
 uint64_t vk_launch_count(void);          /* kernels launched by this library so far */
 
-/* Which kernel vk_decode_filter uses: VK_FILTER_AUTO picks from the threshold (conf < 0.05: the dense,
- * persistent kernel; else the group kernel that gathers surviving rows).  Both produce identical bits;
- * the setter exists for tuning and so that tests can run every case through both.  Returns the old mode. */
-#define VK_FILTER_AUTO 0
-#define VK_FILTER_SPARSE 1
-#define VK_FILTER_DENSE 2
-int vk_set_filter_kernel(int mode);
 int vk_build_arch(void);                 /* 100 => sm_100a */
 
 /* ---------------------------------------------------------------- letterbox
@@ -102,6 +94,13 @@ int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* descs_dev, in
                        int out_h, int out_w, int swap_rb, uint32_t pad_rgb, int dst_fmt,
                        void* dst, void* ws, size_t ws_bytes, vk_stream_t stream);
 
+/* Element type of the tensors a filter / decode call reads (AMP eval: the head's convs emit fp16,
+ * scripts/main.py:41).  Half values are up-cast exactly, so results equal the float32 call on the
+ * up-cast tensor bit for bit. */
+#define VK_F32 0
+#define VK_F16 1
+#define VK_BF16 2
+
 /* ---------------------------------------------------------------- Detect decode
  * Replaces the eval branch of models/heads/yolov5.py:54-78 and
  * models/heads/yolov7.py:62-90 after the 1x1 conv.
@@ -119,10 +118,9 @@ typedef struct VkHeadCfg {
 
 int vk_head_rows(const VkHeadCfg* cfg);  /* sum_l na*ny*nx (25200 at 640) */
 
-/* levels[l]: dev float32 (B, na*no, ny_l, nx_l) contiguous.  pred: dev float32
- * (B, rows, no).  raw[l]: dev float32 (B, na, ny_l, nx_l, no) or raw == NULL to skip the
- * permuted logits copy the reference also returns (yolov5.py:60,78). */
-int vk_detect_decode(const VkHeadCfg* cfg, const float* const* levels, int batch,
+/* levels[l]: dev (B, na*no, ny_l, nx_l) contiguous, element type `dtype` (VK_F32 / VK_F16 / VK_BF16).
+ * pred: dev float32 (B, rows, no).  raw[l]: dev float32 (B, na, ny_l, nx_l, no) or raw == NULL to skip the permuted logits copy the reference also returns (yolov5.py:60,78). */
+int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels, int dtype, int batch,
                      float* pred, float* const* raw, vk_stream_t stream);
 
 /* ---------------------------------------------------------------- candidates
@@ -130,37 +128,59 @@ int vk_detect_decode(const VkHeadCfg* cfg, const float* const* levels, int batch
  * obj > conf, cls *= obj, cxcywh->xyxy (utils/bboxes.py:103-111), multi-label
  * `nonzero` or best-class `max`, optional class filter.
  *
- * A candidate set lives in caller-owned device buffers described by VkCandBuf.  Candidates
- * are written in segments: every 64-row tile owns a fixed slot range of vk_cand_tile_slots()
- * entries, so the buffer needs cap >= segs * vk_cand_tile_slots(nc, multi_label) and can
- * never overflow.  The canonical order of the reference (row ascending, class ascending)
- * is segment order x in-segment order.
+ * A candidate set lives in caller-owned device buffers described by VkCandBuf.  Every 64-row
+ * tile ("segment") owns the fixed slot range [seg * T, (seg + 1) * T), T = vk_cand_tile_slots(),
+ * and writes its candidates there in the reference's order (row ascending, class ascending), so
+ * the buffer needs cap >= segs * T and can never overflow, and SLOT ORDER IS THE CANONICAL ORDER
+ * of the reference's candidate list (the order that breaks score ties in its argsort and NMS).
+ *
+ * Two optional accelerators for vk_nms_batched (results never depend on them):
+ *   list  the sparse filter kernels append every candidate as (ordered score << 32 | ~slot) to
+ *         an unordered per-image list while the image has <= list_cap candidates;
+ *   hist  scratch of vk_nms_batched: when an image has more candidates than the list holds (eval
+ *         thresholds), a sampled score histogram picks the score bound above which a grid-wide pass
+ *         copies the candidates into the list.  Allocate it when such images are expected.
  */
+#define VK_HIST_BINS 1024   /* bin = (0x3f800000 - score bits) >> 20: 8 bins per octave below 1.0 */
+#define VK_CTRL_WORDS 4     /* ctrl rows: 0 candidate count, 1 flags | slots per tile / 64 << 8, 2 list entries, 3 list bound */
+#define VK_FLAG_LIST 2      /* list[b] holds every candidate with ordered score >= bound (set by vk_nms_batched) */
+#define VK_FLAG_APPENDED 4  /* the filter kernel appended its candidates to list[b] (complete iff count <= list_cap) */
+
 typedef struct VkCandBuf {
     uint64_t* cand;      /* dev [batch][cap]: low 32 = score bits, high 32 = row*nc + cls */
     float* boxes;        /* dev [batch][rows][4] xyxy of rows that produced candidates */
-    int32_t* counts;     /* dev [batch] candidates per image (informational; zeroed by the filter call) */
-    int32_t* seg_base;   /* dev [batch][segs] first slot of each segment */
-    int32_t* seg_count;  /* dev [batch][segs] */
+    int32_t* ctrl;       /* dev [VK_CTRL_WORDS][batch]; zeroed by the filter call */
+    int32_t* seg_count;  /* dev [batch][segs] candidates of each segment */
+    uint64_t* list;      /* dev [batch][list_cap] or NULL */
+    uint32_t* hist;      /* dev [batch][VK_HIST_BINS] or NULL */
     int32_t cap;         /* candidate slots per image */
     int32_t rows;        /* prediction rows per image */
     int32_t segs;        /* segments per image (vk_filter_segments / vk_decode_filter_segments) */
     int32_t nc;
+    int32_t list_cap;    /* entries per image in `list` (0 with list == NULL) */
+    int32_t reserved;
 } VkCandBuf;
 
 int vk_cand_tile_slots(int nc, int multi_label);     /* 64 * nc (multi-label, nc > 1) or 64 */
 int vk_filter_segments(int rows);                    /* for vk_filter_pred */
 int vk_decode_filter_segments(const VkHeadCfg* cfg); /* for vk_decode_filter */
 
+/* Which kernel a filter call uses (per call; both produce identical candidates, boxes and counts):
+ * AUTO picks from the threshold (conf < 0.05, where most rows survive: DENSE); SPARSE = one warp per
+ * 64-row tile gathering only the rows with obj > conf; DENSE = persistent, whole tiles staged in shared memory. */
+#define VK_FILTER_AUTO 0
+#define VK_FILTER_SPARSE 1
+#define VK_FILTER_DENSE 2
+
 /* class_mask: dev uint32[(nc+31)/32] bitmap of allowed classes or NULL (classes=None). */
-int vk_filter_pred(const float* pred, int batch, int rows, int nc, float conf_thres,
-                   int multi_label, const uint32_t* class_mask, const VkCandBuf* out,
+int vk_filter_pred(const void* pred, int dtype, int batch, int rows, int nc, float conf_thres,
+                   int multi_label, const uint32_t* class_mask, int kernel, const VkCandBuf* out,
                    vk_stream_t stream);
 
 /* Fused Detect decode + confidence filter straight from the conv outputs: the
  * (B, rows, no) prediction tensor is never materialised. */
-int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch,
-                     float conf_thres, int multi_label, const uint32_t* class_mask,
+int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels, int dtype, int batch,
+                     float conf_thres, int multi_label, const uint32_t* class_mask, int kernel,
                      const VkCandBuf* out, vk_stream_t stream);
 
 /* Fused Detect head: the 1x1 conv of models/heads/yolov5.py:58 / yolov7.py:67-71
@@ -172,17 +192,15 @@ int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch
  *   out        the candidate buffer of vk_decode_filter (same sizes), consumed by vk_nms_batched
  *   fault      dev int32, set to 1 if a tensor-core completion wait timed out (never observed; the
  *              kernel then terminates instead of hanging)
+ *   kernel     VK_CONV_PERSISTENT (one CTA per SM: two producer teams, one MMA-issuing lane, two epilogue
+ *              groups over a double-buffered TMEM accumulator) or VK_CONV_TILE (one tile per CTA, 2 CTAs
+ *              per SM); identical results.
  * Logits differ from an fp32 conv by TF32 input rounding (~1e-3 relative). */
-/* Two implementations with identical results: VK_CONV_PERSISTENT (default; one CTA per SM: two producer
- * teams, one MMA-issuing lane, two epilogue groups over a double-buffered TMEM accumulator) and
- * VK_CONV_TILE (one tile per CTA, 2 CTAs per SM; 281 vs 239 us per 64 images at YOLOv5s widths).
- * The setter exists for tuning and so that the tests cover both.  Returns the old mode. */
 #define VK_CONV_TILE 0
 #define VK_CONV_PERSISTENT 1
-int vk_set_conv_kernel(int mode);
 int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const int32_t* cin,
                           const float* const* weights, const float* const* biases, int batch,
-                          float conf_thres, int multi_label, const uint32_t* class_mask,
+                          float conf_thres, int multi_label, const uint32_t* class_mask, int kernel,
                           const VkCandBuf* out, int32_t* fault, vk_stream_t stream);
 
 /* ---------------------------------------------------------------- NMS
@@ -194,15 +212,16 @@ int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const
  * dets: dev float32 (B, max_det, 6) [x1,y1,x2,y2,conf,cls], rows >= det_counts[b] zeroed.
  * keep_idx: dev int64 (B, max_det) or NULL -- indices torchvision.ops.nms returned
  *   (into the candidate list the reference handed it), -1 padded.
- * status: dev int32[batch] or NULL; bit0 = a segment reached past cap (results invalid;
- *   cannot happen with buffers sized as above).
+ * status: dev int32[batch] or NULL; always written 0 (kept for callers that check it: a
+ *   candidate buffer sized as above cannot overflow).
+ * Two launches: a grid-wide selection pass that builds the per-image top list from the filter's
+ * score histogram (returns at once for images without one), and one CTA per image that consumes
+ * candidates in descending score order, a stage of <= 2048 at a time, until max_det boxes are kept.
+ * Writes ctrl rows 1-3 of the candidate buffer (the list it builds); needs no workspace.
  */
-size_t vk_nms_workspace_bytes(int batch, int max_nms);
-
-int vk_nms_batched(const VkCandBuf* cand, int batch, float conf_unused, double iou_thres,
-                   int agnostic, int max_nms, int max_det, float max_wh, float* dets,
-                   int32_t* det_counts, int64_t* keep_idx, int32_t* status, void* ws,
-                   size_t ws_bytes, vk_stream_t stream);
+int vk_nms_batched(const VkCandBuf* cand, int batch, double iou_thres, int agnostic, int max_nms,
+                   int max_det, float max_wh, float* dets, int32_t* det_counts, int64_t* keep_idx,
+                   int32_t* status, vk_stream_t stream);
 
 /* ---------------------------------------------------------------- small ops */
 /* utils/image_proc.py:63-80 `scale_coords` (+ utils/bboxes.py:50-59 `clip_coords`):

@@ -8,7 +8,7 @@ NMS overlapped on the side stream): python profiles/config_bench.py > gpurun_out
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from vision_kit_b200 import synth
+from tests import synth
 from vision_kit_b200.pipeline import DetectPipeline
 dev = torch.device("cuda:0")
 res = {}

@@ -5,7 +5,8 @@ B = 64 at 640: python profiles/conv_head_bench.py > gpurun_out/conv_head.json"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from vision_kit_b200 import ops, synth
+from vision_kit_b200 import ops
+from tests import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 from vision_kit_b200 import _lib
 _lib.lib().vk_set_conv_kernel(int(os.environ.get("VK_CONV_MODE", "1")))   # 1 = persistent warp-specialised kernel (default), 0 = tile kernel

@@ -8,7 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from oracle import ref_port
-from vision_kit_b200 import ops, synth
+from vision_kit_b200 import ops
+from tests import synth
 from vision_kit_b200.processing import ImageProcessor
 
 dev = torch.device("cuda:0")

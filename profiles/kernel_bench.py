@@ -9,7 +9,8 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from vision_kit_b200 import _lib, ops, synth
+from vision_kit_b200 import _lib, ops
+from tests import synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -78,6 +79,9 @@ report("detect_decode -> pred", ms, 2 * in_bytes)
 ms = timeit(lambda: ops.detect_decode(cfg, lv, want_raw=True))
 report("detect_decode -> pred + raw", ms, 3 * in_bytes, "the reference's full return value")
 pred = ops.detect_decode(cfg, lv)
+lv16 = [t.half() for t in lv]
+ms = timeit(lambda: ops.detect_decode(cfg, lv16))
+report("detect_decode fp16 in -> pred", ms, in_bytes // 2 + in_bytes, "AMP eval: fp16 conv outputs")
 for mode, conf, ml, iou in (("demo", 0.25, False, 0.45), ("eval", 0.001, True, 0.6)):
     buf = ops.filter_pred(pred, conf, ml)
     ncand = int(buf.counts.sum())
@@ -86,10 +90,21 @@ for mode, conf, ml, iou in (("demo", 0.25, False, 0.45), ("eval", 0.001, True, 0
     buf2 = ops.decode_filter(cfg, lv, conf, ml)
     ms = timeit(lambda: ops.decode_filter(cfg, lv, conf, ml, buf=buf2))
     report(f"decode_filter {mode}", ms, in_bytes + 8 * ncand)
+    buf16 = ops.decode_filter(cfg, lv16, conf, ml)
+    ms = timeit(lambda: ops.decode_filter(cfg, lv16, conf, ml, buf=buf16))
+    report(f"decode_filter {mode} fp16 in", ms, in_bytes // 2 + 8 * int(buf16.counts.sum()), "bytes = full fp16 conv-output read")
     outb = ops.nms_batched(buf2, iou)
-    ws = torch.empty(_lib.lib().vk_nms_workspace_bytes(B, 30000), dtype=torch.uint8, device=dev)
-    ms = timeit(lambda: ops.nms_batched(buf2, iou, out=outb, ws=ws), iters=10)
+    ms = timeit(lambda: ops.nms_batched(buf2, iou, out=outb), iters=10)
     report(f"nms {mode}", ms, 24 * ncand + B * 300 * 24, f"{int(outb.counts.sum()) // B} dets/img")
+    if mode == "eval":
+        outa = ops.nms_batched(buf2, iou, agnostic=True)
+        ms = timeit(lambda: ops.nms_batched(buf2, iou, agnostic=True, out=outa), iters=10)
+        report("nms eval agnostic", ms, 24 * ncand + B * 300 * 24, f"{int(outa.counts.sum()) // B} dets/img")
+        h = B // 2
+        bufh = ops.decode_filter(cfg, [t[:h] for t in lv], conf, ml)
+        outh = ops.nms_batched(bufh, iou)
+        ms = timeit(lambda: ops.nms_batched(bufh, iou, out=outh), iters=10)
+        report(f"nms eval, {h} images", ms * 2, 24 * ncand + B * 300 * 24, f"(ms, GB/s scaled to {B} images) actual {ms*1e3:.1f} us per {h}")
 # plain logits (no planted clusters): SURVEY.md §8d base workload
 lv0 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=0)]
 buf3 = ops.decode_filter(cfg, lv0, 0.25, False)

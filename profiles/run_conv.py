@@ -3,7 +3,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from vision_kit_b200 import _lib, ops, synth
+from vision_kit_b200 import _lib, ops
+from tests import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 conf = float(sys.argv[2]) if len(sys.argv) > 2 else 0.25
 _lib.lib().vk_set_conv_kernel(int(sys.argv[3]) if len(sys.argv) > 3 else 1)

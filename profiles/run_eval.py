@@ -3,7 +3,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from vision_kit_b200 import ops, synth
+from vision_kit_b200 import ops
+from tests import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]

@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from vision_kit_b200 import dist as vkd, ops, synth
+from vision_kit_b200 import dist as vkd, ops
+from tests import synth
 
 N_IMAGES = 22          # not a multiple of the world size: shards differ by one image
 

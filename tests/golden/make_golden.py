@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import live                      # noqa: E402
-from vision_kit_b200 import synth            # noqa: E402
+from tests import synth                      # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 

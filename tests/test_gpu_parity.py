@@ -11,7 +11,7 @@ import torch
 
 from oracle import ref_port, restate
 from tests.golden.make_golden import LETTERBOX_CASES, NMS_CASES, case_seed
-from vision_kit_b200 import synth
+from tests import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -285,11 +285,15 @@ def test_fused_decode_filter_equals_two_step_and_oracle(variant, kw, vk, cuda):
 
 
 def _canonical(buf):
-    """Candidate lists in canonical order + boxes of the candidate rows, per image (host copies)."""
-    cand, base, cnt, boxes = buf.cand.cpu().numpy(), buf.seg_base.cpu().numpy(), buf.seg_count.cpu().numpy(), buf.boxes.cpu().numpy()
+    """Candidate lists in canonical order + boxes of the candidate rows, per image (host copies).
+    Segment s owns the slots [s * T, (s + 1) * T), T as the filter kernel recorded it."""
+    cand, cnt, boxes = buf.cand.cpu().numpy(), buf.seg_count.cpu().numpy(), buf.boxes.cpu().numpy()
+    slots = buf.tile_slots.cpu().numpy()
     out = []
     for b in range(cand.shape[0]):
-        lst = np.concatenate([cand[b, base[b, s]: base[b, s] + cnt[b, s]] for s in range(buf.segs)] or [np.zeros(0, np.int64)])
+        T = int(slots[b])
+        assert T in (64, 64 * buf.nc) and int(cnt[b].sum()) == int(buf.counts[b])
+        lst = np.concatenate([cand[b, s * T: s * T + cnt[b, s]] for s in range(buf.segs)] or [np.zeros(0, np.int64)])
         rows = np.unique((lst >> 32) // buf.nc)
         out.append((lst, rows, boxes[b, rows]))
     return out
@@ -312,21 +316,16 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
     candidates (order included), boxes, counts and therefore the same detections."""
     cfg, _ = _cfg(vk, variant, img=img, nc=nc)
     lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(3, seed=77 + nc, img=img, nc=nc, clusters=12)]
-    from vision_kit_b200 import _lib
-    L = _lib.lib()
     res, resp = {}, {}
     pred = vk.ops.detect_decode(cfg, lv)
-    try:
-        for mode in (1, 2):       # VK_FILTER_SPARSE, VK_FILTER_DENSE
-            L.vk_set_filter_kernel(mode)
-            buf = vk.ops.decode_filter(cfg, lv, conf, ml, classes=classes)
-            out = vk.ops.nms_batched(buf, 0.6, want_keep=True)
-            bufp = vk.ops.filter_pred(pred, conf, ml, classes=classes)      # the nms(prediction) drop-in path
-            torch.cuda.synchronize()
-            res[mode] = (_canonical(buf), buf.counts.cpu().numpy(), out)
-            resp[mode] = (_canonical(bufp), bufp.counts.cpu().numpy())
-    finally:
-        L.vk_set_filter_kernel(0)
+    for mode, kernel in ((1, "sparse"), (2, "dense")):
+        buf = vk.ops.decode_filter(cfg, lv, conf, ml, classes=classes, kernel=kernel)
+        out = vk.ops.nms_batched(buf, 0.6, want_keep=True)
+        bufp = vk.ops.filter_pred(pred, conf, ml, classes=classes, kernel=kernel)      # the nms(prediction) drop-in path
+        outp = vk.ops.nms_batched(bufp, 0.6, want_keep=True)
+        torch.cuda.synchronize()
+        res[mode] = (_canonical(buf), buf.counts.cpu().numpy(), out)
+        resp[mode] = (_canonical(bufp), bufp.counts.cpu().numpy(), outp)
     (ca, na, oa), (cb, nb, ob) = res[1], res[2]
     assert np.array_equal(na, nb)
     assert na.sum() > 0 or conf >= 0.25
@@ -338,6 +337,44 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
         assert np.array_equal(resp[m][1], na)
         for (lp, rp, bp), (la, ra, ba) in zip(resp[m][0], ca):
             assert np.array_equal(lp, la) and np.array_equal(rp, ra) and np.array_equal(bp, ba)
+        op = resp[m][2]
+        assert torch.equal(op.counts, oa.counts) and torch.equal(op.dets, oa.dets) and torch.equal(op.keep, oa.keep)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("variant,nc,img,conf,ml", [
+    ("v5", 80, 640, 0.25, False),
+    ("v7", 80, 640, 0.001, True),
+    ("v5", 17, 672, 0.01, True),          # 84/42/21 grids: unaligned planes, partial tiles
+    ("v7", 3, 320, 0.3, False),
+])
+def test_half_precision_logits_equal_upcast_float32(dtype, variant, nc, img, conf, ml, vk, cuda):
+    """AMP eval hands the head's conv outputs over in float16 (scripts/main.py:41).  The kernels up-cast
+    exactly, so every result must equal the float32 kernels fed the up-cast tensor, bit for bit."""
+    cfg, _ = _cfg(vk, variant, img=img, nc=nc)
+    lvh = [torch.from_numpy(x).to(cuda).to(dtype) for x in synth.head_logits(2, seed=5 + nc, img=img, nc=nc, clusters=10)]
+    lvf = [t.float() for t in lvh]
+    ph, rh = vk.ops.detect_decode(cfg, lvh, want_raw=True)
+    pf, rf = vk.ops.detect_decode(cfg, lvf, want_raw=True)
+    assert torch.equal(ph, pf)
+    for a, b in zip(rh, rf):
+        assert torch.equal(a, b)
+    for kernel in ("sparse", "dense"):
+        bh = vk.ops.decode_filter(cfg, lvh, conf, ml, kernel=kernel)
+        bf = vk.ops.decode_filter(cfg, lvf, conf, ml, kernel=kernel)
+        assert torch.equal(bh.counts, bf.counts) and int(bf.counts.sum()) > 0
+        for (la, ra, ba), (lb, rb, bb) in zip(_canonical(bh), _canonical(bf)):
+            assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
+        oh = vk.ops.nms_batched(bh, 0.5, want_keep=True)
+        of = vk.ops.nms_batched(bf, 0.5, want_keep=True)
+        assert torch.equal(oh.dets, of.dets) and torch.equal(oh.keep, of.keep) and torch.equal(oh.counts, of.counts)
+        # a half-precision prediction tensor through the nms(prediction) drop-in path
+        predh = pf.to(dtype)
+        qh = vk.ops.filter_pred(predh, conf, ml, kernel=kernel)
+        qf = vk.ops.filter_pred(predh.float(), conf, ml, kernel=kernel)
+        assert torch.equal(qh.counts, qf.counts)
+        for (la, ra, ba), (lb, rb, bb) in zip(_canonical(qh), _canonical(qf)):
+            assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
 
 
 def test_head_forward_nms(vk, cuda):
@@ -510,8 +547,8 @@ def test_nms_many_stages_heavy_suppression(vk, cuda):
     assert np.array_equal(dets[0].cpu().numpy(), outs[0].numpy())
 
 
-def test_nms_oversized_tie_group_falls_back(vk, cuda):
-    # 5000 bit-identical scores: larger than a stage -> the one-shot kernel redoes the image
+def test_nms_oversized_tie_group_is_split_by_slot(vk, cuda):
+    # 5000 bit-identical scores: larger than a stage -> the radix selection runs on into the slot bits
     rng = np.random.Generator(np.random.PCG64(23))
     rows, nc = 6000, 4
     p = np.zeros((2, rows, 5 + nc), np.float32)
@@ -691,13 +728,8 @@ def test_conv_head_matches_conv_then_filter(variant, conf, ml, cins, B, vk, cuda
     ref = vk.ops.decode_filter(cfg, logits, conf, ml)
     got = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
     # the one-tile-per-CTA variant must produce the very same bits as the (default) persistent kernel
-    from vision_kit_b200 import _lib
-    _lib.lib().vk_set_conv_kernel(0)
-    try:
-        got2 = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
-        torch.cuda.synchronize()
-    finally:
-        _lib.lib().vk_set_conv_kernel(1)
+    got2 = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml, persistent=False)
+    torch.cuda.synchronize()
     assert int(got.fault.item()) == 0 and int(got2.fault.item()) == 0
     assert torch.equal(got.counts, got2.counts)
     for (la, ra, ba), (lb, rb, bb) in zip(_canonical(got), _canonical(got2)):

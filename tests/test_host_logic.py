@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.VkLbDesc) == 48
     assert C.sizeof(_lib.VkLbGeom) == 64
     assert C.sizeof(_lib.VkHeadCfg) == 4 * 4 + 4 * 4 * 2 + 4 * 4 + 4 * 16 * 4
-    assert C.sizeof(_lib.VkCandBuf) == 5 * 8 + 4 * 4
+    assert C.sizeof(_lib.VkCandBuf) == 6 * 8 + 6 * 4
 
 
 def test_geometry_equals_oracle(vk_lib):
@@ -68,11 +68,9 @@ def test_argument_validation_without_gpu(vk_lib):
     with pytest.raises(_lib.VkError):
         ops.head_rows(cfg)
     assert vk_lib.vk_letterbox_workspace_bytes(64, 640, 640) == 3072 + 64 * 1280 * 16
-    assert vk_lib.vk_nms_workspace_bytes(4, 30000) == 4 * 32768 * 4 + 4 * 4   # sel + need_big flags
-    assert vk_lib.vk_nms_workspace_bytes(4, 40000) == 0          # > VK_MAX_NMS
     # null pointers / out-of-range thresholds are rejected before any launch
-    assert vk_lib.vk_nms_batched(None, 1, 0.0, 0.5, 0, 30000, 300, 7680.0, None, None, None, None, None, 0, None) == -1
-    assert vk_lib.vk_filter_pred(None, 1, 100, 80, 0.25, 0, None, None, None) == -1
+    assert vk_lib.vk_nms_batched(None, 1, 0.5, 0, 30000, 300, 7680.0, None, None, None, None, None) == -1
+    assert vk_lib.vk_filter_pred(None, 0, 1, 100, 80, 0.25, 0, None, 0, None, None) == -1
     assert vk_lib.vk_scale_coords(None, 0, 4, 0.0, 0.0, 1.0, 1, -1.0, -1.0, None) == 0   # n = 0 is a no-op
 
 
@@ -180,11 +178,30 @@ def test_dataset_geometry_equals_oracle(vk_lib):
     assert vk_lib.vk_dataset_geometry(1000, 500, 512, 640, C.byref(g)) == -1      # 640 tall on a 512 canvas
 
 
-def test_kernel_selectors_validate_and_restore(vk_lib):
-    """vk_set_filter_kernel / vk_set_conv_kernel: return the previous mode, reject unknown ones."""
-    assert vk_lib.vk_set_filter_kernel(2) == 0 and vk_lib.vk_set_filter_kernel(0) == 2
-    assert vk_lib.vk_set_filter_kernel(7) == -1 and b"mode 7" in vk_lib.vk_last_error()
-    assert vk_lib.vk_set_conv_kernel(0) == 1 and vk_lib.vk_set_conv_kernel(1) == 0     # default: persistent
-    assert vk_lib.vk_set_conv_kernel(5) == -1
+def test_filter_and_nms_argument_validation(vk_lib):
+    """Entry points reject bad arguments before touching the device: unknown kernel selector / dtype,
+    thresholds outside [0, 1], inconsistent candidate buffers."""
+    from vision_kit_b200 import _lib, ops
+    cfg = ops.head_cfg("v5", 80, [[10, 13, 16, 30, 33, 23]] * 3, (8, 16, 32), [(80, 80), (40, 40), (20, 20)])
+    lv = (C.c_void_p * 4)(256, 256, 256, 0)
+    cb = _lib.VkCandBuf()
+    cb.cand = cb.boxes = cb.ctrl = cb.seg_count = 256
+    cb.cap, cb.rows, cb.segs, cb.nc = 396 * 64, 25200, 396, 80
+    args = lambda dtype, conf, kernel: (C.byref(cfg), C.cast(lv, C.c_void_p), dtype, 2, C.c_float(conf), 0, None, kernel,
+                                        C.byref(cb), None)
+    assert vk_lib.vk_decode_filter(*args(0, 0.25, 7)) == -1 and b"kernel 7" in vk_lib.vk_last_error()
+    assert vk_lib.vk_decode_filter(*args(5, 0.25, 0)) == -1 and b"dtype 5" in vk_lib.vk_last_error()
+    assert vk_lib.vk_decode_filter(*args(0, 1.5, 0)) == -1 and b"conf_thres" in vk_lib.vk_last_error()
+    cb.list_cap = 100                                                  # list_cap without a list
+    assert vk_lib.vk_decode_filter(*args(0, 0.25, 0)) == -1 and b"list" in vk_lib.vk_last_error()
+    cb.list_cap = 0
+    cb.cap = 100                                                       # too few slots: every tile owns 64
+    assert vk_lib.vk_decode_filter(*args(0, 0.25, 0)) == -1 and b"cap 100" in vk_lib.vk_last_error()
+    assert vk_lib.vk_nms_batched(C.byref(cb), 2, C.c_double(1.5), 0, 30000, 300, C.c_float(7680.0), 256, 256, None, None,
+                                 None) == -1 and b"iou_thres" in vk_lib.vk_last_error()
+    assert vk_lib.vk_nms_batched(C.byref(cb), 2, C.c_double(0.5), 0, 30000, 5000, C.c_float(7680.0), 256, 256, None, None,
+                                 None) == -3                            # VK_E_LIMIT: max_det
     assert vk_lib.vk_eval_match_smem_bytes(10, 100) == 100 * 6 * 4 + 10 * 100 * 4
     assert vk_lib.vk_eval_match_smem_bytes(0, 100) == 0
+    assert ops.expects_dense("auto", 0.001) and not ops.expects_dense("auto", 0.25) and ops.expects_dense("dense", 0.25)
+    assert _lib.C.sizeof(_lib.VkCandBuf) == 6 * 8 + 6 * 4

@@ -15,11 +15,16 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "vk_b200.h")
 
 VK_MAX_LEVELS = 4
 VK_MAX_ANCHORS = 8
-VK_MAX_NMS = 32768
 VK_MAX_DET = 1024
 VK_MAX_SEGMENTS = 2048
 VK_LB_F32_NCHW, VK_LB_BF16_NCHW, VK_LB_U8_NHWC = 0, 1, 2
 VK_HEAD_V5, VK_HEAD_V7 = 0, 1
+VK_F32, VK_F16, VK_BF16 = 0, 1, 2
+VK_FILTER_AUTO, VK_FILTER_SPARSE, VK_FILTER_DENSE = 0, 1, 2
+VK_CONV_TILE, VK_CONV_PERSISTENT = 0, 1
+VK_HIST_BINS = 1024
+VK_CTRL_WORDS = 4
+VK_FLAG_LIST, VK_FLAG_APPENDED = 2, 4
 
 
 class VkError(RuntimeError):
@@ -52,9 +57,10 @@ class VkHeadCfg(C.Structure):
 
 
 class VkCandBuf(C.Structure):
-    _fields_ = [("cand", C.c_void_p), ("boxes", C.c_void_p), ("counts", C.c_void_p),
-                ("seg_base", C.c_void_p), ("seg_count", C.c_void_p),
-                ("cap", C.c_int32), ("rows", C.c_int32), ("segs", C.c_int32), ("nc", C.c_int32)]
+    _fields_ = [("cand", C.c_void_p), ("boxes", C.c_void_p), ("ctrl", C.c_void_p),
+                ("seg_count", C.c_void_p), ("list", C.c_void_p), ("hist", C.c_void_p),
+                ("cap", C.c_int32), ("rows", C.c_int32), ("segs", C.c_int32), ("nc", C.c_int32),
+                ("list_cap", C.c_int32), ("reserved", C.c_int32)]
 
 
 assert C.sizeof(VkLbDesc) == 48 and C.sizeof(VkLbGeom) == 64
@@ -64,8 +70,6 @@ _PROTOS = {
     "vk_version": (C.c_int, []),
     "vk_last_error": (C.c_char_p, []),
     "vk_launch_count": (C.c_uint64, []),
-    "vk_set_filter_kernel": (C.c_int, [C.c_int]),
-    "vk_set_conv_kernel": (C.c_int, [C.c_int]),
     "vk_build_arch": (C.c_int, []),
     "vk_letterbox_geometry": (C.c_int, [C.c_int] * 8 + [C.POINTER(VkLbGeom)]),
     "vk_dataset_geometry": (C.c_int, [C.c_int] * 4 + [C.POINTER(VkLbGeom)]),
@@ -73,19 +77,18 @@ _PROTOS = {
     "vk_letterbox_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                      C.c_int, _P, _P, C.c_size_t, _P]),
     "vk_head_rows": (C.c_int, [C.POINTER(VkHeadCfg)]),
-    "vk_detect_decode": (C.c_int, [C.POINTER(VkHeadCfg), _P, C.c_int, _P, _P, _P]),
+    "vk_detect_decode": (C.c_int, [C.POINTER(VkHeadCfg), _P, C.c_int, C.c_int, _P, _P, _P]),
     "vk_cand_tile_slots": (C.c_int, [C.c_int, C.c_int]),
     "vk_filter_segments": (C.c_int, [C.c_int]),
     "vk_decode_filter_segments": (C.c_int, [C.POINTER(VkHeadCfg)]),
-    "vk_filter_pred": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P,
+    "vk_filter_pred": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.c_int,
                                  C.POINTER(VkCandBuf), _P]),
-    "vk_decode_filter": (C.c_int, [C.POINTER(VkHeadCfg), _P, C.c_int, C.c_float, C.c_int, _P,
+    "vk_decode_filter": (C.c_int, [C.POINTER(VkHeadCfg), _P, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.c_int,
                                    C.POINTER(VkCandBuf), _P]),
-    "vk_conv_decode_filter": (C.c_int, [C.POINTER(VkHeadCfg), _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P,
+    "vk_conv_decode_filter": (C.c_int, [C.POINTER(VkHeadCfg), _P, _P, _P, _P, C.c_int, C.c_float, C.c_int, _P, C.c_int,
                                         C.POINTER(VkCandBuf), _P, _P]),
-    "vk_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
-    "vk_nms_batched": (C.c_int, [C.POINTER(VkCandBuf), C.c_int, C.c_float, C.c_double, C.c_int,
-                                 C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vk_nms_batched": (C.c_int, [C.POINTER(VkCandBuf), C.c_int, C.c_double, C.c_int,
+                                 C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P]),
     "vk_scale_coords": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                   C.c_float, C.c_float, _P]),
     "vk_cxcywh_to_xyxy": (C.c_int, [_P, _P, C.c_int, _P]),

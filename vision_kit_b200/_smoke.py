@@ -10,7 +10,8 @@ def run() -> None:
     if not torch.cuda.is_available():
         raise RuntimeError("smoke() needs a CUDA device")
     from oracle import ref_port
-    from . import _lib, ops, synth
+    from tests import synth
+    from . import _lib, ops
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     n0 = _lib.launch_count()

@@ -1,6 +1,10 @@
 // Error reporting, launch accounting and the small element-wise entry points.
 #include "vk_common.cuh"
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace vk {
 
 static thread_local char g_err[512] = "";
@@ -33,6 +37,37 @@ int check_launch(const char* what) {
     return (int)e;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static std::mutex g_attr_mutex;
+static std::map<std::pair<int, const void*>, size_t> g_smem_set;                       // (device, kernel) -> limit set
+static std::map<std::tuple<int, const void*, int, size_t>, int> g_occupancy;
+
+int ensure_dyn_smem(const void* func, size_t bytes, const char* who) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    size_t& cur = g_smem_set[{dev, func}];
+    if (bytes <= cur) return VK_OK;
+    if (bytes > 48 * 1024 || cur > 0) {
+        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail_code((int)e, "%s: %zu B of shared memory: %s", who, bytes, cudaGetErrorString(e));
+    }
+    cur = bytes;
+    return VK_OK;
+}
+
+int blocks_per_sm(const void* func, int threads, size_t dyn_smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    auto key = std::make_tuple(dev, func, threads, dyn_smem);
+    auto it = g_occupancy.find(key);
+    if (it != g_occupancy.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, func, threads, dyn_smem) != cudaSuccess || n < 1) n = 1;
+    g_occupancy[key] = n;
+    return n;
+}
 
 // utils/image_proc.py:76-79: coords[:, [0,2]] -= pad[0]; coords[:, [1,3]] -= pad[1];
 // coords[:, :4] /= gain; clip_coords (utils/bboxes.py:50-59).  float32 ops, one rounding each.
@@ -68,18 +103,6 @@ using namespace vk;
 
 extern "C" int vk_version(void) { return 100; }
 extern "C" const char* vk_last_error(void) { return g_err; }
-static std::atomic<int> g_filter_mode{VK_FILTER_AUTO};
-int vk::filter_mode() { return g_filter_mode.load(std::memory_order_relaxed); }
-extern "C" int vk_set_filter_kernel(int mode) {
-    if (mode < VK_FILTER_AUTO || mode > VK_FILTER_DENSE) return fail_arg("vk_set_filter_kernel: mode %d", mode);
-    return g_filter_mode.exchange(mode, std::memory_order_relaxed);
-}
-static std::atomic<int> g_conv_mode{VK_CONV_PERSISTENT};
-int vk::conv_mode() { return g_conv_mode.load(std::memory_order_relaxed); }
-extern "C" int vk_set_conv_kernel(int mode) {
-    if (mode != VK_CONV_TILE && mode != VK_CONV_PERSISTENT) return fail_arg("vk_set_conv_kernel: mode %d", mode);
-    return g_conv_mode.exchange(mode, std::memory_order_relaxed);
-}
 extern "C" uint64_t vk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int vk_build_arch(void) { return 100; }
 

@@ -200,8 +200,8 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
                                  decode_elem(box_l[3], 3, 0.f, gbase.stride, ah, gbase.variant));
         }
         if ((tid & 63) == 0 && seg_exists) {
-            A.seg_base[(size_t)b * A.segs + seg] = seg_total ? seg * A.tile_cap : 0;
             A.seg_count[(size_t)b * A.segs + seg] = seg_total;
+            if (seg == 0) A.flags[b] = cand_flags(A, false);
             if (seg_total) atomicAdd(A.counts + b, seg_total);
         }
         ch_bar_sync(bar_id);                                       // s_wtot is reused by the next anchor
@@ -580,12 +580,13 @@ using namespace vk;
 
 extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const int32_t* cin,
                                      const float* const* weights, const float* const* biases, int batch,
-                                     float conf_thres, int multi_label, const uint32_t* class_mask,
+                                     float conf_thres, int multi_label, const uint32_t* class_mask, int kernel,
                                      const VkCandBuf* out, int32_t* fault, vk_stream_t stream_) {
     HeadDev H;
     if (int rc = make_head(cfg, &H, "vk_conv_decode_filter")) return rc;
     if (batch == 0) return VK_OK;
     if (!feats || !cin || !weights || !fault || batch < 0) return fail_arg("vk_conv_decode_filter: null/negative argument");
+    if (kernel != VK_CONV_TILE && kernel != VK_CONV_PERSISTENT) return fail_arg("vk_conv_decode_filter: kernel %d", kernel);
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_conv_decode_filter: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: batch %d > 65535", batch);
     if (H.na * H.no > kChN || (H.na - 1) * H.no + 5 + 16 * ceil_div(H.nc, 16) > kChN)
@@ -606,18 +607,18 @@ extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* f
     for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) C.mtile_start[l] = mt;
     C.mtiles = mt;
     cudaStream_t stream = as_stream(stream_);
-    cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(fault, 0, sizeof(int32_t), stream);
+    if (int rc = reset_cand(out, batch, "vk_conv_decode_filter", stream)) return rc;
+    cudaError_t e = cudaMemsetAsync(fault, 0, sizeof(int32_t), stream);
     if (e != cudaSuccess) return fail_code((int)e, "vk_conv_decode_filter: memset: %s", cudaGetErrorString(e));
-    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
-    if (conv_mode() == VK_CONV_PERSISTENT) {
+    FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
+    if (kernel == VK_CONV_PERSISTENT) {
         const int total = mt * batch;
-        cudaFuncSetAttribute(conv_decode_filter_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem);
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv_decode_filter_ws_kernel), kWsSmem, "vk_conv_decode_filter")) return rc;
         conv_decode_filter_ws_kernel<<<total < kNumSMs ? total : kNumSMs, kWsThreads, kWsSmem, stream>>>(H, C, A, total, fault);
         count_launch();
         return check_launch("conv_decode_filter_ws_kernel");
     }
-    cudaFuncSetAttribute(conv_decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem);
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv_decode_filter_kernel), kChSmem, "vk_conv_decode_filter")) return rc;
     conv_decode_filter_kernel<<<dim3(mt, batch), kChThreads, kChSmem, stream>>>(H, C, A, fault);
     count_launch();
     return check_launch("conv_decode_filter_kernel");

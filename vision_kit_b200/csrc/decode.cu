@@ -4,81 +4,25 @@
 //                      copy with the sigmoid/grid/anchor decode fused in.  HBM-bound:
 //                      8 568 000 B read + 8 568 000 B written per 640x640 image.
 //   vk_decode_filter   the same tiles, but only rows with obj > conf are decoded and only
-//                      candidates leave the SM: pred is never materialised.  A tile whose
-//                      objectness plane has few survivors gathers just those rows.
+//                      candidates leave the SM: pred is never materialised.  Two kernels with
+//                      identical results: one warp per tile gathering just the surviving rows
+//                      (demo thresholds), and a persistent whole-tile kernel (eval thresholds).
 //   vk_filter_pred     drop-in filter for an existing pred tensor (`nms(prediction)`).
 //
 // Candidate order: the reference's candidate list is ordered (row asc, class asc)
 // (`nonzero`, utils/image_proc.py:141-143).  Here every tile writes its candidates, in that
 // order, into the fixed slot range its tile owns (64 rows x nc slots, or 64 in best-class
-// mode) and records (base, count) in a segment table indexed by tile; canonical order =
-// segment order x in-segment order.  No tile ever waits for an atomic, the buffer cannot
-// overflow, and the consumer (nms.cu) walks the table.
+// mode) and records its count in a segment table indexed by tile, so slot order IS the
+// canonical order.  No tile ever waits for another, the buffer cannot overflow, and the
+// consumer (nms.cu) breaks score ties by slot.
 #include "decode_common.cuh"
 
 namespace vk {
 
 
-struct TileLoc {
-    int l, a, s0, nvalid, row0;
-};
-
-__device__ __forceinline__ TileLoc locate_tile(const HeadDev& H, int t) {
-    TileLoc q;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < VK_MAX_LEVELS; ++i)
-        if (i < H.nl && t >= H.tile_start[i]) l = i;
-    const int rel = t - H.tile_start[l];
-    q.l = l;
-    q.a = rel / H.tpa[l];
-    q.s0 = (rel - q.a * H.tpa[l]) * kTileS;
-    q.nvalid = min(kTileS, H.nynx[l] - q.s0);
-    q.row0 = H.row_base[l] + q.a * H.nynx[l] + q.s0;
-    return q;
-}
-
 // ---------------------------------------------------------------------------------------
 // materialised decode
 // ---------------------------------------------------------------------------------------
-// Coalesced load of one tile's logits into shared memory [no][PITCH] (the filter kernels).  Loads are issued in
-// batches of four 128-bit requests per thread before the first shared store, so that a block
-// keeps ~16 KB in flight instead of one request per thread.
-template <int PITCH>
-__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ in, int no, int nynx,
-                                          int nvalid, bool vec) {
-    if (vec) {
-        const int total = no * (kTileS / 4);
-        for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kDecThreads) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * kDecThreads;
-                const int c = e >> 4, sq = (e & 15) << 2;
-                v[u] = (e < total && sq < nvalid) ? ld_stream_f4(in + (size_t)c * nynx + sq)
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * kDecThreads;
-                if (e < total) {
-                    float* d = tile + (e >> 4) * PITCH + ((e & 15) << 2);
-                    if constexpr ((PITCH & 3) == 0) {          // rows 16-byte aligned: one STS.128
-                        *reinterpret_cast<float4*>(d) = v[u];
-                    } else {
-                        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
-                    }
-                }
-            }
-        }
-    } else {
-        for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
-            const int c = e >> 6, sq = e & 63;
-            if (sq < nvalid) tile[c * PITCH + sq] = ld_stream_f32(in + (size_t)c * nynx + sq);
-        }
-    }
-}
-
 // Persistent blocks, each walking tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with a
 // two-deep shared-memory pipeline: while tile k is decoded and stored, the loads of tile k+1 are
 // already in flight, so every resident block keeps a full tile (64*no*4 B) of reads outstanding.
@@ -102,7 +46,7 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const float* gsrc
 }
 
 struct DecTile {
-    const float* src;     // first logit of the tile: channel 0, row s0 of plane (b, a)
+    const void* src;      // first logit of the tile: channel 0, row s0 of plane (b, a); element type T
     float* out;           // pred chunk
     float* raw;           // raw chunk or null
     int nynx, nvalid, nx, gy0, gx0;   // (gy0, gx0): grid cell of the tile's first row
@@ -139,6 +83,7 @@ struct TilePos {          // what the filter kernel needs on top of DecTile
     int b, seg, row0, s0; // image, tile index inside the image, first pred row, first row inside the plane
 };
 
+template <class T>
 __device__ __forceinline__ void decode_tile_at(const HeadDev& H, float* pred, const DecCursor& cur, DecTile* d,
                                                TilePos* loc = nullptr) {
     const int b = cur.b;
@@ -157,14 +102,14 @@ __device__ __forceinline__ void decode_tile_at(const HeadDev& H, float* pred, co
     int gx0 = s0 - gy0 * nx;
     if (gx0 < 0) { --gy0; gx0 += nx; }
     if (gx0 >= nx) { ++gy0; gx0 -= nx; }
-    d->src = H.lv[l] + ((size_t)(b * H.na + a) * no) * nynx + s0;
+    d->src = static_cast<const T*>(H.lv[l]) + ((size_t)(b * H.na + a) * no) * nynx + s0;
     d->out = pred ? pred + ((size_t)b * H.rows + row0) * no : nullptr;
     d->raw = H.raw[l] ? H.raw[l] + (((size_t)b * H.na + a) * nynx + s0) * no : nullptr;
     d->nynx = nynx; d->nvalid = nvalid; d->nx = nx;
     d->gy0 = gy0; d->gx0 = gx0;
     if (loc) { loc->b = b; loc->seg = cur.ti; loc->row0 = row0; loc->s0 = s0; }
     d->raw_bulk = d->raw != nullptr && ((reinterpret_cast<uintptr_t>(d->raw) & 15) == 0) && (((nvalid * no) & 3) == 0);
-    d->vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[l]) & 15) == 0);
+    d->vec = ((nynx & (16 / (int)sizeof(T) - 1)) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[l]) & 15) == 0);
     d->stride = H.stride[l]; d->aw = H.anchors[l][2 * a]; d->ah = H.anchors[l][2 * a + 1];
 }
 
@@ -172,10 +117,11 @@ __device__ __forceinline__ int swz(int c, int s) { return c * kTileS + ((((s >> 
 
 __device__ __forceinline__ void decode_prefetch(const DecTile& d, float* tile, int no) {
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
+    const float* const tsrc = static_cast<const float*>(d.src);
     if (d.vec) {
         const int q = threadIdx.x & 15, c0 = threadIdx.x >> 4;      // 16 chunks per channel, 16 channels per pass
         if (4 * q < d.nvalid) {
-            const float* src = d.src + (size_t)c0 * d.nynx + 4 * q;
+            const float* src = tsrc + (size_t)c0 * d.nynx + 4 * q;
             const size_t step = (size_t)(kDecThreads / 16) * d.nynx;
             // c advances by 16: (c & 7) and with it the chunk position stay the same, dst moves 16 channel rows
             uint32_t dst = base + 4u * (uint32_t)swz(c0, 4 * q);
@@ -184,7 +130,7 @@ __device__ __forceinline__ void decode_prefetch(const DecTile& d, float* tile, i
     } else {
         const int r = threadIdx.x & (kTileS - 1), c0 = threadIdx.x >> 6;
         if (r < d.nvalid) {
-            const float* src = d.src + (size_t)c0 * d.nynx + r;
+            const float* src = tsrc + (size_t)c0 * d.nynx + r;
             const size_t step = (size_t)(kDecThreads / kTileS) * d.nynx;
             for (int c = c0; c < no; c += kDecThreads / kTileS, src += step)
                 cp_async_4(base + 4u * (uint32_t)swz(c, r), src);
@@ -193,44 +139,94 @@ __device__ __forceinline__ void decode_prefetch(const DecTile& d, float* tile, i
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// Tile layout of detect_decode_kernel per input element type.
+//   float       [c][64] floats, 16-byte chunks swizzled (swz), 16-byte async copies
+//   half types  [c][68] elements (136-byte pitch: lanes over channels reading 4 rows = 8 bytes are
+//               conflict-free per half-warp), 8-byte async copies of 4 rows
+template <class T>
+struct DecLayout {
+    static constexpr int kPitch = kTileS + 4;                                   // elements
+    static __device__ __forceinline__ int tile_bytes(int no) { return (no * kPitch * 2 + 15) & ~15; }
+    static __device__ __forceinline__ void prefetch(const DecTile& d, unsigned char* tile, int no) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
+        const T* const tsrc = static_cast<const T*>(d.src);
+        const bool vec8 = ((d.nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(tsrc) & 7) == 0);
+        if (vec8) {
+            const int q = threadIdx.x & 15, c0 = threadIdx.x >> 4;              // 16 chunks of 4 rows per channel
+            if (4 * q < d.nvalid)
+                for (int c = c0; c < no; c += kDecThreads / 16)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+                                 :: "r"(base + 2u * (uint32_t)(c * kPitch + 4 * q)), "l"(tsrc + (size_t)c * d.nynx + 4 * q) : "memory");
+        } else {
+            T* const t = reinterpret_cast<T*>(tile);
+            for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
+                const int c = e >> 6, r = e & 63;
+                if (r < d.nvalid) t[c * kPitch + r] = tsrc[(size_t)c * d.nynx + r];
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    static __device__ __forceinline__ float4 load4(const unsigned char* tile, int c, int q) {   // rows 4q..4q+3 of channel c
+        const uint2 u = *reinterpret_cast<const uint2*>(tile + 2 * (c * kPitch + 4 * q));
+        const T* e = reinterpret_cast<const T*>(&u);
+        return make_float4(to_f32(e[0]), to_f32(e[1]), to_f32(e[2]), to_f32(e[3]));
+    }
+    static __device__ __forceinline__ float elem(const unsigned char* tile, int c, int s) {
+        return to_f32(reinterpret_cast<const T*>(tile)[c * kPitch + s]);
+    }
+};
+template <>
+struct DecLayout<float> {
+    static __device__ __forceinline__ int tile_bytes(int no) { return no * kTileS * 4; }
+    static __device__ __forceinline__ void prefetch(const DecTile& d, unsigned char* tile, int no) {
+        decode_prefetch(d, reinterpret_cast<float*>(tile), no);
+    }
+    static __device__ __forceinline__ float4 load4(const unsigned char* tile, int c, int q) {
+        return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tile) + swz(c, 4 * q));
+    }
+    static __device__ __forceinline__ float elem(const unsigned char* tile, int c, int s) {
+        return reinterpret_cast<const float*>(tile)[swz(c, s)];
+    }
+};
+
 // NCG > 0: no <= 32*NCG channels, item loop unrolled; NCG == 0: runtime loop over channel groups.
-template <int NCG>
+template <class T, int NCG>
 __global__ void __launch_bounds__(kDecThreads, 3)
 detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles, int have_lin) {
-    extern __shared__ __align__(16) float tiles_sm[];  // 2 x [no][kTileS] logits, chunk-swizzled (+ [kTileS][no] raw staging)
+    extern __shared__ __align__(16) unsigned char tiles_sm[];  // 2 x tile of logits (DecLayout<T>) (+ [kTileS][no] floats of raw staging)
     __shared__ DecTile s_dt[3];
     const int no = H.no;
-    const int tile_floats = kTileS * no;
+    const int tile_bytes = DecLayout<T>::tile_bytes(no);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int t = blockIdx.x;
     if (t >= total_tiles) return;
     __shared__ DecCursor cur;                       // thread 0 only (shared: keeps it out of everyone's registers)
     if (threadIdx.x == 0) {
         cur = cursor_begin(H, t, gridDim.x);
-        decode_tile_at(H, pred, cur, &s_dt[0]);
+        decode_tile_at<T>(H, pred, cur, &s_dt[0]);
         cursor_next(H, cur);
-        if (cur.t < total_tiles) decode_tile_at(H, pred, cur, &s_dt[1]);
+        if (cur.t < total_tiles) decode_tile_at<T>(H, pred, cur, &s_dt[1]);
         cursor_next(H, cur);
     }
     __syncthreads();
-    decode_prefetch(s_dt[0], tiles_sm, no);
+    DecLayout<T>::prefetch(s_dt[0], tiles_sm, no);
     for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
-        const float* tile = tiles_sm + (k & 1) * tile_floats;
+        const unsigned char* tile = tiles_sm + (k & 1) * tile_bytes;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (have_lin && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();                      // tile k landed; everyone is done with the other buffer (and `lin`)
         const int slot = k % 3;
         if (t + (int)gridDim.x < total_tiles)
-            decode_prefetch(s_dt[slot == 2 ? 0 : slot + 1], tiles_sm + ((k + 1) & 1) * tile_floats, no);
+            DecLayout<T>::prefetch(s_dt[slot == 2 ? 0 : slot + 1], tiles_sm + ((k + 1) & 1) * tile_bytes, no);
         if (threadIdx.x == 0) {                                            // slot (k+2)%3 was tile k-1's: free
-            if (cur.t < total_tiles) decode_tile_at(H, pred, cur, &s_dt[slot == 0 ? 2 : slot - 1]);
+            if (cur.t < total_tiles) decode_tile_at<T>(H, pred, cur, &s_dt[slot == 0 ? 2 : slot - 1]);
             cursor_next(H, cur);
         }
         const DecTile& d = s_dt[slot];
         const int nvalid = d.nvalid;
         float* __restrict__ out = d.out;
         float* __restrict__ raw = d.raw;
-        float* const lin = tiles_sm + 2 * tile_floats;       // raw logits of the tile in output order
+        float* const lin = reinterpret_cast<float*>(tiles_sm + 2 * tile_bytes);   // raw logits of the tile in output order
         const bool raw_bulk = have_lin && d.raw_bulk;
 
         // Box channels.  Warp w owns rows 4w..4w+3 and 4(w+8)..4(w+8)+3 in the first channel group:
@@ -245,7 +241,7 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
             int gx = d.gx0 + br, gy = d.gy0;
             if (gx >= nx) { const int wq = gx / nx; gy += wq; gx -= wq * nx; }
             const float anc = (cb & 1) ? d.ah : d.aw;
-            boxv = decode_elem(tile[swz(cb, br)], cb, (float)((cb & 1) ? gy : gx), d.stride, anc, H.variant);
+            boxv = decode_elem(DecLayout<T>::elem(tile, cb, br), cb, (float)((cb & 1) ? gy : gx), d.stride, anc, H.variant);
         }
         auto item = [&](int cgp, int q, const float4 v) {
             // rows 4q..4q+3 of channel c = 32*cgp + lane
@@ -287,7 +283,7 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
 #pragma unroll
             for (int j = 0; j < 2 * NCG; ++j) {
                 const int c = 32 * (j >> 1) + lane, q = w + 8 * (j & 1);
-                v[j] = (c < no) ? *reinterpret_cast<const float4*>(tile + swz(c, 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[j] = (c < no) ? DecLayout<T>::load4(tile, c, q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 2 * NCG; ++j) {
@@ -299,8 +295,7 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
                 for (int q = w; q < 16; q += kWarps) {
                     const int c = 32 * cgp + lane;
                     if (4 * q < nvalid)
-                        item(cgp, q, (c < no) ? *reinterpret_cast<const float4*>(tile + swz(c, 4 * q))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f));
+                        item(cgp, q, (c < no) ? DecLayout<T>::load4(tile, c, q) : make_float4(0.f, 0.f, 0.f, 0.f));
                 }
         }
         if (raw_bulk) {
@@ -317,51 +312,35 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
     if (have_lin && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
 // ---------------------------------------------------------------------------------------
-// confidence filter: one block walks a GROUP of up to 8 consecutive tiles of one plane.
+// confidence filter, sparse form (demo thresholds: a few percent of the rows survive).
 //
-//   stage A  objectness of the whole group (<= 512 rows, 2 per thread, one DRAM round trip),
-//            ordered list of surviving rows per tile
-//   stage B  tiles with <= 8 survivors are "sparse": their rows (<= 64 for the group) are
-//            gathered into one staging buffer in a single round trip, evaluated, and their
-//            candidates written into the slot range of the group's first sparse tile
-//   stage C  the remaining "dense" tiles are loaded whole (coalesced planes / rows), one tile
-//            at a time, each into its own slot range
+// One WARP owns one 64-row tile from its objectness to its segment-table entry, so nothing in
+// the kernel waits on a block barrier and a tile's candidates are ordered by construction:
 //
-// At demo thresholds (0.7 % of rows survive) a group costs ~3 dependent memory round trips
-// instead of 3 per tile; at eval thresholds every tile is dense and HBM-bound.
+//   1  objectness of the tile: two coalesced loads per lane, sigmoid, two ballots -> a 64-bit
+//      survivor mask (utils/image_proc.py:99)
+//   2  the surviving rows are gathered four at a time: lane j reads channels j, j+32, j+64 of a
+//      row (one 32-byte sector each from the NCHW conv output; coalesced from a pred tensor),
+//      so a warp keeps up to 12 loads per lane in flight
+//   3  per row: class products on all lanes, best class by a warp arg-max that prefers the
+//      lower class on ties (= the first maximum the reference's `max(1)` returns, :145), or
+//      multi-label ballots in channel order (`nonzero` order, :141-143); lane 0 decodes the box
+//   4  candidates go to the tile's own slot range in order; an emitting row also reserves
+//      list space with one atomicAdd on the image's candidate counter and appends
+//      (ordered score << 32 | ~slot) -- the unordered top list vk_nms_batched sorts from
+//
+// 25 344 tiles per 64 images = 3 168 blocks of 8 warps; with ~1.8 surviving rows per tile the
+// kernel is bound by the DRAM sector rate of the gathers (85 sectors per surviving row).
 // ---------------------------------------------------------------------------------------
 #ifndef VK_DENSE_BPS
 #define VK_DENSE_BPS 4
 #endif
-constexpr int kGroupMax = 8;
-constexpr int kItems = kTileS;  // rows evaluated per back-end call (64)
+constexpr int kRowBatch = 4;      // surviving rows whose gathers are in flight together
 
-
-struct FilterSmem {
-    float obj[kGroupMax * kTileS];
-    short tile_list[kGroupMax][kTileS];  // surviving rows of each tile, ascending
-    int wcnt[2 * kWarps];
-    int tile_np[kGroupMax];
-    int tile_first[kGroupMax + 1];       // first sparse item of each tile
-    int it_ai[kItems];                   // accessor index (staging slot or tile row)
-    int it_row[kItems];                  // prediction row within the image
-    float it_obj[kItems];
-    int it_cnt[kItems];
-    int it_excl[kItems + 1];
-    float it_bv[kItems];
-    int it_bj[kItems];
-    int part[kDecThreads + 1];           // per (item, class part): count, then exclusive offset
-    float part_bv[kDecThreads];          // best-class partial maxima
-    int part_bj[kDecThreads];
-    int wsum[33];
-    int base;
-};
-
-
-// ---- accessors: where the 5+nc values of item `ai` live and how they turn into numbers
 struct PlaneGeom {       // fused path: what is needed to decode a box from logits
-    int variant, nx, s0; // s0: spatial index of the group's first row inside its plane
+    int variant, nx, s0; // s0: spatial index of the tile's first row inside its plane
     float stride, aw, ah;
     __device__ __forceinline__ float4 box(float l0, float l1, float l2, float l3, int sp) const {
         const int gy = sp / nx, gx = sp - gy * nx;
@@ -371,332 +350,262 @@ struct PlaneGeom {       // fused path: what is needed to decode a box from logi
                                 decode_elem(l3, 3, 0.f, stride, ah, variant));
     }
 };
-struct LogitTile {       // dense tile of logits [no][kFiltPitch]; ai = row inside the tile
-    float* t; PlaneGeom g; int tile_s0;
-    __device__ __forceinline__ float prob(int ai, int c) const { return sigmoidf_vk(t[(5 + c) * kFiltPitch + ai]); }
-    __device__ __forceinline__ void put(int ai, int c, float v) { t[(5 + c) * kFiltPitch + ai] = v; }
-    __device__ __forceinline__ float get(int ai, int c) const { return t[(5 + c) * kFiltPitch + ai]; }
-    __device__ __forceinline__ float4 box(int ai) const {
-        return g.box(t[ai], t[kFiltPitch + ai], t[2 * kFiltPitch + ai], t[3 * kFiltPitch + ai], tile_s0 + ai);
+
+// ---- where the 5+nc values of row r of a tile live and how they turn into numbers
+template <class T>
+struct LogitRows {       // conv output plane (b, a): element (row r, channel c) at base[c * nynx + r]
+    const T* base; int nynx; PlaneGeom g;
+    __device__ __forceinline__ float obj(int r) const { return sigmoidf_vk(ld_elem(base + (size_t)4 * nynx + r)); }
+    __device__ __forceinline__ float raw(int r, int c) const { return ld_elem(base + (size_t)c * nynx + r); }
+    __device__ __forceinline__ float prob(float x) const { return sigmoidf_vk(x); }
+    __device__ __forceinline__ float4 box(float l0, float l1, float l2, float l3, int r) const {
+        return g.box(l0, l1, l2, l3, g.s0 + r);
     }
 };
-struct LogitStage {      // gathered rows of logits [slot][no]; sp[slot] = spatial index in the plane
-    float* t; int no; PlaneGeom g; const int* sp;
-    __device__ __forceinline__ float prob(int ai, int c) const { return sigmoidf_vk(t[ai * no + 5 + c]); }
-    __device__ __forceinline__ void put(int ai, int c, float v) { t[ai * no + 5 + c] = v; }
-    __device__ __forceinline__ float get(int ai, int c) const { return t[ai * no + 5 + c]; }
-    __device__ __forceinline__ float4 box(int ai) const {
-        const float* p = t + ai * no;
-        return g.box(p[0], p[1], p[2], p[3], sp[ai]);
-    }
-};
-struct PredRows {        // decoded prediction rows [ai][no] (dense tile or gathered rows alike)
-    float* t; int no;
-    __device__ __forceinline__ float prob(int ai, int c) const { return t[ai * no + 5 + c]; }
-    __device__ __forceinline__ void put(int ai, int c, float v) { t[ai * no + 5 + c] = v; }
-    __device__ __forceinline__ float get(int ai, int c) const { return t[ai * no + 5 + c]; }
-    __device__ __forceinline__ float4 box(int ai) const {
-        const float* p = t + ai * no;
-        return xyxy_from_cxcywh(p[0], p[1], p[2], p[3]);
+template <class T>
+struct PredRows {        // decoded prediction rows: element (row r, channel c) at base[r * no + c]
+    const T* base; int no;
+    __device__ __forceinline__ float obj(int r) const { return ld_elem(base + (size_t)r * no + 4); }
+    __device__ __forceinline__ float raw(int r, int c) const { return ld_elem(base + (size_t)r * no + c); }
+    __device__ __forceinline__ float prob(float x) const { return x; }
+    __device__ __forceinline__ float4 box(float l0, float l1, float l2, float l3, int) const {
+        return xyxy_from_cxcywh(l0, l1, l2, l3);
     }
 };
 
-// Evaluates S.it_*[0..n_items): class products, per-item candidate counts, then the ordered
-// candidate writes starting at slot `base` (a range the caller's tile owns).  Ends with
-// S.it_excl[0..n_items] valid and S.base = base.  All threads of the block must call it.
-//
-// Thread = (class part q, item i): lanes run over items, every thread walks its own consecutive
-// class range, so counting needs no ballot and the class order inside a row is the part order.
-// One exclusive scan over the 256 (item, part) counts gives every thread its first slot.
-template <class Acc>
-__device__ __forceinline__ void filter_items(FilterSmem& S, Acc& T, const FilterArgs& A, int b, int n_items,
-                                             int base) {
-    const int tid = threadIdx.x;
-    const int nc = A.nc;
-    // Q class parts per item, as many as 256 threads allow (4..8): an eval-mode tile with ~43
-    // surviving rows runs 5 parts on 215 threads instead of 4 parts on 172
-    const int ni = max(n_items, 32);
-    const int Q = min(8, kDecThreads / ni);
-    const int qd = tid / ni, i = tid - qd * ni;
-    const int cpp = (nc + Q - 1) / Q;
-    const int c_lo = min(nc, qd * cpp), c_hi = min(nc, c_lo + cpp);
-    const bool act = i < n_items && qd < Q;
-    const int ai = act ? S.it_ai[i] : 0;
-    const int slot = (qd < Q) ? i * Q + qd : tid;       // item-major, part-minor: canonical order; idle threads
-                                                        // own the unused tail slots
-    {
-        int count = 0;
-        float bv = -INFINITY;
-        int bj = 0x7fffffff;
-        if (act) {
-            const float obj = S.it_obj[i];
-            if (A.multi_label) {
-                if (A.class_mask == nullptr) {
-#pragma unroll 4
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        const float prod = __fmul_rn(T.prob(ai, c), obj);              // image_proc.py:135
-                        const bool flag = prod > A.conf;                               // :141
-                        T.put(ai, c, flag ? prod : -1.0f);
-                        count += flag;
-                    }
-                } else {
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        const float prod = __fmul_rn(T.prob(ai, c), obj);
-                        const bool flag = (prod > A.conf) && class_allowed(A.class_mask, c);   // :141,151
-                        T.put(ai, c, flag ? prod : -1.0f);
-                        count += flag;
-                    }
-                }
-            } else {
-#pragma unroll 4
-                for (int c = c_lo; c < c_hi; ++c) {
-                    const float prod = __fmul_rn(T.prob(ai, c), obj);
-                    if (prod > bv) { bv = prod; bj = c; }      // first max within the part (:145)
-                }
-            }
-        }
-        S.part[slot] = count;
-        S.part_bv[slot] = bv;
-        S.part_bj[slot] = bj;
-    }
-    __syncthreads();
-    if (!A.multi_label) {
-        if (act && qd == 0) {                                   // first max across the parts
-            float bv = S.part_bv[slot];
-            int bj = S.part_bj[slot];
-            for (int q2 = 1; q2 < Q; ++q2)
-                if (S.part_bv[slot + q2] > bv) { bv = S.part_bv[slot + q2]; bj = S.part_bj[slot + q2]; }
-            const bool sel = (bj != 0x7fffffff) && (bv > A.conf) && class_allowed(A.class_mask, bj);  // :147,151
-            S.it_bv[i] = bv;
-            S.it_bj[i] = bj;
-            S.part[slot] = sel ? 1 : 0;
-        }
-        __syncthreads();
-    }
-    {   // exclusive scan of the 256 part counts in slot order
-        int total;
-        const int v = S.part[tid];
-        const int ex = block_excl_scan(v, S.wsum, &total);
-        S.part[tid] = ex;
-        if (tid == 0) {
-            S.part[kDecThreads] = total;
-            S.base = base;
-            if (total) atomicAdd(A.counts + b, total);         // result unused: fire-and-forget
-        }
-    }
-    __syncthreads();
-    if (tid <= kItems) {
-        const int t = tid;
-        S.it_excl[t] = (t < n_items) ? S.part[t * Q] : S.part[kDecThreads];
-    }
-    if (tid < kItems) S.it_cnt[tid] = (tid < n_items) ? S.part[(tid + 1) * Q] - S.part[tid * Q] : 0;
-    uint64_t* cand = A.cand + (size_t)b * A.cap;
-    if (act) {
-        const int row = S.it_row[i];
-        int pos = base + S.part[slot];
-        if (A.multi_label) {
-            const int end = base + S.part[slot + 1];
-            if (pos < end) {
-                uint32_t idx = (uint32_t)(row * nc + c_lo);
-                if (end <= A.cap) {            // always, with a buffer sized per include/vk_b200.h
-                    uint2* wp = reinterpret_cast<uint2*>(cand) + pos;   // .x = score bits, .y = row*nc + cls
-                    for (int c = c_lo; c < c_hi; ++c, ++idx) {
-                        const float v = T.get(ai, c);
-                        if (v >= 0.0f) *wp++ = make_uint2(__float_as_uint(v), idx);
-                    }
-                } else {
-                    for (int c = c_lo; c < c_hi; ++c, ++idx) {
-                        const float v = T.get(ai, c);
-                        if (v >= 0.0f) {
-                            if (pos < A.cap) cand[pos] = ((uint64_t)idx << 32) | __float_as_uint(v);
-                            ++pos;
-                        }
-                    }
-                }
-            }
-        } else if (qd == 0 && S.part[slot + 1] > S.part[slot] && pos < A.cap) {
-            cand[pos] = ((uint64_t)(uint32_t)(row * nc + S.it_bj[i]) << 32) | __float_as_uint(S.it_bv[i]);
-        }
-        if (qd == 0 && S.part[(i + 1) * Q] > S.part[slot]) A.boxes[(size_t)b * A.rows + row] = T.box(ai);
-    }
-    __syncthreads();
-}
+// Everything a warp needs to emit candidates of its tile.
+struct TileOut {
+    uint2* cand;         // the tile's slot range
+    uint64_t* list;      // the image's list or null
+    float4* boxes;       // the image's boxes
+    int32_t* count;      // the image's candidate counter
+    uint32_t slot0;      // first slot of the tile
+    int row0;            // first prediction row of the tile
+    int cnt;             // candidates written so far (warp-uniform)
+};
 
-// Stage A for both kernels: S.obj holds the group's objectness (-1 for rows past the end).
-// Builds the per-tile ordered survivor lists and counts.  Returns the group's survivor count.
-__device__ __forceinline__ int survivors(FilterSmem& S, float conf, int ntiles) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const bool pa = S.obj[threadIdx.x] > conf;                 // image_proc.py:99
-    const bool pb = S.obj[threadIdx.x + kDecThreads] > conf;
-    const unsigned ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
-    if (lane == 0) { S.wcnt[w] = __popc(ma); S.wcnt[kWarps + w] = __popc(mb); }
-    const int total = __syncthreads_count(pa) + __syncthreads_count(pb);
-    if (total == 0) return 0;
+// One surviving row whose channels lane, lane+32, ... are in x[0..NK): emits its candidates.
+template <class Src, int NK, bool ML>
+__device__ __forceinline__ void emit_row(const Src& S, const FilterArgs& A, TileOut& O, int r, float o, const float* x) {
+    const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    if (pa) S.tile_list[w >> 1][__popc(ma & lt) + ((w & 1) ? S.wcnt[w - 1] : 0)] = (short)(threadIdx.x & 63);
-    if (pb) S.tile_list[4 + (w >> 1)][__popc(mb & lt) + ((w & 1) ? S.wcnt[kWarps + w - 1] : 0)] = (short)(threadIdx.x & 63);
-    if (threadIdx.x < kGroupMax) {
-        const int k = threadIdx.x;
-        const int base = (k < 4) ? 2 * k : kWarps + 2 * (k - 4);
-        S.tile_np[k] = (k < ntiles) ? S.wcnt[base] + S.wcnt[base + 1] : 0;
-    }
-    __syncthreads();
-    return total;
-}
-
-__device__ __forceinline__ bool tile_is_sparse(int np, int nvalid) { return np > 0 && np * 8 <= nvalid; }
-
-// Lays the sparse tiles' survivors out as items 0..n (staging slot = item index).
-// Returns n (<= 64).  tile_nvalid(k) = rows of tile k.
-template <class NV>
-__device__ __forceinline__ int plan_sparse_items(FilterSmem& S, int ntiles, int row0_group, NV tile_nvalid) {
-    if (threadIdx.x <= kGroupMax) {
-        int run = 0;
-        for (int k = 0; k < (int)threadIdx.x; ++k)
-            if (k < ntiles && tile_is_sparse(S.tile_np[k], tile_nvalid(k))) run += S.tile_np[k];
-        S.tile_first[threadIdx.x] = run;
-    }
-    __syncthreads();
-    const int run = S.tile_first[kGroupMax];
-    if (threadIdx.x < run) {
-        int k = 0;
+    const int nc = A.nc;
+    const int row = O.row0 + r;
+    int total;
+    float p[NK];
+    unsigned bal[NK];
+    float bv = -INFINITY;
+    int bj = 0x7fffffff;
+    if (ML) {
+        total = 0;
 #pragma unroll
-        for (int q = 1; q < kGroupMax; ++q)
-            if ((int)threadIdx.x >= S.tile_first[q]) k = q;
-        const int r = S.tile_list[k][threadIdx.x - S.tile_first[k]];
-        S.it_ai[threadIdx.x] = threadIdx.x;
-        S.it_row[threadIdx.x] = row0_group + k * kTileS + r;
-        S.it_obj[threadIdx.x] = S.obj[k * kTileS + r];
+        for (int k = 0; k < NK; ++k) {
+            const int cls = lane + 32 * k - 5;
+            p[k] = __fmul_rn(S.prob(x[k]), o);                                                   // image_proc.py:135
+            const bool f = cls >= 0 && cls < nc && p[k] > A.conf && class_allowed(A.class_mask, cls);   // :141,151
+            bal[k] = __ballot_sync(0xffffffffu, f);
+            total += __popc(bal[k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int cls = lane + 32 * k - 5;
+            const float pk = __fmul_rn(S.prob(x[k]), o);
+            if (cls >= 0 && cls < nc && pk > bv) { bv = pk; bj = cls; }                          // first max of the lane
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {                                                 // first max of the row (:145)
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+            if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+        }
+        total = (bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;    // :147,151
     }
-    __syncthreads();
-    return run;
-}
-
-// All sparse survivors of a group (<= 64 rows) fit the slot range of its first sparse tile.
-template <class NV>
-__device__ __forceinline__ int first_sparse_tile(const FilterSmem& S, int ntiles, NV tile_nvalid) {
-    for (int k = 0; k < ntiles; ++k)
-        if (tile_is_sparse(S.tile_np[k], tile_nvalid(k))) return k;
-    return 0;
-}
-
-// Items of one dense tile: its survivors, accessor index = row inside the tile.
-__device__ __forceinline__ int plan_dense_items(FilterSmem& S, int k, int row0_group) {
-    const int np = S.tile_np[k];
-    if (threadIdx.x < np) {
-        const int r = S.tile_list[k][threadIdx.x];
-        S.it_ai[threadIdx.x] = r;
-        S.it_row[threadIdx.x] = row0_group + k * kTileS + r;
-        S.it_obj[threadIdx.x] = S.obj[k * kTileS + r];
+    if (total == 0) return;
+    // list space for the row's candidates: one reservation on the image's counter
+    int lbase = 0;
+    if (O.list) {
+        if (lane == 0) lbase = atomicAdd(O.count, total);
+        lbase = __shfl_sync(0xffffffffu, lbase, 0);
     }
-    return np;
-}
-
-__device__ __forceinline__ void write_empty_segments(const FilterArgs& A, int b, int seg0, int ntiles) {
-    if (threadIdx.x < ntiles) {
-        A.seg_base[(size_t)b * A.segs + seg0 + threadIdx.x] = 0;
-        A.seg_count[(size_t)b * A.segs + seg0 + threadIdx.x] = 0;
-    }
-}
-
-// Segment table entries of the group's sparse and empty tiles after filter_items().
-template <class NV>
-__device__ __forceinline__ void write_sparse_segments(FilterSmem& S, const FilterArgs& A, int b, int seg0,
-                                                      int ntiles, int n_items, NV tile_nvalid) {
-    if (threadIdx.x < ntiles) {
-        const int k = threadIdx.x;
-        const int np = S.tile_np[k];
-        const bool sparse = tile_is_sparse(np, tile_nvalid(k));
-        if (sparse || np == 0) {
-            int sb = 0, sc = 0;
-            if (sparse && n_items > 0) {
-                const int f = S.tile_first[k];
-                const int e0 = S.it_excl[f];
-                const int e1 = (f + np >= n_items) ? S.it_excl[kItems] : S.it_excl[f + np];
-                sb = S.base + e0;
-                sc = e1 - e0;
+    const bool to_list = O.list != nullptr && lbase + total <= A.list_cap;
+    if (ML) {
+        int pos = O.cnt;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            if ((bal[k] >> lane) & 1u) {
+                const int at = pos + __popc(bal[k] & lt);
+                const uint32_t bits = __float_as_uint(p[k]);
+                O.cand[at] = make_uint2(bits, (uint32_t)(row * nc + lane + 32 * k - 5));
+                if (to_list) O.list[lbase + at - O.cnt] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)at);
             }
-            A.seg_base[(size_t)b * A.segs + seg0 + k] = sb;
-            A.seg_count[(size_t)b * A.segs + seg0 + k] = sc;
+            pos += __popc(bal[k]);
+        }
+    } else if (lane == 0) {
+        const uint32_t bits = __float_as_uint(bv);
+        O.cand[O.cnt] = make_uint2(bits, (uint32_t)(row * nc + bj));
+        if (to_list) O.list[lbase] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)O.cnt);
+    }
+    const float l1 = __shfl_sync(0xffffffffu, x[0], 1), l2 = __shfl_sync(0xffffffffu, x[0], 2),
+                l3 = __shfl_sync(0xffffffffu, x[0], 3);
+    if (lane == 0) O.boxes[row] = S.box(x[0], l1, l2, l3, r);
+    O.cnt += total;
+}
+
+// The whole tile: objectness -> surviving rows -> candidates -> segment count.  NK > 0: no <= 32 * NK
+// channels, rows gathered kRowBatch at a time; NK == 0: any channel count, one row at a time.
+template <class Src, int NK, bool ML>
+__device__ __forceinline__ void filter_tile_rows(const Src& S, const FilterArgs& A, int b, int seg, int row0, int nvalid) {
+    const int lane = threadIdx.x & 31;
+    const int no = A.nc + 5;
+    const float o0 = (lane < nvalid) ? S.obj(lane) : -1.0f;
+    const float o1 = (lane + 32 < nvalid) ? S.obj(lane + 32) : -1.0f;
+    const unsigned m0 = __ballot_sync(0xffffffffu, o0 > A.conf);                                 // image_proc.py:99
+    const unsigned m1 = __ballot_sync(0xffffffffu, o1 > A.conf);
+    unsigned long long mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+    TileOut O;
+    O.slot0 = (uint32_t)seg * (uint32_t)A.tile_cap;
+    O.cand = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + O.slot0;
+    O.list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
+    O.boxes = A.boxes + (size_t)b * A.rows;
+    O.count = A.counts + b;
+    O.row0 = row0;
+    O.cnt = 0;
+    if (NK > 0) {
+        constexpr int NKx = NK > 0 ? NK : 1;
+        while (mask) {
+            int rr[kRowBatch];
+            float x[kRowBatch][NKx];
+#pragma unroll
+            for (int j = 0; j < kRowBatch; ++j) {
+                rr[j] = mask ? __ffsll((long long)mask) - 1 : -1;
+                if (mask) mask &= mask - 1;
+#pragma unroll
+                for (int k = 0; k < NKx; ++k) {
+                    const int c = lane + 32 * k;
+                    x[j][k] = (rr[j] >= 0 && c < no) ? S.raw(rr[j], c) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kRowBatch; ++j) {
+                if (rr[j] < 0) break;                                  // warp-uniform
+                const float o = __shfl_sync(0xffffffffu, rr[j] < 32 ? o0 : o1, rr[j] & 31);
+                emit_row<Src, NKx, ML>(S, A, O, rr[j], o, x[j]);
+            }
+        }
+    } else {
+        // any class count: the row is walked 32 channels at a time with running state
+        const unsigned lt = (1u << lane) - 1u;
+        const int nc = A.nc;
+        while (mask) {
+            const int r = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            const float o = __shfl_sync(0xffffffffu, r < 32 ? o0 : o1, r & 31);
+            const int row = row0 + r;
+            const float x0 = (lane < no) ? S.raw(r, lane) : 0.0f;
+            if (ML) {
+                // pass 1 counts (the list reservation needs the row total), pass 2 writes
+                int total = 0;
+                for (int c0 = 0; c0 < no; c0 += 32) {
+                    const int c = c0 + lane, cls = c - 5;
+                    const float pv = (c < no) ? __fmul_rn(S.prob(c0 ? S.raw(r, c) : x0), o) : 0.0f;
+                    const bool f = cls >= 0 && cls < nc && pv > A.conf && class_allowed(A.class_mask, cls);
+                    total += __popc(__ballot_sync(0xffffffffu, f));
+                }
+                if (total == 0) continue;
+                int lbase = 0;
+                if (O.list) {
+                    if (lane == 0) lbase = atomicAdd(O.count, total);
+                    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+                }
+                const bool to_list = O.list != nullptr && lbase + total <= A.list_cap;
+                int pos = O.cnt;
+                for (int c0 = 0; c0 < no; c0 += 32) {
+                    const int c = c0 + lane, cls = c - 5;
+                    const float pv = (c < no) ? __fmul_rn(S.prob(c0 ? S.raw(r, c) : x0), o) : 0.0f;
+                    const bool f = cls >= 0 && cls < nc && pv > A.conf && class_allowed(A.class_mask, cls);
+                    const unsigned bal = __ballot_sync(0xffffffffu, f);
+                    if (f) {
+                        const int at = pos + __popc(bal & lt);
+                        const uint32_t bits = __float_as_uint(pv);
+                        O.cand[at] = make_uint2(bits, (uint32_t)(row * nc + cls));
+                        if (to_list) O.list[lbase + at - O.cnt] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)at);
+                    }
+                    pos += __popc(bal);
+                }
+                O.cnt += total;
+            } else {
+                float bv = -INFINITY;
+                int bj = 0x7fffffff;
+                for (int c0 = 0; c0 < no; c0 += 32) {
+                    const int c = c0 + lane, cls = c - 5;
+                    if (c < no && cls >= 0) {
+                        const float pv = __fmul_rn(S.prob(c0 ? S.raw(r, c) : x0), o);
+                        if (pv > bv) { bv = pv; bj = cls; }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                    if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+                }
+                if (!(bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj))) continue;
+                if (lane == 0) {
+                    const uint32_t bits = __float_as_uint(bv);
+                    O.cand[O.cnt] = make_uint2(bits, (uint32_t)(row * nc + bj));
+                    if (O.list) {
+                        const int lbase = atomicAdd(O.count, 1);
+                        if (lbase < A.list_cap) O.list[lbase] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)O.cnt);
+                    }
+                }
+                O.cnt += 1;
+            }
+            const float l1 = __shfl_sync(0xffffffffu, x0, 1), l2 = __shfl_sync(0xffffffffu, x0, 2),
+                        l3 = __shfl_sync(0xffffffffu, x0, 3);
+            if (lane == 0) O.boxes[row] = S.box(x0, l1, l2, l3, r);
         }
     }
-}
-
-__device__ __forceinline__ void write_dense_segment(FilterSmem& S, const FilterArgs& A, int b, int seg) {
-    if (threadIdx.x == 0) {
-        A.seg_base[(size_t)b * A.segs + seg] = S.base;
-        A.seg_count[(size_t)b * A.segs + seg] = S.it_excl[kItems];
+    if (lane == 0) {
+        A.seg_count[(size_t)b * A.segs + seg] = O.cnt;
+        if (O.cnt && !O.list) atomicAdd(O.count, O.cnt);              // with a list the rows reserved as they went
+        if (seg == 0) A.flags[b] = cand_flags(A, O.list != nullptr);
     }
 }
 
-__global__ void __launch_bounds__(kDecThreads, 6)
-decode_filter_kernel(const HeadDev H, const FilterArgs A) {
-    extern __shared__ __align__(16) float buf[];  // dense tile [no][kFiltPitch] or staging [64][no]
-    __shared__ FilterSmem S;
-    __shared__ int s_sp[kItems];
-    const int b = blockIdx.y;
-    const int G = A.group;
-    // locate the group: planes are (level, anchor); groups never straddle a plane
+template <class T, int NK, bool ML>
+__global__ void __launch_bounds__(kDecThreads, 4)
+decode_filter_rows_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
+    const int t = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (t >= total_tiles) return;
+    const int b = t / H.tiles, ti = t - b * H.tiles;
     int l = 0;
 #pragma unroll
     for (int i = 1; i < VK_MAX_LEVELS; ++i)
-        if (i < H.nl && (int)blockIdx.x >= H.group_start[i]) l = i;
-    const int rel = blockIdx.x - H.group_start[l];
-    const int gpa = ceil_div(H.tpa[l], G);
-    const int a = rel / gpa;
-    const int tile0 = (rel - a * gpa) * G;                 // first tile of the group inside the plane
-    const int ntiles = min(G, H.tpa[l] - tile0);
-    const int s0 = tile0 * kTileS;
-    const int no = H.no, nynx = H.nynx[l];
-    const int nrows = min(ntiles * kTileS, nynx - s0);
+        if (i < H.nl && ti >= H.tile_start[i]) l = i;
+    const int rel = ti - H.tile_start[l];
+    const int a = rel / H.tpa[l];
+    const int s0 = (rel - a * H.tpa[l]) * kTileS;
+    const int nynx = H.nynx[l];
+    const int nvalid = min(kTileS, nynx - s0);
     const int row0 = H.row_base[l] + a * nynx + s0;
-    const int seg0 = H.tile_start[l] + a * H.tpa[l] + tile0;
-    const float* __restrict__ in = H.lv[l] + ((size_t)(b * H.na + a) * no) * nynx + s0;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    auto tile_nvalid = [&](int k) { return min(kTileS, nrows - k * kTileS); };
-
-    // stage A: objectness plane of the group (coalesced)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int r = threadIdx.x + h * kDecThreads;
-        S.obj[r] = (r < nrows) ? sigmoidf_vk(ld_stream_f32(in + (size_t)4 * nynx + r)) : -1.0f;
-    }
-    __syncthreads();
-    if (survivors(S, A.conf, ntiles) == 0) {
-        write_empty_segments(A, b, seg0, ntiles);
-        return;
-    }
-    const PlaneGeom geom{H.variant, H.nx[l], s0, H.stride[l], H.anchors[l][2 * a], H.anchors[l][2 * a + 1]};
-
-    // stage B: sparse tiles, one gather for the whole group
-    const int n_sparse = plan_sparse_items(S, ntiles, row0, tile_nvalid);
-    if (n_sparse > 0) {
-        for (int i = w; i < n_sparse; i += kWarps) {
-            const int sp = S.it_row[i] - row0;              // row inside the group
-            if (lane == 0) s_sp[i] = s0 + sp;
-            for (int c = lane; c < no; c += 32) buf[i * no + c] = __ldg(in + (size_t)c * nynx + sp);
-        }
-        __syncthreads();
-        LogitStage T{buf, no, geom, s_sp};
-        filter_items(S, T, A, b, n_sparse, (seg0 + first_sparse_tile(S, ntiles, tile_nvalid)) * A.tile_cap);
-    }
-    write_sparse_segments(S, A, b, seg0, ntiles, n_sparse, tile_nvalid);
-    __syncthreads();
-
-    // stage C: dense tiles, coalesced plane loads
-    const bool vec = ((nynx & 3) == 0) && ((reinterpret_cast<uintptr_t>(H.lv[l]) & 15) == 0);
-    for (int k = 0; k < ntiles; ++k) {
-        const int np = S.tile_np[k], nv = tile_nvalid(k);
-        if (np == 0 || tile_is_sparse(np, nv)) continue;
-        load_tile<kFiltPitch>(buf, in + k * kTileS, no, nynx, nv, vec);
-        const int n_items = plan_dense_items(S, k, row0);
-        __syncthreads();
-        LogitTile T{buf, geom, s0 + k * kTileS};
-        filter_items(S, T, A, b, n_items, (seg0 + k) * A.tile_cap);
-        write_dense_segment(S, A, b, seg0 + k);
-        __syncthreads();
-    }
+    const LogitRows<T> S{static_cast<const T*>(H.lv[l]) + ((size_t)(b * H.na + a) * H.no) * nynx + s0, nynx,
+                         PlaneGeom{H.variant, H.nx[l], s0, H.stride[l], H.anchors[l][2 * a], H.anchors[l][2 * a + 1]}};
+    filter_tile_rows<LogitRows<T>, NK, ML>(S, A, b, ti, row0, nvalid);
 }
+
+template <class T, int NK, bool ML>
+__global__ void __launch_bounds__(kDecThreads, 4)
+filter_pred_rows_kernel(const T* __restrict__ pred, int no, const FilterArgs A, int total_tiles) {
+    const int t = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (t >= total_tiles) return;
+    const int b = t / A.segs, seg = t - b * A.segs;
+    const int row0 = seg * kTileS;
+    const int nvalid = min(kTileS, A.rows - row0);
+    const PredRows<T> S{pred + ((size_t)b * A.rows + row0) * no, no};
+    filter_tile_rows<PredRows<T>, NK, ML>(S, A, b, seg, row0, nvalid);
+}
+
 
 // ---------------------------------------------------------------------------------------
 // Dense variant of the fused filter (eval thresholds: most rows survive, every tile is read
@@ -707,31 +616,86 @@ decode_filter_kernel(const HeadDev H, const FilterArgs A) {
 // consecutive classes and keeps the products in registers, so there is no second pass over
 // shared memory.  One scan over the 256 (row, part) counts in canonical order gives every
 // thread its first slot inside the range the tile owns.
-// ML = multi_label.  Results are bit-identical to decode_filter_kernel (same sigmoid, same
-// product, same order); the host picks the kernel from the threshold only (vk_decode_filter).
+// ML = multi_label, T = element type of the conv outputs.  Results are bit-identical to
+// decode_filter_rows_kernel (same sigmoid, same product, same order).
 // ---------------------------------------------------------------------------------------
 constexpr int kParts = kDecThreads / kTileS;   // 4 class parts per row
 
+// How a staged tile [no][kTileS] of element type T is laid out, filled and read.
+//   float       chunk-swizzled (the layout detect_decode_kernel needs for its transposed reads)
+//   half types  plain [c][64]: lanes over rows read 64 contiguous bytes, 16-byte copies of 8 rows
+template <class T>
+struct DenseTile {
+    static __device__ __forceinline__ int offset(int c, int s) { return c * kTileS + s; }        // in elements
+    static __device__ __forceinline__ void prefetch(const DecTile& d, void* tile, int no) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
+        const T* const tsrc = static_cast<const T*>(d.src);
+        if (d.vec) {
+            const int q = threadIdx.x & 7, c0 = threadIdx.x >> 3;      // 8 chunks of 8 rows per channel, 32 channels per pass
+            if (8 * q < d.nvalid)
+                for (int c = c0; c < no; c += kDecThreads / 8)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                 :: "r"(base + 2u * (uint32_t)(c * kTileS + 8 * q)), "l"(tsrc + (size_t)c * d.nynx + 8 * q) : "memory");
+        } else {                                                       // unaligned planes: plain 2-byte loads
+            T* const t = static_cast<T*>(tile);
+            for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
+                const int c = e >> 6, r = e & 63;
+                if (r < d.nvalid) t[e] = tsrc[(size_t)c * d.nynx + r];
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    static __device__ __forceinline__ float elem(const void* tile, int c, int s) {
+        return to_f32(static_cast<const T*>(tile)[c * kTileS + s]);
+    }
+};
+template <>
+struct DenseTile<float> {
+    static __device__ __forceinline__ void prefetch(const DecTile& d, void* tile, int no) {
+        decode_prefetch(d, static_cast<float*>(tile), no);
+    }
+    static __device__ __forceinline__ float elem(const void* tile, int c, int s) {
+        return static_cast<const float*>(tile)[swz(c, s)];
+    }
+};
+
 // p[I] = sigmoid(logit of the thread's I-th class) * obj, the logit read with an immediate offset
-// from one of eight base addresses (compile-time recursion: the offset must be a constant).
-template <int I, int N>
+// (compile-time recursion: the offset must be a constant).  float tiles: the 16-byte chunk of
+// channel ch0 + I sits at position (row/4 ^ channel) & 7, which repeats with period 8 in I -- eight
+// base addresses; half tiles: one base address, channels 128 bytes apart.
+template <class T, int I, int N>
 struct ClassProducts {
+    static __device__ __forceinline__ void run(float* p, const uint32_t* tq, float obj) {
+        unsigned short h;
+        asm("ld.shared.u16 %0, [%1+%2];" : "=h"(h) : "r"(tq[0]), "n"(I * kTileS * 2));
+        float x;
+        x = to_f32(*reinterpret_cast<const T*>(&h));
+        p[I] = __fmul_rn(sigmoidf_vk(x), obj);                                                    // image_proc.py:135
+        ClassProducts<T, I + 1, N>::run(p, tq, obj);
+    }
+};
+template <int I, int N>
+struct ClassProducts<float, I, N> {
     static __device__ __forceinline__ void run(float* p, const uint32_t* tq, float obj) {
         float x;
         asm("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(tq[I & 7]), "n"(I * kTileS * 4));
         p[I] = __fmul_rn(sigmoidf_vk(x), obj);                                                    // image_proc.py:135
-        ClassProducts<I + 1, N>::run(p, tq, obj);
+        ClassProducts<float, I + 1, N>::run(p, tq, obj);
     }
 };
+template <class T, int N>
+struct ClassProducts<T, N, N> {
+    static __device__ __forceinline__ void run(float*, const uint32_t*, float) {}
+};
 template <int N>
-struct ClassProducts<N, N> {
+struct ClassProducts<float, N, N> {
     static __device__ __forceinline__ void run(float*, const uint32_t*, float) {}
 };
 
-template <int CPP, bool ML>
+template <class T, int CPP, bool ML>
 __global__ void __launch_bounds__(kDecThreads, VK_DENSE_BPS)
 decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
-    extern __shared__ __align__(16) float tiles_sm[];  // 2 x [no][kTileS] logits, chunk-swizzled
+    extern __shared__ __align__(16) unsigned char tiles_sm[];  // 2 x [no][kTileS] logits of type T (DenseTile<T> layout)
     __shared__ DecTile s_dt[3];
     __shared__ TilePos s_pos[3];
     __shared__ int s_cnt[kDecThreads];      // counts, slot = row * kParts + part (canonical order)
@@ -740,7 +704,7 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     __shared__ float s_bv[kDecThreads];     // best-class partials
     __shared__ int s_bj[kDecThreads];
     const int no = H.no, nc = A.nc;
-    const int tile_floats = kTileS * no;
+    const int tile_bytes = kTileS * no * (int)sizeof(T);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row = threadIdx.x & (kTileS - 1), qd = threadIdx.x >> 6;
     const int cpp = (nc + kParts - 1) / kParts;            // <= CPP
@@ -755,43 +719,45 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     __shared__ DecCursor cur;                       // thread 0 only (shared: keeps it out of everyone's registers)
     if (threadIdx.x == 0) {
         cur = cursor_begin(H, t, gridDim.x);
-        decode_tile_at(H, nullptr, cur, &s_dt[0], &s_pos[0]);
+        decode_tile_at<T>(H, nullptr, cur, &s_dt[0], &s_pos[0]);
         cursor_next(H, cur);
-        if (cur.t < total_tiles) decode_tile_at(H, nullptr, cur, &s_dt[1], &s_pos[1]);
+        if (cur.t < total_tiles) decode_tile_at<T>(H, nullptr, cur, &s_dt[1], &s_pos[1]);
         cursor_next(H, cur);
     }
     __syncthreads();
-    decode_prefetch(s_dt[0], tiles_sm, no);
+    DenseTile<T>::prefetch(s_dt[0], tiles_sm, no);
     for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
-        const float* tile = tiles_sm + (k & 1) * tile_floats;
+        const unsigned char* tile = tiles_sm + (k & 1) * tile_bytes;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                      // tile k landed; everyone is done with the other buffer and the scratch arrays
         const int slot3 = k % 3;
         if (t + (int)gridDim.x < total_tiles)
-            decode_prefetch(s_dt[slot3 == 2 ? 0 : slot3 + 1], tiles_sm + ((k + 1) & 1) * tile_floats, no);
+            DenseTile<T>::prefetch(s_dt[slot3 == 2 ? 0 : slot3 + 1], tiles_sm + ((k + 1) & 1) * tile_bytes, no);
         if (threadIdx.x == 0) {
-            if (cur.t < total_tiles) decode_tile_at(H, nullptr, cur, &s_dt[slot3 == 0 ? 2 : slot3 - 1], &s_pos[slot3 == 0 ? 2 : slot3 - 1]);
+            if (cur.t < total_tiles) decode_tile_at<T>(H, nullptr, cur, &s_dt[slot3 == 0 ? 2 : slot3 - 1], &s_pos[slot3 == 0 ? 2 : slot3 - 1]);
             cursor_next(H, cur);
         }
         const DecTile& d = s_dt[slot3];
         const TilePos& tp = s_pos[slot3];
 
         // ---- products of this thread's classes (registers), flags as a bit mask.
-        // Element i of the thread is channel ch0 + i of its row; its 16-byte chunk sits at position
-        // (row/4 ^ channel) & 7, which repeats with period 8 in i: eight base pointers, immediate offsets.
-        const float* trow = tile + ((row & 32) | (row & 3));
-        const int rq = row >> 2;
-        const float o = sigmoidf_vk(trow[4 * kTileS + (((rq ^ 4) & 7) << 2)]);
+        const float o = sigmoidf_vk(DenseTile<T>::elem(tile, 4, row));
         const float obj = (row < d.nvalid && o > A.conf) ? o : 0.0f;  // image_proc.py:99 (dead rows: products 0)
         const int ch0 = 5 + c_lo;
         uint32_t tq[8];
-        {
+        if (sizeof(T) == 4) {
+            // element i of the thread is channel ch0 + i of its row; its 16-byte chunk sits at position
+            // (row/4 ^ channel) & 7, which repeats with period 8 in i: eight base pointers, immediate offsets
+            const float* trow = reinterpret_cast<const float*>(tile) + ((row & 32) | (row & 3));
+            const int rq = row >> 2;
             const uint32_t trow_s = (uint32_t)__cvta_generic_to_shared(trow + ch0 * kTileS);
 #pragma unroll
             for (int j = 0; j < 8; ++j) tq[j] = trow_s + ((((uint32_t)(rq ^ (ch0 + j))) & 7u) << 4);
+        } else {
+            tq[0] = (uint32_t)__cvta_generic_to_shared(tile) + 2u * (uint32_t)(ch0 * kTileS + row);
         }
         float p[CPP];
-        ClassProducts<0, CPP>::run(p, tq, obj);   // reads past the thread's last class stay inside the (padded) buffer
+        ClassProducts<T, 0, CPP>::run(p, tq, obj);   // reads past the thread's last class stay inside the (padded) buffer
         uint32_t flags = 0;
         float bv = -INFINITY;
         int bj = 0x7fffffff;
@@ -858,12 +824,13 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
             if (n > 0) {
                 const PlaneGeom geom{H.variant, d.nx, tp.s0, d.stride, d.aw, d.ah};
                 A.boxes[(size_t)tp.b * A.rows + tp.row0 + row] =
-                    geom.box(tile[swz(0, row)], tile[swz(1, row)], tile[swz(2, row)], tile[swz(3, row)], tp.s0 + row);
+                    geom.box(DenseTile<T>::elem(tile, 0, row), DenseTile<T>::elem(tile, 1, row), DenseTile<T>::elem(tile, 2, row),
+                             DenseTile<T>::elem(tile, 3, row), tp.s0 + row);
             }
         }
         if (threadIdx.x == 0) {
-            A.seg_base[(size_t)tp.b * A.segs + tp.seg] = total ? tile_base : 0;
             A.seg_count[(size_t)tp.b * A.segs + tp.seg] = total;
+            if (tp.seg == 0) A.flags[tp.b] = cand_flags(A, false);
             if (total) atomicAdd(A.counts + tp.b, total);
         }
     }
@@ -876,41 +843,55 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
 // 64*no floats, copied as it is ([row][no], odd pitch: lanes over rows are conflict-free); the
 // values are probabilities already, boxes are cxcywh.
 // ---------------------------------------------------------------------------------------
-template <int I, int N>
+template <class T, int I, int N>
 struct PredProducts {
     static __device__ __forceinline__ void run(float* p, uint32_t base, float obj) {
         float x;
-        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(base), "n"(I * 4));
+        if (sizeof(T) == 4) {
+            asm("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(base), "n"(I * 4));
+        } else {
+            unsigned short h;
+            asm("ld.shared.u16 %0, [%1+%2];" : "=h"(h) : "r"(base), "n"(I * 2));
+            x = to_f32(*reinterpret_cast<const T*>(&h));
+        }
         p[I] = __fmul_rn(x, obj);                                                                 // image_proc.py:135
-        PredProducts<I + 1, N>::run(p, base, obj);
+        PredProducts<T, I + 1, N>::run(p, base, obj);
     }
 };
-template <int N>
-struct PredProducts<N, N> {
+template <class T, int N>
+struct PredProducts<T, N, N> {
     static __device__ __forceinline__ void run(float*, uint32_t, float) {}
 };
 
-__device__ __forceinline__ void pred_prefetch(const float* __restrict__ src, int nfloats, float* tile) {
+// nelem contiguous elements of one tile of prediction rows -> shared memory (16-byte copies when aligned)
+template <class T>
+__device__ __forceinline__ void pred_prefetch(const T* __restrict__ src, int nelem, T* tile) {
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
-    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((nfloats & 3) == 0)) {
-        for (int e = threadIdx.x; 4 * e < nfloats; e += kDecThreads) cp_async_16(base + 16u * e, src + 4 * e);
+    constexpr int per16 = 16 / (int)sizeof(T);
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((nelem & (per16 - 1)) == 0)) {
+        for (int e = threadIdx.x; per16 * e < nelem; e += kDecThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(base + 16u * e), "l"(src + per16 * e) : "memory");
+    } else if (sizeof(T) == 4) {
+        for (int e = threadIdx.x; e < nelem; e += kDecThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(base + 4u * e), "l"(src + e) : "memory");
     } else {
-        for (int e = threadIdx.x; e < nfloats; e += kDecThreads) cp_async_4(base + 4u * e, src + e);
+        for (int e = threadIdx.x; e < nelem; e += kDecThreads) tile[e] = src[e];
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int CPP, bool ML>
+template <class T, int CPP, bool ML>
 __global__ void __launch_bounds__(kDecThreads, VK_DENSE_BPS)
-filter_pred_dense_kernel(const float* __restrict__ pred, int no, const FilterArgs A, int total_tiles) {
-    extern __shared__ __align__(16) float tiles_sm[];  // 2 x [kTileS][no] prediction rows
+filter_pred_dense_kernel(const T* __restrict__ pred, int no, const FilterArgs A, int total_tiles) {
+    extern __shared__ __align__(16) unsigned char tiles_raw[];  // 2 x [kTileS][no] prediction rows
+    T* const tiles_sm = reinterpret_cast<T*>(tiles_raw);
     __shared__ int s_cnt[kDecThreads];
     __shared__ int s_off[kDecThreads + 1];
     __shared__ int s_wsum[kWarps];
     __shared__ float s_bv[kDecThreads];
     __shared__ int s_bj[kDecThreads];
     const int nc = A.nc;
-    const int tile_floats = kTileS * no;
+    const int tile_floats = (kTileS * no + 7) & ~7;        // elements per buffer, 16-byte multiple
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row = threadIdx.x & (kTileS - 1), qd = threadIdx.x >> 6;
     const int cpp = (nc + kParts - 1) / kParts;
@@ -929,24 +910,24 @@ filter_pred_dense_kernel(const float* __restrict__ pred, int no, const FilterArg
     };
     int b, seg, nvalid;
     {
-        const float* src = tile_src(t, b, seg, nvalid);
-        pred_prefetch(src, nvalid * no, tiles_sm);
+        const T* src = tile_src(t, b, seg, nvalid);
+        pred_prefetch<T>(src, nvalid * no, tiles_sm);
     }
     for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
-        const float* tile = tiles_sm + (k & 1) * tile_floats;
+        const T* tile = tiles_sm + (k & 1) * tile_floats;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                      // tile k landed; everyone is done with the other buffer and the scratch arrays
         if (t + (int)gridDim.x < total_tiles) {
             int b2, seg2, nv2;
-            const float* src = tile_src(t + gridDim.x, b2, seg2, nv2);
-            pred_prefetch(src, nv2 * no, tiles_sm + ((k + 1) & 1) * tile_floats);
+            const T* src = tile_src(t + gridDim.x, b2, seg2, nv2);
+            pred_prefetch<T>(src, nv2 * no, tiles_sm + ((k + 1) & 1) * tile_floats);
         }
         tile_src(t, b, seg, nvalid);
-        const float* prow = tile + row * no;
-        const float o = prow[4];
+        const T* prow = tile + row * no;
+        const float o = to_f32(prow[4]);
         const float obj = (row < nvalid && o > A.conf) ? o : 0.0f;    // image_proc.py:99 (dead rows: products 0)
         float p[CPP];
-        PredProducts<0, CPP>::run(p, (uint32_t)__cvta_generic_to_shared(prow + 5 + c_lo), obj);
+        PredProducts<T, 0, CPP>::run(p, (uint32_t)__cvta_generic_to_shared(prow + 5 + c_lo), obj);
         uint32_t flags = 0;
         float bv = -INFINITY;
         int bj = 0x7fffffff;
@@ -1010,82 +991,15 @@ filter_pred_dense_kernel(const float* __restrict__ pred, int no, const FilterArg
         }
         if (qd == 0) {
             const int n = s_cnt[slot] + s_cnt[slot + 1] + s_cnt[slot + 2] + s_cnt[slot + 3];
-            if (n > 0) A.boxes[(size_t)b * A.rows + grow] = xyxy_from_cxcywh(prow[0], prow[1], prow[2], prow[3]);
+            if (n > 0) A.boxes[(size_t)b * A.rows + grow] = xyxy_from_cxcywh(to_f32(prow[0]), to_f32(prow[1]), to_f32(prow[2]), to_f32(prow[3]));
         }
         if (threadIdx.x == 0) {
-            A.seg_base[(size_t)b * A.segs + seg] = total ? tile_base : 0;
             A.seg_count[(size_t)b * A.segs + seg] = total;
+            if (seg == 0) A.flags[b] = cand_flags(A, false);
             if (total) atomicAdd(A.counts + b, total);
         }
     }
 }
-
-__global__ void __launch_bounds__(kDecThreads, 5)
-filter_pred_kernel(const float* __restrict__ pred, int no, const FilterArgs A) {
-    extern __shared__ float buf[];  // [64][no]: a dense tile or the gathered rows
-    __shared__ FilterSmem S;
-    const int b = blockIdx.y;
-    const int G = A.group;
-    const int seg0 = blockIdx.x * G;
-    const int ntiles = min(G, A.segs - seg0);
-    const int row0 = seg0 * kTileS;
-    const int nrows = min(ntiles * kTileS, A.rows - row0);
-    const float* __restrict__ in = pred + ((size_t)b * A.rows + row0) * no;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    auto tile_nvalid = [&](int k) { return min(kTileS, nrows - k * kTileS); };
-
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int r = threadIdx.x + h * kDecThreads;
-        S.obj[r] = (r < nrows) ? __ldg(in + (size_t)r * no + 4) : -1.0f;
-    }
-    __syncthreads();
-    if (survivors(S, A.conf, ntiles) == 0) {
-        write_empty_segments(A, b, seg0, ntiles);
-        return;
-    }
-    const int n_sparse = plan_sparse_items(S, ntiles, row0, tile_nvalid);
-    if (n_sparse > 0) {
-        for (int i = w; i < n_sparse; i += kWarps) {
-            const float* src = in + (size_t)(S.it_row[i] - row0) * no;
-            for (int c = lane; c < no; c += 32) buf[i * no + c] = __ldg(src + c);
-        }
-        __syncthreads();
-        PredRows T{buf, no};
-        filter_items(S, T, A, b, n_sparse, (seg0 + first_sparse_tile(S, ntiles, tile_nvalid)) * A.tile_cap);
-    }
-    write_sparse_segments(S, A, b, seg0, ntiles, n_sparse, tile_nvalid);
-    __syncthreads();
-
-    for (int k = 0; k < ntiles; ++k) {
-        const int np = S.tile_np[k], nv = tile_nvalid(k);
-        if (np == 0 || tile_is_sparse(np, nv)) continue;
-        const float* __restrict__ tin = in + (size_t)k * kTileS * no;   // nv*no contiguous floats
-        const int n = nv * no;
-        if (((reinterpret_cast<uintptr_t>(tin) & 15) == 0) && ((n & 3) == 0)) {
-            for (int e = threadIdx.x; e < (n >> 2); e += kDecThreads)
-                reinterpret_cast<float4*>(buf)[e] = ld_stream_f4(tin + 4 * (size_t)e);
-        } else {
-            for (int e = threadIdx.x; e < n; e += kDecThreads) buf[e] = ld_stream_f32(tin + e);
-        }
-        const int n_items = plan_dense_items(S, k, row0);
-        __syncthreads();
-        PredRows T{buf, no};
-        filter_items(S, T, A, b, n_items, (seg0 + k) * A.tile_cap);
-        write_dense_segment(S, A, b, seg0 + k);
-        __syncthreads();
-    }
-}
-
-// Tiles per block: enough blocks for ~2 full waves of 8 resident blocks per SM, at most 8.
-static int choose_group(int batch, int tiles) {
-    const long blocks = (long)batch * tiles;
-    long g = blocks / (2L * kNumSMs * 8);
-    if (g < 1) g = 1;
-    if (g > kGroupMax) g = kGroupMax;
-    return (int)g;
-}
-
 }  // namespace vk
 
 using namespace vk;
@@ -1106,151 +1020,208 @@ extern "C" int vk_cand_tile_slots(int nc, int multi_label) { return kTileS * ((m
 
 extern "C" int vk_filter_segments(int rows) { return rows > 0 ? ceil_div(rows, kTileS) : 0; }
 
-extern "C" int vk_detect_decode(const VkHeadCfg* cfg, const float* const* levels, int batch,
+// dtype dispatch: F(float) / F(__half) / F(__nv_bfloat16)
+#define VK_BY_DTYPE(dtype, F)                       \
+    do {                                            \
+        if ((dtype) == VK_F32) { F(float); }        \
+        else if ((dtype) == VK_F16) { F(__half); }  \
+        else { F(__nv_bfloat16); }                  \
+    } while (0)
+
+static bool bad_dtype(int dtype) { return dtype != VK_F32 && dtype != VK_F16 && dtype != VK_BF16; }
+static int elem_size(int dtype) { return dtype == VK_F32 ? 4 : 2; }
+
+template <class T, int NCG>
+static int launch_detect_decode(const HeadDev& H, float* pred, int total_tiles, int have_lin, cudaStream_t stream) {
+    const size_t tile_bytes = sizeof(T) == 4 ? (size_t)H.no * kTileS * 4 : (((size_t)H.no * (kTileS + 4) * 2 + 15) & ~(size_t)15);
+    const size_t smem = 2 * tile_bytes + (have_lin ? (size_t)kTileS * H.no * sizeof(float) : 0);
+    if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_detect_decode: nc=%d needs %zu B of shared memory", H.nc, smem);
+    const void* fn = reinterpret_cast<const void*>(&detect_decode_kernel<T, NCG>);
+    if (int rc = ensure_dyn_smem(fn, smem, "vk_detect_decode")) return rc;
+    int per_sm = blocks_per_sm(fn, kDecThreads, smem);
+    if (per_sm > 3) per_sm = 3;                   // more concurrent tile streams cost DRAM locality
+    const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;   // persistent: every block is resident
+    detect_decode_kernel<T, NCG><<<grid, kDecThreads, smem, stream>>>(H, pred, total_tiles, have_lin);
+    count_launch();
+    return check_launch("detect_decode_kernel");
+}
+
+extern "C" int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels, int dtype, int batch,
                                 float* pred, float* const* raw, vk_stream_t stream) {
     HeadDev H;
     if (int rc = make_head(cfg, &H, "vk_detect_decode")) return rc;
     if (batch == 0) return VK_OK;
     if (!levels || !pred || batch < 0) return fail_arg("vk_detect_decode: null/negative argument");
+    if (bad_dtype(dtype)) return fail_arg("vk_detect_decode: dtype %d", dtype);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_detect_decode: batch %d > 65535", batch);
     for (int l = 0; l < H.nl; ++l) {
         if (!levels[l]) return fail_arg("vk_detect_decode: level %d is NULL", l);
+        if (reinterpret_cast<uintptr_t>(levels[l]) & (elem_size(dtype) - 1)) return fail_arg("vk_detect_decode: level %d is misaligned", l);
         H.lv[l] = levels[l];
         H.raw[l] = raw ? raw[l] : nullptr;
     }
     const int have_lin = raw != nullptr;
-    const size_t smem = (size_t)(have_lin ? 3 : 2) * kTileS * H.no * sizeof(float);
-    if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_detect_decode: nc=%d needs %zu B of shared memory", H.nc, smem);
     if ((long)H.tiles * batch > 0x7fffffffL) return fail_code(VK_E_LIMIT, "vk_detect_decode: %d x %d tiles", H.tiles, batch);
     const int total_tiles = H.tiles * batch;
-#define VK_DEC_LAUNCH(NCG)                                                                                  \
+#define VK_DEC_T(T)                                                                                          \
     do {                                                                                                     \
-        cudaFuncSetAttribute(detect_decode_kernel<NCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        int per_sm = 0;                                                                                      \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, detect_decode_kernel<NCG>, kDecThreads, smem); \
-        if (per_sm > 3) per_sm = 3;               /* more concurrent tile streams cost DRAM locality */      \
-        if (per_sm < 1) per_sm = 1;                                                                          \
-        const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;                    \
-        detect_decode_kernel<NCG><<<grid, kDecThreads, smem, as_stream(stream)>>>(H, pred, total_tiles, have_lin); \
+        if (H.no <= 32) return launch_detect_decode<T, 1>(H, pred, total_tiles, have_lin, as_stream(stream));       \
+        if (H.no <= 64) return launch_detect_decode<T, 2>(H, pred, total_tiles, have_lin, as_stream(stream));       \
+        if (H.no <= 96) return launch_detect_decode<T, 3>(H, pred, total_tiles, have_lin, as_stream(stream));       \
+        if (H.no <= 128) return launch_detect_decode<T, 4>(H, pred, total_tiles, have_lin, as_stream(stream));      \
+        return launch_detect_decode<T, 0>(H, pred, total_tiles, have_lin, as_stream(stream));                       \
     } while (0)
-    // persistent: every block is resident
-    if (H.no <= 32) VK_DEC_LAUNCH(1);
-    else if (H.no <= 64) VK_DEC_LAUNCH(2);
-    else if (H.no <= 96) VK_DEC_LAUNCH(3);
-    else if (H.no <= 128) VK_DEC_LAUNCH(4);
-    else VK_DEC_LAUNCH(0);
-#undef VK_DEC_LAUNCH
-    count_launch();
-    return check_launch("detect_decode_kernel");
+    VK_BY_DTYPE(dtype, VK_DEC_T);
+#undef VK_DEC_T
+    return VK_OK;
 }
 
-extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const float* const* levels, int batch,
-                                float conf_thres, int multi_label, const uint32_t* class_mask,
+// ---- filter launches.  `dense` = whole tiles staged in shared memory (persistent); else one warp per tile.
+static bool pick_dense(int kernel, float conf_thres) {
+    return kernel == VK_FILTER_DENSE || (kernel == VK_FILTER_AUTO && conf_thres < 0.05f);
+}
+
+template <class T, int CPP, bool ML>
+static int launch_decode_filter_dense(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
+    // + one part's worth of rows: the unrolled class loop may read past channel no-1
+    const size_t dsmem = (2 * (size_t)kTileS * H.no + (size_t)kTileS * CPP) * sizeof(T);
+    if (dsmem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_decode_filter: nc=%d needs %zu B of shared memory", H.nc, dsmem);
+    const void* fn = reinterpret_cast<const void*>(&decode_filter_dense_kernel<T, CPP, ML>);
+    if (int rc = ensure_dyn_smem(fn, dsmem, "vk_decode_filter")) return rc;
+    int per_sm = blocks_per_sm(fn, kDecThreads, dsmem);
+    if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;
+    const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;
+    decode_filter_dense_kernel<T, CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(H, A, total_tiles);
+    count_launch();
+    return check_launch("decode_filter_dense_kernel");
+}
+
+template <class T, int NK, bool ML>
+static int launch_decode_filter_rows(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
+    decode_filter_rows_kernel<T, NK, ML><<<ceil_div(total_tiles, kWarps), kDecThreads, 0, stream>>>(H, A, total_tiles);
+    count_launch();
+    return check_launch("decode_filter_rows_kernel");
+}
+
+extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels, int dtype, int batch,
+                                float conf_thres, int multi_label, const uint32_t* class_mask, int kernel,
                                 const VkCandBuf* out, vk_stream_t stream_) {
     HeadDev H;
     if (int rc = make_head(cfg, &H, "vk_decode_filter")) return rc;
     if (batch == 0) return VK_OK;
     if (!levels || batch < 0) return fail_arg("vk_decode_filter: null/negative argument");
+    if (bad_dtype(dtype)) return fail_arg("vk_decode_filter: dtype %d", dtype);
+    if (kernel < VK_FILTER_AUTO || kernel > VK_FILTER_DENSE) return fail_arg("vk_decode_filter: kernel %d", kernel);
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_decode_filter: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_decode_filter: batch %d > 65535", batch);
+    if ((long)H.tiles * batch > 0x7fffffffL) return fail_code(VK_E_LIMIT, "vk_decode_filter: %d x %d tiles", H.tiles, batch);
     if (int rc = check_cand(out, H.rows, H.tiles, H.nc, multi_label, "vk_decode_filter")) return rc;
     for (int l = 0; l < H.nl; ++l) {
         if (!levels[l]) return fail_arg("vk_decode_filter: level %d is NULL", l);
+        if (reinterpret_cast<uintptr_t>(levels[l]) & (elem_size(dtype) - 1)) return fail_arg("vk_decode_filter: level %d is misaligned", l);
         H.lv[l] = levels[l];
     }
     cudaStream_t stream = as_stream(stream_);
-    cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
-    if (e != cudaSuccess) return fail_code((int)e, "vk_decode_filter: memset: %s", cudaGetErrorString(e));
-    const size_t smem = (size_t)H.no * kFiltPitch * sizeof(float);
-    if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_decode_filter: nc=%d needs %zu B of shared memory", H.nc, smem);
-    cudaFuncSetAttribute(decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
-    A.group = choose_group(batch, H.tiles);
-    int groups = 0;
-    for (int l = 0; l < H.nl; ++l) {
-        H.group_start[l] = groups;
-        groups += H.na * ceil_div(H.tpa[l], A.group);
-    }
-    for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) H.group_start[l] = groups;
-    // Eval thresholds (most rows survive) -> the dense, persistent kernel; otherwise the group
-    // kernel that gathers only surviving rows.  Both give identical bits; vk_set_filter_kernel()
-    // overrides the choice (tests run every case through both).
-    const int mode = filter_mode();
-    const bool dense = mode == VK_FILTER_DENSE || (mode == VK_FILTER_AUTO && conf_thres < 0.05f);
-    if (dense && H.nc <= 128 && (long)H.tiles * batch <= 0x7fffffffL) {
-        const int cpp_max = H.nc <= 32 ? 8 : H.nc <= 80 ? 20 : 32;
-        // + one part's worth of rows: the unrolled class loop may read past channel no-1
-        const size_t dsmem = (2 * (size_t)kTileS * H.no + (size_t)kTileS * cpp_max) * sizeof(float);
-        const int total_tiles = H.tiles * batch;
-#define VK_DF_LAUNCH(CPP, ML)                                                                                      \
-        do {                                                                                                        \
-            cudaFuncSetAttribute(decode_filter_dense_kernel<CPP, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); \
-            int per_sm = 0;                                                                                         \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_filter_dense_kernel<CPP, ML>, kDecThreads, dsmem); \
-            if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;                                                       \
-            if (per_sm < 1) per_sm = 1;                                                                             \
-            const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;                       \
-            decode_filter_dense_kernel<CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(H, A, total_tiles);           \
+    if (int rc = reset_cand(out, batch, "vk_decode_filter", stream)) return rc;
+    const FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
+    const int total_tiles = H.tiles * batch;
+    const bool ml = A.multi_label != 0;
+    if (pick_dense(kernel, conf_thres) && H.nc <= 128) {
+#define VK_DF_T(T)                                                                                                   \
+        do {                                                                                                          \
+            if (H.nc <= 32) return ml ? launch_decode_filter_dense<T, 8, true>(H, A, total_tiles, stream)            \
+                                      : launch_decode_filter_dense<T, 8, false>(H, A, total_tiles, stream);          \
+            if (H.nc <= 80) return ml ? launch_decode_filter_dense<T, 20, true>(H, A, total_tiles, stream)           \
+                                      : launch_decode_filter_dense<T, 20, false>(H, A, total_tiles, stream);         \
+            return ml ? launch_decode_filter_dense<T, 32, true>(H, A, total_tiles, stream)                           \
+                      : launch_decode_filter_dense<T, 32, false>(H, A, total_tiles, stream);                         \
         } while (0)
-#define VK_DF_CPP(CPP) do { if (A.multi_label) VK_DF_LAUNCH(CPP, true); else VK_DF_LAUNCH(CPP, false); } while (0)
-        if (H.nc <= 32) VK_DF_CPP(8);                 // classes per part = ceil(nc / 4)
-        else if (H.nc <= 80) VK_DF_CPP(20);
-        else VK_DF_CPP(32);
-#undef VK_DF_CPP
-#undef VK_DF_LAUNCH
-        count_launch();
-        return check_launch("decode_filter_dense_kernel");
+        VK_BY_DTYPE(dtype, VK_DF_T);
+#undef VK_DF_T
     }
-    decode_filter_kernel<<<dim3(groups, batch), kDecThreads, smem, stream>>>(H, A);
-    count_launch();
-    return check_launch("decode_filter_kernel");
+#define VK_DR_NK(T, NK) return ml ? launch_decode_filter_rows<T, NK, true>(H, A, total_tiles, stream) \
+                                  : launch_decode_filter_rows<T, NK, false>(H, A, total_tiles, stream)
+#define VK_DR_T(T)                                  \
+    do {                                            \
+        if (H.no <= 32) { VK_DR_NK(T, 1); }         \
+        if (H.no <= 64) { VK_DR_NK(T, 2); }         \
+        if (H.no <= 96) { VK_DR_NK(T, 3); }         \
+        if (H.no <= 128) { VK_DR_NK(T, 4); }        \
+        VK_DR_NK(T, 0);                             \
+    } while (0)
+    VK_BY_DTYPE(dtype, VK_DR_T);
+#undef VK_DR_T
+#undef VK_DR_NK
+    return VK_OK;
 }
 
-extern "C" int vk_filter_pred(const float* pred, int batch, int rows, int nc, float conf_thres,
-                              int multi_label, const uint32_t* class_mask, const VkCandBuf* out,
+template <class T, int CPP, bool ML>
+static int launch_filter_pred_dense(const void* pred, int no, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
+    const size_t dsmem = (2 * (size_t)kTileS * no + (size_t)CPP + 16) * sizeof(T);        // + slack: unrolled class loop
+    if (dsmem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_filter_pred: nc=%d needs %zu B of shared memory", A.nc, dsmem);
+    const void* fn = reinterpret_cast<const void*>(&filter_pred_dense_kernel<T, CPP, ML>);
+    if (int rc = ensure_dyn_smem(fn, dsmem, "vk_filter_pred")) return rc;
+    int per_sm = blocks_per_sm(fn, kDecThreads, dsmem);
+    if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;
+    const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;
+    filter_pred_dense_kernel<T, CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(static_cast<const T*>(pred), no, A, total_tiles);
+    count_launch();
+    return check_launch("filter_pred_dense_kernel");
+}
+
+template <class T, int NK, bool ML>
+static int launch_filter_pred_rows(const void* pred, int no, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
+    filter_pred_rows_kernel<T, NK, ML><<<ceil_div(total_tiles, kWarps), kDecThreads, 0, stream>>>(
+        static_cast<const T*>(pred), no, A, total_tiles);
+    count_launch();
+    return check_launch("filter_pred_rows_kernel");
+}
+
+extern "C" int vk_filter_pred(const void* pred, int dtype, int batch, int rows, int nc, float conf_thres,
+                              int multi_label, const uint32_t* class_mask, int kernel, const VkCandBuf* out,
                               vk_stream_t stream_) {
     if (batch == 0) return VK_OK;
     if (!pred || batch < 0 || rows <= 0 || nc < 1) return fail_arg("vk_filter_pred: null/negative argument");
+    if (bad_dtype(dtype)) return fail_arg("vk_filter_pred: dtype %d", dtype);
+    if (reinterpret_cast<uintptr_t>(pred) & (elem_size(dtype) - 1)) return fail_arg("vk_filter_pred: pred is misaligned");
+    if (kernel < VK_FILTER_AUTO || kernel > VK_FILTER_DENSE) return fail_arg("vk_filter_pred: kernel %d", kernel);
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_filter_pred: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_filter_pred: batch %d > 65535", batch);
     const int segs = ceil_div(rows, kTileS);
     if (segs > VK_MAX_SEGMENTS) return fail_code(VK_E_LIMIT, "vk_filter_pred: %d rows > %d", rows, VK_MAX_SEGMENTS * kTileS);
+    if ((long)segs * batch > 0x7fffffffL) return fail_code(VK_E_LIMIT, "vk_filter_pred: %d x %d tiles", segs, batch);
     if (int rc = check_cand(out, rows, segs, nc, multi_label, "vk_filter_pred")) return rc;
     cudaStream_t stream = as_stream(stream_);
-    cudaError_t e = cudaMemsetAsync(out->counts, 0, (size_t)batch * sizeof(int32_t), stream);
-    if (e != cudaSuccess) return fail_code((int)e, "vk_filter_pred: memset: %s", cudaGetErrorString(e));
+    if (int rc = reset_cand(out, batch, "vk_filter_pred", stream)) return rc;
     const int no = nc + 5;
-    const size_t smem = (size_t)no * kTileS * sizeof(float);
-    if (smem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_filter_pred: nc=%d needs %zu B of shared memory", nc, smem);
-    cudaFuncSetAttribute(filter_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    FilterArgs A = make_filter_args(out, conf_thres, multi_label, class_mask);
-    const int mode = filter_mode();
-    const bool dense = mode == VK_FILTER_DENSE || (mode == VK_FILTER_AUTO && conf_thres < 0.05f);
-    if (dense && nc <= 128 && (long)segs * batch <= 0x7fffffffL) {
-        const int cpp_max = nc <= 32 ? 8 : nc <= 80 ? 20 : 32;
-        const size_t dsmem = (2 * (size_t)kTileS * no + (size_t)cpp_max + 8) * sizeof(float);   // + slack: unrolled class loop
-        const int total_tiles = segs * batch;
-#define VK_FP_LAUNCH(CPP, ML)                                                                                      \
-        do {                                                                                                        \
-            cudaFuncSetAttribute(filter_pred_dense_kernel<CPP, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); \
-            int per_sm = 0;                                                                                         \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pred_dense_kernel<CPP, ML>, kDecThreads, dsmem); \
-            if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;                                                       \
-            if (per_sm < 1) per_sm = 1;                                                                             \
-            const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;                       \
-            filter_pred_dense_kernel<CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(pred, no, A, total_tiles);      \
+    const FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
+    const int total_tiles = segs * batch;
+    const bool ml = A.multi_label != 0;
+    if (pick_dense(kernel, conf_thres) && nc <= 128) {
+#define VK_FP_T(T)                                                                                                   \
+        do {                                                                                                          \
+            if (nc <= 32) return ml ? launch_filter_pred_dense<T, 8, true>(pred, no, A, total_tiles, stream)         \
+                                    : launch_filter_pred_dense<T, 8, false>(pred, no, A, total_tiles, stream);       \
+            if (nc <= 80) return ml ? launch_filter_pred_dense<T, 20, true>(pred, no, A, total_tiles, stream)        \
+                                    : launch_filter_pred_dense<T, 20, false>(pred, no, A, total_tiles, stream);      \
+            return ml ? launch_filter_pred_dense<T, 32, true>(pred, no, A, total_tiles, stream)                      \
+                      : launch_filter_pred_dense<T, 32, false>(pred, no, A, total_tiles, stream);                    \
         } while (0)
-#define VK_FP_CPP(CPP) do { if (A.multi_label) VK_FP_LAUNCH(CPP, true); else VK_FP_LAUNCH(CPP, false); } while (0)
-        if (nc <= 32) VK_FP_CPP(8);
-        else if (nc <= 80) VK_FP_CPP(20);
-        else VK_FP_CPP(32);
-#undef VK_FP_CPP
-#undef VK_FP_LAUNCH
-        count_launch();
-        return check_launch("filter_pred_dense_kernel");
+        VK_BY_DTYPE(dtype, VK_FP_T);
+#undef VK_FP_T
     }
-    A.group = choose_group(batch, segs);
-    filter_pred_kernel<<<dim3(ceil_div(segs, A.group), batch), kDecThreads, smem, stream>>>(pred, no, A);
-    count_launch();
-    return check_launch("filter_pred_kernel");
+#define VK_FR_NK(T, NK) return ml ? launch_filter_pred_rows<T, NK, true>(pred, no, A, total_tiles, stream) \
+                                  : launch_filter_pred_rows<T, NK, false>(pred, no, A, total_tiles, stream)
+#define VK_FR_T(T)                                \
+    do {                                          \
+        if (no <= 32) { VK_FR_NK(T, 1); }         \
+        if (no <= 64) { VK_FR_NK(T, 2); }         \
+        if (no <= 96) { VK_FR_NK(T, 3); }         \
+        if (no <= 128) { VK_FR_NK(T, 4); }        \
+        VK_FR_NK(T, 0);                           \
+    } while (0)
+    VK_BY_DTYPE(dtype, VK_FR_T);
+#undef VK_FR_T
+#undef VK_FR_NK
+    return VK_OK;
 }

@@ -14,10 +14,9 @@ struct HeadDev {
     int variant, nl, na, nc, no, rows, tiles;
     int ny[VK_MAX_LEVELS], nx[VK_MAX_LEVELS], nynx[VK_MAX_LEVELS];
     int row_base[VK_MAX_LEVELS], tile_start[VK_MAX_LEVELS + 1], tpa[VK_MAX_LEVELS];
-    int group_start[VK_MAX_LEVELS + 1];  // first block of each level for the chosen group size
     float stride[VK_MAX_LEVELS];
     float anchors[VK_MAX_LEVELS][2 * VK_MAX_ANCHORS];
-    const float* lv[VK_MAX_LEVELS];
+    const void* lv[VK_MAX_LEVELS];        // element type: the kernel's template parameter
     float* raw[VK_MAX_LEVELS];
 };
 
@@ -27,13 +26,39 @@ struct FilterArgs {
     const uint32_t* class_mask;  // dev or null
     uint64_t* cand;
     float4* boxes;
-    int32_t* counts;
-    int32_t* seg_base;
+    int32_t* counts;             // ctrl row 0: candidates per image (also the list reservation counter)
+    int32_t* flags;              // ctrl row 1: VK_FLAG_* | (tile_cap / 64) << 8, written by the tile with seg == 0
     int32_t* seg_count;
+    uint64_t* list;              // dev or null: unordered (ordered score << 32 | ~slot) entries
+    uint32_t* hist;              // dev or null: [batch][VK_HIST_BINS]
     int cap, rows, segs, nc;
-    int group;                   // tiles per block, 1..kGroupMax
+    int list_cap;
     int tile_cap;                // candidate slots each tile owns
 };
+
+// float order -> unsigned order (and back); scores are compared as these keys everywhere
+__host__ __device__ __forceinline__ uint32_t order_key(uint32_t fbits) {
+    return fbits ^ ((fbits >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__host__ __device__ __forceinline__ uint32_t unorder_key(uint32_t k) {
+    return k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu);
+}
+// histogram bin of a score (monotone: higher scores -> lower bins; everything >= 1.0 and
+// anything that is not a positive float lands in bin 0, so "bin <= j" is always "key >= bound(j)")
+__host__ __device__ __forceinline__ int hist_bin(uint32_t fbits) {
+    return fbits >= 0x3f800000u ? 0 : (int)((0x3f800000u - fbits) >> 20);
+}
+// smallest ordered key whose bin is <= j
+__host__ __device__ __forceinline__ uint32_t hist_bound(int j) {
+    const uint32_t span = (uint32_t)(j + 1) << 20;
+    return span >= 0x3f800000u ? 0u : order_key(0x3f800000u - span + 1u);
+}
+
+// what the tile with seg == 0 stores in the image's flags word: slots per tile (the consumer maps
+// slot <-> (segment, position) with it) and whether the kernel appended to the list
+__device__ __forceinline__ int cand_flags(const FilterArgs& A, bool appended) {
+    return ((A.tile_cap >> 6) << 8) | (appended ? VK_FLAG_APPENDED : 0);
+}
 
 __device__ __forceinline__ bool class_allowed(const uint32_t* m, int c) {
     return m == nullptr || ((__ldg(m + (c >> 5)) >> (c & 31)) & 1u);
@@ -70,7 +95,7 @@ inline int make_head(const VkHeadCfg* cfg, HeadDev* H, const char* who) {
 }
 
 inline int check_cand(const VkCandBuf* o, int rows, int segs, int nc, int multi_label, const char* who) {
-    if (!o || !o->cand || !o->boxes || !o->counts || !o->seg_base || !o->seg_count)
+    if (!o || !o->cand || !o->boxes || !o->ctrl || !o->seg_count)
         return fail_arg("%s: candidate buffer has a NULL member", who);
     if (o->cap <= 0 || o->rows != rows || o->segs != segs || o->nc != nc)
         return fail_arg("%s: candidate buffer shape (cap=%d rows=%d segs=%d nc=%d) != (rows=%d segs=%d nc=%d)",
@@ -81,21 +106,29 @@ inline int check_cand(const VkCandBuf* o, int rows, int segs, int nc, int multi_
         return fail_arg("%s: cap %d < %ld (= segs * 64 * %s): every tile owns a fixed slot range", who, o->cap, need,
                         (multi_label && nc > 1) ? "nc" : "1");
     if (reinterpret_cast<uintptr_t>(o->boxes) & 15) return fail_arg("%s: boxes must be 16-byte aligned", who);
+    if ((o->list != nullptr) != (o->list_cap > 0)) return fail_arg("%s: list and list_cap disagree", who);
     return VK_OK;
 }
 
-inline FilterArgs make_filter_args(const VkCandBuf* o, float conf, int multi_label, const uint32_t* mask) {
+inline FilterArgs make_filter_args(const VkCandBuf* o, int batch, float conf, int multi_label, const uint32_t* mask) {
     FilterArgs A;
     A.conf = conf;
     A.multi_label = (multi_label && o->nc > 1) ? 1 : 0;   // image_proc.py:111
     A.class_mask = mask;
     A.cand = o->cand;
     A.boxes = reinterpret_cast<float4*>(o->boxes);
-    A.counts = o->counts; A.seg_base = o->seg_base; A.seg_count = o->seg_count;
+    A.counts = o->ctrl; A.flags = o->ctrl + (size_t)batch; A.seg_count = o->seg_count;
+    A.list = o->list; A.hist = o->hist; A.list_cap = o->list_cap;
     A.cap = o->cap; A.rows = o->rows; A.segs = o->segs; A.nc = o->nc;
-    A.group = 1;
     A.tile_cap = kTileS * (A.multi_label ? o->nc : 1);
     return A;
+}
+
+// Zeroes the control words of the candidate buffer (counts, list entries, bound, flags).
+inline int reset_cand(const VkCandBuf* o, int batch, const char* who, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(o->ctrl, 0, (size_t)VK_CTRL_WORDS * batch * sizeof(int32_t), stream);
+    if (e != cudaSuccess) return fail_code((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
+    return VK_OK;
 }
 
 }  // namespace vk

@@ -150,7 +150,7 @@ extern "C" int vk_eval_match(const float* dets, const int32_t* det_counts, int b
     const size_t smem = vk_eval_match_smem_bytes(niou, ml);
     if (smem > 200 * 1024)
         return fail_code(VK_E_LIMIT, "vk_eval_match: %d labels in one image need %zu B of shared memory", max_labels, smem);
-    cudaFuncSetAttribute(eval_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&eval_match_kernel), smem, "vk_eval_match")) return rc;
     eval_match_kernel<<<batch, kEvalThreads, smem, as_stream(stream)>>>(
         dets, det_counts, max_det, labels, label_offsets, img0_hw, img1_h, img1_w, iouv, niou, ml, prescaled,
         predn, labeln, correct);

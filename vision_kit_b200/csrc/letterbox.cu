@@ -596,7 +596,7 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
     const size_t smem = (size_t)max_rows * row_words * 4;
 #define VK_LB_LAUNCH(FMT, T)                                                                              \
     do {                                                                                                   \
-        cudaFuncSetAttribute(lb_general_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&lb_general_kernel<FMT>), smem, "vk_letterbox_batch")) return rc; \
         lb_general_kernel<FMT><<<grid, kGenThreads, smem, stream>>>(dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, \
                                                                     static_cast<T*>(dst), row_words, max_rows); \
     } while (0)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -24,10 +25,15 @@ int fail_arg(const char* fmt, ...);        // sets message, returns VK_E_ARG
 int fail_code(int code, const char* fmt, ...);
 int check_launch(const char* what);        // cudaGetLastError -> return code
 void count_launch(int n = 1);
-int filter_mode();                         // VK_FILTER_AUTO / _SPARSE / _DENSE
-int conv_mode();                           // VK_CONV_TILE / _PERSISTENT
 
 inline cudaStream_t as_stream(vk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) / occupancy queries cost microseconds of host time per
+// call and would race between host threads if every launch set its own size: the library raises a
+// kernel's limit only when a launch needs more than any launch before it (monotone, under a mutex) and
+// remembers occupancy answers per (kernel, block size, shared memory).
+int ensure_dyn_smem(const void* func, size_t bytes, const char* who);        // VK_OK or an error code
+int blocks_per_sm(const void* func, int threads, size_t dyn_smem);           // cached occupancy (>= 1)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -57,6 +63,13 @@ __device__ __forceinline__ float ld_stream_f32(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+// element loads of the filter / decode kernels: fp16 and bf16 inputs are up-cast exactly
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class T>
+__device__ __forceinline__ float ld_elem(const T* p) { return to_f32(__ldg(p)); }
+
 // streaming stores (evict-first: the output is not re-read by this kernel)
 __device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"

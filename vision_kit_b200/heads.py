@@ -71,7 +71,9 @@ class _DetectBase(nn.Module):
         return self._cfg_cache
 
     def _conv_all(self, x):
-        return [self._conv(i, x[i]).float().contiguous() for i in range(self.num_det_layers)]
+        # the kernels read float32, float16 and bfloat16 conv outputs as they are (AMP eval emits
+        # float16, scripts/main.py:41): no up-cast pass
+        return [self._conv(i, x[i]).contiguous() for i in range(self.num_det_layers)]
 
     def forward(self, x):
         x = list(x)
@@ -112,7 +114,9 @@ class _DetectBase(nn.Module):
         ``fused_conv=True`` also folds the Detect 1x1 convs in (``vk_conv_decode_filter``: tcgen05,
         TF32 inputs -- what cuDNN does by default for fp32 convs -- fp32 accumulation): the neck
         outputs go in, the (B, 255, ny, nx) conv outputs are never written.
-        Returns an ``ops.NmsOut`` (device tensors; no synchronisation)."""
+        Returns an ``ops.NmsOut`` (device tensors; no synchronisation).  With ``fused_conv`` its ``fault``
+        member carries the tensor-core kernel's time-out flag; ``NmsOut.check()`` / ``DetectPipeline.to_list``
+        raise if it is set."""
         if fused_conv:
             feats = [f.float().contiguous() for f in x]
             cfg = self._cfg(feats)

@@ -69,26 +69,48 @@ def _append_labels(prediction: torch.Tensor, labels, conf_thres: float) -> torch
     return torch.cat((prediction, extra), 1).contiguous()
 
 
+_BUF_CACHE = {}
+
+
+def _cand_buffer(dev, stream, bs: int, rows: int, nc: int, multi_label: bool, hist: bool) -> ops.CandBuf:
+    """The worst-case candidate buffer of a drop-in call is large (segs * 64 * nc slots per image in
+    multi-label mode), so one per (device, stream, shape) is kept and reused; work on one stream is
+    ordered, which makes the reuse safe."""
+    key = (dev, stream, bs, rows, nc, multi_label, hist)
+    buf = _BUF_CACHE.get(key)
+    if buf is None:
+        if len(_BUF_CACHE) >= 4:
+            _BUF_CACHE.clear()
+        segs = _lib.lib().vk_filter_segments(rows)
+        buf = ops.CandBuf.alloc(bs, rows, segs, nc, ops.default_cap(segs, nc, multi_label), dev, hist=hist)
+        _BUF_CACHE[key] = buf
+    return buf
+
+
 def _run_nms(prediction: torch.Tensor, conf_thres: float, iou_thres: float, classes, agnostic: bool,
              multi_label: bool, labels, max_det: int, max_nms: int, want_keep: bool = False):
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     _lib.require_cuda(prediction, "nms(prediction)")
     pred = prediction
-    if pred.dtype != torch.float32:
+    if pred.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         pred = pred.float()
-    if labels and len(labels) == pred.shape[0]:
+    if labels:
+        if len(labels) != pred.shape[0]:           # the reference indexes labels[xi] (:122-123) and fails
+            raise IndexError(f"nms: {len(labels)} label sets for a batch of {pred.shape[0]}")
         pred = _append_labels(pred, labels, conf_thres)
     pred = pred.contiguous()
     bs, rows, no = pred.shape
     nc = no - 5
     multi_label = bool(multi_label) and nc > 1                        # :111
-    buf = ops.filter_pred(pred, conf_thres, multi_label, classes)
+    buf = _cand_buffer(pred.device, torch.cuda.current_stream(pred.device).cuda_stream, bs, rows, nc, multi_label,
+                       ops.expects_dense("auto", conf_thres))
+    ops.filter_pred(pred, conf_thres, multi_label, classes, buf=buf)
     out = ops.nms_batched(buf, iou_thres, agnostic, max_nms, max_det, want_keep=want_keep)
-    counts, status = torch.stack((out.counts, out.status)).cpu().tolist()       # the one sync
-    if any(status):
-        raise RuntimeError("nms: candidate buffer overflow (internal sizing error)")
+    counts = out.counts.cpu().tolist()                                # the one sync
     dets = [out.dets[i, :k] for i, k in enumerate(counts)]
+    if pred.dtype != torch.float32:                                   # the reference returns prediction's dtype
+        dets = [d.to(pred.dtype) for d in dets]
     if want_keep:
         return dets, [out.keep[i, :k] for i, k in enumerate(counts)]
     return dets

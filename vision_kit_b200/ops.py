@@ -14,10 +14,23 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (VK_HEAD_V5, VK_HEAD_V7, VK_LB_BF16_NCHW, VK_LB_F32_NCHW, VK_LB_U8_NHWC,
-                   VK_MAX_ANCHORS, VK_MAX_LEVELS, VkCandBuf, VkHeadCfg, VkLbDesc, VkLbGeom)
+from ._lib import (VK_BF16, VK_CONV_PERSISTENT, VK_CONV_TILE, VK_CTRL_WORDS, VK_F16, VK_F32, VK_FILTER_AUTO,
+                   VK_FILTER_DENSE, VK_FILTER_SPARSE, VK_HEAD_V5, VK_HEAD_V7, VK_HIST_BINS, VK_LB_BF16_NCHW,
+                   VK_LB_F32_NCHW, VK_LB_U8_NHWC, VK_MAX_ANCHORS, VK_MAX_LEVELS, VkCandBuf, VkHeadCfg, VkLbDesc,
+                   VkLbGeom)
 
 MAX_WH = 7680          # utils/image_proc.py:107
+LIST_CAP = 8192        # entries of the per-image top list the NMS kernel sorts from
+_DTYPE = {torch.float32: VK_F32, torch.float16: VK_F16, torch.bfloat16: VK_BF16}
+_KERNEL = {"auto": VK_FILTER_AUTO, "sparse": VK_FILTER_SPARSE, "dense": VK_FILTER_DENSE,
+           None: VK_FILTER_AUTO, VK_FILTER_AUTO: VK_FILTER_AUTO, VK_FILTER_SPARSE: VK_FILTER_SPARSE,
+           VK_FILTER_DENSE: VK_FILTER_DENSE}
+
+
+def expects_dense(kernel, conf_thres: float) -> bool:
+    """The library's rule for the filter kernel (and for whether a candidate buffer wants a histogram)."""
+    k = _KERNEL[kernel]
+    return k == VK_FILTER_DENSE or (k == VK_FILTER_AUTO and float(conf_thres) < 0.05)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -174,22 +187,27 @@ def head_rows(cfg: VkHeadCfg) -> int:
 
 
 def _level_ptrs(levels: Sequence[torch.Tensor], cfg: VkHeadCfg):
+    """Validates the head's conv outputs and returns (pointer array, batch, VK_F32 / VK_F16 / VK_BF16)."""
     no = cfg.nc + 5
     arr = (C.c_void_p * VK_MAX_LEVELS)()
     bs = int(levels[0].shape[0])
+    dt = levels[0].dtype
+    if dt not in _DTYPE:
+        raise ValueError(f"Detect levels must be float32, float16 or bfloat16, got {dt}")
     for l, t in enumerate(levels):
         _lib.require_cuda(t, "Detect level")
-        if t.dtype != torch.float32 or not t.is_contiguous():
-            raise ValueError("Detect levels must be contiguous float32")
+        if t.dtype != dt or not t.is_contiguous():
+            raise ValueError("Detect levels must be contiguous tensors of one dtype")
         if tuple(t.shape) != (bs, cfg.na * no, cfg.ny[l], cfg.nx[l]):
             raise ValueError(f"level {l}: shape {tuple(t.shape)} != {(bs, cfg.na * no, cfg.ny[l], cfg.nx[l])}")
         arr[l] = t.data_ptr()
-    return arr, bs
+    return arr, bs, _DTYPE[dt]
 
 
 def detect_decode(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], want_raw: bool = False):
-    """(B, na*no, ny, nx) x nl -> pred (B, rows, no) [+ raw (B, na, ny, nx, no) per level]."""
-    arr, bs = _level_ptrs(levels, cfg)
+    """(B, na*no, ny, nx) x nl (float32 / float16 / bfloat16) -> pred (B, rows, no) float32
+    [+ raw (B, na, ny, nx, no) float32 per level]."""
+    arr, bs, dt = _level_ptrs(levels, cfg)
     no = cfg.nc + 5
     pred = torch.empty((bs, head_rows(cfg), no), dtype=torch.float32, device=levels[0].device)
     raws, raw_arr = None, None
@@ -200,7 +218,7 @@ def detect_decode(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], want_raw: bool
         for l, t in enumerate(raws):
             raw_arr[l] = t.data_ptr()
     _lib.check("vk_detect_decode", _lib.lib().vk_detect_decode(
-        C.byref(cfg), C.cast(arr, C.c_void_p), bs, _ptr(pred),
+        C.byref(cfg), C.cast(arr, C.c_void_p), dt, bs, _ptr(pred),
         C.cast(raw_arr, C.c_void_p) if raw_arr is not None else C.c_void_p(0), _lib.stream_ptr()))
     return (pred, raws) if want_raw else pred
 
@@ -208,35 +226,55 @@ def detect_decode(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], want_raw: bool
 # ---------------------------------------------------------------------------- candidates
 @dataclass
 class CandBuf:
-    cand: torch.Tensor       # int64 (B, cap): low 32 = score bits, high 32 = row*nc + cls
+    """Caller-owned device buffers of one candidate set (include/vk_b200.h `VkCandBuf`)."""
+    cand: torch.Tensor       # int64 (B, cap): low 32 = score bits, high 32 = row*nc + cls; slot = seg * T + position
     boxes: torch.Tensor      # float32 (B, rows, 4)
-    counts: torch.Tensor     # int32 (B,)
-    seg_base: torch.Tensor   # int32 (B, segs)
+    ctrl: torch.Tensor       # int32 (4 * B [+ B * 1024]): counts | flags | list entries | bound [| histogram]
     seg_count: torch.Tensor  # int32 (B, segs)
+    list: Optional[torch.Tensor]   # int64 (B, list_cap): ordered score << 32 | ~slot, unordered
     cap: int
     rows: int
     segs: int
     nc: int
+    list_cap: int
+    has_hist: bool
 
     @staticmethod
-    def alloc(batch: int, rows: int, segs: int, nc: int, cap: int, device) -> "CandBuf":
+    def alloc(batch: int, rows: int, segs: int, nc: int, cap: int, device, list_cap: int = LIST_CAP,
+              hist: bool = False) -> "CandBuf":
+        """hist=True adds the histogram scratch of vk_nms_batched's selection pass: for buffers that will
+        hold more than `list_cap` candidates per image (eval thresholds)."""
+        hist = bool(hist) and list_cap > 0
+        words = VK_CTRL_WORDS * batch + (VK_HIST_BINS * batch if hist else 0)
         return CandBuf(torch.empty((batch, cap), dtype=torch.int64, device=device),
                        torch.empty((batch, rows, 4), dtype=torch.float32, device=device),
-                       torch.empty((batch,), dtype=torch.int32, device=device),
+                       torch.zeros((words,), dtype=torch.int32, device=device),
                        torch.empty((batch, segs), dtype=torch.int32, device=device),
-                       torch.empty((batch, segs), dtype=torch.int32, device=device),
-                       int(cap), int(rows), int(segs), int(nc))
+                       torch.empty((batch, list_cap), dtype=torch.int64, device=device) if list_cap > 0 else None,
+                       int(cap), int(rows), int(segs), int(nc), int(list_cap), hist)
 
     def c_struct(self) -> VkCandBuf:
         s = VkCandBuf()
-        s.cand, s.boxes, s.counts = self.cand.data_ptr(), self.boxes.data_ptr(), self.counts.data_ptr()
-        s.seg_base, s.seg_count = self.seg_base.data_ptr(), self.seg_count.data_ptr()
-        s.cap, s.rows, s.segs, s.nc = self.cap, self.rows, self.segs, self.nc
+        s.cand, s.boxes, s.ctrl = self.cand.data_ptr(), self.boxes.data_ptr(), self.ctrl.data_ptr()
+        s.seg_count = self.seg_count.data_ptr()
+        s.list = self.list.data_ptr() if self.list is not None else None
+        s.hist = self.ctrl.data_ptr() + 4 * VK_CTRL_WORDS * self.batch if self.has_hist else None
+        s.cap, s.rows, s.segs, s.nc, s.list_cap = self.cap, self.rows, self.segs, self.nc, self.list_cap
         return s
 
     @property
     def batch(self) -> int:
-        return int(self.counts.shape[0])
+        return int(self.seg_count.shape[0])
+
+    @property
+    def counts(self) -> torch.Tensor:
+        """int32 (B,): candidates per image."""
+        return self.ctrl[: self.batch]
+
+    @property
+    def tile_slots(self) -> torch.Tensor:
+        """int32 (B,): slots each 64-row tile owns, as the filter kernel recorded it."""
+        return (self.ctrl[self.batch: 2 * self.batch] >> 8) << 6
 
 
 def class_mask(classes, nc: int, device) -> Optional[torch.Tensor]:
@@ -257,47 +295,51 @@ def default_cap(segs: int, nc: int, multi_label: bool) -> int:
 
 
 def filter_pred(pred: torch.Tensor, conf_thres: float, multi_label: bool = False, classes=None,
-                cap: Optional[int] = None, buf: Optional[CandBuf] = None) -> CandBuf:
+                cap: Optional[int] = None, buf: Optional[CandBuf] = None, kernel="auto") -> CandBuf:
+    """Candidates of an existing (B, rows, 5+nc) prediction tensor (float32 / float16 / bfloat16)."""
     _lib.require_cuda(pred, "prediction")
-    if pred.dtype != torch.float32 or not pred.is_contiguous() or pred.dim() != 3:
-        raise ValueError("prediction must be a contiguous float32 (B, rows, 5+nc) tensor")
+    if pred.dtype not in _DTYPE or not pred.is_contiguous() or pred.dim() != 3:
+        raise ValueError("prediction must be a contiguous float32/float16/bfloat16 (B, rows, 5+nc) tensor")
     bs, rows, no = (int(v) for v in pred.shape)
     nc = no - 5
     segs = _lib.lib().vk_filter_segments(rows)
     if buf is None:
-        buf = CandBuf.alloc(bs, rows, segs, nc, cap or default_cap(segs, nc, multi_label), pred.device)
+        buf = CandBuf.alloc(bs, rows, segs, nc, cap or default_cap(segs, nc, multi_label), pred.device,
+                            hist=expects_dense(kernel, conf_thres))
     mask = class_mask(classes, nc, pred.device)
     cs = buf.c_struct()
     _lib.check("vk_filter_pred", _lib.lib().vk_filter_pred(
-        _ptr(pred), bs, rows, nc, float(conf_thres), int(bool(multi_label)), _ptr(mask),
-        C.byref(cs), _lib.stream_ptr()))
+        _ptr(pred), _DTYPE[pred.dtype], bs, rows, nc, float(conf_thres), int(bool(multi_label)), _ptr(mask),
+        _KERNEL[kernel], C.byref(cs), _lib.stream_ptr()))
     buf._mask = mask
     return buf
 
 
 def decode_filter(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], conf_thres: float,
                   multi_label: bool = False, classes=None, cap: Optional[int] = None,
-                  buf: Optional[CandBuf] = None) -> CandBuf:
-    arr, bs = _level_ptrs(levels, cfg)
+                  buf: Optional[CandBuf] = None, kernel="auto") -> CandBuf:
+    arr, bs, dt = _level_ptrs(levels, cfg)
     rows = head_rows(cfg)
     segs = _lib.lib().vk_decode_filter_segments(C.byref(cfg))
     if buf is None:
         buf = CandBuf.alloc(bs, rows, segs, cfg.nc, cap or default_cap(segs, cfg.nc, multi_label),
-                            levels[0].device)
+                            levels[0].device, hist=expects_dense(kernel, conf_thres))
     mask = class_mask(classes, cfg.nc, levels[0].device)
     cs = buf.c_struct()
     _lib.check("vk_decode_filter", _lib.lib().vk_decode_filter(
-        C.byref(cfg), C.cast(arr, C.c_void_p), bs, float(conf_thres), int(bool(multi_label)),
-        _ptr(mask), C.byref(cs), _lib.stream_ptr()))
+        C.byref(cfg), C.cast(arr, C.c_void_p), dt, bs, float(conf_thres), int(bool(multi_label)),
+        _ptr(mask), _KERNEL[kernel], C.byref(cs), _lib.stream_ptr()))
     buf._mask = mask
     return buf
 
 
 def conv_decode_filter(cfg: VkHeadCfg, feats: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
                        biases: Optional[Sequence[Optional[torch.Tensor]]], conf_thres: float,
-                       multi_label: bool = False, classes=None, buf: Optional[CandBuf] = None) -> CandBuf:
+                       multi_label: bool = False, classes=None, buf: Optional[CandBuf] = None,
+                       persistent: bool = True) -> CandBuf:
     """vk_conv_decode_filter: Detect 1x1 conv (tcgen05, TF32) + decode + filter in one kernel.
-    feats[l] (B, cin, ny, nx) float32; weights[l] (na*no, cin) or (na*no, cin, 1, 1); biases[l] (na*no) or None."""
+    feats[l] (B, cin, ny, nx) float32; weights[l] (na*no, cin) or (na*no, cin, 1, 1); biases[l] (na*no) or None.
+    persistent=False selects the one-tile-per-CTA kernel (identical results)."""
     nl = cfg.nl
     bs = int(feats[0].shape[0])
     dev = feats[0].device
@@ -319,13 +361,15 @@ def conv_decode_filter(cfg: VkHeadCfg, feats: Sequence[torch.Tensor], weights: S
     rows = head_rows(cfg)
     segs = _lib.lib().vk_decode_filter_segments(C.byref(cfg))
     if buf is None:
-        buf = CandBuf.alloc(bs, rows, segs, cfg.nc, default_cap(segs, cfg.nc, multi_label), dev)
+        buf = CandBuf.alloc(bs, rows, segs, cfg.nc, default_cap(segs, cfg.nc, multi_label), dev,
+                            hist=float(conf_thres) < 0.05)
     mask = class_mask(classes, cfg.nc, dev)
     fault = torch.zeros(1, dtype=torch.int32, device=dev)
     cs = buf.c_struct()
     _lib.check("vk_conv_decode_filter", _lib.lib().vk_conv_decode_filter(
         C.byref(cfg), C.cast(fp, C.c_void_p), C.cast(cin, C.c_void_p), C.cast(wp, C.c_void_p), C.cast(bp, C.c_void_p),
-        bs, float(conf_thres), int(bool(multi_label)), _ptr(mask), C.byref(cs), _ptr(fault), _lib.stream_ptr()))
+        bs, float(conf_thres), int(bool(multi_label)), _ptr(mask), VK_CONV_PERSISTENT if persistent else VK_CONV_TILE,
+        C.byref(cs), _ptr(fault), _lib.stream_ptr()))
     buf._mask, buf._keep, buf.fault = mask, keep, fault
     return buf
 
@@ -335,12 +379,18 @@ class NmsOut:
     dets: torch.Tensor        # float32 (B, max_det, 6), rows >= count zero
     counts: torch.Tensor      # int32 (B,)
     keep: Optional[torch.Tensor]   # int64 (B, max_det), -1 padded
-    status: torch.Tensor      # int32 (B,), bit0 = candidate overflow
+    status: torch.Tensor      # int32 (B,), always 0 (a candidate buffer sized by default_cap cannot overflow)
+    fault: Optional[torch.Tensor] = None   # int32 (1,) of the fused conv head: 1 = a tensor-core wait timed out
+
+    def check(self) -> None:
+        """Raises if the fused conv head reported a fault (synchronises; `to_list` calls it)."""
+        if self.fault is not None and int(self.fault.item()) != 0:
+            raise RuntimeError("vk_conv_decode_filter: a tensor-core completion wait timed out; detections are incomplete")
 
 
 def nms_batched(buf: CandBuf, iou_thres: float, agnostic: bool = False, max_nms: int = 30000,
                 max_det: int = 300, max_wh: float = MAX_WH, want_keep: bool = False,
-                out: Optional[NmsOut] = None, ws: Optional[torch.Tensor] = None) -> NmsOut:
+                out: Optional[NmsOut] = None) -> NmsOut:
     dev = buf.cand.device
     bs = buf.batch
     if out is None:
@@ -348,13 +398,11 @@ def nms_batched(buf: CandBuf, iou_thres: float, agnostic: bool = False, max_nms:
                      torch.empty((bs,), dtype=torch.int32, device=dev),
                      torch.empty((bs, max_det), dtype=torch.int64, device=dev) if want_keep else None,
                      torch.empty((bs,), dtype=torch.int32, device=dev))
-    if ws is None:
-        ws = torch.empty(_lib.lib().vk_nms_workspace_bytes(bs, int(max_nms)), dtype=torch.uint8, device=dev)
+    out.fault = getattr(buf, "fault", None)
     cs = buf.c_struct()
     _lib.check("vk_nms_batched", _lib.lib().vk_nms_batched(
-        C.byref(cs), bs, 0.0, float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det),
-        float(max_wh), _ptr(out.dets), _ptr(out.counts), _ptr(out.keep), _ptr(out.status), _ptr(ws),
-        ws.numel(), _lib.stream_ptr()))
+        C.byref(cs), bs, float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det),
+        float(max_wh), _ptr(out.dets), _ptr(out.counts), _ptr(out.keep), _ptr(out.status), _lib.stream_ptr()))
     return out
 
 

@@ -8,7 +8,11 @@ eval loop calls once per batch.
     dets = pipe.to_list(out)             # the reference's list[(k,6)] (one synchronisation)
 
 Replaces, per batch, demo/processing.py:45-52 + models/heads/*.py eval forward +
-utils/image_proc.py:83-187, with no host synchronisation between the three kernels.
+utils/image_proc.py:83-187, with no host synchronisation between the kernels.
+
+A loop whose buffers stay put (a staging buffer for the sources, the model's static output
+tensors) can `capture()` the step once and `replay()` it: one CUDA-graph launch per batch
+instead of three C calls and their stream bookkeeping.
 """
 from __future__ import annotations
 
@@ -17,7 +21,11 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import _lib, ops, synth
+from . import _lib, ops
+
+# default anchors of the reference's heads (models/heads/yolov5.py:24-28, yolov7.py:23-27), pixels
+V5_ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
+V7_ANCHORS = [[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 110, 192, 243, 459, 401]]
 
 
 class DetectPipeline:
@@ -26,7 +34,7 @@ class DetectPipeline:
                  multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                  anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
                  swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False,
-                 overlap: bool = False):
+                 overlap: bool = False, filter_kernel="auto", list_cap: int = ops.LIST_CAP):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
@@ -34,28 +42,27 @@ class DetectPipeline:
         self.conf_thres, self.iou_thres, self.classes = conf_thres, iou_thres, classes
         self.agnostic, self.multi_label, self.max_det, self.max_nms = agnostic, multi_label, max_det, max_nms
         if anchors is None:
-            anchors = synth.V5_ANCHORS if variant == "v5" else synth.V7_ANCHORS
+            anchors = V5_ANCHORS if variant == "v5" else V7_ANCHORS
         grids = [(img_sz[0] // int(s), img_sz[1] // int(s)) for s in strides]
         self.cfg = ops.head_cfg(variant, nc, anchors, strides, grids)
         self.rows = ops.head_rows(self.cfg)
-        import ctypes as C
         segs = _lib.lib().vk_decode_filter_segments(C.byref(self.cfg))
         ml = bool(multi_label) and nc > 1
         cap = cand_cap or ops.default_cap(segs, nc, ml)
+        self._kernel = ops._KERNEL[filter_kernel]
         # two sets of candidate / output buffers: with overlap=True the NMS of batch k runs on a
         # side stream while the letterbox and filter kernels of batch k+1 run on the main one
         self.overlap = bool(overlap)
         nsets = 2 if self.overlap else 1
-        self._cands = [ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device) for _ in range(nsets)]
+        self._cands = [ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device, list_cap=list_cap,
+                                         hist=ops.expects_dense(filter_kernel, conf_thres)) for _ in range(nsets)]
         self._outs = [ops.NmsOut(
             torch.empty((batch, max_det, 6), dtype=torch.float32, device=self.device),
             torch.empty((batch,), dtype=torch.int32, device=self.device),
             torch.empty((batch, max_det), dtype=torch.int64, device=self.device) if want_keep else None,
             torch.empty((batch,), dtype=torch.int32, device=self.device)) for _ in range(nsets)]
-        self._nms_ws = [torch.empty(_lib.lib().vk_nms_workspace_bytes(batch, max_nms), dtype=torch.uint8,
-                                    device=self.device) for _ in range(nsets)]
         self._set = 0
-        self.cand, self.out, self.nms_ws = self._cands[0], self._outs[0], self._nms_ws[0]
+        self.cand, self.out = self._cands[0], self._outs[0]
         if self.overlap:
             self.side = torch.cuda.Stream(device=self.device)
             self._ev_filter = [torch.cuda.Event() for _ in range(2)]
@@ -63,9 +70,7 @@ class DetectPipeline:
             self._nms_pending = [False, False]
         self.input = torch.empty((batch, 3, img_sz[0], img_sz[1]), dtype=dtype, device=self.device)
         self.plan: Optional[ops.LetterboxPlan] = None
-        # Pre-marshalled ctypes arguments: a step of the loop is three C calls with constant arguments,
-        # and at ~150 us of GPU work per step the Python around them decides whether 8 ranks on one host
-        # stay GPU-bound (host time to enqueue a step: 113 -> see profiles/).
+        # Pre-marshalled ctypes arguments: a step of the loop is three C calls with constant arguments
         self._lib = _lib.lib()
         self._mask = ops.class_mask(classes, nc, self.device)
         self._mask_p = ops._ptr(self._mask)
@@ -73,13 +78,17 @@ class DetectPipeline:
         self._cfg_ref = C.byref(self.cfg)
         self._ml = int(ml)
         self._conf = C.c_float(float(conf_thres))
-        self._nms_args = [(C.byref(cs), batch, C.c_float(0.0), C.c_double(float(iou_thres)), int(bool(agnostic)),
+        self._nms_args = [(C.byref(cs), batch, C.c_double(float(iou_thres)), int(bool(agnostic)),
                            int(max_nms), int(max_det), C.c_float(ops.MAX_WH), ops._ptr(o.dets), ops._ptr(o.counts),
-                           ops._ptr(o.keep), ops._ptr(o.status), ops._ptr(w), C.c_size_t(w.numel()))
-                          for cs, o, w in zip(self._cs, self._outs, self._nms_ws)]
+                           ops._ptr(o.keep), ops._ptr(o.status))
+                          for cs, o in zip(self._cs, self._outs)]
         self._lv_key = None
         self._lv_arr = None
+        self._lv_dt = 0
         self._lb_args = None
+        self._graphs: List[torch.cuda.CUDAGraph] = []
+        self._graph_feats = None
+        self._graph_step = 0
 
     # -- letterbox + normalise
     def plan_sources(self, srcs: Sequence[torch.Tensor]) -> ops.LetterboxPlan:
@@ -111,18 +120,18 @@ class DetectPipeline:
     def filter(self, feats: Sequence[torch.Tensor]) -> ops.CandBuf:
         if self.overlap:
             self._set ^= 1
-            self.cand, self.out, self.nms_ws = (self._cands[self._set], self._outs[self._set],
-                                                self._nms_ws[self._set])
+            self.cand, self.out = self._cands[self._set], self._outs[self._set]
             if self._nms_pending[self._set]:        # the NMS that last read this buffer set
                 torch.cuda.current_stream().wait_event(self._ev_nms[self._set])
-        key = tuple(t.data_ptr() for t in feats)
-        if key != self._lv_key:                     # new tensors: validate and marshal once
-            self._lv_arr, bs = ops._level_ptrs(feats, self.cfg)
+        # the marshalled pointer array is reused while the same tensors (address, dtype, shape, layout) come back
+        key = tuple((t.data_ptr(), t.dtype, t.shape, t.stride()) for t in feats)
+        if key != self._lv_key:
+            self._lv_arr, bs, self._lv_dt = ops._level_ptrs(feats, self.cfg)
             if bs != self.batch:
                 raise ValueError(f"expected a batch of {self.batch}, got {bs}")
             self._lv_key = key
-        rc = self._lib.vk_decode_filter(self._cfg_ref, C.cast(self._lv_arr, C.c_void_p), self.batch, self._conf,
-                                        self._ml, self._mask_p, C.byref(self._cs[self._set]),
+        rc = self._lib.vk_decode_filter(self._cfg_ref, C.cast(self._lv_arr, C.c_void_p), self._lv_dt, self.batch,
+                                        self._conf, self._ml, self._mask_p, self._kernel, C.byref(self._cs[self._set]),
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc:
             _lib.check("vk_decode_filter", rc)
@@ -161,6 +170,77 @@ class DetectPipeline:
             self.join()
         return out
 
+    # -- the same step as one CUDA-graph launch
+    def capture(self, feats: Sequence[torch.Tensor], with_preprocess: bool = True) -> None:
+        """Captures preprocess (optional; needs plan_sources) + filter + NMS on THESE tensors into a CUDA
+        graph.  The source buffers of the plan and `feats` must keep their addresses; refill them in place
+        between `replay()` calls.  With overlap=True two graphs alternate over the two buffer sets and
+        every launch runs the NMS of the previous batch beside the letterbox and filter of the current one."""
+        if with_preprocess and self._lb_args is None:
+            raise RuntimeError("capture(with_preprocess=True) needs plan_sources() first")
+        for _ in range(2):                       # eager warm-up: kernel attributes, validation, caches
+            if with_preprocess:
+                self.preprocess()
+            self.postprocess(feats)
+        torch.cuda.synchronize(self.device)
+        self._graph_feats = list(feats)          # keep them alive
+        self._graphs = []
+        if not self.overlap:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if with_preprocess:
+                    self.preprocess()
+                self.filter(feats)
+                self.nms()
+            self._graphs = [g]
+        else:
+            # graph s: [letterbox, filter -> set s] beside [NMS of set s^1]
+            self._nms_pending = [False, False]
+            for s in (0, 1):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    main = torch.cuda.current_stream()
+                    self.side.wait_stream(main)
+                    rc = self._lib.vk_nms_batched(*self._nms_args[s ^ 1], C.c_void_p(self.side.cuda_stream))
+                    if rc:
+                        _lib.check("vk_nms_batched", rc)
+                    if with_preprocess:
+                        self.preprocess()
+                    rc = self._lib.vk_decode_filter(self._cfg_ref, C.cast(self._lv_arr, C.c_void_p), self._lv_dt,
+                                                    self.batch, self._conf, self._ml, self._mask_p, self._kernel,
+                                                    C.byref(self._cs[s]), C.c_void_p(main.cuda_stream))
+                    if rc:
+                        _lib.check("vk_decode_filter", rc)
+                    main.wait_stream(self.side)
+                self._graphs.append(g)
+            self._set = 1                        # the eager warm-up left valid candidates in both sets
+        self._graph_step = 0
+
+    def replay(self) -> ops.NmsOut:
+        """One launch of the captured step.  Without overlap: the NmsOut of this batch.  With overlap: the
+        NmsOut of the PREVIOUS batch (its NMS ran inside this launch); call `flush()` after the last batch."""
+        if not self._graphs:
+            raise RuntimeError("replay() before capture()")
+        if not self.overlap:
+            self._graphs[0].replay()
+            return self.out
+        s = self._graph_step & 1
+        self._graph_step += 1
+        self._graphs[s].replay()
+        self._set = s
+        self.cand = self._cands[s]
+        self.out = self._outs[s ^ 1]
+        return self.out
+
+    def flush(self) -> ops.NmsOut:
+        """overlap=True graphs: runs the NMS of the last replayed batch (eagerly, on the current stream)."""
+        s = self._set
+        rc = self._lib.vk_nms_batched(*self._nms_args[s], C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            _lib.check("vk_nms_batched", rc)
+        self.out = self._outs[s]
+        return self.out
+
     # -- drop-in layout: decode to the (B, rows, no) tensor, then filter + NMS from it
     def postprocess_materialised(self, feats: Sequence[torch.Tensor]):
         pred = ops.detect_decode(self.cfg, feats)
@@ -169,5 +249,6 @@ class DetectPipeline:
 
     @staticmethod
     def to_list(out: ops.NmsOut) -> List[torch.Tensor]:
+        out.check()
         counts = out.counts.cpu().tolist()
         return [out.dets[i, :k] for i, k in enumerate(counts)]
