@@ -134,17 +134,15 @@ int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels, int dtype,
  * the buffer needs cap >= segs * T and can never overflow, and SLOT ORDER IS THE CANONICAL ORDER
  * of the reference's candidate list (the order that breaks score ties in its argsort and NMS).
  *
- * Two optional accelerators for vk_nms_batched (results never depend on them):
- *   list  the sparse filter kernels append every candidate as (ordered score << 32 | ~slot) to
- *         an unordered per-image list while the image has <= list_cap candidates;
- *   hist  scratch of vk_nms_batched: when an image has more candidates than the list holds (eval
- *         thresholds), a sampled score histogram picks the score bound above which a grid-wide pass
- *         copies the candidates into the list.  Allocate it when such images are expected.
+ * list + hist: optional scratch of vk_nms_batched for images with more than list_cap candidates
+ * (eval thresholds, ~240 k per image): a sampled score histogram picks the score bound above which a
+ * grid-wide pass copies the candidates, as (ordered score << 32 | ~slot), into the image's list, and
+ * the per-image kernel sorts from that list.  Results never depend on them; allocate both when such
+ * images are expected.
  */
 #define VK_HIST_BINS 1024   /* bin = (0x3f800000 - score bits) >> 20: 8 bins per octave below 1.0 */
 #define VK_CTRL_WORDS 4     /* ctrl rows: 0 candidate count, 1 flags | slots per tile / 64 << 8, 2 list entries, 3 list bound */
 #define VK_FLAG_LIST 2      /* list[b] holds every candidate with ordered score >= bound (set by vk_nms_batched) */
-#define VK_FLAG_APPENDED 4  /* the filter kernel appended its candidates to list[b] (complete iff count <= list_cap) */
 
 typedef struct VkCandBuf {
     uint64_t* cand;      /* dev [batch][cap]: low 32 = score bits, high 32 = row*nc + cls */

@@ -10,7 +10,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvk_b200.so")
+LIB_PATH = os.environ.get("VK_B200_LIB") or os.path.join(HERE, "libvk_b200.so")   # (override: profiling builds)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vk_b200.h")
 
 VK_MAX_LEVELS = 4
@@ -24,7 +24,7 @@ VK_FILTER_AUTO, VK_FILTER_SPARSE, VK_FILTER_DENSE = 0, 1, 2
 VK_CONV_TILE, VK_CONV_PERSISTENT = 0, 1
 VK_HIST_BINS = 1024
 VK_CTRL_WORDS = 4
-VK_FLAG_LIST, VK_FLAG_APPENDED = 2, 4
+VK_FLAG_LIST = 2
 
 
 class VkError(RuntimeError):

@@ -48,10 +48,9 @@ int ensure_dyn_smem(const void* func, size_t bytes, const char* who) {
     std::lock_guard<std::mutex> lock(g_attr_mutex);
     size_t& cur = g_smem_set[{dev, func}];
     if (bytes <= cur) return VK_OK;
-    if (bytes > 48 * 1024 || cur > 0) {
-        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return fail_code((int)e, "%s: %zu B of shared memory: %s", who, bytes, cudaGetErrorString(e));
-    }
+    // (static + dynamic shared memory above 48 KB needs the opt-in even when the dynamic part alone is below it)
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail_code((int)e, "%s: %zu B of shared memory: %s", who, bytes, cudaGetErrorString(e));
     cur = bytes;
     return VK_OK;
 }

@@ -201,7 +201,7 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
         }
         if ((tid & 63) == 0 && seg_exists) {
             A.seg_count[(size_t)b * A.segs + seg] = seg_total;
-            if (seg == 0) A.flags[b] = cand_flags(A, false);
+            if (seg == 0) A.flags[b] = cand_flags(A);
             if (seg_total) atomicAdd(A.counts + b, seg_total);
         }
         ch_bar_sync(bar_id);                                       // s_wtot is reused by the next anchor

@@ -327,17 +327,29 @@ detect_decode_kernel(const HeadDev H, float* __restrict__ pred, int total_tiles,
 //   3  per row: class products on all lanes, best class by a warp arg-max that prefers the
 //      lower class on ties (= the first maximum the reference's `max(1)` returns, :145), or
 //      multi-label ballots in channel order (`nonzero` order, :141-143); lane 0 decodes the box
-//   4  candidates go to the tile's own slot range in order; an emitting row also reserves
-//      list space with one atomicAdd on the image's candidate counter and appends
-//      (ordered score << 32 | ~slot) -- the unordered top list vk_nms_batched sorts from
+//   4  candidates go to the tile's own slot range in order; the tile's count joins the image's
+//      counter with a fire-and-forget atomic (nothing in the kernel waits for an atomic's result)
 //
-// 25 344 tiles per 64 images = 3 168 blocks of 8 warps; with ~1.8 surviving rows per tile the
-// kernel is bound by the DRAM sector rate of the gathers (85 sectors per surviving row).
+// With ~1.8 surviving rows per tile the kernel is bound by the rate at which HBM serves scattered sectors
+// (85 per surviving row, each in a different DRAM page; profiles/micro/sector_gather.cu).
 // ---------------------------------------------------------------------------------------
 #ifndef VK_DENSE_BPS
 #define VK_DENSE_BPS 4
 #endif
-constexpr int kRowBatch = 4;      // surviving rows whose gathers are in flight together
+#ifndef VK_ROW_BATCH
+#define VK_ROW_BATCH 4
+#endif
+#ifndef VK_ROWS_BPS
+#define VK_ROWS_BPS 8
+#endif
+#ifndef VK_ROWS_WARPS
+#define VK_ROWS_WARPS 4
+#endif
+#ifndef VK_ROWS_PERSISTENT
+#define VK_ROWS_PERSISTENT 0
+#endif
+constexpr int kRowBatch = VK_ROW_BATCH;      // surviving rows whose gathers are in flight together
+constexpr int kRowWarps = VK_ROWS_WARPS;     // warps (= tiles in flight) per block of the sparse kernels
 
 struct PlaneGeom {       // fused path: what is needed to decode a box from logits
     int variant, nx, s0; // s0: spatial index of the tile's first row inside its plane
@@ -355,7 +367,7 @@ struct PlaneGeom {       // fused path: what is needed to decode a box from logi
 template <class T>
 struct LogitRows {       // conv output plane (b, a): element (row r, channel c) at base[c * nynx + r]
     const T* base; int nynx; PlaneGeom g;
-    __device__ __forceinline__ float obj(int r) const { return sigmoidf_vk(ld_elem(base + (size_t)4 * nynx + r)); }
+    __device__ __forceinline__ float obj_val(float raw) const { return sigmoidf_vk(raw); }
     __device__ __forceinline__ float raw(int r, int c) const { return ld_elem(base + (size_t)c * nynx + r); }
     __device__ __forceinline__ float prob(float x) const { return sigmoidf_vk(x); }
     __device__ __forceinline__ float4 box(float l0, float l1, float l2, float l3, int r) const {
@@ -365,7 +377,7 @@ struct LogitRows {       // conv output plane (b, a): element (row r, channel c)
 template <class T>
 struct PredRows {        // decoded prediction rows: element (row r, channel c) at base[r * no + c]
     const T* base; int no;
-    __device__ __forceinline__ float obj(int r) const { return ld_elem(base + (size_t)r * no + 4); }
+    __device__ __forceinline__ float obj_val(float raw) const { return raw; }
     __device__ __forceinline__ float raw(int r, int c) const { return ld_elem(base + (size_t)r * no + c); }
     __device__ __forceinline__ float prob(float x) const { return x; }
     __device__ __forceinline__ float4 box(float l0, float l1, float l2, float l3, int) const {
@@ -376,10 +388,7 @@ struct PredRows {        // decoded prediction rows: element (row r, channel c) 
 // Everything a warp needs to emit candidates of its tile.
 struct TileOut {
     uint2* cand;         // the tile's slot range
-    uint64_t* list;      // the image's list or null
     float4* boxes;       // the image's boxes
-    int32_t* count;      // the image's candidate counter
-    uint32_t slot0;      // first slot of the tile
     int row0;            // first prediction row of the tile
     int cnt;             // candidates written so far (warp-uniform)
 };
@@ -392,11 +401,9 @@ __device__ __forceinline__ void emit_row(const Src& S, const FilterArgs& A, Tile
     const int nc = A.nc;
     const int row = O.row0 + r;
     int total;
-    float p[NK];
-    unsigned bal[NK];
-    float bv = -INFINITY;
-    int bj = 0x7fffffff;
     if (ML) {
+        float p[NK];
+        unsigned bal[NK];
         total = 0;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
@@ -406,7 +413,17 @@ __device__ __forceinline__ void emit_row(const Src& S, const FilterArgs& A, Tile
             bal[k] = __ballot_sync(0xffffffffu, f);
             total += __popc(bal[k]);
         }
+        if (total == 0) return;
+        int pos = O.cnt;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            if ((bal[k] >> lane) & 1u)
+                O.cand[pos + __popc(bal[k] & lt)] = make_uint2(__float_as_uint(p[k]), (uint32_t)(row * nc + lane + 32 * k - 5));
+            pos += __popc(bal[k]);
+        }
     } else {
+        float bv = -INFINITY;
+        int bj = 0x7fffffff;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
             const int cls = lane + 32 * k - 5;
@@ -420,31 +437,8 @@ __device__ __forceinline__ void emit_row(const Src& S, const FilterArgs& A, Tile
             if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
         }
         total = (bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;    // :147,151
-    }
-    if (total == 0) return;
-    // list space for the row's candidates: one reservation on the image's counter
-    int lbase = 0;
-    if (O.list) {
-        if (lane == 0) lbase = atomicAdd(O.count, total);
-        lbase = __shfl_sync(0xffffffffu, lbase, 0);
-    }
-    const bool to_list = O.list != nullptr && lbase + total <= A.list_cap;
-    if (ML) {
-        int pos = O.cnt;
-#pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            if ((bal[k] >> lane) & 1u) {
-                const int at = pos + __popc(bal[k] & lt);
-                const uint32_t bits = __float_as_uint(p[k]);
-                O.cand[at] = make_uint2(bits, (uint32_t)(row * nc + lane + 32 * k - 5));
-                if (to_list) O.list[lbase + at - O.cnt] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)at);
-            }
-            pos += __popc(bal[k]);
-        }
-    } else if (lane == 0) {
-        const uint32_t bits = __float_as_uint(bv);
-        O.cand[O.cnt] = make_uint2(bits, (uint32_t)(row * nc + bj));
-        if (to_list) O.list[lbase] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)O.cnt);
+        if (total == 0) return;
+        if (lane == 0) O.cand[O.cnt] = make_uint2(__float_as_uint(bv), (uint32_t)(row * nc + bj));
     }
     const float l1 = __shfl_sync(0xffffffffu, x[0], 1), l2 = __shfl_sync(0xffffffffu, x[0], 2),
                 l3 = __shfl_sync(0xffffffffu, x[0], 3);
@@ -452,23 +446,20 @@ __device__ __forceinline__ void emit_row(const Src& S, const FilterArgs& A, Tile
     O.cnt += total;
 }
 
-// The whole tile: objectness -> surviving rows -> candidates -> segment count.  NK > 0: no <= 32 * NK
-// channels, rows gathered kRowBatch at a time; NK == 0: any channel count, one row at a time.
+// The tile's surviving rows (objectness o0: rows 0-31, o1: rows 32-63, already evaluated) -> candidates
+// -> segment count.  NK > 0: no <= 32 * NK channels, rows gathered kRowBatch at a time; NK == 0: any
+// channel count, one row at a time.
 template <class Src, int NK, bool ML>
-__device__ __forceinline__ void filter_tile_rows(const Src& S, const FilterArgs& A, int b, int seg, int row0, int nvalid) {
+__device__ __forceinline__ void filter_tile_rows(const Src& S, const FilterArgs& A, int b, int seg, int row0,
+                                                 float o0, float o1) {
     const int lane = threadIdx.x & 31;
     const int no = A.nc + 5;
-    const float o0 = (lane < nvalid) ? S.obj(lane) : -1.0f;
-    const float o1 = (lane + 32 < nvalid) ? S.obj(lane + 32) : -1.0f;
     const unsigned m0 = __ballot_sync(0xffffffffu, o0 > A.conf);                                 // image_proc.py:99
     const unsigned m1 = __ballot_sync(0xffffffffu, o1 > A.conf);
     unsigned long long mask = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
     TileOut O;
-    O.slot0 = (uint32_t)seg * (uint32_t)A.tile_cap;
-    O.cand = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + O.slot0;
-    O.list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
+    O.cand = reinterpret_cast<uint2*>(A.cand + (size_t)b * A.cap) + (size_t)seg * A.tile_cap;
     O.boxes = A.boxes + (size_t)b * A.rows;
-    O.count = A.counts + b;
     O.row0 = row0;
     O.cnt = 0;
     if (NK > 0) {
@@ -504,36 +495,17 @@ __device__ __forceinline__ void filter_tile_rows(const Src& S, const FilterArgs&
             const int row = row0 + r;
             const float x0 = (lane < no) ? S.raw(r, lane) : 0.0f;
             if (ML) {
-                // pass 1 counts (the list reservation needs the row total), pass 2 writes
-                int total = 0;
-                for (int c0 = 0; c0 < no; c0 += 32) {
-                    const int c = c0 + lane, cls = c - 5;
-                    const float pv = (c < no) ? __fmul_rn(S.prob(c0 ? S.raw(r, c) : x0), o) : 0.0f;
-                    const bool f = cls >= 0 && cls < nc && pv > A.conf && class_allowed(A.class_mask, cls);
-                    total += __popc(__ballot_sync(0xffffffffu, f));
-                }
-                if (total == 0) continue;
-                int lbase = 0;
-                if (O.list) {
-                    if (lane == 0) lbase = atomicAdd(O.count, total);
-                    lbase = __shfl_sync(0xffffffffu, lbase, 0);
-                }
-                const bool to_list = O.list != nullptr && lbase + total <= A.list_cap;
                 int pos = O.cnt;
                 for (int c0 = 0; c0 < no; c0 += 32) {
                     const int c = c0 + lane, cls = c - 5;
                     const float pv = (c < no) ? __fmul_rn(S.prob(c0 ? S.raw(r, c) : x0), o) : 0.0f;
                     const bool f = cls >= 0 && cls < nc && pv > A.conf && class_allowed(A.class_mask, cls);
                     const unsigned bal = __ballot_sync(0xffffffffu, f);
-                    if (f) {
-                        const int at = pos + __popc(bal & lt);
-                        const uint32_t bits = __float_as_uint(pv);
-                        O.cand[at] = make_uint2(bits, (uint32_t)(row * nc + cls));
-                        if (to_list) O.list[lbase + at - O.cnt] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)at);
-                    }
+                    if (f) O.cand[pos + __popc(bal & lt)] = make_uint2(__float_as_uint(pv), (uint32_t)(row * nc + cls));
                     pos += __popc(bal);
                 }
-                O.cnt += total;
+                if (pos == O.cnt) continue;
+                O.cnt = pos;
             } else {
                 float bv = -INFINITY;
                 int bj = 0x7fffffff;
@@ -551,14 +523,7 @@ __device__ __forceinline__ void filter_tile_rows(const Src& S, const FilterArgs&
                     if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
                 }
                 if (!(bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj))) continue;
-                if (lane == 0) {
-                    const uint32_t bits = __float_as_uint(bv);
-                    O.cand[O.cnt] = make_uint2(bits, (uint32_t)(row * nc + bj));
-                    if (O.list) {
-                        const int lbase = atomicAdd(O.count, 1);
-                        if (lbase < A.list_cap) O.list[lbase] = ((uint64_t)order_key(bits) << 32) | (uint32_t)~(O.slot0 + (uint32_t)O.cnt);
-                    }
-                }
+                if (lane == 0) O.cand[O.cnt] = make_uint2(__float_as_uint(bv), (uint32_t)(row * nc + bj));
                 O.cnt += 1;
             }
             const float l1 = __shfl_sync(0xffffffffu, x0, 1), l2 = __shfl_sync(0xffffffffu, x0, 2),
@@ -568,44 +533,114 @@ __device__ __forceinline__ void filter_tile_rows(const Src& S, const FilterArgs&
     }
     if (lane == 0) {
         A.seg_count[(size_t)b * A.segs + seg] = O.cnt;
-        if (O.cnt && !O.list) atomicAdd(O.count, O.cnt);              // with a list the rows reserved as they went
-        if (seg == 0) A.flags[b] = cand_flags(A, O.list != nullptr);
+        if (O.cnt) atomicAdd(A.counts + b, O.cnt);                    // result unused: fire-and-forget
+        if (seg == 0) A.flags[b] = cand_flags(A);
     }
 }
 
-template <class T, int NK, bool ML>
-__global__ void __launch_bounds__(kDecThreads, 4)
-decode_filter_rows_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
-    const int t = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (t >= total_tiles) return;
-    const int b = t / H.tiles, ti = t - b * H.tiles;
-    int l = 0;
+// ---- tile locators: which tile a linear index is, where its values live
+template <class T>
+struct LogitTileRef {
+    const T* base;       // channel 0, row s0 of plane (b, a)
+    int b, seg, l, a, s0, nvalid, row0, nynx;
+    __device__ __forceinline__ float obj_raw(int r) const { return r < nvalid ? ld_elem(base + (size_t)4 * nynx + r) : 0.0f; }
+};
+template <class T>
+struct LogitLocator {
+    const HeadDev& H;
+    typedef LogitTileRef<T> Ref;
+    typedef LogitRows<T> Src;
+    __device__ __forceinline__ Ref locate(int t) const {
+        Ref q;
+        q.b = t / H.tiles; q.seg = t - q.b * H.tiles;
+        int l = 0;
 #pragma unroll
-    for (int i = 1; i < VK_MAX_LEVELS; ++i)
-        if (i < H.nl && ti >= H.tile_start[i]) l = i;
-    const int rel = ti - H.tile_start[l];
-    const int a = rel / H.tpa[l];
-    const int s0 = (rel - a * H.tpa[l]) * kTileS;
-    const int nynx = H.nynx[l];
-    const int nvalid = min(kTileS, nynx - s0);
-    const int row0 = H.row_base[l] + a * nynx + s0;
-    const LogitRows<T> S{static_cast<const T*>(H.lv[l]) + ((size_t)(b * H.na + a) * H.no) * nynx + s0, nynx,
-                         PlaneGeom{H.variant, H.nx[l], s0, H.stride[l], H.anchors[l][2 * a], H.anchors[l][2 * a + 1]}};
-    filter_tile_rows<LogitRows<T>, NK, ML>(S, A, b, ti, row0, nvalid);
+        for (int i = 1; i < VK_MAX_LEVELS; ++i)
+            if (i < H.nl && q.seg >= H.tile_start[i]) l = i;
+        const int rel = q.seg - H.tile_start[l];
+        q.l = l; q.a = rel / H.tpa[l];
+        q.s0 = (rel - q.a * H.tpa[l]) * kTileS;
+        q.nynx = H.nynx[l];
+        q.nvalid = min(kTileS, q.nynx - q.s0);
+        q.row0 = H.row_base[l] + q.a * q.nynx + q.s0;
+        q.base = static_cast<const T*>(H.lv[l]) + ((size_t)(q.b * H.na + q.a) * H.no) * q.nynx + q.s0;
+        return q;
+    }
+    __device__ __forceinline__ Src source(const Ref& q) const {
+        return Src{q.base, q.nynx, PlaneGeom{H.variant, H.nx[q.l], q.s0, H.stride[q.l], H.anchors[q.l][2 * q.a], H.anchors[q.l][2 * q.a + 1]}};
+    }
+};
+template <class T>
+struct PredTileRef {
+    const T* base;       // row row0 of image b
+    int b, seg, nvalid, row0, no;
+    __device__ __forceinline__ float obj_raw(int r) const { return r < nvalid ? ld_elem(base + (size_t)r * no + 4) : 0.0f; }
+};
+template <class T>
+struct PredLocator {
+    const T* pred; int no, rows, segs;
+    typedef PredTileRef<T> Ref;
+    typedef PredRows<T> Src;
+    __device__ __forceinline__ Ref locate(int t) const {
+        Ref q;
+        q.b = t / segs; q.seg = t - q.b * segs;
+        q.row0 = q.seg * kTileS;
+        q.nvalid = min(kTileS, rows - q.row0);
+        q.no = no;
+        q.base = pred + ((size_t)q.b * rows + q.row0) * no;
+        return q;
+    }
+    __device__ __forceinline__ Src source(const Ref& q) const { return Src{q.base, q.no}; }
+};
+
+// One tile per warp: the hardware block scheduler balances the very uneven tiles (a tile costs one more
+// dependent round trip per four surviving rows).  Persistent warps with the next tile's objectness
+// prefetched (VK_ROWS_PERSISTENT) were measured slower: static striding lets the slowest warp decide.
+template <class Loc, int NK, bool ML>
+__device__ __forceinline__ void rows_loop(const Loc& L, const FilterArgs& A, int total_tiles) {
+    const int lane = threadIdx.x & 31;
+    int t = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (t >= total_tiles) return;
+    typename Loc::Ref cur = L.locate(t);
+    float r0 = cur.obj_raw(lane), r1 = cur.obj_raw(lane + 32);
+#if VK_ROWS_PERSISTENT
+    const int nwarps = gridDim.x * kRowWarps;
+    for (;;) {
+        const int tn = t + nwarps;
+        const bool more = tn < total_tiles;
+        typename Loc::Ref nxt = cur;
+        float n0 = 0.0f, n1 = 0.0f;
+        if (more) {
+            nxt = L.locate(tn);
+            n0 = nxt.obj_raw(lane);
+            n1 = nxt.obj_raw(lane + 32);
+        }
+        const typename Loc::Src S = L.source(cur);
+        const float o0 = (lane < cur.nvalid) ? S.obj_val(r0) : -1.0f;
+        const float o1 = (lane + 32 < cur.nvalid) ? S.obj_val(r1) : -1.0f;
+        filter_tile_rows<typename Loc::Src, NK, ML>(S, A, cur.b, cur.seg, cur.row0, o0, o1);
+        if (!more) break;
+        cur = nxt; r0 = n0; r1 = n1; t = tn;
+    }
+#else
+    const typename Loc::Src S = L.source(cur);
+    const float o0 = (lane < cur.nvalid) ? S.obj_val(r0) : -1.0f;
+    const float o1 = (lane + 32 < cur.nvalid) ? S.obj_val(r1) : -1.0f;
+    filter_tile_rows<typename Loc::Src, NK, ML>(S, A, cur.b, cur.seg, cur.row0, o0, o1);
+#endif
 }
 
 template <class T, int NK, bool ML>
-__global__ void __launch_bounds__(kDecThreads, 4)
-filter_pred_rows_kernel(const T* __restrict__ pred, int no, const FilterArgs A, int total_tiles) {
-    const int t = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (t >= total_tiles) return;
-    const int b = t / A.segs, seg = t - b * A.segs;
-    const int row0 = seg * kTileS;
-    const int nvalid = min(kTileS, A.rows - row0);
-    const PredRows<T> S{pred + ((size_t)b * A.rows + row0) * no, no};
-    filter_tile_rows<PredRows<T>, NK, ML>(S, A, b, seg, row0, nvalid);
+__global__ void __launch_bounds__(32 * kRowWarps, VK_ROWS_BPS)
+decode_filter_rows_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
+    rows_loop<LogitLocator<T>, NK, ML>(LogitLocator<T>{H}, A, total_tiles);
 }
 
+template <class T, int NK, bool ML>
+__global__ void __launch_bounds__(32 * kRowWarps, VK_ROWS_BPS)
+filter_pred_rows_kernel(const T* __restrict__ pred, int no, const FilterArgs A, int total_tiles) {
+    rows_loop<PredLocator<T>, NK, ML>(PredLocator<T>{pred, no, A.rows, A.segs}, A, total_tiles);
+}
 
 // ---------------------------------------------------------------------------------------
 // Dense variant of the fused filter (eval thresholds: most rows survive, every tile is read
@@ -830,7 +865,7 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
         }
         if (threadIdx.x == 0) {
             A.seg_count[(size_t)tp.b * A.segs + tp.seg] = total;
-            if (tp.seg == 0) A.flags[tp.b] = cand_flags(A, false);
+            if (tp.seg == 0) A.flags[tp.b] = cand_flags(A);
             if (total) atomicAdd(A.counts + tp.b, total);
         }
     }
@@ -995,7 +1030,7 @@ filter_pred_dense_kernel(const T* __restrict__ pred, int no, const FilterArgs A,
         }
         if (threadIdx.x == 0) {
             A.seg_count[(size_t)b * A.segs + seg] = total;
-            if (seg == 0) A.flags[b] = cand_flags(A, false);
+            if (seg == 0) A.flags[b] = cand_flags(A);
             if (total) atomicAdd(A.counts + b, total);
         }
     }
@@ -1098,7 +1133,11 @@ static int launch_decode_filter_dense(const HeadDev& H, const FilterArgs& A, int
 
 template <class T, int NK, bool ML>
 static int launch_decode_filter_rows(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
-    decode_filter_rows_kernel<T, NK, ML><<<ceil_div(total_tiles, kWarps), kDecThreads, 0, stream>>>(H, A, total_tiles);
+    int grid = ceil_div(total_tiles, kRowWarps);
+#if VK_ROWS_PERSISTENT
+    grid = min(grid, blocks_per_sm(reinterpret_cast<const void*>(&decode_filter_rows_kernel<T, NK, ML>), 32 * kRowWarps, 0) * kNumSMs);
+#endif
+    decode_filter_rows_kernel<T, NK, ML><<<grid, 32 * kRowWarps, 0, stream>>>(H, A, total_tiles);
     count_launch();
     return check_launch("decode_filter_rows_kernel");
 }
@@ -1171,8 +1210,11 @@ static int launch_filter_pred_dense(const void* pred, int no, const FilterArgs& 
 
 template <class T, int NK, bool ML>
 static int launch_filter_pred_rows(const void* pred, int no, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
-    filter_pred_rows_kernel<T, NK, ML><<<ceil_div(total_tiles, kWarps), kDecThreads, 0, stream>>>(
-        static_cast<const T*>(pred), no, A, total_tiles);
+    int grid = ceil_div(total_tiles, kRowWarps);
+#if VK_ROWS_PERSISTENT
+    grid = min(grid, blocks_per_sm(reinterpret_cast<const void*>(&filter_pred_rows_kernel<T, NK, ML>), 32 * kRowWarps, 0) * kNumSMs);
+#endif
+    filter_pred_rows_kernel<T, NK, ML><<<grid, 32 * kRowWarps, 0, stream>>>(static_cast<const T*>(pred), no, A, total_tiles);
     count_launch();
     return check_launch("filter_pred_rows_kernel");
 }

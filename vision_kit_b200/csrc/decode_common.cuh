@@ -29,10 +29,7 @@ struct FilterArgs {
     int32_t* counts;             // ctrl row 0: candidates per image (also the list reservation counter)
     int32_t* flags;              // ctrl row 1: VK_FLAG_* | (tile_cap / 64) << 8, written by the tile with seg == 0
     int32_t* seg_count;
-    uint64_t* list;              // dev or null: unordered (ordered score << 32 | ~slot) entries
-    uint32_t* hist;              // dev or null: [batch][VK_HIST_BINS]
     int cap, rows, segs, nc;
-    int list_cap;
     int tile_cap;                // candidate slots each tile owns
 };
 
@@ -55,10 +52,8 @@ __host__ __device__ __forceinline__ uint32_t hist_bound(int j) {
 }
 
 // what the tile with seg == 0 stores in the image's flags word: slots per tile (the consumer maps
-// slot <-> (segment, position) with it) and whether the kernel appended to the list
-__device__ __forceinline__ int cand_flags(const FilterArgs& A, bool appended) {
-    return ((A.tile_cap >> 6) << 8) | (appended ? VK_FLAG_APPENDED : 0);
-}
+// slot <-> (segment, position) with it)
+__device__ __forceinline__ int cand_flags(const FilterArgs& A) { return (A.tile_cap >> 6) << 8; }
 
 __device__ __forceinline__ bool class_allowed(const uint32_t* m, int c) {
     return m == nullptr || ((__ldg(m + (c >> 5)) >> (c & 31)) & 1u);
@@ -118,7 +113,6 @@ inline FilterArgs make_filter_args(const VkCandBuf* o, int batch, float conf, in
     A.cand = o->cand;
     A.boxes = reinterpret_cast<float4*>(o->boxes);
     A.counts = o->ctrl; A.flags = o->ctrl + (size_t)batch; A.seg_count = o->seg_count;
-    A.list = o->list; A.hist = o->hist; A.list_cap = o->list_cap;
     A.cap = o->cap; A.rows = o->rows; A.segs = o->segs; A.nc = o->nc;
     A.tile_cap = kTileS * (A.multi_label ? o->nc : 1);
     return A;

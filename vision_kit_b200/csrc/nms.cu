@@ -9,7 +9,7 @@
 // reference's cut and torchvision's NMS are defined on, and keys are unique.
 //
 //   nms_sample_kernel   images with more candidates than their list holds (eval thresholds, ~240 k):
-//   nms_select_kernel   every 8th 32-byte sector of the candidate slots feeds a score histogram; the
+//   nms_select_kernel   every 8th 128-byte line of the candidate slots feeds a score histogram; the
 //                       largest bound whose estimated count fits 3/4 of the list is chosen, and a
 //                       grid-wide streaming pass copies every candidate at or above it into the
 //                       image's list.  All SMs work on every image, whatever the batch size.
@@ -24,8 +24,8 @@
 //            whose predecessors are all removed is kept.  The lowest undecided box is always
 //            decidable, so this ends with exactly the sequential greedy result after as many
 //            rounds as the longest suppression chain -- not after 256 dependent steps.
-//       The stage source is the image's list (the filter kernel appended it, or the select pass
-//       built it) while it lasts, then the segments of the full candidate buffer.  Because keys
+//       The stage source is the image's list (built by the select pass) while it lasts, then the
+//       segments of the candidate buffer; a small image (demo thresholds) is one stage read directly.  Because keys
 //       are unique the selection always terminates: a tie group of thousands of bit-identical
 //       scores is split by slot.  The exact cut at max_nms falls out of the order (the stage
 //       crossing rank max_nms is truncated).
@@ -48,6 +48,7 @@ constexpr int kHistBins = 2048;
 constexpr int kHash = 256;          // class hash buckets
 constexpr uint32_t kNil = 0xffffu;  // end of a hash list
 constexpr int kSelThreads = 256;
+constexpr int kSelStage = 128;      // keys a warp of the select pass stages before it reserves list space
 
 struct NmsArgs {
     const uint64_t* cand;
@@ -81,7 +82,9 @@ __device__ __forceinline__ bool wants_select(const NmsArgs& A, int b) {
     return A.list != nullptr && A.hist != nullptr && A.counts[b] > A.list_cap;
 }
 
-// Sampled histogram: sector k (4 candidates) of segment seg is read when (k + seg) % 8 == 0.
+// Sampled histogram: the 128-byte line l (16 candidates) of segment seg is read when (l + seg) % 8 == 0.
+// Most candidates of an eval-mode image share a handful of low-score bins, so lanes with the same bin
+// elect one of them to add the group's size (match.any) instead of colliding 32 ways on one counter.
 __global__ void __launch_bounds__(kSelThreads)
 nms_sample_kernel(const NmsArgs A) {
     const int b = blockIdx.y;
@@ -93,14 +96,29 @@ nms_sample_kernel(const NmsArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint2* cand = reinterpret_cast<const uint2*>(A.cand + (size_t)b * A.cap);
     const int32_t* seg_count = A.seg_count + (size_t)b * A.segs;
-    for (int seg = blockIdx.x * (kSelThreads / 32) + warp; seg < A.segs; seg += gridDim.x * (kSelThreads / 32)) {
-        const int cnt = seg_count[seg];
+    const int stride = gridDim.x * (kSelThreads / 32);
+    int seg = blockIdx.x * (kSelThreads / 32) + warp;
+    int cnt = seg < A.segs ? seg_count[seg] : 0;
+    for (; seg < A.segs; seg += stride) {
+        const int nseg = seg + stride;
+        const int ncnt = nseg < A.segs ? seg_count[nseg] : 0;        // the next count is in flight during this segment
         const uint2* cp = cand + (size_t)seg * tile_cap;
-        // lane = (sampled sector m = lane / 4, entry e = lane % 4)
-        for (int k = ((8 - (seg & 7)) & 7) + 8 * (lane >> 2); 4 * k < cnt; k += 64) {
-            const int j = 4 * k + (lane & 3);
-            if (j < cnt) atomicAdd(&s_hist[hist_bin(cp[j].x)], 1u);
+        const int l0 = (8 - (seg & 7)) & 7;
+        // lane = (line m = lane / 16 of the pair of sampled lines, entry e = lane % 16); two pairs per trip
+        for (int l = l0; 16 * l < cnt; l += 32) {
+            int bin[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = 16 * (l + 8 * (2 * u + (lane >> 4))) + (lane & 15);
+                bin[u] = (j < cnt) ? hist_bin(cp[j].x) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const unsigned peers = __match_any_sync(0xffffffffu, bin[u]);
+                if (bin[u] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin[u]], (uint32_t)__popc(peers));
+            }
         }
+        cnt = ncnt;
     }
     __syncthreads();
     uint32_t* gh = A.hist + (size_t)b * VK_HIST_BINS;
@@ -146,39 +164,58 @@ nms_select_kernel(const NmsArgs A) {
         atomicOr(const_cast<int32_t*>(A.flags) + b, VK_FLAG_LIST);
     }
     if (j < 0) return;
-    // ---- streaming pass over this block's share of the segments
+    // ---- streaming pass over this block's share of the segments.  Selected keys are staged per warp in
+    //      shared memory and flushed with ONE reservation on the image's list counter per ~100 keys: a
+    //      reservation per 32 candidates would serialise thousands of same-address atomics per image.
+    __shared__ unsigned long long s_stage[kSelThreads / 32][kSelStage];
+    unsigned long long* stage = s_stage[warp];
+    int staged = 0;                                               // warp-uniform
     const int tile_cap = tile_slots_of(A.flags[b]);
     const uint2* cand = reinterpret_cast<const uint2*>(A.cand + (size_t)b * A.cap);
     const int32_t* seg_count = A.seg_count + (size_t)b * A.segs;
     uint64_t* list = A.list + (size_t)b * A.list_cap;
     const unsigned lt = (1u << lane) - 1u;
-    for (int seg = blockIdx.x * (kSelThreads / 32) + warp; seg < A.segs; seg += gridDim.x * (kSelThreads / 32)) {
-        const int cnt = seg_count[seg];
+    auto flush = [&]() {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&A.list_count[b], staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int i = lane; i < staged; i += 32)
+            if (base + i < A.list_cap) list[base + i] = stage[i];
+        __syncwarp();
+        staged = 0;
+    };
+    const int stride = gridDim.x * (kSelThreads / 32);
+    int seg = blockIdx.x * (kSelThreads / 32) + warp;
+    int cnt = seg < A.segs ? seg_count[seg] : 0;
+    for (; seg < A.segs; seg += stride) {
+        const int nseg = seg + stride;
+        const int ncnt = nseg < A.segs ? seg_count[nseg] : 0;        // the next count is in flight during this segment
         const uint32_t slot0 = (uint32_t)seg * (uint32_t)tile_cap;
         const uint2* cp = cand + slot0;
-        for (int j0 = 0; j0 < cnt; j0 += 128) {          // 4 loads in flight per lane
-            uint32_t s[4];
+        for (int j0 = 0; j0 < cnt; j0 += 256) {          // 8 loads in flight per lane
+            uint32_t sc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int jj = j0 + 32 * u + lane;
-                s[u] = (jj < cnt) ? cp[jj].x : 0u;
+                sc[u] = (jj < cnt) ? cp[jj].x : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int jj = j0 + 32 * u + lane;
-                const uint32_t key = order_key(s[u]);
+                const uint32_t key = order_key(sc[u]);
                 const bool take = jj < cnt && key >= bound;
                 const unsigned m = __ballot_sync(0xffffffffu, take);
                 if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&A.list_count[b], __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const int pos = base + __popc(m & lt);
-                    if (take && pos < A.list_cap) list[pos] = ((uint64_t)key << 32) | (uint32_t)~(slot0 + (uint32_t)jj);
+                    if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~(slot0 + (uint32_t)jj);
+                    staged += __popc(m);
+                    if (staged > kSelStage - 32) flush();
                 }
             }
         }
+        cnt = ncnt;
     }
+    if (staged) flush();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -238,6 +275,13 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, cons
     return __fdiv_rn(inter, den) > thr;
 }
 
+#ifdef VK_NMS_PROFILE
+__device__ long long* g_nms_timing = nullptr;   // [batch][32] clock64 stamps (profiling builds only)
+#define VK_STAMP(k) do { if (g_nms_timing && threadIdx.x == 0 && ((k) < 22 || (k) == 30)) g_nms_timing[(size_t)blockIdx.x * 32 + (k)] = clock64(); } while (0)
+#else
+#define VK_STAMP(k) do { } while (0)
+#endif
+
 // Everything a chunk needs: the sorted stage in shared memory and where the results go.
 struct ChunkCtx {
     ScratchB XB;
@@ -255,7 +299,7 @@ struct ChunkCtx {
 // One chunk of <= 256 sorted candidates [chunk0, chunk0 + cn) of the stage against the kept list.
 // Returns the new kept count.  All T threads call it; ends with a block barrier.
 template <int T>
-__device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, int kept0, bool by_class) {
+__device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, int kept0, bool by_class, int mark = -1) {
     constexpr int NW = T / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float4* cbox = C.sbox + chunk0;
@@ -294,6 +338,7 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
             const uint32_t v = (old >> (16 * (bk & 1))) & 0xffffu;      // 1..count: a unique slot
             C.XB.members[C.XB.cstart[bk] + v - 1] = (uint16_t)i;
         }
+        if (mark >= 0) VK_STAMP(mark);
         // 1: same-class kept boxes only (hash list of the kept set)
         for (int i = tid; i < cn; i += T) {
             const float4 cb = cbox[i];
@@ -311,22 +356,38 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
             if (sup) C.XB.state[i] = 2;
         }
         __syncthreads();
-        // 2: same-class predecessors inside the chunk.  One warp per row, lanes over the
-        //    members of the row's class bucket (rows of a crowded class would otherwise walk
-        //    a long list one dependent step at a time).
-        for (int i = warp; i < cn; i += NW) {
-            if (C.XB.state[i] != 0) continue;
-            const uint32_t ic = ccls[i];
-            const uint32_t bk = ic & (kHash - 1);
-            const int e = C.XB.cstart[bk + 1];
-            const float4 ib = cbox[i];
-            const float ia = box_area(ib);
-            for (int m = C.XB.cstart[bk] + lane; m < e; m += 32) {
-                const int j = C.XB.members[m];
-                if (j >= i || ccls[j] != ic || C.XB.state[j] != 0) continue;
-                const float4 jb = cbox[j];
-                if (iou_exceeds(jb, box_area(jb), ib, ia, C.thr))
-                    atomicOr(&C.XB.pred[i * kChunkWords + (j >> 5)], 1u << (j & 31));
+        if (mark >= 0) VK_STAMP(mark + 1);
+        // 2: same-class predecessors inside the chunk: T / 256 threads per row, each walking its share of
+        //    the members of the row's class bucket
+        {
+            constexpr int TPR = T / kChunk > 0 ? T / kChunk : 1;
+            for (int i = tid % kChunk; i < cn; i += (T < kChunk ? T : kChunk)) {
+                if (C.XB.state[i] != 0) continue;
+                const uint32_t ic = ccls[i];
+                const uint32_t bk = ic & (kHash - 1);
+                const int e = C.XB.cstart[bk + 1];
+                const float4 ib = cbox[i];
+                const float ia = box_area(ib);
+                uint32_t acc[kChunkWords];
+#pragma unroll
+                for (int wd = 0; wd < kChunkWords; ++wd) acc[wd] = 0u;
+                bool any = false;
+                for (int m = C.XB.cstart[bk] + tid / kChunk; m < e; m += TPR) {
+                    const int j = C.XB.members[m];
+                    if (j >= i || ccls[j] != ic || C.XB.state[j] != 0) continue;
+                    const float4 jb = cbox[j];
+                    if (iou_exceeds(jb, box_area(jb), ib, ia, C.thr)) {
+                        any = true;
+#pragma unroll
+                        for (int wd = 0; wd < kChunkWords; ++wd)
+                            if (wd == (j >> 5)) acc[wd] |= 1u << (j & 31);
+                    }
+                }
+                if (any) {
+#pragma unroll
+                    for (int wd = 0; wd < kChunkWords; ++wd)
+                        if (acc[wd]) atomicOr(&C.XB.pred[i * kChunkWords + wd], acc[wd]);
+                }
             }
         }
     } else {
@@ -339,9 +400,13 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
                 const float4 cb = cbox[i];
                 const float ca = box_area(cb);
                 bool sup = false;
-                for (int k = part; k < kept0 && !sup; k += NP) {
-                    const float4 kb = C.XB.kbox[k];
-                    sup = iou_exceeds(kb, box_area(kb), cb, ca, C.thr);
+                for (int k = part; k < kept0 && !sup; k += 2 * NP) {       // two independent chains per step
+                    const float4 ka = C.XB.kbox[k];
+                    const bool second = k + NP < kept0;
+                    const float4 kb = C.XB.kbox[second ? k + NP : k];
+                    const bool sa = iou_exceeds(ka, box_area(ka), cb, ca, C.thr);
+                    const bool sb = second && iou_exceeds(kb, box_area(kb), cb, ca, C.thr);
+                    sup = sa || sb;
                 }
                 if (sup) C.XB.state[i] = 2;
             }
@@ -357,17 +422,27 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
                 const float4 ib = cbox[i];
                 const float ia = box_area(ib);
                 const int jn = min(32, i - wd * 32);       // columns j < i only
-                for (int bit = 0; bit < jn; ++bit) {
-                    const int j = wd * 32 + bit;
-                    if (C.XB.state[j] != 0) continue;        // already removed: cannot suppress
-                    const float4 jb = cbox[j];
-                    if (iou_exceeds(jb, box_area(jb), ib, ia, C.thr)) m |= 1u << bit;
+                for (int bit = 0; bit < jn; bit += 4) {     // four independent chains per step
+                    bool hit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = wd * 32 + bit + u;
+                        hit[u] = false;
+                        if (bit + u < jn && C.XB.state[j] == 0) {      // already removed: cannot suppress
+                            const float4 jb = cbox[j];
+                            hit[u] = iou_exceeds(jb, box_area(jb), ib, ia, C.thr);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (hit[u]) m |= 1u << (bit + u);
                 }
             }
             C.XB.pred[i * kChunkWords + wd] = m;
         }
     }
     __syncthreads();
+    if (mark >= 0) VK_STAMP(mark + 2);
     // 3: fixed-point resolve; thread i < 256 owns row i.  Only those 8 warps iterate (named
     //    barrier 2, one per round; the word buffers ping-pong so a buffer is rewritten only
     //    after everyone has passed the next barrier).
@@ -403,6 +478,7 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
         }
     }
     __syncthreads();
+    if (mark >= 0) VK_STAMP(mark + 3);
     // 4: kept boxes, in order, join the kept list and the output (image_proc.py:170-182)
     int total = 0;
 #pragma unroll
@@ -429,21 +505,16 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
     }
     const int kept = min(C.max_det, kept0 + total);
     __syncthreads();
+    if (mark >= 0) VK_STAMP(mark + 4);
     return kept;
 }
 
 template <int CAP>
 static size_t nms_smem_bytes(int threads, int segs, int max_det) {
-    return (size_t)CAP * (8 + 16 + 4 + 2) + (size_t)threads * 16 + (size_t)kHistBins * 4 +
+    (void)threads;
+    return (size_t)CAP * (8 + 8 + 16 + 4 + 2) + (size_t)kHistBins * 4 +
            align16((size_t)(segs + 1) * 4) + align16(ScratchB::bytes(max_det));
 }
-
-#ifdef VK_NMS_PROFILE
-__device__ long long* g_nms_timing = nullptr;   // [batch][32] clock64 stamps (profiling builds only)
-#define VK_STAMP(k) do { if (g_nms_timing && threadIdx.x == 0 && (k) < 32) g_nms_timing[(size_t)blockIdx.x * 32 + (k)] = clock64(); } while (0)
-#else
-#define VK_STAMP(k) do { } while (0)
-#endif
 
 template <int T, int CAP>
 __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (T >= 512 ? 2 : 3)))
@@ -456,11 +527,11 @@ nms_kernel(const NmsArgs A) {
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float4* sbox = reinterpret_cast<float4*>(keys + CAP);
     unsigned long long* xchg = reinterpret_cast<unsigned long long*>(sbox + CAP);
-    uint32_t* sidx = reinterpret_cast<uint32_t*>(xchg + 2 * T);
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(xchg + CAP);
     int* hist = reinterpret_cast<int*>(sidx + CAP);
     uint16_t* scls = reinterpret_cast<uint16_t*>(hist + kHistBins);
-    int* segc = reinterpret_cast<int*>(scls + CAP);
-    ScratchB XB(reinterpret_cast<unsigned char*>(segc) + align16((size_t)(A.segs + 1) * 4), A.max_det);
+    int* segoff = reinterpret_cast<int*>(scls + CAP);     // [segs + 1] exclusive prefix of the segment counts
+    ScratchB XB(reinterpret_cast<unsigned char*>(segoff) + align16((size_t)(A.segs + 1) * 4), A.max_det);
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -474,30 +545,37 @@ nms_kernel(const NmsArgs A) {
     const int n = A.counts[b];
     const int flags = A.flags[b];
     const int tile_cap = tile_slots_of(flags);
-    // the image's list: complete (the filter kernel appended every candidate) or the top part
-    // above `lbound` (built by the select pass); -1 = none
+    // the image's list: every candidate at or above `lbound`, built by the select pass; -1 = none
     int list_n = -1;
     uint32_t lbound = 0;
-    if (A.list != nullptr) {
-        if ((flags & VK_FLAG_APPENDED) && n <= A.list_cap) list_n = n;
-        else if (flags & VK_FLAG_LIST) {
-            const int lc = A.list_count[b];
-            if (lc <= A.list_cap) { list_n = lc; lbound = (uint32_t)A.bound[b]; }
-        }
+    if (A.list != nullptr && (flags & VK_FLAG_LIST)) {
+        const int lc = A.list_count[b];
+        if (lc <= A.list_cap) { list_n = lc; lbound = (uint32_t)A.bound[b]; }
     }
     const uint64_t* list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
     const int K = min(n, A.max_nms);
     const bool cut = n > A.max_nms;
 
     for (int i = tid; i < kHash; i += T) XB.khead[i] = (int)kNil;
-    bool have_segc = false;
-    auto load_segc = [&]() {
-        for (int t = tid; t < A.segs; t += T) segc[t] = seg_count[t];
+    // segment offsets (exclusive scan of the segment counts): needed to walk the candidate buffer itself
+    // and to report torchvision's indices; an image served from its list never loads them
+    bool have_segoff = false;
+    auto load_segoff = [&]() {
+        int carry = 0;
+        for (int t0 = 0; t0 < A.segs; t0 += T) {
+            const int t = t0 + tid;
+            const int c = (t < A.segs) ? seg_count[t] : 0;
+            int total;
+            const int ex = block_excl_scan(c, wsum, &total);
+            if (t < A.segs) segoff[t] = carry + ex;
+            carry += total;
+        }
+        if (tid == 0) segoff[A.segs] = carry;
         __syncthreads();
-        have_segc = true;
+        have_segoff = true;
     };
     bool use_list = list_n >= 0;
-    if (!use_list) load_segc();
+    if (!use_list) load_segoff();
     __syncthreads();
 
     // every candidate of the current source: f(valid, key)
@@ -515,7 +593,7 @@ nms_kernel(const NmsArgs A) {
     };
     auto for_each_segment = [&](auto&& f) {
         for (int t = warp; t < A.segs; t += NW) {
-            const int cnt = segc[t];
+            const int cnt = segoff[t + 1] - segoff[t];
             if (cnt == 0) continue;
             const uint32_t slot0 = (uint32_t)t * (uint32_t)tile_cap;
             const uint2* cp = cand + slot0;
@@ -550,7 +628,7 @@ nms_kernel(const NmsArgs A) {
         if (use_list && rank_base >= list_n) {            // the list is used up
             if (lbound == 0) break;                       // it held every candidate
             use_list = false;                             // U == lbound << 32: the rest comes from the segments
-            if (!have_segc) load_segc();
+            if (!have_segoff) load_segoff();
         }
         const int remaining = (use_list ? list_n : n) - rank_base;
         unsigned long long v = use_list ? ((unsigned long long)lbound << 32) : 0ull;   // inclusive lower bound of this stage
@@ -597,67 +675,100 @@ nms_kernel(const NmsArgs A) {
             }
             // keys are unique, so the last pass always finds a bound (count_ge <= rem_t <= CAP / 2)
         }
+        VK_STAMP(stamp);
         // ---- compaction of the stage [v, U) into shared memory
         if (tid == 0) s_cnt = 0;
         __syncthreads();
-        for_each([&](bool ok, unsigned long long key) {
-            const bool take = ok && key >= v && key < U;
-            const unsigned m = __ballot_sync(0xffffffffu, take);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < CAP) keys[pos] = key;
+        if (!use_list && rank_base == 0 && n <= CAP) {
+            // small image (demo thresholds), its only stage: one thread per candidate, segment by binary search
+            for (int p = tid; p < n; p += T) {
+                int lo = 0, hi = A.segs;                       // last t with segoff[t] <= p
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (segoff[mid] <= p) lo = mid; else hi = mid;
                 }
+                const uint32_t slot = (uint32_t)lo * (uint32_t)tile_cap + (uint32_t)(p - segoff[lo]);
+                keys[p] = ((unsigned long long)order_key(cand[slot].x) << 32) | (uint32_t)~slot;
             }
-        });
+            if (tid == 0) s_cnt = n;
+        } else {
+            for_each([&](bool ok, unsigned long long key) {
+                const bool take = ok && key >= v && key < U;
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < CAP) keys[pos] = key;
+                    }
+                }
+            });
+        }
         __syncthreads();
+        VK_STAMP(stamp + 1);
         const int cnt = min(s_cnt, CAP);
         int Ps = 32;
         while (Ps < cnt) Ps <<= 1;
-        for (int i = cnt + tid; i < Ps; i += T) keys[i] = 0ull;
+        for (int i = cnt + tid; i < Ps; i += T) keys[i] = (unsigned long long)(Ps - 1 - i);   // unique, below every real key
         __syncthreads();
-        // ---- sort, descending
-        if (cnt > 1 && Ps <= T) {
-            // one key per thread in registers; strides below 32 exchange by shuffle, the rest through
-            // shared memory (ping-pong: a buffer is rewritten only two barriers after it was read)
-            if (tid < Ps) {
-                unsigned long long x = keys[tid];
-                int pp = 0;
-                for (int k = 2; k <= Ps; k <<= 1) {
-                    for (int j = k >> 1; j > 0; j >>= 1) {
-                        unsigned long long o;
-                        if (j >= 32) {
-                            unsigned long long* xb = xchg + pp * T;
-                            xb[tid] = x;
-                            asm volatile("bar.sync 1, %0;" :: "r"(Ps) : "memory");
-                            o = xb[tid ^ j];
-                            pp ^= 1;
-                        } else {
-                            o = __shfl_xor_sync(0xffffffffu, x, j);
-                        }
-                        const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
-                        x = keep_max ? (x > o ? x : o) : (x < o ? x : o);
+        // ---- sort, descending: every warp sorts runs of 32 keys in registers (bitonic, shuffles only), then
+        //      log2(Ps / 32) merge rounds: a key's place in the merged run is its index in its own run plus
+        //      the number of keys of the partner run that precede it (binary search; keys are unique, so
+        //      ranks never collide).  ~3 us for 2048 keys against ~17 us for a block-wide bitonic network.
+        if (cnt > 1) {
+            constexpr int E = CAP / T > 0 ? CAP / T : 1;           // keys per thread
+            int rounds = 0;
+            for (int L = 32; L < Ps; L <<= 1) ++rounds;
+            unsigned long long* src = (rounds & 1) ? xchg : keys;   // the last round writes into `keys`
+            unsigned long long* dst = (rounds & 1) ? keys : xchg;
+            unsigned long long x[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int e = tid + q * T;
+                x[q] = (e < Ps) ? keys[e] : 0ull;
+            }
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0 || k == 32);
+#pragma unroll
+                    for (int q = 0; q < E; ++q) {
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, x[q], j);
+                        x[q] = keep_max ? (x[q] > o ? x[q] : o) : (x[q] < o ? x[q] : o);
                     }
                 }
-                keys[tid] = x;
+            }
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int e = tid + q * T;
+                if (e < Ps) src[e] = x[q];
             }
             __syncthreads();
-        } else if (cnt > 1) {
-            for (int k = 2; k <= Ps; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < (Ps >> 1); i += T) {
-                        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                        const int hi = lo | j;
-                        const unsigned long long ka = keys[lo], kb = keys[hi];
-                        if ((kb > ka) == ((lo & k) == 0)) { keys[lo] = kb; keys[hi] = ka; }
+            for (int sh = 5; (1 << sh) < Ps; ++sh) {                // runs of L = 1 << sh keys
+                const int L = 1 << sh;
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const int e = tid + q * T;
+                    if (e < Ps) {
+                        const unsigned long long xe = src[e];
+                        const int r = e >> sh, i = e & (L - 1);
+                        const unsigned long long* pr = src + ((r ^ 1) << sh);    // partner run, descending
+                        int lo = 0, hi = L;                                      // first index with pr[idx] < xe
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (pr[mid] > xe) lo = mid + 1; else hi = mid;
+                        }
+                        dst[((r >> 1) << (sh + 1)) + i + lo] = xe;
                     }
-                    __syncthreads();
                 }
+                __syncthreads();
+                unsigned long long* t2 = src; src = dst; dst = t2;
             }
         }
+        VK_STAMP(stamp + 2);
         // ---- the stage's boxes, once: candidate slot -> (row, class) -> class-offset box
         const int M = min(cnt, K - rank_base);             // truncated at rank max_nms (image_proc.py:161-163)
         bool ok = true;
@@ -674,12 +785,13 @@ nms_kernel(const NmsArgs A) {
             scls[p] = (uint16_t)cls;
         }
         safe = __syncthreads_and(ok) && safe;
-        VK_STAMP(stamp); ++stamp;
+        VK_STAMP(stamp + 3);
         // ---- NMS over the stage
         CC.rank_base = rank_base;
         for (int chunk0 = 0; chunk0 < M && kept0 < A.max_det; chunk0 += kChunk)
-            kept0 = nms_chunk<T>(CC, chunk0, min(kChunk, M - chunk0), kept0, safe && !A.agnostic);
-        VK_STAMP(stamp); ++stamp;
+            kept0 = nms_chunk<T>(CC, chunk0, min(kChunk, M - chunk0), kept0, safe && !A.agnostic, chunk0 == 0 ? stamp + 4 : -1);
+        VK_STAMP(stamp + 9);
+        stamp += 10;
         rank_base += cnt;
         U = v;
         if (v == 0) break;                   // everything has been processed
@@ -690,21 +802,11 @@ nms_kernel(const NmsArgs A) {
         if (!cut && kept0 > 0) {
             // torchvision's index = position in the reference's candidate list = candidates in earlier
             // segments + position inside the segment
-            if (!have_segc) load_segc();
-            int carry = 0;
-            for (int t0 = 0; t0 < A.segs; t0 += T) {
-                const int t = t0 + tid;
-                const int c = (t < A.segs) ? segc[t] : 0;
-                int total;
-                const int ex = block_excl_scan(c, wsum, &total);
-                if (t < A.segs) segc[t] = carry + ex;
-                carry += total;
-            }
-            __syncthreads();
+            if (!have_segoff) load_segoff();
             for (int k = tid; k < kept0; k += T) {
                 const uint32_t slot = XB.kkeep[k];
                 const uint32_t seg = slot / (uint32_t)tile_cap;
-                keep_out[k] = (int64_t)segc[seg] + (int64_t)(slot - seg * (uint32_t)tile_cap);
+                keep_out[k] = (int64_t)segoff[seg] + (int64_t)(slot - seg * (uint32_t)tile_cap);
             }
         } else {
             for (int k = tid; k < kept0; k += T) keep_out[k] = (int64_t)XB.kkeep[k];
@@ -795,5 +897,12 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, double iou_thres, i
         if (int rc = check_launch("nms_select_kernel")) return rc;
         return launch_nms<1024, 2048>(A, batch, c->segs, max_det, stream);
     }
-    return launch_nms<256, 1024>(A, batch, c->segs, max_det, stream);
+#ifdef VK_NMS_TUNE
+    if (const char* e = getenv("VK_NMS_T")) {              // tuning builds: CTA size of the list-less kernel
+        const int t = atoi(e);
+        if (t == 256) return launch_nms<256, 1024>(A, batch, c->segs, max_det, stream);
+        if (t == 512) return launch_nms<512, 1024>(A, batch, c->segs, max_det, stream);
+    }
+#endif
+    return launch_nms<1024, 1024>(A, batch, c->segs, max_det, stream);
 }
