@@ -6,8 +6,12 @@ confidence filter -> NMS) on BASELINE.json configs[1]: YOLOv5s, synthetic batch 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One process per GPU (torchrun for N > 1); images shard across ranks with no collective on
-the hot path ("weak" scaling: 64 images per GPU per step).  A step is one pass of the three
+the hot path ("weak" scaling: 64 images per GPU per step).  A step is one pass of the
 kernels over one batch.  Prints ONE JSON line on rank 0.
+
+The line also carries, under "configs", the device-timed throughput of BASELINE configs 3, 4
+and 5 (eval-mode NMS; config 5 with the mixed-size letterbox and the NCCL all-gather of the
+detections) on this run's GPUs, the batch of each config split over the ranks.
 """
 from __future__ import annotations
 
@@ -78,7 +82,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def result(self):
         self.stop_flag = True
@@ -88,78 +92,215 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# --------------------------------------------------------------------------- reference arm
-def cpu_reference_pass(imgs, levels):
-    """The reference's CPU path on one sample: cv2 letterbox + normalise per image, torch
-    Detect decode, torch + torchvision.ops.nms (oracle/ref_port.py, pinned to the live
-    reference by tests/test_oracle_golden.py)."""
-    from oracle import ref_port
-    from tests import synth
-    xs = [ref_port.preprocess(im, (IMG, IMG), is_bgr=True)[0] for im in imgs]
-    pred, _ = ref_port.detect_decode(levels, synth.V5_ANCHORS, synth.STRIDES, "v5")
-    dets = ref_port.nms(pred, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
-    return xs, dets
+# --------------------------------------------------------------------------- reference arm (host CPU)
+def host_threads() -> int:
+    """Every host core this process may use -- the same at every N: torch.distributed.run exports
+    OMP_NUM_THREADS=1, which would otherwise make the CPU arm single-threaded."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    try:
+        import cv2
+        cv2.setNumThreads(n)
+    except Exception:
+        pass
+    return n
 
 
-def cpu_sample(n: int, seed: int = 0):
-    from tests import synth
-    imgs = list(synth.images_u8(n, IMG, IMG, seed=seed))
-    levels = [torch.from_numpy(x) for x in synth.head_logits(n, seed=2 + seed, clusters=20)]
-    return imgs, levels
+class CpuPath:
+    """The reference's CPU implementation of the path on one batch: per image `ImageProcessor.preprocess`
+    (cv2 letterbox + normalise), the Detect head's eval forward with identity convs, `nms`.
+    kind "reference": the unmodified reference from baseline/_ref (oracle/live.py; NMS time limit
+    neutralised); kind "port": oracle/ref_port.py, the same path written against the same libraries,
+    when the reference files are not there."""
+
+    def __init__(self):
+        from oracle import live
+        from tests import synth
+        self.synth = synth
+        self.kind = "port"
+        self.ns = None
+        if live.available():
+            try:
+                self.ns = live.load()
+                self.ip = self.ns.ImageProcessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, img_sz=(IMG, IMG))
+                # the reference head pins its tensors to CUDA whenever torch sees a GPU (models/heads/yolov5.py:30-31);
+                # this arm is the reference's CPU path, so the head is built while torch reports none
+                seen, torch.cuda.is_available = torch.cuda.is_available, (lambda: False)
+                try:
+                    head = self.ns.YoloV5Head()
+                finally:
+                    torch.cuda.is_available = seen
+                head.m = torch.nn.ModuleList([torch.nn.Identity() for _ in range(3)])
+                self.head = head.eval()
+                self.kind = "reference"
+            except Exception as e:                       # an import that fails here must not kill the bench
+                sys.stderr.write(f"reference import failed ({e}); timing the port\n")
+                self.ns = None
+        if self.ns is None:
+            from oracle import ref_port
+            self.ref_port = ref_port
+
+    def sample(self, n: int, seed: int = 0):
+        imgs = list(self.synth.images_u8(n, IMG, IMG, seed=seed))
+        levels = [torch.from_numpy(x) for x in self.synth.head_logits(n, seed=2 + seed, clusters=20)]
+        return imgs, levels
+
+    def run(self, imgs, levels):
+        if self.ns is not None:
+            xs = [self.ip.preprocess(im, is_BGR=True)[0] for im in imgs]
+            with torch.no_grad():
+                pred = self.head([t.clone() for t in levels])[0]
+            dets = self.ns.image_proc.nms(pred, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
+            return xs, dets
+        xs = [self.ref_port.preprocess(im, (IMG, IMG), is_bgr=True)[0] for im in imgs]
+        pred, _ = self.ref_port.detect_decode(levels, self.synth.V5_ANCHORS, self.synth.STRIDES, "v5")
+        return xs, self.ref_port.nms(pred, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET)
 
 
 def time_cpu(n_imgs: int, budget_s: float, max_passes: int = 1000):
-    imgs, levels = cpu_sample(n_imgs)
-    cpu_reference_pass(imgs, levels)                       # warm-up (first call is 10-20x slower)
+    cores = host_threads()
+    path = CpuPath()
+    imgs, levels = path.sample(n_imgs)
+    path.run(imgs, levels)                                 # warm-up (first call is 10-20x slower)
     t0 = time.perf_counter()
     passes = 0
     while passes < max_passes:
-        cpu_reference_pass(imgs, levels)
+        path.run(imgs, levels)
         passes += 1
         if time.perf_counter() - t0 >= budget_s:
             break
     dt = time.perf_counter() - t0
-    return n_imgs * passes / dt, passes, dt
+    return n_imgs * passes / dt, passes, dt, cores, path.kind
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    n = 16
-    imgs, levels = cpu_sample(n)
-    for _ in range(max(args.warmup, 1)):
-        cpu_reference_pass(imgs, levels)
-    steps = max(1, min(args.steps, 40))                    # each step = one 16-image sample
+    cores = host_threads()
+    path = CpuPath()
+    imgs, levels = path.sample(BATCH)                      # the same 64-image batch per step as our arm
+    warm = max(args.warmup, 1)
+    for _ in range(min(warm, 3)):
+        path.run(imgs, levels)
+    steps = max(1, min(args.steps, 40))                    # bounded: a step is ~0.2 s of CPU work
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_pass(imgs, levels)
+        path.run(imgs, levels)
     dt = time.perf_counter() - t0
-    value = n * steps / dt
-    cores = torch.get_num_threads()
-    sample = f"{n} images per step of the {BATCH}-image batch, {steps} steps"
+    value = BATCH * steps / dt
+    sample = f"{BATCH} images per step (the whole batch of one GPU), {steps} steps"
     print(json.dumps({
         "impl": "reference", "metric": baseline_metric(), "value": value, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / steps,
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(warm, 3), "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": sample, "os_cpu_count": os.cpu_count()},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": path.kind,
+                         "sample": sample, "os_cpu_count": os.cpu_count(),
+                         "torch_threads": torch.get_num_threads()},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# --------------------------------------------------------------------------- other BASELINE configs
+def bench_configs(dev, rank: int, world: int, steps: int, warm: int):
+    """Device-timed pipeline throughput of BASELINE configs 3, 4, 5 on this run's GPUs: the config's batch
+    is split over the ranks (strong scaling, as BASELINE states them), every rank times its shard with CUDA
+    events, the slowest rank counts.  Inputs are synthetic and resident; 64 distinct images per rank are
+    repeated to fill larger shards (the path treats every image independently)."""
+    import torch.distributed as dist
+    from tests import synth
+    from vision_kit_b200 import dist as vkd
+    from vision_kit_b200.pipeline import DetectPipeline
+    out = {}
+
+    def tiled(tensors, B):
+        return [t.repeat((B + t.shape[0] - 1) // t.shape[0], *([1] * (t.dim() - 1)))[:B].contiguous() for t in tensors]
+
+    def run(name, variant, B_total, srcs_fn, lv, gather=False, **kw):
+        B = vkd.shard_range(B_total, rank, world)[1] - vkd.shard_range(B_total, rank, world)[0]
+        pipe = DetectPipeline(variant, batch=B, device=dev, overlap=True, **kw)
+        srcs = srcs_fn(B)
+        pipe.plan_sources(srcs)
+        feats = tiled(lv, B)
+        pipe.capture(feats)
+        gat_ms = None
+
+        def step():
+            o = pipe.replay()
+            if gather:
+                vkd.allgather_detections(o.dets, o.counts, B_total)
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if gather:                                        # the collective alone, same tensors
+            o = pipe.out
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(steps):
+                vkd.allgather_detections(o.dets, o.counts, B_total)
+            g1.record()
+            torch.cuda.synchronize()
+            gat_ms = g0.elapsed_time(g1) / steps
+        t = torch.tensor([ms, gat_ms or 0.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        dets = int(pipe.flush().counts.sum())
+        torch.cuda.synchronize()
+        out[name] = {"global_batch": B_total, "batch_per_gpu": B, "ms_per_step": round(ms, 4),
+                     "images_per_s": round(B_total / (ms * 1e-3)), "detections_per_image": dets // max(B, 1)}
+        if gather:
+            out[name]["allgather_us"] = round(float(t[1]) * 1e3, 1)
+            out[name]["allgather"] = ("torch.distributed all_gather_into_tensor (NCCL) of (B/N, 300, 6) fp32 + counts"
+                                      if world > 1 else "single rank: no collective issued")
+        del pipe, feats, srcs
+        torch.cuda.empty_cache()
+
+    ident = torch.from_numpy(synth.images_u8(64, IMG, IMG, seed=10 + rank)).to(dev)
+
+    def ident_srcs(B):
+        return [ident[i % 64] for i in range(B)]
+    ev = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)
+    lv3 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(64, seed=3 + 16 * rank, clusters=20)]
+    run("config3 YOLOv5x B=256 eval NMS", "v5", 256, ident_srcs, lv3, **ev)
+    del lv3
+    lv4 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(64, seed=4 + 16 * rank, clusters=20)]
+    run("config4 YOLOv7 B=256 eval NMS class-aware", "v7", 256, ident_srcs, lv4, **ev)
+    run("config4 YOLOv7 B=256 eval NMS agnostic", "v7", 256, ident_srcs, lv4, agnostic=True, **ev)
+    sizes = synth.mixed_sizes(64, seed=5 + rank)
+    mixed = [torch.from_numpy(synth.image_u8(h, w, 50 + i)).to(dev) for i, (h, w) in enumerate(sizes)]
+    run("config5 YOLOv7-x B=512 mixed 480-1280 letterbox + eval NMS + allgather", "v7", 512,
+        lambda B: [mixed[i % 64] for i in range(B)], lv4, gather=True, **ev)
+    return out
 
 
 # --------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--config-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 3/4/5 section")
     ap.add_argument("--no-overlap", action="store_true",
-                    help="run the NMS on the main stream instead of overlapping it with the next batch")
+                    help="run the NMS on the main stream instead of beside the next batch's letterbox + filter")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,9 +310,10 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    import ctypes as C
     import torch.distributed as dist
-    from vision_kit_b200 import _lib
     from tests import synth
+    from vision_kit_b200 import _lib
     from vision_kit_b200.pipeline import DetectPipeline
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
@@ -190,20 +332,50 @@ def main():
     lv_host = [torch.from_numpy(x).pin_memory() for x in synth.head_logits(BATCH, seed=2 + rank, clusters=20)]
     imgs_dev = imgs_host.to(dev)
     lv_dev = [t.to(dev) for t in lv_host]
+    overlap = not args.no_overlap
     pipe = DetectPipeline("v5", nc=80, img_sz=(IMG, IMG), batch=BATCH, conf_thres=CONF, iou_thres=IOU,
-                          max_det=MAX_DET, swap_rb=True, device=dev, overlap=not args.no_overlap)
+                          max_det=MAX_DET, swap_rb=True, device=dev, overlap=overlap)
     pipe.plan_sources(list(imgs_dev))
+    n0 = _lib.launch_count()
+    pipe.preprocess()
+    pipe.postprocess(lv_dev)
+    launches_per_step = _lib.launch_count() - n0           # our kernels in one step (memset nodes not counted)
+    pipe.capture(lv_dev)                                   # the step as a CUDA graph (two graphs when overlapping)
+    main_stream = torch.cuda.current_stream()
+    side = pipe.side if overlap else main_stream
+    sptr = lambda s: C.c_void_p(s.cuda_stream)
+    L = pipe._lib
 
-    def step():
-        pipe.preprocess()
-        pipe.filter(lv_dev)
-        pipe.nms()
-
-    side = pipe.side if pipe.overlap else torch.cuda.current_stream()
+    def eager_step(ev=None):
+        """The captured step issued call by call, with CUDA events on the stream of each kernel:
+        [NMS of the previous batch] on the side stream beside [letterbox, filter of this batch]."""
+        s = pipe._graph_step & 1 if overlap else 0
+        if overlap:
+            pipe._graph_step += 1
+            side.wait_stream(main_stream)
+            if ev: ev[3].record(side)
+            _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[s ^ 1], sptr(side)))
+            if ev: ev[4].record(side)
+        if ev: ev[0].record(main_stream)
+        _lib.check("vk_letterbox_batch", L.vk_letterbox_batch(*pipe._lb_args, sptr(main_stream)))
+        if ev: ev[1].record(main_stream)
+        _lib.check("vk_decode_filter", L.vk_decode_filter(pipe._cfg_ref, C.cast(pipe._lv_arr, C.c_void_p), pipe._lv_dt,
+                                                            BATCH, pipe._conf, pipe._ml, pipe._mask_p, pipe._kernel,
+                                                            C.byref(pipe._cs[s]), sptr(main_stream)))
+        if ev: ev[2].record(main_stream)
+        if overlap:
+            main_stream.wait_stream(side)
+            pipe._set = s
+        else:
+            if ev: ev[3].record(main_stream)
+            _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[0], sptr(main_stream)))
+            if ev: ev[4].record(main_stream)
 
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     for _ in range(args.warmup):
-        step()
+        pipe.replay()
+    eager_step()
+    eager_step()
     torch.cuda.synchronize()
     sampler.start()
 
@@ -212,121 +384,119 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- timed region: K steps, device-resident inputs (626 MB per step > 126 MB L2)
+    # ---- timed region: K steps, device-resident inputs (626 MB per step > 126 MB L2).  Steps are CUDA-graph
+    # launches; every EVth step is the same step issued call by call with events around each kernel (on the
+    # stream it runs on), which is where the per-kernel durations of the roofline come from.
     K = args.steps
-    # Events sit on the stream each kernel is launched on (NMS: the side stream when overlapping).  Per-kernel
-    # events are recorded on every 4th step of the timed region (5 records cost ~20 us of host time, and
-    # with 8 ranks on one host the loop must stay GPU-bound); the step time itself uses all K steps.
-    EV = 4
-    sampled = [k for k in range(K) if k % EV == 0]
+    EV = 8
+    sampled = [k for k in range(K) if k % EV == EV - 1]
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(5)] for k in sampled}
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    n0 = _lib.launch_count()
     t_issue0 = time.perf_counter()
     t_begin.record()
     for k in range(K):
-        if k % EV == 0:
-            e = ev[k]
-            e[0].record()
-            pipe.preprocess()
-            e[1].record()
-            pipe.filter(lv_dev)
-            e[2].record()
-            e[3].record(side)       # queued behind the previous NMS on the side stream
-            pipe.nms()
-            e[4].record(side)
+        if k in ev:
+            eager_step(ev[k])
         else:
-            pipe.preprocess()
-            pipe.filter(lv_dev)
-            pipe.nms()
-    pipe.join()
+            pipe.replay()
     t_end.record()
     host_issue_us = (time.perf_counter() - t_issue0) / K * 1e6     # host time to enqueue one step (no waiting)
     barrier()
-    launches = _lib.launch_count() - n0
     total_ms = t_begin.elapsed_time(t_end)
-    kern_ms = [sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in sampled) / len(sampled) for i in range(2)]
-    # NMS duration: from the later of (filter done, previous NMS done) to its own end
-    nms_ms = 0.0
-    for k in sampled:
-        nms_ms += min(ev[k][2].elapsed_time(ev[k][4]), ev[k][3].elapsed_time(ev[k][4]))
-    kern_ms.append(nms_ms / len(sampled))
+    kern_ms = [sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in sampled) / max(len(sampled), 1) for i in (0, 1, 3)]
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * BATCH * K / (total_ms * 1e-3)
-    if world > 1:                                       # launches of the whole job
-        tl = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
-        launches = int(tl.item())
+    launches = launches_per_step * K * world
+    out_last = pipe.flush()
+    torch.cuda.synchronize()
+    n_dets = int(out_last.counts.sum())
+    n_cand = int(pipe._cands[pipe._set].counts.sum().item())
+    clocks = sampler.result()
 
-    # ---- end to end through the public API with HOST buffers: H2D of the step's inputs
-    # (uint8 images and the head's conv outputs), the three kernels, D2H of detections+counts
+    # ---- end to end through the public API with HOST buffers.  Per step: host geometry of the 64 sources
+    # + descriptor upload (plan_sources), H2D of the step's inputs, the kernels, D2H of detections + counts.
     Ke = max(1, min(args.e2e_steps, K))
     dets_host = torch.empty((BATCH, MAX_DET, 6), dtype=torch.float32).pin_memory()
     cnt_host = torch.empty((BATCH,), dtype=torch.int32).pin_memory()
+    epipe = DetectPipeline("v5", nc=80, img_sz=(IMG, IMG), batch=BATCH, conf_thres=CONF, iou_thres=IOU,
+                           max_det=MAX_DET, swap_rb=True, device=dev, overlap=False)
+    srcs = list(imgs_dev)
 
-    def e2e_step():
+    def e2e_step(with_logits: bool):
         imgs_dev.copy_(imgs_host, non_blocking=True)
-        for d, h in zip(lv_dev, lv_host):
-            d.copy_(h, non_blocking=True)
-        pipe.preprocess()
-        out = pipe.postprocess(lv_dev, join=True)
+        if with_logits:
+            for d, h in zip(lv_dev, lv_host):
+                d.copy_(h, non_blocking=True)
+        epipe.preprocess(srcs)                               # plan (geometry, descriptors) + letterbox
+        out = epipe.postprocess(lv_dev)
         dets_host.copy_(out.dets, non_blocking=True)
         cnt_host.copy_(out.counts, non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(Ke):
-        e2e_step()
-    e1.record()
-    barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * Ke / (float(te.item()) * 1e-3)
-    h2d = imgs_host.numel() + sum(t_.numel() * 4 for t_ in lv_host)
+    def time_e2e(with_logits: bool):
+        for _ in range(2):
+            e2e_step(with_logits)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Ke):
+            e2e_step(with_logits)
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * BATCH * Ke / (float(te.item()) * 1e-3)
+
+    e2e_value = time_e2e(True)
+    e2e_images = time_e2e(False)
+    h2d_img = imgs_host.numel()
+    h2d = h2d_img + sum(t_.numel() * 4 for t_ in lv_host)
     d2h = dets_host.numel() * 4 + cnt_host.numel() * 4
-    clocks = sampler.result()
-    n_dets = int(cnt_host.sum())
-    n_cand = int(pipe.cand.counts.sum().item())
+
+    # ---- the other BASELINE configs on this run's GPUs
+    configs = None
+    if not args.no_configs:
+        del epipe
+        torch.cuda.empty_cache()
+        configs = bench_configs(dev, rank, world, max(3, args.config_steps), 3)
 
     # ---- roofline of the dominant kernel (algorithmic bytes)
     peak, peak_kind = measured_peak()
     src_bytes = BATCH * IMG * IMG * 3
     alg = {
         "lb_copy_kernel": src_bytes + BATCH * 3 * IMG * IMG * 4,
-        "decode_filter_kernel": BATCH * pipe.rows * (pipe.cfg.nc + 5) * 4 + 8 * n_cand,
-        "nms_staged_kernel": 24 * n_cand + BATCH * MAX_DET * 24,   # + the (idle) nms_image_kernel fallback launch
+        "decode_filter_rows_kernel": BATCH * pipe.rows * (pipe.cfg.nc + 5) * 4 + 8 * n_cand,
+        "nms_kernel": 24 * n_cand + BATCH * MAX_DET * 24,
     }
-    names = list(alg)
-    kernels = {n_: {"ms": kern_ms[i], "algorithmic_bytes": alg[n_],
-                    "achieved_gbs": alg[n_] / (kern_ms[i] * 1e-3) / 1e9,
-                    "frac_of_peak": alg[n_] / (kern_ms[i] * 1e-3) / 1e9 / peak}
-               for i, n_ in enumerate(names)}
-    # the kernel that bounds a step: with the NMS overlapped on its side stream, the longest of the
-    # two HBM-bound kernels on the main stream; otherwise the longest of all three
-    crit = names[:2] if pipe.overlap else names
-    dom = max(crit, key=lambda n_: kernels[n_]["ms"])
-    traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dom]["frac_of_peak"], "traffic": traffic,
+        traffic_all = {}
+    names = list(alg)
+    kernels = {}
+    for i, n_ in enumerate(names):
+        kernels[n_] = {"ms": kern_ms[i], "algorithmic_bytes": alg[n_],
+                       "algorithmic_gbs": alg[n_] / (kern_ms[i] * 1e-3) / 1e9}
+        tr = traffic_all.get(n_)
+        if tr:                                               # DRAM bytes per launch from the committed ncu capture
+            kernels[n_]["dram_bytes_ncu"] = tr
+            kernels[n_]["dram_gbs"] = tr / (kern_ms[i] * 1e-3) / 1e9
+            kernels[n_]["dram_frac_of_peak"] = tr / (kern_ms[i] * 1e-3) / 1e9 / peak
+    kernels["decode_filter_rows_kernel"]["note"] = (
+        "gathers only the rows with obj > conf: one 32-byte sector per channel per surviving row, so it is bound by "
+        "the rate at which HBM serves scattered sectors (profiles/micro/sector_gather.cu: ~60 G sectors/s on this "
+        "part), not by bytes; algorithmic_gbs counts the full conv-output read it avoids")
+    dom = "lb_copy_kernel"                                   # the longest kernel of the main stream and an HBM stream
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["algorithmic_gbs"] / peak, "traffic": traffic_all.get(dom),
                 "peak_kind": f"of {peak_kind}",
-                "note": ("achieved = algorithmic bytes (full conv-output read) / time; the kernel gathers only "
-                         "surviving rows, so its DRAM traffic is below the algorithmic bytes and frac can exceed 1"
-                         if dom == "decode_filter_kernel" else
-                         ("duration measured while the NMS of the previous batch runs concurrently on the side stream "
-                          "(it shares the SMs); the same kernel alone: 64 us = 0.94 of peak, profiles/r1z_kernels.txt"
-                          if pipe.overlap else ""))}
+                "note": ("duration measured inside the step: the NMS of the previous batch runs beside it on the side "
+                         "stream and shares the SMs; the same kernel timed alone is in profiles/ (kernel_bench)"
+                         if overlap else "")}
 
     if rank != 0:
         if world > 1:
@@ -334,8 +504,8 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, passes, dt = time_cpu(8, args.cpu_seconds)
-        cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+        v, passes, dt, cores, kind = time_cpu(8, args.cpu_seconds)
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
                "sample": f"8 images of the batch x {passes} passes ({dt:.1f} s): cv2 letterbox+normalise, "
                          f"torch decode, torch+torchvision NMS", "os_cpu_count": os.cpu_count()}
     sys.stdout.flush()
@@ -346,16 +516,22 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                    "pipeline": "letterbox(u8 HWC->f32 NCHW /255) -> fused Detect decode+filter -> per-image sort+NMS",
-                   "streams": ("NMS of batch k on a side stream, overlapped with letterbox+filter of batch k+1"
-                               if pipe.overlap else "single stream"),
+                   "streams": ("one CUDA-graph launch per step: NMS of batch k on a side stream beside letterbox+filter "
+                               "of batch k+1" if overlap else "one CUDA-graph launch per step, single stream"),
                    "parallelism": f"images sharded over {world} GPU(s), no collective on the hot path",
                    "l2": "inputs larger than L2: 627 MB read per step per GPU vs 126 MB L2, no flush needed",
                    "detections_per_step": n_dets, "candidates_per_step": n_cand,
-                   "host_issue_us_per_step": round(host_issue_us, 1)},
+                   "host_issue_us_per_step": round(host_issue_us, 1),
+                   "event_steps": f"every {EV}th step is issued call by call with CUDA events around each kernel"},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "note": "PCIe-bound: the head's conv outputs (548 MB/step) are copied from host "
-                                     "memory too, as the contract asks; in deployment they are produced on the GPU"},
+                                     "memory too, as the contract asks; in deployment they are produced on the GPU. "
+                                     "The step includes the host geometry + descriptor upload of the 64 sources"},
+        "e2e_images_only": {"value": e2e_images, "unit": "images/s", "h2d_bytes_per_step": h2d_img,
+                            "d2h_bytes_per_step": d2h, "steps": Ke,
+                            "note": "the path's own copies: uint8 images in, detections out; conv outputs resident"},
+        "configs": configs,
         "gpu_launches": int(launches), "clocks": clocks,
     }), flush=True)
     if world > 1:

@@ -134,11 +134,11 @@ int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels, int dtype,
  * the buffer needs cap >= segs * T and can never overflow, and SLOT ORDER IS THE CANONICAL ORDER
  * of the reference's candidate list (the order that breaks score ties in its argsort and NMS).
  *
- * list + hist: optional scratch of vk_nms_batched for images with more than list_cap candidates
- * (eval thresholds, ~240 k per image): a sampled score histogram picks the score bound above which a
+ * list: optional scratch of vk_nms_batched for images with more than list_cap candidates (eval
+ * thresholds, ~240 k per image): a sampled score histogram picks the score bound above which a
  * grid-wide pass copies the candidates, as (ordered score << 32 | ~slot), into the image's list, and
- * the per-image kernel sorts from that list.  Results never depend on them; allocate both when such
- * images are expected.
+ * the per-image kernel sorts from that list.  Results never depend on it; allocate it (8192 entries
+ * per image is plenty) when such images are expected.
  */
 #define VK_HIST_BINS 1024   /* bin = (0x3f800000 - score bits) >> 20: 8 bins per octave below 1.0 */
 #define VK_CTRL_WORDS 4     /* ctrl rows: 0 candidate count, 1 flags | slots per tile / 64 << 8, 2 list entries, 3 list bound */
@@ -150,7 +150,6 @@ typedef struct VkCandBuf {
     int32_t* ctrl;       /* dev [VK_CTRL_WORDS][batch]; zeroed by the filter call */
     int32_t* seg_count;  /* dev [batch][segs] candidates of each segment */
     uint64_t* list;      /* dev [batch][list_cap] or NULL */
-    uint32_t* hist;      /* dev [batch][VK_HIST_BINS] or NULL */
     int32_t cap;         /* candidate slots per image */
     int32_t rows;        /* prediction rows per image */
     int32_t segs;        /* segments per image (vk_filter_segments / vk_decode_filter_segments) */
@@ -212,8 +211,8 @@ int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const
  *   (into the candidate list the reference handed it), -1 padded.
  * status: dev int32[batch] or NULL; always written 0 (kept for callers that check it: a
  *   candidate buffer sized as above cannot overflow).
- * Two launches: a grid-wide selection pass that builds the per-image top list from the filter's
- * score histogram (returns at once for images without one), and one CTA per image that consumes
+ * Two launches: a grid-wide selection pass that builds the per-image top list (only with a `list`;
+ * it returns at once for images that fit a stage anyway), and one CTA per image that consumes
  * candidates in descending score order, a stage of <= 2048 at a time, until max_det boxes are kept.
  * Writes ctrl rows 1-3 of the candidate buffer (the list it builds); needs no workspace.
  */

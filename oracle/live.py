@@ -1,7 +1,9 @@
-"""Live import of the real reference (TEST INFRASTRUCTURE ONLY; dev container).
+"""Live import of the real reference (TEST INFRASTRUCTURE ONLY).
 
-``/root/reference`` is read-only here and absent on the GPU box, so nothing
-that runs there may import this module; callers check ``available()``.
+``/root/reference`` exists in the dev container only.  ``__graft_entry__.build()`` therefore installs the
+unmodified reference package into ``baseline/_ref`` (git-ignored; it travels to the GPU box with the
+snapshot) with ``pip install --no-deps --target``, and this module imports it from whichever of the two
+is there; callers check ``available()``.
 Recipe from SURVEY.md §8c: stub the two uninstallable imports
 (``pycocotools``, ``omegaconf``) and neutralise the wall-clock NMS time limit
 (utils/image_proc.py:109,183-185) by freezing the clock that module sees.
@@ -12,7 +14,11 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("VK_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("VK_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "baseline", "_ref")]
+REF_ROOT = next((p for p in _CANDIDATES if p and os.path.isdir(os.path.join(p, "vision_kit"))), "/root/reference")
+ASSETS = next((p for p in (os.path.join(REF_ROOT, "assets"), os.path.join(_HERE, "baseline", "_ref", "assets"))
+               if os.path.isdir(p)), None)
 _cache = {}
 
 
@@ -52,7 +58,7 @@ def load():
 
     image_proc.time = _FrozenClock          # time limit never fires
     ns = types.SimpleNamespace(image_proc=image_proc, ImageProcessor=ImageProcessor,
-                               YoloV5Head=YoloV5Head, YoloV7Head=YoloV7Head)
+                               YoloV5Head=YoloV5Head, YoloV7Head=YoloV7Head, root=REF_ROOT)
     _cache["ns"] = ns
     return ns
 
@@ -92,3 +98,20 @@ def head_decode(variant: str, levels):
     with torch.no_grad():
         pred, raws = head([t.clone() for t in levels])
     return pred, raws
+
+
+def demo_model(seed: int = 0):
+    """The demo's model (scripts/demo.py:48-53: ``YOLOV5(variant='s')``) with seeded random weights (the
+    weight file is not part of the reference tree) and the objectness / class priors lifted so that
+    detections exist.  One model per process: the neck mutates its default arguments."""
+    import torch
+    load()
+    from vision_kit.models.architectures import YOLOV5
+    torch.manual_seed(seed)
+    model = YOLOV5("s")
+    with torch.no_grad():
+        for m in model.head.m:
+            b = m.bias.view(3, -1)
+            b[:, 4] += 4.0
+            b[:, 5:] += 2.5
+    return model.eval()

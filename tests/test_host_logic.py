@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.VkLbDesc) == 48
     assert C.sizeof(_lib.VkLbGeom) == 64
     assert C.sizeof(_lib.VkHeadCfg) == 4 * 4 + 4 * 4 * 2 + 4 * 4 + 4 * 16 * 4
-    assert C.sizeof(_lib.VkCandBuf) == 6 * 8 + 6 * 4
+    assert C.sizeof(_lib.VkCandBuf) == 5 * 8 + 6 * 4
 
 
 def test_geometry_equals_oracle(vk_lib):
@@ -204,4 +204,4 @@ def test_filter_and_nms_argument_validation(vk_lib):
     assert vk_lib.vk_eval_match_smem_bytes(10, 100) == 100 * 6 * 4 + 10 * 100 * 4
     assert vk_lib.vk_eval_match_smem_bytes(0, 100) == 0
     assert ops.expects_dense("auto", 0.001) and not ops.expects_dense("auto", 0.25) and ops.expects_dense("dense", 0.25)
-    assert _lib.C.sizeof(_lib.VkCandBuf) == 6 * 8 + 6 * 4
+    assert _lib.C.sizeof(_lib.VkCandBuf) == 5 * 8 + 6 * 4

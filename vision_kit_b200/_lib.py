@@ -58,7 +58,7 @@ class VkHeadCfg(C.Structure):
 
 class VkCandBuf(C.Structure):
     _fields_ = [("cand", C.c_void_p), ("boxes", C.c_void_p), ("ctrl", C.c_void_p),
-                ("seg_count", C.c_void_p), ("list", C.c_void_p), ("hist", C.c_void_p),
+                ("seg_count", C.c_void_p), ("list", C.c_void_p),
                 ("cap", C.c_int32), ("rows", C.c_int32), ("segs", C.c_int32), ("nc", C.c_int32),
                 ("list_cap", C.c_int32), ("reserved", C.c_int32)]
 

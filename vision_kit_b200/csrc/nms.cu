@@ -8,15 +8,14 @@
 // candidate order (include/vk_b200.h), so descending keys = the stable descending argsort the
 // reference's cut and torchvision's NMS are defined on, and keys are unique.
 //
-//   nms_sample_kernel   images with more candidates than their list holds (eval thresholds, ~240 k):
-//   nms_select_kernel   every 8th 128-byte line of the candidate slots feeds a score histogram; the
-//                       largest bound whose estimated count fits 3/4 of the list is chosen, and a
-//                       grid-wide streaming pass copies every candidate at or above it into the
-//                       image's list.  All SMs work on every image, whatever the batch size.
+//   nms_select_kernel   images with more candidates than their list holds (eval thresholds, ~240 k): a
+//                       sampled score histogram gives the largest bound whose estimated count fits half
+//                       the list, and a grid-wide streaming pass copies every candidate at or above it
+//                       into the image's list.  All SMs work on every image, whatever the batch size.
 //   nms_kernel          one CTA per image.  Stages of <= CAP candidates: a radix selection over the
 //                       key bits (11/11/10 bits per pass, stopping at the first prefix whose count
 //                       fits a stage) finds the stage's lower bound, one pass compacts the stage into
-//                       shared memory, a bitonic sort orders it, boxes are fetched once, and chunks
+//                       shared memory, a counting sort orders it, boxes are fetched once, and chunks
 //                       of 256 run:
 //         1. each chunk box against the kept boxes of earlier chunks
 //         2. predecessor bit matrix pred[i] = { j < i in the chunk : IoU(j, i) > thr }
@@ -59,7 +58,6 @@ struct NmsArgs {
     int32_t* bound;             // ctrl row 3 (ordered score bits)
     const int32_t* seg_count;
     uint64_t* list;
-    uint32_t* hist;
     int cap, rows, segs, nc, list_cap;
     float iou_thr;  // largest float <= the double threshold
     int agnostic, max_nms, max_det;
@@ -79,75 +77,94 @@ __device__ __forceinline__ int tile_slots_of(int flags) { return (flags >> 8) <<
 
 // true when image b needs the select pass: it has a list, and more candidates than the list holds
 __device__ __forceinline__ bool wants_select(const NmsArgs& A, int b) {
-    return A.list != nullptr && A.hist != nullptr && A.counts[b] > A.list_cap;
+    return A.list != nullptr && A.counts[b] > A.list_cap;
 }
 
-// Sampled histogram: the 128-byte line l (16 candidates) of segment seg is read when (l + seg) % 8 == 0.
-// Most candidates of an eval-mode image share a handful of low-score bins, so lanes with the same bin
-// elect one of them to add the group's size (match.any) instead of colliding 32 ways on one counter.
-__global__ void __launch_bounds__(kSelThreads)
-nms_sample_kernel(const NmsArgs A) {
-    const int b = blockIdx.y;
-    if (!wants_select(A, b)) return;
-    __shared__ uint32_t s_hist[VK_HIST_BINS];
-    for (int i = threadIdx.x; i < VK_HIST_BINS; i += kSelThreads) s_hist[i] = 0u;
-    __syncthreads();
-    const int tile_cap = tile_slots_of(A.flags[b]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint2* cand = reinterpret_cast<const uint2*>(A.cand + (size_t)b * A.cap);
-    const int32_t* seg_count = A.seg_count + (size_t)b * A.segs;
-    const int stride = gridDim.x * (kSelThreads / 32);
-    int seg = blockIdx.x * (kSelThreads / 32) + warp;
-    int cnt = seg < A.segs ? seg_count[seg] : 0;
-    for (; seg < A.segs; seg += stride) {
-        const int nseg = seg + stride;
-        const int ncnt = nseg < A.segs ? seg_count[nseg] : 0;        // the next count is in flight during this segment
-        const uint2* cp = cand + (size_t)seg * tile_cap;
-        const int l0 = (8 - (seg & 7)) & 7;
-        // lane = (line m = lane / 16 of the pair of sampled lines, entry e = lane % 16); two pairs per trip
-        for (int l = l0; 16 * l < cnt; l += 32) {
-            int bin[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = 16 * (l + 8 * (2 * u + (lane >> 4))) + (lane & 15);
-                bin[u] = (j < cnt) ? hist_bin(cp[j].x) : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const unsigned peers = __match_any_sync(0xffffffffu, bin[u]);
-                if (bin[u] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin[u]], (uint32_t)__popc(peers));
-            }
-        }
-        cnt = ncnt;
+// Work items of one image for the two passes below: segment t contributes ceil(count / piece) items of
+// `piece` consecutive candidates, so warps get equal shares whatever the spread of the segment counts
+// (a tile on a cluster of objects holds thousands of candidates, most tiles a few hundred).
+// Fills s_cnt[t] and the exclusive item prefix s_pre[t] (s_pre[segs] = total) and returns the total.
+__device__ __forceinline__ int build_items(const int32_t* __restrict__ seg_count, int segs, int piece, int* s_cnt,
+                                           int* s_pre, int* wsum) {
+    int carry = 0;
+    for (int t0 = 0; t0 < segs; t0 += kSelThreads) {
+        const int t = t0 + threadIdx.x;
+        const int c = (t < segs) ? seg_count[t] : 0;
+        int total;
+        const int ex = block_excl_scan((c + piece - 1) / piece, wsum, &total);
+        if (t < segs) { s_cnt[t] = c; s_pre[t] = carry + ex; }
+        carry += total;
     }
+    if (threadIdx.x == 0) s_pre[segs] = carry;
     __syncthreads();
-    uint32_t* gh = A.hist + (size_t)b * VK_HIST_BINS;
-    for (int i = threadIdx.x; i < VK_HIST_BINS; i += kSelThreads) {
-        const uint32_t v = s_hist[i];
-        if (v) atomicAdd(&gh[i], v);
+    return carry;
+}
+__device__ __forceinline__ int item_segment(const int* s_pre, int segs, int item) {   // last t with s_pre[t] <= item
+    int lo = 0, hi = segs;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pre[mid] <= item) lo = mid; else hi = mid;
     }
+    return lo;
 }
 
-// Bound from the histogram, then every candidate at or above it is appended to the image's list.
+// Score bound + list of one image, one streaming pass.  The work items of an image are dealt out round-robin
+// to its blocks, so a block's share is a uniform sample of the image.  Each block first reads every 8th
+// 128-byte line of ITS OWN items (one round trip: ~10 loads in flight per lane), estimates the image's
+// score distribution from that (x 8 x blocks), and picks the last histogram bin whose estimated cumulative
+// count fits HALF the list (~40 samples at that rank: overflowing the list would need an error of 2x).
+// Blocks of one image may pick neighbouring bins; the image's bound is the highest of them (atomicMax), every
+// block appends everything at or above ITS bound, so the list holds every candidate at or above the image's
+// bound plus a few below it, which nms_kernel skips.  Most candidates of an eval-mode image share a handful
+// of low-score bins, so lanes with the same bin elect one of them to add the group's size (match.any)
+// instead of colliding 32 ways on one shared-memory counter.
+constexpr int kSampleEvery = 8;
+constexpr int kSelectPiece = 256;                     // candidates per work item: 16 lines, 8 loads per lane
 __global__ void __launch_bounds__(kSelThreads)
 nms_select_kernel(const NmsArgs A) {
     const int b = blockIdx.y;
     if (!wants_select(A, b)) return;
-    __shared__ int wsum[33];
+    __shared__ uint32_t s_hist[VK_HIST_BINS];
+    __shared__ int s_cnt[VK_MAX_SEGMENTS], s_pre[VK_MAX_SEGMENTS + 1], wsum[33];
     __shared__ int s_j;
+    __shared__ unsigned long long s_stage[kSelThreads / 32][kSelStage];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // ---- bound: the last bin whose estimated cumulative count (8 x sampled) fits 3/4 of the list
+    const int tile_cap = tile_slots_of(A.flags[b]);
+    const uint2* cand = reinterpret_cast<const uint2*>(A.cand + (size_t)b * A.cap);
+    for (int i = threadIdx.x; i < VK_HIST_BINS; i += kSelThreads) s_hist[i] = 0u;
+    const int items = build_items(A.seg_count + (size_t)b * A.segs, A.segs, kSelectPiece, s_cnt, s_pre, wsum);
+    const int first = blockIdx.x * (kSelThreads / 32) + warp, step = gridDim.x * (kSelThreads / 32);
+    // ---- sample: lines 2 and 10 of each of this warp's items (16 lines per item), 32 lanes = 2 lines
+    for (int item0 = first; item0 < items; item0 += 4 * step) {          // four items' loads in flight
+        int bin[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int item = item0 + u * step;
+            bin[u] = -1;
+            if (item < items) {
+                const int seg = item_segment(s_pre, A.segs, item);
+                const int j = (item - s_pre[seg]) * kSelectPiece + 16 * (2 + kSampleEvery * (lane >> 4)) + (lane & 15);
+                if (j < s_cnt[seg]) bin[u] = hist_bin(cand[(size_t)seg * tile_cap + j].x);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned peers = __match_any_sync(0xffffffffu, bin[u]);
+            if (bin[u] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin[u]], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    // ---- this block's bound: the last bin whose estimated cumulative count fits half the list
     {
         constexpr int BPT = VK_HIST_BINS / kSelThreads;
-        const uint32_t* gh = A.hist + (size_t)b * VK_HIST_BINS;
         uint32_t v[BPT];
         int sum = 0;
 #pragma unroll
-        for (int k = 0; k < BPT; ++k) { v[k] = gh[BPT * threadIdx.x + k]; sum += (int)v[k]; }
+        for (int k = 0; k < BPT; ++k) { v[k] = s_hist[BPT * threadIdx.x + k]; sum += (int)v[k]; }
         if (threadIdx.x == 0) s_j = -1;
         int total;
         int run = block_excl_scan(sum, wsum, &total);
-        const long limit = ((long)A.list_cap * 3 / 4) / 8;
+        const long limit = ((long)A.list_cap / 2) / ((long)kSampleEvery * gridDim.x);
         int best = -1;
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
@@ -157,22 +174,18 @@ nms_select_kernel(const NmsArgs A) {
         if (best >= 0) atomicMax(&s_j, best);
         __syncthreads();
     }
-    const int j = s_j;
-    const uint32_t bound = j < 0 ? 0xffffffffu : hist_bound(j);     // no bin fits: an empty list, nms_kernel streams the segments
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        A.bound[b] = (int32_t)bound;
+    const int jb = s_j;
+    const uint32_t bound = jb < 0 ? 0xffffffffu : hist_bound(jb);   // no bin fits: nothing from this block, and the image's bound says so
+    if (threadIdx.x == 0) {
+        atomicMax(reinterpret_cast<unsigned int*>(A.bound) + b, bound);
         atomicOr(const_cast<int32_t*>(A.flags) + b, VK_FLAG_LIST);
     }
-    if (j < 0) return;
-    // ---- streaming pass over this block's share of the segments.  Selected keys are staged per warp in
-    //      shared memory and flushed with ONE reservation on the image's list counter per ~100 keys: a
-    //      reservation per 32 candidates would serialise thousands of same-address atomics per image.
-    __shared__ unsigned long long s_stage[kSelThreads / 32][kSelStage];
+    if (jb < 0) return;
+    // ---- streaming pass over this block's items.  Selected keys are staged per warp in shared memory and
+    //      flushed with ONE reservation on the image's list counter per ~100 keys: a reservation per 32
+    //      candidates would serialise thousands of same-address atomics per image.
     unsigned long long* stage = s_stage[warp];
     int staged = 0;                                               // warp-uniform
-    const int tile_cap = tile_slots_of(A.flags[b]);
-    const uint2* cand = reinterpret_cast<const uint2*>(A.cand + (size_t)b * A.cap);
-    const int32_t* seg_count = A.seg_count + (size_t)b * A.segs;
     uint64_t* list = A.list + (size_t)b * A.list_cap;
     const unsigned lt = (1u << lane) - 1u;
     auto flush = [&]() {
@@ -185,35 +198,46 @@ nms_select_kernel(const NmsArgs A) {
         __syncwarp();
         staged = 0;
     };
-    const int stride = gridDim.x * (kSelThreads / 32);
-    int seg = blockIdx.x * (kSelThreads / 32) + warp;
-    int cnt = seg < A.segs ? seg_count[seg] : 0;
-    for (; seg < A.segs; seg += stride) {
-        const int nseg = seg + stride;
-        const int ncnt = nseg < A.segs ? seg_count[nseg] : 0;        // the next count is in flight during this segment
-        const uint32_t slot0 = (uint32_t)seg * (uint32_t)tile_cap;
-        const uint2* cp = cand + slot0;
-        for (int j0 = 0; j0 < cnt; j0 += 256) {          // 8 loads in flight per lane
-            uint32_t sc[8];
+    // (the loads of a warp's next item are issued before the current one is examined)
+    struct Item { uint32_t slot0; int j0, cnt; };
+    auto locate = [&](int item) {
+        const int seg = item_segment(s_pre, A.segs, item);
+        return Item{(uint32_t)seg * (uint32_t)tile_cap, (item - s_pre[seg]) * kSelectPiece, s_cnt[seg]};
+    };
+    auto fetch = [&](const Item& it, uint32_t* sc) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jj = it.j0 + 32 * u + lane;
+            sc[u] = (jj < it.cnt) ? cand[it.slot0 + jj].x : 0u;
+        }
+    };
+    if (first < items) {
+        Item cur = locate(first);
+        uint32_t sc[8];
+        fetch(cur, sc);
+        for (int item = first; item < items; item += step) {
+            const bool more = item + step < items;
+            Item nxt = cur;
+            uint32_t sn[8];
+            if (more) { nxt = locate(item + step); fetch(nxt, sn); }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int jj = j0 + 32 * u + lane;
-                sc[u] = (jj < cnt) ? cp[jj].x : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jj = j0 + 32 * u + lane;
+                const int jj = cur.j0 + 32 * u + lane;
                 const uint32_t key = order_key(sc[u]);
-                const bool take = jj < cnt && key >= bound;
+                const bool take = jj < cur.cnt && key >= bound;
                 const unsigned m = __ballot_sync(0xffffffffu, take);
                 if (m) {
-                    if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~(slot0 + (uint32_t)jj);
+                    if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~(cur.slot0 + (uint32_t)jj);
                     staged += __popc(m);
                     if (staged > kSelStage - 32) flush();
                 }
             }
+            if (more) {
+                cur = nxt;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sc[u] = sn[u];
+            }
         }
-        cnt = ncnt;
     }
     if (staged) flush();
 }
@@ -368,25 +392,17 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
                 const int e = C.XB.cstart[bk + 1];
                 const float4 ib = cbox[i];
                 const float ia = box_area(ib);
-                uint32_t acc[kChunkWords];
-#pragma unroll
-                for (int wd = 0; wd < kChunkWords; ++wd) acc[wd] = 0u;
-                bool any = false;
-                for (int m = C.XB.cstart[bk] + tid / kChunk; m < e; m += TPR) {
-                    const int j = C.XB.members[m];
-                    if (j >= i || ccls[j] != ic || C.XB.state[j] != 0) continue;
-                    const float4 jb = cbox[j];
-                    if (iou_exceeds(jb, box_area(jb), ib, ia, C.thr)) {
-                        any = true;
-#pragma unroll
-                        for (int wd = 0; wd < kChunkWords; ++wd)
-                            if (wd == (j >> 5)) acc[wd] |= 1u << (j & 31);
-                    }
-                }
-                if (any) {
-#pragma unroll
-                    for (int wd = 0; wd < kChunkWords; ++wd)
-                        if (acc[wd]) atomicOr(&C.XB.pred[i * kChunkWords + wd], acc[wd]);
+                for (int m = C.XB.cstart[bk] + tid / kChunk; m < e; m += 2 * TPR) {     // two independent chains per step
+                    const int ja = C.XB.members[m];
+                    const bool two = m + TPR < e;
+                    const int jb_ = C.XB.members[two ? m + TPR : m];
+                    const bool ta = ja < i && ccls[ja] == ic && C.XB.state[ja] == 0;
+                    const bool tb = two && jb_ < i && ccls[jb_] == ic && C.XB.state[jb_] == 0;
+                    const float4 ba = cbox[ja], bb = cbox[jb_];
+                    const bool ha = ta && iou_exceeds(ba, box_area(ba), ib, ia, C.thr);
+                    const bool hb = tb && iou_exceeds(bb, box_area(bb), ib, ia, C.thr);
+                    if (ha) atomicOr(&C.XB.pred[i * kChunkWords + (ja >> 5)], 1u << (ja & 31));
+                    if (hb) atomicOr(&C.XB.pred[i * kChunkWords + (jb_ >> 5)], 1u << (jb_ & 31));
                 }
             }
         }
@@ -512,7 +528,7 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
 template <int CAP>
 static size_t nms_smem_bytes(int threads, int segs, int max_det) {
     (void)threads;
-    return (size_t)CAP * (8 + 8 + 16 + 4 + 2) + (size_t)kHistBins * 4 +
+    return (size_t)CAP * (8 + 8 + 16 + 4 + 2) + (size_t)(kHistBins + 4) * 4 +
            align16((size_t)(segs + 1) * 4) + align16(ScratchB::bytes(max_det));
 }
 
@@ -523,13 +539,14 @@ nms_kernel(const NmsArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wsum[33];
     __shared__ int s_bin, s_above, s_cnt;
+    __shared__ unsigned long long s_max, s_min;
 
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     float4* sbox = reinterpret_cast<float4*>(keys + CAP);
     unsigned long long* xchg = reinterpret_cast<unsigned long long*>(sbox + CAP);
     uint32_t* sidx = reinterpret_cast<uint32_t*>(xchg + CAP);
     int* hist = reinterpret_cast<int*>(sidx + CAP);
-    uint16_t* scls = reinterpret_cast<uint16_t*>(hist + kHistBins);
+    uint16_t* scls = reinterpret_cast<uint16_t*>(hist + kHistBins + 4);    // (+4: the counting sort's end marker)
     int* segoff = reinterpret_cast<int*>(scls + CAP);     // [segs + 1] exclusive prefix of the segment counts
     ScratchB XB(reinterpret_cast<unsigned char*>(segoff) + align16((size_t)(A.segs + 1) * 4), A.max_det);
 
@@ -545,14 +562,27 @@ nms_kernel(const NmsArgs A) {
     const int n = A.counts[b];
     const int flags = A.flags[b];
     const int tile_cap = tile_slots_of(flags);
-    // the image's list: every candidate at or above `lbound`, built by the select pass; -1 = none
-    int list_n = -1;
+    // the image's list, built by the select pass: every candidate at or above `lbound` (and a few below it,
+    // which are skipped); -1 = none
+    int list_n = -1, list_len = 0;
     uint32_t lbound = 0;
-    if (A.list != nullptr && (flags & VK_FLAG_LIST)) {
-        const int lc = A.list_count[b];
-        if (lc <= A.list_cap) { list_n = lc; lbound = (uint32_t)A.bound[b]; }
-    }
     const uint64_t* list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
+    if (list != nullptr && (flags & VK_FLAG_LIST)) {
+        const int lc = A.list_count[b];
+        if (lc <= A.list_cap) {
+            lbound = (uint32_t)A.bound[b];
+            list_len = lc;
+            int mine = 0;
+            for (int i = tid; i < lc; i += T) mine += (uint32_t)(list[i] >> 32) >= lbound ? 1 : 0;
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            mine = warp_incl_scan(mine, lane);
+            if (lane == 31 && mine) atomicAdd(&s_cnt, mine);
+            __syncthreads();
+            list_n = s_cnt;
+            __syncthreads();
+        }
+    }
     const int K = min(n, A.max_nms);
     const bool cut = n > A.max_nms;
 
@@ -579,16 +609,17 @@ nms_kernel(const NmsArgs A) {
     __syncthreads();
 
     // every candidate of the current source: f(valid, key)
+    const unsigned long long lfloor = (unsigned long long)lbound << 32;
     auto for_each_list = [&](auto&& f) {
-        for (int i0 = 0; i0 < list_n; i0 += 4 * T) {
+        for (int i0 = 0; i0 < list_len; i0 += 4 * T) {
             unsigned long long e[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * T + tid;
-                e[u] = (i < list_n) ? list[i] : 0ull;
+                e[u] = (i < list_len) ? list[i] : 0ull;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) f(i0 + u * T + tid < list_n, e[u]);
+            for (int u = 0; u < 4; ++u) f(i0 + u * T + tid < list_len && e[u] >= lfloor, e[u]);
         }
     };
     auto for_each_segment = [&](auto&& f) {
@@ -631,7 +662,7 @@ nms_kernel(const NmsArgs A) {
             if (!have_segoff) load_segoff();
         }
         const int remaining = (use_list ? list_n : n) - rank_base;
-        unsigned long long v = use_list ? ((unsigned long long)lbound << 32) : 0ull;   // inclusive lower bound of this stage
+        unsigned long long v = use_list ? lfloor : 0ull;   // inclusive lower bound of this stage
         if (remaining > CAP) {
             const int tgt = min(CAP / 2, K - rank_base);
             unsigned long long prefix = 0, pmask = 0;
@@ -709,64 +740,72 @@ nms_kernel(const NmsArgs A) {
         __syncthreads();
         VK_STAMP(stamp + 1);
         const int cnt = min(s_cnt, CAP);
-        int Ps = 32;
-        while (Ps < cnt) Ps <<= 1;
-        for (int i = cnt + tid; i < Ps; i += T) keys[i] = (unsigned long long)(Ps - 1 - i);   // unique, below every real key
-        __syncthreads();
-        // ---- sort, descending: every warp sorts runs of 32 keys in registers (bitonic, shuffles only), then
-        //      log2(Ps / 32) merge rounds: a key's place in the merged run is its index in its own run plus
-        //      the number of keys of the partner run that precede it (binary search; keys are unique, so
-        //      ranks never collide).  ~3 us for 2048 keys against ~17 us for a block-wide bitonic network.
+        // ---- sort, descending: a counting sort on the leading 11 bits in which the stage's keys differ
+        //      (bin = 2047 - ((key - min) >> shift), shift from the spread max - min), then every key ranks itself
+        //      inside its bin by comparison.  Scores of a stage are spread over its bins, so bins hold a few keys;
+        //      a block-wide bitonic or merge network costs 4x as much for 2048 keys.  (Thousands of equal
+        //      scores in one stage make the in-bin step quadratic -- still correct.)
         if (cnt > 1) {
             constexpr int E = CAP / T > 0 ? CAP / T : 1;           // keys per thread
-            int rounds = 0;
-            for (int L = 32; L < Ps; L <<= 1) ++rounds;
-            unsigned long long* src = (rounds & 1) ? xchg : keys;   // the last round writes into `keys`
-            unsigned long long* dst = (rounds & 1) ? keys : xchg;
-            unsigned long long x[E];
+            unsigned long long kq[E];
+            unsigned long long mx = 0ull, mn = ~0ull;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int e = tid + q * T;
-                x[q] = (e < Ps) ? keys[e] : 0ull;
+                const bool in = e < cnt;
+                kq[q] = in ? keys[e] : 0ull;
+                mx = (in && kq[q] > mx) ? kq[q] : mx;
+                mn = (in && kq[q] < mn) ? kq[q] : mn;
             }
 #pragma unroll
-            for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0 || k == 32);
-#pragma unroll
-                    for (int q = 0; q < E; ++q) {
-                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, x[q], j);
-                        x[q] = keep_max ? (x[q] > o ? x[q] : o) : (x[q] < o ? x[q] : o);
-                    }
-                }
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, off);
+                const unsigned long long u = __shfl_xor_sync(0xffffffffu, mn, off);
+                mx = o > mx ? o : mx;
+                mn = u < mn ? u : mn;
             }
+            if (tid == 0) { s_max = 0ull; s_min = ~0ull; }
+            for (int i = tid; i < kHistBins; i += T) hist[i] = 0;
+            __syncthreads();
+            if (lane == 0) { atomicMax(&s_max, mx); atomicMin(&s_min, mn); }
+            __syncthreads();
+            const unsigned long long base = s_min;
+            const unsigned long long span = s_max - base;
+            const int shift = (span >> 11) == 0ull ? 0 : (64 - __clzll((long long)span)) - 11;   // (span >> shift) < 2048
+            int bin[E], ord[E];
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int e = tid + q * T;
-                if (e < Ps) src[e] = x[q];
+                bin[q] = (kHistBins - 1) - (int)((kq[q] - base) >> shift);
+                ord[q] = (e < cnt) ? atomicAdd(&hist[bin[q]], 1) : 0;
             }
             __syncthreads();
-            for (int sh = 5; (1 << sh) < Ps; ++sh) {                // runs of L = 1 << sh keys
-                const int L = 1 << sh;
+            {   // exclusive scan of the bins (bins ascending = keys descending); hist[kHistBins] = cnt
+                constexpr int BPT = kHistBins / T;
+                int vals[BPT], sum = 0;
 #pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const int e = tid + q * T;
-                    if (e < Ps) {
-                        const unsigned long long xe = src[e];
-                        const int r = e >> sh, i = e & (L - 1);
-                        const unsigned long long* pr = src + ((r ^ 1) << sh);    // partner run, descending
-                        int lo = 0, hi = L;                                      // first index with pr[idx] < xe
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (pr[mid] > xe) lo = mid + 1; else hi = mid;
-                        }
-                        dst[((r >> 1) << (sh + 1)) + i + lo] = xe;
-                    }
-                }
-                __syncthreads();
-                unsigned long long* t2 = src; src = dst; dst = t2;
+                for (int k = 0; k < BPT; ++k) { vals[k] = hist[BPT * tid + k]; sum += vals[k]; }
+                int total;
+                int run = block_excl_scan(sum, wsum, &total);
+#pragma unroll
+                for (int k = 0; k < BPT; ++k) { hist[BPT * tid + k] = run; run += vals[k]; }
+                if (tid == 0) hist[kHistBins] = total;
             }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < E; ++q)
+                if (tid + q * T < cnt) xchg[hist[bin[q]] + ord[q]] = kq[q];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                if (tid + q * T < cnt) {
+                    const int s0 = hist[bin[q]], s1 = hist[bin[q] + 1];
+                    int r = 0;
+                    for (int p = s0; p < s1; ++p) r += xchg[p] > kq[q] ? 1 : 0;
+                    keys[s0 + r] = kq[q];
+                }
+            }
+            __syncthreads();
         }
         VK_STAMP(stamp + 2);
         // ---- the stage's boxes, once: candidate slot -> (row, class) -> class-offset box
@@ -860,38 +899,29 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, double iou_thres, i
     if (c->segs < 1 || c->segs > VK_MAX_SEGMENTS) return fail_code(VK_E_LIMIT, "vk_nms_batched: %d segments outside [1,%d]", c->segs, VK_MAX_SEGMENTS);
     if (c->cap < 1 || c->rows < 1 || c->nc < 1) return fail_arg("vk_nms_batched: bad candidate buffer shape");
     if ((c->list != nullptr) != (c->list_cap > 0)) return fail_arg("vk_nms_batched: list and list_cap disagree");
-    if (c->hist && !c->list) return fail_arg("vk_nms_batched: hist without a list");
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return fail_arg("vk_nms_batched: iou_thres %g outside [0,1]", iou_thres);
     cudaStream_t stream = as_stream(stream_);
     NmsArgs A;
     A.cand = c->cand; A.boxes = reinterpret_cast<const float4*>(c->boxes);
     A.counts = c->ctrl; A.flags = c->ctrl + (size_t)batch; A.list_count = c->ctrl + 2 * (size_t)batch; A.bound = c->ctrl + 3 * (size_t)batch;
-    A.seg_count = c->seg_count; A.list = c->list; A.hist = c->hist;
+    A.seg_count = c->seg_count; A.list = c->list;
     A.cap = c->cap; A.rows = c->rows; A.segs = c->segs; A.nc = c->nc; A.list_cap = c->list_cap;
     float thr = (float)iou_thres;                       // double compare == float compare against
     if ((double)thr > iou_thres) thr = nextafterf(thr, -INFINITY);  // the largest float <= threshold
     A.iou_thr = thr;
     A.agnostic = agnostic ? 1 : 0; A.max_nms = max_nms; A.max_det = max_det; A.max_wh = max_wh;
     A.dets = dets; A.det_counts = det_counts; A.keep_idx = keep_idx; A.status = status;
-    if (c->hist) {
-        // selection pass for images with more candidates than their list holds: list entries, bound and the
-        // histogram start from zero (one memset when the caller laid ctrl and hist out back to back)
-        cudaError_t e;
-        if (reinterpret_cast<const void*>(c->hist) == reinterpret_cast<const void*>(c->ctrl + (size_t)VK_CTRL_WORDS * batch)) {
-            e = cudaMemsetAsync(A.list_count, 0, (size_t)batch * (2 * sizeof(int32_t) + VK_HIST_BINS * sizeof(uint32_t)), stream);
-        } else {
-            e = cudaMemsetAsync(A.list_count, 0, (size_t)batch * 2 * sizeof(int32_t), stream);
-            if (e == cudaSuccess) e = cudaMemsetAsync(c->hist, 0, (size_t)batch * VK_HIST_BINS * sizeof(uint32_t), stream);
-        }
+    if (c->list) {
+        // selection pass for images with more candidates than their list holds (it returns at once for the
+        // others): list entries and bound start from zero
+        cudaError_t e = cudaMemsetAsync(A.list_count, 0, (size_t)batch * 2 * sizeof(int32_t), stream);
         if (e != cudaSuccess) return fail_code((int)e, "vk_nms_batched: memset: %s", cudaGetErrorString(e));
-        // enough blocks per image that every SM streams candidates, whatever the batch
-        int parts = ceil_div(8 * kNumSMs, batch);
+        // one wave of blocks, every SM streaming candidates whatever the batch
+        const int per_sm = blocks_per_sm(reinterpret_cast<const void*>(&nms_select_kernel), kSelThreads, 0);
+        int parts = (per_sm * kNumSMs) / batch;
         const int max_parts = ceil_div(c->segs, kSelThreads / 32);
         if (parts > max_parts) parts = max_parts;
         if (parts < 1) parts = 1;
-        nms_sample_kernel<<<dim3(parts, batch), kSelThreads, 0, stream>>>(A);
-        count_launch();
-        if (int rc = check_launch("nms_sample_kernel")) return rc;
         nms_select_kernel<<<dim3(parts, batch), kSelThreads, 0, stream>>>(A);
         count_launch();
         if (int rc = check_launch("nms_select_kernel")) return rc;

@@ -72,17 +72,17 @@ def _append_labels(prediction: torch.Tensor, labels, conf_thres: float) -> torch
 _BUF_CACHE = {}
 
 
-def _cand_buffer(dev, stream, bs: int, rows: int, nc: int, multi_label: bool, hist: bool) -> ops.CandBuf:
+def _cand_buffer(dev, stream, bs: int, rows: int, nc: int, multi_label: bool, top_list: bool) -> ops.CandBuf:
     """The worst-case candidate buffer of a drop-in call is large (segs * 64 * nc slots per image in
     multi-label mode), so one per (device, stream, shape) is kept and reused; work on one stream is
     ordered, which makes the reuse safe."""
-    key = (dev, stream, bs, rows, nc, multi_label, hist)
+    key = (dev, stream, bs, rows, nc, multi_label, top_list)
     buf = _BUF_CACHE.get(key)
     if buf is None:
         if len(_BUF_CACHE) >= 4:
             _BUF_CACHE.clear()
         segs = _lib.lib().vk_filter_segments(rows)
-        buf = ops.CandBuf.alloc(bs, rows, segs, nc, ops.default_cap(segs, nc, multi_label), dev, hist=hist)
+        buf = ops.CandBuf.alloc(bs, rows, segs, nc, ops.default_cap(segs, nc, multi_label), dev, top_list=top_list)
         _BUF_CACHE[key] = buf
     return buf
 

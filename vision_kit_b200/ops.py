@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import (VK_BF16, VK_CONV_PERSISTENT, VK_CONV_TILE, VK_CTRL_WORDS, VK_F16, VK_F32, VK_FILTER_AUTO,
-                   VK_FILTER_DENSE, VK_FILTER_SPARSE, VK_HEAD_V5, VK_HEAD_V7, VK_HIST_BINS, VK_LB_BF16_NCHW,
+                   VK_FILTER_DENSE, VK_FILTER_SPARSE, VK_HEAD_V5, VK_HEAD_V7, VK_LB_BF16_NCHW,
                    VK_LB_F32_NCHW, VK_LB_U8_NHWC, VK_MAX_ANCHORS, VK_MAX_LEVELS, VkCandBuf, VkHeadCfg, VkLbDesc,
                    VkLbGeom)
 
@@ -28,7 +28,8 @@ _KERNEL = {"auto": VK_FILTER_AUTO, "sparse": VK_FILTER_SPARSE, "dense": VK_FILTE
 
 
 def expects_dense(kernel, conf_thres: float) -> bool:
-    """The library's rule for the filter kernel (and for whether a candidate buffer wants a histogram)."""
+    """The library's rule for the filter kernel (and for whether a candidate buffer wants the top list of
+    vk_nms_batched's selection pass: eval thresholds leave ~240 k candidates per image)."""
     k = _KERNEL[kernel]
     return k == VK_FILTER_DENSE or (k == VK_FILTER_AUTO and float(conf_thres) < 0.05)
 
@@ -229,36 +230,33 @@ class CandBuf:
     """Caller-owned device buffers of one candidate set (include/vk_b200.h `VkCandBuf`)."""
     cand: torch.Tensor       # int64 (B, cap): low 32 = score bits, high 32 = row*nc + cls; slot = seg * T + position
     boxes: torch.Tensor      # float32 (B, rows, 4)
-    ctrl: torch.Tensor       # int32 (4 * B [+ B * 1024]): counts | flags | list entries | bound [| histogram]
+    ctrl: torch.Tensor       # int32 (4 * B): counts | flags | list entries | bound
     seg_count: torch.Tensor  # int32 (B, segs)
-    list: Optional[torch.Tensor]   # int64 (B, list_cap): ordered score << 32 | ~slot, unordered
+    list: Optional[torch.Tensor]   # int64 (B, list_cap): ordered score << 32 | ~slot, unordered; None = no selection pass
     cap: int
     rows: int
     segs: int
     nc: int
     list_cap: int
-    has_hist: bool
 
     @staticmethod
-    def alloc(batch: int, rows: int, segs: int, nc: int, cap: int, device, list_cap: int = LIST_CAP,
-              hist: bool = False) -> "CandBuf":
-        """hist=True adds the histogram scratch of vk_nms_batched's selection pass: for buffers that will
-        hold more than `list_cap` candidates per image (eval thresholds)."""
-        hist = bool(hist) and list_cap > 0
-        words = VK_CTRL_WORDS * batch + (VK_HIST_BINS * batch if hist else 0)
+    def alloc(batch: int, rows: int, segs: int, nc: int, cap: int, device, top_list: bool = False,
+              list_cap: int = LIST_CAP) -> "CandBuf":
+        """top_list=True adds the list of vk_nms_batched's selection pass: for buffers that will hold more
+        candidates per image than a stage of the NMS kernel (eval thresholds)."""
+        list_cap = int(list_cap) if top_list else 0
         return CandBuf(torch.empty((batch, cap), dtype=torch.int64, device=device),
                        torch.empty((batch, rows, 4), dtype=torch.float32, device=device),
-                       torch.zeros((words,), dtype=torch.int32, device=device),
+                       torch.zeros((VK_CTRL_WORDS * batch,), dtype=torch.int32, device=device),
                        torch.empty((batch, segs), dtype=torch.int32, device=device),
                        torch.empty((batch, list_cap), dtype=torch.int64, device=device) if list_cap > 0 else None,
-                       int(cap), int(rows), int(segs), int(nc), int(list_cap), hist)
+                       int(cap), int(rows), int(segs), int(nc), list_cap)
 
     def c_struct(self) -> VkCandBuf:
         s = VkCandBuf()
         s.cand, s.boxes, s.ctrl = self.cand.data_ptr(), self.boxes.data_ptr(), self.ctrl.data_ptr()
         s.seg_count = self.seg_count.data_ptr()
         s.list = self.list.data_ptr() if self.list is not None else None
-        s.hist = self.ctrl.data_ptr() + 4 * VK_CTRL_WORDS * self.batch if self.has_hist else None
         s.cap, s.rows, s.segs, s.nc, s.list_cap = self.cap, self.rows, self.segs, self.nc, self.list_cap
         return s
 
@@ -305,7 +303,7 @@ def filter_pred(pred: torch.Tensor, conf_thres: float, multi_label: bool = False
     segs = _lib.lib().vk_filter_segments(rows)
     if buf is None:
         buf = CandBuf.alloc(bs, rows, segs, nc, cap or default_cap(segs, nc, multi_label), pred.device,
-                            hist=expects_dense(kernel, conf_thres))
+                            top_list=expects_dense(kernel, conf_thres))
     mask = class_mask(classes, nc, pred.device)
     cs = buf.c_struct()
     _lib.check("vk_filter_pred", _lib.lib().vk_filter_pred(
@@ -323,7 +321,7 @@ def decode_filter(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], conf_thres: fl
     segs = _lib.lib().vk_decode_filter_segments(C.byref(cfg))
     if buf is None:
         buf = CandBuf.alloc(bs, rows, segs, cfg.nc, cap or default_cap(segs, cfg.nc, multi_label),
-                            levels[0].device, hist=expects_dense(kernel, conf_thres))
+                            levels[0].device, top_list=expects_dense(kernel, conf_thres))
     mask = class_mask(classes, cfg.nc, levels[0].device)
     cs = buf.c_struct()
     _lib.check("vk_decode_filter", _lib.lib().vk_decode_filter(
@@ -362,7 +360,7 @@ def conv_decode_filter(cfg: VkHeadCfg, feats: Sequence[torch.Tensor], weights: S
     segs = _lib.lib().vk_decode_filter_segments(C.byref(cfg))
     if buf is None:
         buf = CandBuf.alloc(bs, rows, segs, cfg.nc, default_cap(segs, cfg.nc, multi_label), dev,
-                            hist=float(conf_thres) < 0.05)
+                            top_list=float(conf_thres) < 0.05)
     mask = class_mask(classes, cfg.nc, dev)
     fault = torch.zeros(1, dtype=torch.int32, device=dev)
     cs = buf.c_struct()

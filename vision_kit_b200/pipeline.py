@@ -55,7 +55,7 @@ class DetectPipeline:
         self.overlap = bool(overlap)
         nsets = 2 if self.overlap else 1
         self._cands = [ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device, list_cap=list_cap,
-                                         hist=ops.expects_dense(filter_kernel, conf_thres)) for _ in range(nsets)]
+                                         top_list=ops.expects_dense(filter_kernel, conf_thres)) for _ in range(nsets)]
         self._outs = [ops.NmsOut(
             torch.empty((batch, max_det, 6), dtype=torch.float32, device=self.device),
             torch.empty((batch,), dtype=torch.int32, device=self.device),
