@@ -101,17 +101,24 @@ def head_decode(variant: str, levels):
 
 
 def demo_model(seed: int = 0):
-    """The demo's model (scripts/demo.py:48-53: ``YOLOV5(variant='s')``) with seeded random weights (the
-    weight file is not part of the reference tree) and the objectness / class priors lifted so that
-    detections exist.  One model per process: the neck mutates its default arguments."""
+    """The demo's model (scripts/demo.py:48-53: ``YOLOV5(variant='s')``) with seeded random weights -- the
+    weight file is not part of the reference tree -- conditioned so that it produces a few hundred
+    detections on a photograph: BatchNorm layers use batch statistics (with the initial running statistics
+    the activations of a random network vanish and every logit equals its bias), the Detect convolutions are
+    scaled by 4 and their objectness / class priors lifted.  Modules and code paths are the reference's own.
+    One model per process: the neck mutates its default arguments."""
     import torch
     load()
     from vision_kit.models.architectures import YOLOV5
     torch.manual_seed(seed)
-    model = YOLOV5("s")
+    model = YOLOV5("s").eval()
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.train()
     with torch.no_grad():
         for m in model.head.m:
+            m.weight.mul_(4.0)
             b = m.bias.view(3, -1)
-            b[:, 4] += 4.0
+            b[:, 4] += 0.3
             b[:, 5:] += 2.5
-    return model.eval()
+    return model

@@ -34,7 +34,8 @@ class DetectPipeline:
                  multi_label: bool = False, max_det: int = 300, max_nms: int = 30000,
                  anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
                  swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False,
-                 overlap: bool = False, filter_kernel="auto", list_cap: int = ops.LIST_CAP):
+                 overlap: bool = False, filter_kernel="auto", list_cap: int = ops.LIST_CAP,
+                 fork_preprocess: bool = False):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
@@ -53,6 +54,8 @@ class DetectPipeline:
         # two sets of candidate / output buffers: with overlap=True the NMS of batch k runs on a
         # side stream while the letterbox and filter kernels of batch k+1 run on the main one
         self.overlap = bool(overlap)
+        # captured graphs only: the letterbox on a third branch, beside the filter (they share no data)
+        self.fork_preprocess = bool(fork_preprocess)
         nsets = 2 if self.overlap else 1
         self._cands = [ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device, list_cap=list_cap,
                                          top_list=ops.expects_dense(filter_kernel, conf_thres)) for _ in range(nsets)]
@@ -63,6 +66,8 @@ class DetectPipeline:
             torch.empty((batch,), dtype=torch.int32, device=self.device)) for _ in range(nsets)]
         self._set = 0
         self.cand, self.out = self._cands[0], self._outs[0]
+        if self.fork_preprocess:
+            self.pre_stream = torch.cuda.Stream(device=self.device)
         if self.overlap:
             self.side = torch.cuda.Stream(device=self.device)
             self._ev_filter = [torch.cuda.Event() for _ in range(2)]
@@ -204,7 +209,12 @@ class DetectPipeline:
                     rc = self._lib.vk_nms_batched(*self._nms_args[s ^ 1], C.c_void_p(self.side.cuda_stream))
                     if rc:
                         _lib.check("vk_nms_batched", rc)
-                    if with_preprocess:
+                    if with_preprocess and self.fork_preprocess:
+                        self.pre_stream.wait_stream(main)
+                        rc = self._lib.vk_letterbox_batch(*self._lb_args, C.c_void_p(self.pre_stream.cuda_stream))
+                        if rc:
+                            _lib.check("vk_letterbox_batch", rc)
+                    elif with_preprocess:
                         self.preprocess()
                     rc = self._lib.vk_decode_filter(self._cfg_ref, C.cast(self._lv_arr, C.c_void_p), self._lv_dt,
                                                     self.batch, self._conf, self._ml, self._mask_p, self._kernel,
@@ -212,6 +222,8 @@ class DetectPipeline:
                     if rc:
                         _lib.check("vk_decode_filter", rc)
                     main.wait_stream(self.side)
+                    if with_preprocess and self.fork_preprocess:
+                        main.wait_stream(self.pre_stream)
                 self._graphs.append(g)
             self._set = 1                        # the eager warm-up left valid candidates in both sets
         self._graph_step = 0
