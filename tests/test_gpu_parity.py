@@ -874,3 +874,19 @@ def test_head_forward_nms_fused_conv(vk, cuda):
             k = min(int(a.counts[i]), int(b.counts[i]), 20)
             # the highest-scoring detections agree within TF32 tolerance
             np.testing.assert_allclose(b.dets[i, :k, 4].cpu().numpy(), a.dets[i, :k, 4].cpu().numpy(), rtol=5e-3, atol=1e-3)
+
+
+# --------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
+def test_nccl_allgather_config5_two_gpus(cuda):
+    """BASELINE config 5 in miniature over NCCL: tests/dist_eval_check.py under torch.distributed.run, one rank
+    per GPU (shards of unequal size, mixed-size letterbox, eval NMS, all-gather of the padded detections)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617",
+                        os.path.join(root, "tests", "dist_eval_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout

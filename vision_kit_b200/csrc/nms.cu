@@ -135,6 +135,8 @@ nms_select_kernel(const NmsArgs A) {
     const int items = build_items(A.seg_count + (size_t)b * A.segs, A.segs, kSelectPiece, s_cnt, s_pre, wsum);
     const int first = blockIdx.x * (kSelThreads / 32) + warp, step = gridDim.x * (kSelThreads / 32);
     // ---- sample: lines 2 and 10 of each of this warp's items (16 lines per item), 32 lanes = 2 lines
+    // (a warp's items ascend, so after one binary search the segment of the next item is found by walking on)
+    int wseg = first < items ? item_segment(s_pre, A.segs, first) : 0;
     for (int item0 = first; item0 < items; item0 += 4 * step) {          // four items' loads in flight
         int bin[4];
 #pragma unroll
@@ -142,9 +144,9 @@ nms_select_kernel(const NmsArgs A) {
             const int item = item0 + u * step;
             bin[u] = -1;
             if (item < items) {
-                const int seg = item_segment(s_pre, A.segs, item);
-                const int j = (item - s_pre[seg]) * kSelectPiece + 16 * (2 + kSampleEvery * (lane >> 4)) + (lane & 15);
-                if (j < s_cnt[seg]) bin[u] = hist_bin(cand[(size_t)seg * tile_cap + j].x);
+                while (s_pre[wseg + 1] <= item) ++wseg;
+                const int j = (item - s_pre[wseg]) * kSelectPiece + 16 * (2 + kSampleEvery * (lane >> 4)) + (lane & 15);
+                if (j < s_cnt[wseg]) bin[u] = hist_bin(cand[(size_t)wseg * tile_cap + j].x);
             }
         }
 #pragma unroll
@@ -200,9 +202,10 @@ nms_select_kernel(const NmsArgs A) {
     };
     // (the loads of a warp's next item are issued before the current one is examined)
     struct Item { uint32_t slot0; int j0, cnt; };
-    auto locate = [&](int item) {
-        const int seg = item_segment(s_pre, A.segs, item);
-        return Item{(uint32_t)seg * (uint32_t)tile_cap, (item - s_pre[seg]) * kSelectPiece, s_cnt[seg]};
+    wseg = first < items ? item_segment(s_pre, A.segs, first) : 0;
+    auto locate = [&](int item) {                       // items are visited in ascending order
+        while (s_pre[wseg + 1] <= item) ++wseg;
+        return Item{(uint32_t)wseg * (uint32_t)tile_cap, (item - s_pre[wseg]) * kSelectPiece, s_cnt[wseg]};
     };
     auto fetch = [&](const Item& it, uint32_t* sc) {
 #pragma unroll

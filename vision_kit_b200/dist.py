@@ -36,6 +36,13 @@ def allgather_detections(dets: torch.Tensor, counts: torch.Tensor, n_images: int
     if int(dets.shape[0]) != sizes[rank]:
         raise ValueError(f"rank {rank} holds {int(dets.shape[0])} images, shard_range gives {sizes[rank]}")
     md = int(dets.shape[1])
+    if min(sizes) == bmax and dets.is_contiguous() and counts.is_contiguous():
+        # equal shards (the BASELINE configs): the tensors go out as they are, nothing is packed or copied first
+        all_d = torch.empty((world * bmax, md, 6), dtype=dets.dtype, device=dets.device)
+        all_c = torch.empty((world * bmax,), dtype=counts.dtype, device=counts.device)
+        dist.all_gather_into_tensor(all_d, dets, group=group)
+        dist.all_gather_into_tensor(all_c, counts, group=group)
+        return all_d, all_c
     # one fused buffer per rank: detections + counts (as float bits) -> a single collective
     pack = torch.zeros((bmax, md * 6 + 1), dtype=torch.float32, device=dets.device)
     pack[: sizes[rank], : md * 6] = dets.reshape(sizes[rank], md * 6)
