@@ -120,6 +120,7 @@ __device__ __forceinline__ int item_segment(const int* s_pre, int segs, int item
 // instead of colliding 32 ways on one shared-memory counter.
 constexpr int kSampleEvery = 8;
 constexpr int kSelectPiece = 256;                     // candidates per work item: 16 lines, 8 loads per lane
+constexpr int kItemTable = 6144;                      // work items whose segment is looked up in a table
 __global__ void __launch_bounds__(kSelThreads)
 nms_select_kernel(const NmsArgs A) {
     const int b = blockIdx.y;
@@ -128,15 +129,21 @@ nms_select_kernel(const NmsArgs A) {
     __shared__ int s_cnt[VK_MAX_SEGMENTS], s_pre[VK_MAX_SEGMENTS + 1], wsum[33];
     __shared__ int s_j;
     __shared__ unsigned long long s_stage[kSelThreads / 32][kSelStage];
+    __shared__ unsigned short s_item_seg[kItemTable];           // item -> segment (a binary search per item otherwise)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_cap = tile_slots_of(A.flags[b]);
     const uint2* cand = reinterpret_cast<const uint2*>(A.cand + (size_t)b * A.cap);
     for (int i = threadIdx.x; i < VK_HIST_BINS; i += kSelThreads) s_hist[i] = 0u;
     const int items = build_items(A.seg_count + (size_t)b * A.segs, A.segs, kSelectPiece, s_cnt, s_pre, wsum);
+    const bool table = items <= kItemTable;
+    if (table) {
+        for (int t = threadIdx.x; t < A.segs; t += kSelThreads)
+            for (int i = s_pre[t]; i < s_pre[t + 1]; ++i) s_item_seg[i] = (unsigned short)t;
+        __syncthreads();
+    }
+    auto seg_of = [&](int item) { return table ? (int)s_item_seg[item] : item_segment(s_pre, A.segs, item); };
     const int first = blockIdx.x * (kSelThreads / 32) + warp, step = gridDim.x * (kSelThreads / 32);
     // ---- sample: lines 2 and 10 of each of this warp's items (16 lines per item), 32 lanes = 2 lines
-    // (a warp's items ascend, so after one binary search the segment of the next item is found by walking on)
-    int wseg = first < items ? item_segment(s_pre, A.segs, first) : 0;
     for (int item0 = first; item0 < items; item0 += 4 * step) {          // four items' loads in flight
         int bin[4];
 #pragma unroll
@@ -144,9 +151,9 @@ nms_select_kernel(const NmsArgs A) {
             const int item = item0 + u * step;
             bin[u] = -1;
             if (item < items) {
-                while (s_pre[wseg + 1] <= item) ++wseg;
-                const int j = (item - s_pre[wseg]) * kSelectPiece + 16 * (2 + kSampleEvery * (lane >> 4)) + (lane & 15);
-                if (j < s_cnt[wseg]) bin[u] = hist_bin(cand[(size_t)wseg * tile_cap + j].x);
+                const int seg = seg_of(item);
+                const int j = (item - s_pre[seg]) * kSelectPiece + 16 * (2 + kSampleEvery * (lane >> 4)) + (lane & 15);
+                if (j < s_cnt[seg]) bin[u] = hist_bin(cand[(size_t)seg * tile_cap + j].x);
             }
         }
 #pragma unroll
@@ -202,10 +209,9 @@ nms_select_kernel(const NmsArgs A) {
     };
     // (the loads of a warp's next item are issued before the current one is examined)
     struct Item { uint32_t slot0; int j0, cnt; };
-    wseg = first < items ? item_segment(s_pre, A.segs, first) : 0;
-    auto locate = [&](int item) {                       // items are visited in ascending order
-        while (s_pre[wseg + 1] <= item) ++wseg;
-        return Item{(uint32_t)wseg * (uint32_t)tile_cap, (item - s_pre[wseg]) * kSelectPiece, s_cnt[wseg]};
+    auto locate = [&](int item) {
+        const int seg = seg_of(item);
+        return Item{(uint32_t)seg * (uint32_t)tile_cap, (item - s_pre[seg]) * kSelectPiece, s_cnt[seg]};
     };
     auto fetch = [&](const Item& it, uint32_t* sc) {
 #pragma unroll

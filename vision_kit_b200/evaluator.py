@@ -29,6 +29,7 @@ class DetEvaluator:
         self.num_iou = self.iouv.numel()
         self.seen = 0
         self.stats: list = []
+        self.coco_data: list = []
         self.precision = self.recall = self.f1 = 0.0
         self.mp = self.mr = self.map50 = self.map95 = 0.0
 
@@ -82,6 +83,57 @@ class DetEvaluator:
         if not predictions:
             return torch.zeros((0, 6), device=dev), torch.zeros((0, 5), device=dev)
         return torch.vstack(predictions), torch.vstack(detections)
+
+    # ------------------------------------------------------------------ COCO json export
+    def convert_to_coco(self, pred: torch.Tensor, img_id) -> None:
+        """core/eval/det_evaluator.py:228-244: detections (k, 6) of one image, already in original-image
+        pixels, appended to ``coco_data`` as COCO result dicts (bbox = x, y, w, h; category = class id + 1)."""
+        self._append_coco(pred.detach().cpu().numpy(), img_id)
+
+    def convert_batch_to_coco(self, predn: torch.Tensor, counts, img_ids: Sequence) -> None:
+        """The same for a whole batch in ONE device-to-host copy: ``predn`` (B, max_det, 6) padded (the
+        ``predn`` of ``ops.eval_match`` / an ``NmsOut.dets`` in original pixels) + counts."""
+        host = predn.detach().cpu().numpy()
+        ks = counts.tolist() if torch.is_tensor(counts) else list(counts)
+        for i, k in enumerate(ks):
+            self._append_coco(host[i, : int(k)], img_ids[i])
+
+    def _append_coco(self, p: np.ndarray, img_id) -> None:
+        p = np.asarray(p, np.float32)
+        if p.size == 0:
+            return
+        xywh = p[:, :4].copy()
+        xywh[:, 2] = p[:, 2] - p[:, 0]                       # utils/bboxes.py:114-119 xyxy_to_xywh
+        xywh[:, 3] = p[:, 3] - p[:, 1]
+        for row, score, c in zip(xywh.tolist(), p[:, 4], p[:, 5]):
+            self.coco_data.append({"image_id": int(img_id), "category_id": self.class_ids[int(c)], "bbox": row,
+                                   "score": score.item(), "segmentation": []})
+
+    def coco_evaluate(self) -> str:
+        """:246-272, verbatim in behaviour: needs pycocotools and ``gt_json`` (neither is part of this
+        repo's scope; the import error of a missing pycocotools is the reference's own)."""
+        import contextlib
+        import io
+        import json
+        import tempfile
+
+        from pycocotools.coco import COCO
+        from pycocotools.cocoeval import COCOeval
+        info = ""
+        if len(self.coco_data) > 0:
+            gt = COCO(self.gt_json)
+            _, tmp = tempfile.mkstemp()
+            with open(tmp, "w") as f:
+                json.dump(self.coco_data, f)
+            dt = gt.loadRes(tmp)
+            ev = COCOeval(gt, dt, "bbox")
+            ev.evaluate()
+            ev.accumulate()
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                ev.summarize()
+            info = buf.getvalue()
+        return info
 
     # ------------------------------------------------------------------ single image
     @staticmethod

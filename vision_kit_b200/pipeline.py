@@ -35,7 +35,7 @@ class DetectPipeline:
                  anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
                  swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False,
                  overlap: bool = False, filter_kernel="auto", list_cap: int = ops.LIST_CAP,
-                 fork_preprocess: bool = False):
+                 fork_preprocess: bool = False, nvtx: bool = False):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
@@ -53,6 +53,9 @@ class DetectPipeline:
         self._kernel = ops._KERNEL[filter_kernel]
         # two sets of candidate / output buffers: with overlap=True the NMS of batch k runs on a
         # side stream while the letterbox and filter kernels of batch k+1 run on the main one
+        # nvtx=True brackets the three C calls with NVTX ranges (vk/letterbox, vk/decode_filter, vk/nms) so that a
+        # timeline tool shows where a batch is inside the pipeline; off by default (two calls per range)
+        self._nvtx = bool(nvtx)
         self.overlap = bool(overlap)
         # captured graphs only: the letterbox on a third branch, beside the filter (they share no data)
         self.fork_preprocess = bool(fork_preprocess)
@@ -113,7 +116,11 @@ class DetectPipeline:
     def preprocess(self, srcs: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
         if srcs is not None:
             self.plan_sources(srcs)
+        if self._nvtx:
+            torch.cuda.nvtx.range_push("vk/letterbox")
         rc = self._lib.vk_letterbox_batch(*self._lb_args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if self._nvtx:
+            torch.cuda.nvtx.range_pop()
         if rc:
             _lib.check("vk_letterbox_batch", rc)
         return self.input
@@ -135,14 +142,27 @@ class DetectPipeline:
             if bs != self.batch:
                 raise ValueError(f"expected a batch of {self.batch}, got {bs}")
             self._lv_key = key
+        if self._nvtx:
+            torch.cuda.nvtx.range_push("vk/decode_filter")
         rc = self._lib.vk_decode_filter(self._cfg_ref, C.cast(self._lv_arr, C.c_void_p), self._lv_dt, self.batch,
                                         self._conf, self._ml, self._mask_p, self._kernel, C.byref(self._cs[self._set]),
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if self._nvtx:
+            torch.cuda.nvtx.range_pop()
         if rc:
             _lib.check("vk_decode_filter", rc)
         return self.cand
 
     def nms(self) -> ops.NmsOut:
+        if self._nvtx:
+            torch.cuda.nvtx.range_push("vk/nms")
+        try:
+            return self._nms()
+        finally:
+            if self._nvtx:
+                torch.cuda.nvtx.range_pop()
+
+    def _nms(self) -> ops.NmsOut:
         k = self._set
         if not self.overlap:
             rc = self._lib.vk_nms_batched(*self._nms_args[k], C.c_void_p(torch.cuda.current_stream().cuda_stream))
