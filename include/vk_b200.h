@@ -136,7 +136,7 @@ int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels, int dtype,
  *
  * list: optional scratch of vk_nms_batched for images with more than list_cap candidates (eval
  * thresholds, ~240 k per image): a sampled score histogram picks the score bound above which a
- * grid-wide pass copies the candidates, as (ordered score << 32 | ~slot), into the image's list, and
+ * grid-wide pass copies the candidates, as {ordered score << 32 | ~slot, row*nc + cls}, into the image's list, and
  * the per-image kernel sorts from that list.  Results never depend on it; allocate it (8192 entries
  * per image is plenty) when such images are expected.
  */
@@ -149,7 +149,7 @@ typedef struct VkCandBuf {
     float* boxes;        /* dev [batch][rows][4] xyxy of rows that produced candidates */
     int32_t* ctrl;       /* dev [VK_CTRL_WORDS][batch]; zeroed by the filter call */
     int32_t* seg_count;  /* dev [batch][segs] candidates of each segment */
-    uint64_t* list;      /* dev [batch][list_cap] or NULL */
+    uint64_t* list;      /* dev [batch][list_cap][2] (16-byte entries: key, row*nc + cls) or NULL */
     int32_t cap;         /* candidate slots per image */
     int32_t rows;        /* prediction rows per image */
     int32_t segs;        /* segments per image (vk_filter_segments / vk_decode_filter_segments) */

@@ -582,6 +582,10 @@ def test_config4_v7_agnostic_vs_class_aware(vk, cuda):
         r2 = vk.ops.nms_batched(vk.ops.decode_filter(cfg, lv, 0.001, True), 0.6, agn, want_keep=True)
         assert torch.equal(r1.dets, r2.dets) and torch.equal(r1.keep, r2.keep) and int(r1.status.sum()) == 0
         _check_nms_properties(r1.dets, r1.counts, 0.6, agn, 300)
+        # without keep indices the agnostic kernel skips the other classes of rows it has already decided:
+        # same detections, and from a longer list too
+        r3 = vk.ops.nms_batched(buf, 0.6, agn)
+        assert torch.equal(r3.dets, r1.dets) and torch.equal(r3.counts, r1.counts)
         res[agn] = r1
     # both runs start from the same best candidate; images 0-3 against the oracle in both modes
     assert torch.equal(res[False].dets[:, 0], res[True].dets[:, 0])
@@ -628,6 +632,30 @@ def test_config5_shard_mixed_letterbox_pipeline(vk, cuda):
 
 
 # --------------------------------------------------------------------------- staged NMS corner cases
+def test_nms_agnostic_pruning_exact_cases(vk, cuda):
+    """The agnostic shortcut (other classes of a decided row are skipped) against the oracle where it could go
+    wrong: zero-area boxes (never suppressed by anything, IoU = 0/0 or 0), iou_thres = 1.0 (nothing is ever
+    suppressed), and a max_nms cut that falls among the skipped candidates."""
+    rng = np.random.Generator(np.random.PCG64(29))
+    rows, nc = 3000, 6
+    p = np.zeros((2, rows, 5 + nc), np.float32)
+    centers = rng.random((25, 2), dtype=np.float32) * np.float32(560) + np.float32(40)
+    k = rng.integers(0, 25, size=(2, rows))
+    p[..., 0:2] = centers[k] + (rng.random((2, rows, 2), dtype=np.float32) - np.float32(0.5)) * np.float32(8)
+    p[..., 2:4] = np.float32(50) + rng.random((2, rows, 2), dtype=np.float32) * np.float32(10)
+    p[:, ::7, 2] = 0.0                                   # zero-width boxes
+    p[:, ::11, 3] = 0.0                                  # zero-height boxes
+    p[..., 4] = np.float32(0.3) + rng.random((2, rows), dtype=np.float32) * np.float32(0.7)
+    p[..., 5:] = rng.random((2, rows, nc), dtype=np.float32)
+    pt = torch.from_numpy(p).to(cuda)
+    for iou, max_nms in ((0.5, 30000), (1.0, 30000), (0.5, 2500), (0.3, 700)):
+        kw = dict(conf_thres=0.1, iou_thres=iou, multi_label=True, agnostic=True)
+        outs = ref_port.nms(torch.from_numpy(p.copy()), max_nms=max_nms, **kw)
+        dets = vk.image_proc._run_nms(pt, classes=None, labels=(), max_det=300, max_nms=max_nms, **kw)
+        for i in range(2):
+            assert np.array_equal(dets[i].cpu().numpy(), outs[i].numpy()), (iou, max_nms, i)
+
+
 def test_nms_many_stages_heavy_suppression(vk, cuda):
     # ~45 k candidates packed into 40 clusters: few boxes survive, so the staged kernel has to walk
     # every stage down to the max_nms cut (rank 30000) instead of stopping after the first one

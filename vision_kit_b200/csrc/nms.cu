@@ -57,10 +57,11 @@ struct NmsArgs {
     int32_t* list_count;        // ctrl row 2
     int32_t* bound;             // ctrl row 3 (ordered score bits)
     const int32_t* seg_count;
-    uint64_t* list;
+    ulonglong2* list;          // [batch][list_cap] {key, row * nc + cls}
     int cap, rows, segs, nc, list_cap;
     float iou_thr;  // largest float <= the double threshold
     int agnostic, max_nms, max_det;
+    int prune;      // agnostic NMS: candidates of rows that are already decided are skipped (see nms_kernel)
     float max_wh;
     float* dets;
     int32_t* det_counts;
@@ -129,6 +130,7 @@ nms_select_kernel(const NmsArgs A) {
     __shared__ int s_cnt[VK_MAX_SEGMENTS], s_pre[VK_MAX_SEGMENTS + 1], wsum[33];
     __shared__ int s_j;
     __shared__ unsigned long long s_stage[kSelThreads / 32][kSelStage];
+    __shared__ uint32_t s_stage_idx[kSelThreads / 32][kSelStage];
     __shared__ unsigned short s_item_seg[kItemTable];           // item -> segment (a binary search per item otherwise)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_cap = tile_slots_of(A.flags[b]);
@@ -194,8 +196,9 @@ nms_select_kernel(const NmsArgs A) {
     //      flushed with ONE reservation on the image's list counter per ~100 keys: a reservation per 32
     //      candidates would serialise thousands of same-address atomics per image.
     unsigned long long* stage = s_stage[warp];
+    uint32_t* stage_idx = s_stage_idx[warp];
     int staged = 0;                                               // warp-uniform
-    uint64_t* list = A.list + (size_t)b * A.list_cap;
+    ulonglong2* list = A.list + (size_t)b * A.list_cap;
     const unsigned lt = (1u << lane) - 1u;
     auto flush = [&]() {
         int base = 0;
@@ -203,7 +206,7 @@ nms_select_kernel(const NmsArgs A) {
         base = __shfl_sync(0xffffffffu, base, 0);
         __syncwarp();
         for (int i = lane; i < staged; i += 32)
-            if (base + i < A.list_cap) list[base + i] = stage[i];
+            if (base + i < A.list_cap) list[base + i] = make_ulonglong2(stage[i], (unsigned long long)stage_idx[i]);
         __syncwarp();
         staged = 0;
     };
@@ -213,30 +216,33 @@ nms_select_kernel(const NmsArgs A) {
         const int seg = seg_of(item);
         return Item{(uint32_t)seg * (uint32_t)tile_cap, (item - s_pre[seg]) * kSelectPiece, s_cnt[seg]};
     };
-    auto fetch = [&](const Item& it, uint32_t* sc) {
+    auto fetch = [&](const Item& it, uint2* sc) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int jj = it.j0 + 32 * u + lane;
-            sc[u] = (jj < it.cnt) ? cand[it.slot0 + jj].x : 0u;
+            sc[u] = (jj < it.cnt) ? cand[it.slot0 + jj] : make_uint2(0u, 0u);
         }
     };
     if (first < items) {
         Item cur = locate(first);
-        uint32_t sc[8];
+        uint2 sc[8];
         fetch(cur, sc);
         for (int item = first; item < items; item += step) {
             const bool more = item + step < items;
             Item nxt = cur;
-            uint32_t sn[8];
+            uint2 sn[8];
             if (more) { nxt = locate(item + step); fetch(nxt, sn); }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int jj = cur.j0 + 32 * u + lane;
-                const uint32_t key = order_key(sc[u]);
+                const uint32_t key = order_key(sc[u].x);
                 const bool take = jj < cur.cnt && key >= bound;
                 const unsigned m = __ballot_sync(0xffffffffu, take);
                 if (m) {
-                    if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~(cur.slot0 + (uint32_t)jj);
+                    if (take) {
+                        stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~(cur.slot0 + (uint32_t)jj);
+                        stage_idx[staged + __popc(m & lt)] = sc[u].y;
+                    }
                     staged += __popc(m);
                     if (staged > kSelStage - 32) flush();
                 }
@@ -535,10 +541,11 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
 }
 
 template <int CAP>
-static size_t nms_smem_bytes(int threads, int segs, int max_det) {
+static size_t nms_smem_bytes(int threads, int segs, int max_det, int prune_rows) {
     (void)threads;
     return (size_t)CAP * (8 + 8 + 16 + 4 + 2) + (size_t)(kHistBins + 4) * 4 +
-           align16((size_t)(segs + 1) * 4) + align16(ScratchB::bytes(max_det));
+           align16((size_t)(segs + 1) * 4) + (prune_rows ? align16((size_t)((prune_rows + 31) / 32) * 4) : 0) +
+           align16(ScratchB::bytes(max_det));
 }
 
 template <int T, int CAP>
@@ -547,7 +554,7 @@ nms_kernel(const NmsArgs A) {
     constexpr int NW = T / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wsum[33];
-    __shared__ int s_bin, s_above, s_cnt;
+    __shared__ int s_bin, s_above, s_cnt, s_all;
     __shared__ unsigned long long s_max, s_min;
 
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -557,7 +564,8 @@ nms_kernel(const NmsArgs A) {
     int* hist = reinterpret_cast<int*>(sidx + CAP);
     uint16_t* scls = reinterpret_cast<uint16_t*>(hist + kHistBins + 4);    // (+4: the counting sort's end marker)
     int* segoff = reinterpret_cast<int*>(scls + CAP);     // [segs + 1] exclusive prefix of the segment counts
-    ScratchB XB(reinterpret_cast<unsigned char*>(segoff) + align16((size_t)(A.segs + 1) * 4), A.max_det);
+    uint32_t* done = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(segoff) + align16((size_t)(A.segs + 1) * 4));   // [rows / 32] (pruning)
+    ScratchB XB(reinterpret_cast<unsigned char*>(done) + (A.prune ? align16((size_t)((A.rows + 31) / 32) * 4) : 0), A.max_det);
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -575,14 +583,14 @@ nms_kernel(const NmsArgs A) {
     // which are skipped); -1 = none
     int list_n = -1, list_len = 0;
     uint32_t lbound = 0;
-    const uint64_t* list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
+    const ulonglong2* list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
     if (list != nullptr && (flags & VK_FLAG_LIST)) {
         const int lc = A.list_count[b];
         if (lc <= A.list_cap) {
             lbound = (uint32_t)A.bound[b];
             list_len = lc;
             int mine = 0;
-            for (int i = tid; i < lc; i += T) mine += (uint32_t)(list[i] >> 32) >= lbound ? 1 : 0;
+            for (int i = tid; i < lc; i += T) mine += (uint32_t)(list[i].x >> 32) >= lbound ? 1 : 0;
             if (tid == 0) s_cnt = 0;
             __syncthreads();
             mine = warp_incl_scan(mine, lane);
@@ -617,18 +625,33 @@ nms_kernel(const NmsArgs A) {
     if (!use_list) load_segoff();
     __syncthreads();
 
-    // every candidate of the current source: f(valid, key)
+    // Agnostic mode: every class candidate of a prediction row has the row's box, so once one of them is
+    // decided -- kept, or removed by a kept box X -- the rest are decided too: IoU(self, self) = 1 > thr removes
+    // them in the first case, IoU(X, box) > thr in the second (torchvision visits them later, in score order).
+    // Rows with a decided candidate and a box of positive finite area are marked here and their remaining
+    // candidates skipped in the selection and compaction passes; multi-label eval has ~10 candidates per row.
+    // (Needs thr < 1; ranks still count every candidate, so the max_nms cut stays exact.)
+    bool prune_now = A.prune != 0;
+    if (A.prune) {
+        for (int i = tid; i < (A.rows + 31) / 32; i += T) done[i] = 0u;
+    }
+    auto pruned = [&](uint32_t idx) -> bool {
+        if (!prune_now) return false;
+        const uint32_t row = idx / (uint32_t)A.nc;
+        return (done[row >> 5] >> (row & 31)) & 1u;
+    };
+    // every candidate of the current source: f(valid, key, row * nc + cls)
     const unsigned long long lfloor = (unsigned long long)lbound << 32;
     auto for_each_list = [&](auto&& f) {
         for (int i0 = 0; i0 < list_len; i0 += 4 * T) {
-            unsigned long long e[4];
+            ulonglong2 e[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * T + tid;
-                e[u] = (i < list_len) ? list[i] : 0ull;
+                e[u] = (i < list_len) ? list[i] : make_ulonglong2(0ull, 0ull);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) f(i0 + u * T + tid < list_len && e[u] >= lfloor, e[u]);
+            for (int u = 0; u < 4; ++u) f(i0 + u * T + tid < list_len && e[u].x >= lfloor, e[u].x, (uint32_t)e[u].y);
         }
     };
     auto for_each_segment = [&](auto&& f) {
@@ -638,16 +661,16 @@ nms_kernel(const NmsArgs A) {
             const uint32_t slot0 = (uint32_t)t * (uint32_t)tile_cap;
             const uint2* cp = cand + slot0;
             for (int j0 = 0; j0 < cnt; j0 += 128) {        // 4 loads in flight per lane
-                uint32_t s[4];
+                uint2 s[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + 32 * u + lane;
-                    s[u] = (j < cnt) ? cp[j].x : 0u;
+                    s[u] = (j < cnt) ? cp[j] : make_uint2(0u, 0u);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + 32 * u + lane;
-                    f(j < cnt, ((unsigned long long)order_key(s[u]) << 32) | (uint32_t)~(slot0 + (uint32_t)j));
+                    f(j < cnt, ((unsigned long long)order_key(s[u].x) << 32) | (uint32_t)~(slot0 + (uint32_t)j), s[u].y);
                 }
             }
         }
@@ -683,8 +706,8 @@ nms_kernel(const NmsArgs A) {
                 const int nb = (pass == 2 || pass == 5) ? 1024 : 2048;
                 for (int i = tid; i < kHistBins; i += T) hist[i] = 0;
                 __syncthreads();
-                for_each([&](bool ok, unsigned long long key) {
-                    if (ok && key < U && (key & pmask) == prefix)
+                for_each([&](bool ok, unsigned long long key, uint32_t idx) {
+                    if (ok && key < U && (key & pmask) == prefix && !pruned(idx))
                         atomicAdd(&hist[(int)(key >> shift) & (nb - 1)], 1);
                 });
                 __syncthreads();
@@ -698,6 +721,11 @@ nms_kernel(const NmsArgs A) {
                 }
                 int total;
                 int run = block_excl_scan(sum, wsum, &total);
+                if (pass == 0 && total <= CAP) {              // (pruning) everything still open fits one stage
+                    found = true;
+                    __syncthreads();
+                    break;
+                }
 #pragma unroll
                 for (int k = 0; k < BPT; ++k) {
                     if (run < rem_t && rem_t <= run + vals[k]) { s_bin = nb - 1 - (BPT * tid + k); s_above = run; }
@@ -717,7 +745,7 @@ nms_kernel(const NmsArgs A) {
         }
         VK_STAMP(stamp);
         // ---- compaction of the stage [v, U) into shared memory
-        if (tid == 0) s_cnt = 0;
+        if (tid == 0) { s_cnt = 0; s_all = 0; }
         __syncthreads();
         if (!use_list && rank_base == 0 && n <= CAP) {
             // small image (demo thresholds), its only stage: one thread per candidate, segment by binary search
@@ -730,11 +758,14 @@ nms_kernel(const NmsArgs A) {
                 const uint32_t slot = (uint32_t)lo * (uint32_t)tile_cap + (uint32_t)(p - segoff[lo]);
                 keys[p] = ((unsigned long long)order_key(cand[slot].x) << 32) | (uint32_t)~slot;
             }
-            if (tid == 0) s_cnt = n;
+            if (tid == 0) { s_cnt = n; s_all = n; }
         } else {
-            for_each([&](bool ok, unsigned long long key) {
-                const bool take = ok && key >= v && key < U;
+            for_each([&](bool ok, unsigned long long key, uint32_t idx) {
+                const bool in_range = ok && key >= v && key < U;
+                const bool take = in_range && !pruned(idx);
+                const unsigned ma = __ballot_sync(0xffffffffu, in_range);
                 const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (ma && lane == 0) atomicAdd(&s_all, __popc(ma));     // ranks count every candidate
                 if (m) {
                     int base = 0;
                     if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
@@ -749,6 +780,12 @@ nms_kernel(const NmsArgs A) {
         __syncthreads();
         VK_STAMP(stamp + 1);
         const int cnt = min(s_cnt, CAP);
+        const int cnt_all = s_all;
+        if (prune_now && rank_base + cnt_all > K) {           // the stage crosses the max_nms cut: redo it unpruned,
+            prune_now = false;                                // the cut is defined on the ranks of ALL candidates
+            __syncthreads();
+            continue;
+        }
         // ---- sort, descending: a counting sort on the leading 11 bits in which the stage's keys differ
         //      (bin = 2047 - ((key - min) >> shift), shift from the spread max - min), then every key ranks itself
         //      inside its bin by comparison.  Scores of a stage are spread over its bins, so bins hold a few keys;
@@ -840,7 +877,17 @@ nms_kernel(const NmsArgs A) {
             kept0 = nms_chunk<T>(CC, chunk0, min(kChunk, M - chunk0), kept0, safe && !A.agnostic, chunk0 == 0 ? stamp + 4 : -1);
         VK_STAMP(stamp + 9);
         stamp += 10;
-        rank_base += cnt;
+        if (prune_now) {                                      // rows decided in this stage
+            for (int p = tid; p < M; p += T) {
+                const float a = box_area(sbox[p]);
+                if (a > 0.f && a < INFINITY) {
+                    const uint32_t row = sidx[p] / (uint32_t)A.nc;
+                    atomicOr(&done[row >> 5], 1u << (row & 31));
+                }
+            }
+            __syncthreads();
+        }
+        rank_base += cnt_all;
         U = v;
         if (v == 0) break;                   // everything has been processed
     }
@@ -887,7 +934,7 @@ extern "C" int vkdbg_nms_timing(void* dev_buf) {
 
 template <int T, int CAP>
 static int launch_nms(const NmsArgs& A, int batch, int segs, int max_det, cudaStream_t stream) {
-    const size_t smem = nms_smem_bytes<CAP>(T, segs, max_det);
+    const size_t smem = nms_smem_bytes<CAP>(T, segs, max_det, A.prune ? A.rows : 0);
     if (smem > 220 * 1024)
         return fail_code(VK_E_LIMIT, "vk_nms_batched: max_det=%d segs=%d need %zu B of shared memory", max_det, segs, smem);
     const void* fn = reinterpret_cast<const void*>(&nms_kernel<T, CAP>);
@@ -913,12 +960,13 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, double iou_thres, i
     NmsArgs A;
     A.cand = c->cand; A.boxes = reinterpret_cast<const float4*>(c->boxes);
     A.counts = c->ctrl; A.flags = c->ctrl + (size_t)batch; A.list_count = c->ctrl + 2 * (size_t)batch; A.bound = c->ctrl + 3 * (size_t)batch;
-    A.seg_count = c->seg_count; A.list = c->list;
+    A.seg_count = c->seg_count; A.list = reinterpret_cast<ulonglong2*>(c->list);
     A.cap = c->cap; A.rows = c->rows; A.segs = c->segs; A.nc = c->nc; A.list_cap = c->list_cap;
     float thr = (float)iou_thres;                       // double compare == float compare against
     if ((double)thr > iou_thres) thr = nextafterf(thr, -INFINITY);  // the largest float <= threshold
     A.iou_thr = thr;
     A.agnostic = agnostic ? 1 : 0; A.max_nms = max_nms; A.max_det = max_det; A.max_wh = max_wh;
+    A.prune = (agnostic && thr < 1.0f && keep_idx == nullptr) ? 1 : 0;
     A.dets = dets; A.det_counts = det_counts; A.keep_idx = keep_idx; A.status = status;
     if (c->list) {
         // selection pass for images with more candidates than their list holds (it returns at once for the

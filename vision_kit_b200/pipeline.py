@@ -60,6 +60,8 @@ class DetectPipeline:
         # captured graphs only: the letterbox on a third branch, beside the filter (they share no data)
         self.fork_preprocess = bool(fork_preprocess)
         nsets = 2 if self.overlap else 1
+        if agnostic and list_cap == ops.LIST_CAP:
+            list_cap *= 2        # agnostic NMS goes deeper: most candidates it meets are other classes of rows already decided
         self._cands = [ops.CandBuf.alloc(batch, self.rows, segs, nc, cap, self.device, list_cap=list_cap,
                                          top_list=ops.expects_dense(filter_kernel, conf_thres)) for _ in range(nsets)]
         self._outs = [ops.NmsOut(
