@@ -130,13 +130,15 @@ int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels, int dtype,
  *
  * A candidate set lives in caller-owned device buffers described by VkCandBuf.  Every 64-row
  * tile ("segment") owns the fixed slot range [seg * T, (seg + 1) * T), T = vk_cand_tile_slots(),
- * and writes its candidates there in the reference's order (row ascending, class ascending), so
- * the buffer needs cap >= segs * T and can never overflow, and SLOT ORDER IS THE CANONICAL ORDER
- * of the reference's candidate list (the order that breaks score ties in its argsort and NMS).
+ * and writes its seg_count[seg] candidates to the front of it, so the buffer needs
+ * cap >= segs * T, can never overflow, and no tile waits for another.  A candidate is the pair
+ * (score, id), id = row * nc + cls: ascending id is the reference's candidate order (row, then
+ * class -- the order that breaks score ties in its argsort and that torchvision's indices refer
+ * to), so the order of the candidates INSIDE a segment is free; segments are in row order.
  *
  * list: optional scratch of vk_nms_batched for images with more than list_cap candidates (eval
  * thresholds, ~240 k per image): a sampled score histogram picks the score bound above which a
- * grid-wide pass copies the candidates, as {ordered score << 32 | ~slot, row*nc + cls}, into the image's list, and
+ * grid-wide pass copies the candidates, as (ordered score << 32 | ~(row*nc + cls)), into the image's list, and
  * the per-image kernel sorts from that list.  Results never depend on it; allocate it (8192 entries
  * per image is plenty) when such images are expected.
  */
@@ -149,7 +151,7 @@ typedef struct VkCandBuf {
     float* boxes;        /* dev [batch][rows][4] xyxy of rows that produced candidates */
     int32_t* ctrl;       /* dev [VK_CTRL_WORDS][batch]; zeroed by the filter call */
     int32_t* seg_count;  /* dev [batch][segs] candidates of each segment */
-    uint64_t* list;      /* dev [batch][list_cap][2] (16-byte entries: key, row*nc + cls) or NULL */
+    uint64_t* list;      /* dev [batch][list_cap] or NULL */
     int32_t cap;         /* candidate slots per image */
     int32_t rows;        /* prediction rows per image */
     int32_t segs;        /* segments per image (vk_filter_segments / vk_decode_filter_segments) */

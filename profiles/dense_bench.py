@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Device time of the eval-mode (dense) fused filter of whichever library VK_B200_LIB names (tuning builds)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vision_kit_b200 import ops
+from tests import synth
+tag = sys.argv[1] if len(sys.argv) > 1 else os.path.basename(os.environ.get("VK_B200_LIB", "default"))
+B = 64
+dev = torch.device("cuda:0")
+grids = [(640 // s, 640 // s) for s in synth.STRIDES]
+cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)
+lv = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
+lvh = [t.half() for t in lv]
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+out = []
+for name, levels, conf, ml in (("eval ML f32", lv, 0.001, True), ("eval ML f16", lvh, 0.001, True), ("best-class dense f32", lv, 0.01, False)):
+    buf = ops.decode_filter(cfg, levels, conf, ml, kernel="dense")
+    out.append(f"{name} {timeit(lambda: ops.decode_filter(cfg, levels, conf, ml, buf=buf, kernel='dense')):7.1f} us")
+print(f"{tag:24s} " + "   ".join(out) + f"   ({int(buf.counts.sum())} cand)")

@@ -371,7 +371,8 @@ def _ref_candidates(pred, conf_thres, multi_label, **_):
 
 def _canonical(buf):
     """Candidate lists in canonical order + boxes of the candidate rows, per image (host copies).
-    Segment s owns the slots [s * T, (s + 1) * T), T as the filter kernel recorded it."""
+    Segment s owns the slots [s * T, (s + 1) * T), T as the filter kernel recorded it; inside a segment the
+    order is the kernel's business, the canonical order is ascending id = row * nc + cls (high 32 bits)."""
     cand, cnt, boxes = buf.cand.cpu().numpy(), buf.seg_count.cpu().numpy(), buf.boxes.cpu().numpy()
     slots = buf.tile_slots.cpu().numpy()
     out = []
@@ -379,6 +380,13 @@ def _canonical(buf):
         T = int(slots[b])
         assert T in (64, 64 * buf.nc) and int(cnt[b].sum()) == int(buf.counts[b])
         lst = np.concatenate([cand[b, s * T: s * T + cnt[b, s]] for s in range(buf.segs)] or [np.zeros(0, np.int64)])
+        ids = lst >> 32
+        assert np.unique(ids).size == ids.size, "a candidate was written twice"
+        seg_of = np.repeat(np.arange(buf.segs), cnt[b])
+        if ids.size:                     # segments own consecutive runs of rows: sorting by id never crosses one
+            order = np.argsort(ids, kind="stable")
+            assert (np.diff(seg_of[order]) >= 0).all(), "a candidate sits outside the segment of its row"
+        lst = lst[np.argsort(ids, kind="stable")]
         rows = np.unique((lst >> 32) // buf.nc)
         out.append((lst, rows, boxes[b, rows]))
     return out

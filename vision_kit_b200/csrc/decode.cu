@@ -872,6 +872,158 @@ decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
 }
 
 // ---------------------------------------------------------------------------------------
+// Dense fused filter without shared memory or barriers ("lanes = rows"), the default at eval thresholds.
+// NCHW conv outputs are already laid out the way a warp wants to read them: the 64 rows of a tile are contiguous
+// inside every channel plane, so lane j reading rows j and j + 32 of one channel is two coalesced 128-byte
+// requests and nothing has to be staged or transposed.  One warp owns one tile and makes ONE pass over it,
+// channel by channel (8 channels = 16 loads in flight per lane): p = sigmoid(x) * obj, and the lanes whose
+// product passes append their candidate at once -- two ballots per class give every one its slot.  That
+// writes a tile's candidates class-major instead of row-major, which is allowed: a candidate is (score, id) and
+// the consumers order by id (include/vk_b200.h).  Best-class mode keeps a running maximum per row and appends
+// once per row.  No staging copies, no swizzled address arithmetic, no block barriers, no scan: ~2500
+// instructions per warp and tile where the shared-memory kernel above spends ~5500.
+// ---------------------------------------------------------------------------------------
+#ifndef VK_LANES_WARPS
+#define VK_LANES_WARPS 4
+#endif
+#ifndef VK_LANES_BPS
+#define VK_LANES_BPS 8
+#endif
+constexpr int kLaneWarps = VK_LANES_WARPS;
+
+template <class T, bool ML>
+__global__ void __launch_bounds__(32 * kLaneWarps, VK_LANES_BPS)
+decode_filter_lanes_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int t = blockIdx.x * kLaneWarps + (threadIdx.x >> 5);
+    if (t >= total_tiles) return;
+    const LogitLocator<T> L{H};
+    const LogitTileRef<T> q = L.locate(t);
+    const int nc = A.nc, nynx = q.nynx;
+    const T* const base = q.base;                         // channel 0, first row of the tile
+    const bool v0 = lane < q.nvalid, v1 = lane + 32 < q.nvalid;
+    // Rows past the end of a ragged tile read row 0 of the tile instead (no per-load predicate) and carry
+    // obj = NaN: every product is NaN and no comparison with it holds.
+    const int j0 = v0 ? lane : 0, j1 = v1 ? lane + 32 : 0;
+    // objectness (image_proc.py:99); rows at or under the threshold keep obj = 0 and never pass
+    const float oa = sigmoidf_vk(ld_elem(base + (size_t)4 * nynx + j0));
+    const float ob = sigmoidf_vk(ld_elem(base + (size_t)4 * nynx + j1));
+    const float obj0 = v0 ? (oa > A.conf ? oa : 0.0f) : __int_as_float(0x7fc00000);
+    const float obj1 = v1 ? (ob > A.conf ? ob : 0.0f) : __int_as_float(0x7fc00000);
+    if (ML && !__any_sync(0xffffffffu, obj0 > 0.0f || obj1 > 0.0f) && A.conf >= 0.0f) {   // no row passes :99
+        if (lane == 0) {
+            A.seg_count[(size_t)q.b * A.segs + q.seg] = 0;
+            if (q.seg == 0) A.flags[q.b] = cand_flags(A);
+        }
+        return;
+    }
+    const T* src0 = base + (size_t)5 * nynx + j0;         // class plane being fetched, the lane's two rows
+    const T* src1 = base + (size_t)5 * nynx + j1;
+    uint2* out = reinterpret_cast<uint2*>(A.cand + (size_t)q.b * A.cap) + (size_t)q.seg * A.tile_cap;
+    asm volatile("" : "+l"(out));                         // one base register (not re-derived per store)
+    const uint32_t id0 = (uint32_t)((q.row0 + lane) * nc), id1 = (uint32_t)((q.row0 + lane + 32) * nc);
+    uint32_t run = 0;                                     // candidates of the tile so far (warp-uniform)
+    bool any0 = false, any1 = false;                      // the lane's rows produced a candidate
+    float bv0 = -INFINITY, bv1 = -INFINITY;               // best class (ML == false)
+    int bj0 = 0x7fffffff, bj1 = 0x7fffffff;
+    // (the loads of the next 8 channels are issued before the current 8 are evaluated; the planes are walked
+    // by pointer increments, classes past nc re-read the last plane and are masked out)
+    float x0[8], x1[8];
+    auto fetch = [&](int c0, float* a, float* b) {
+        if (c0 + 8 <= nc) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a[u] = ld_elem(src0); b[u] = ld_elem(src1);
+                src0 += nynx; src1 += nynx;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool in = c0 + u < nc;
+                a[u] = in ? ld_elem(src0) : 0.0f; b[u] = in ? ld_elem(src1) : 0.0f;
+                src0 += nynx; src1 += nynx;
+            }
+        }
+    };
+    fetch(0, x0, x1);
+    uint32_t allowed = 0xffffffffu;                       // class filter bits of the current 32 classes (:151)
+    unsigned rows0 = 0, rows1 = 0;                        // ballots of the rows that produced candidates
+    for (int c0 = 0; c0 < nc; c0 += 8) {
+        float n0[8], n1[8];
+        fetch(c0 + 8, n0, n1);
+        if ((c0 & 31) == 0) {
+            allowed = (ML && A.class_mask) ? __ldg(A.class_mask + (c0 >> 5)) : 0xffffffffu;
+            if (nc - c0 < 32) allowed &= (1u << (nc - c0)) - 1u;        // classes past nc never pass
+        }
+        const uint32_t al = (allowed >> (c0 & 31)) & 0xffu;
+        if (ML) {
+            // Two ballots per class give every passing lane its slot; the stores are predicated instructions (a
+            // branch around each costs more than the store).  Measured alternatives, both slower on the eval
+            // workload (12% of all (row, class) pairs pass): skipping classes of a tile whose logits all sit under
+            // logit(conf / obj) (almost no class of 64 rows is skippable), and one warp scan per 8 classes with
+            // lane-private runs of slots (scattered 8-byte stores).  POPC shares the XU pipe with the sigmoid's EX2
+            // and RCP and that pipe is this kernel's limiter (77% busy with four POPCs per class), hence the shuffle.
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float p0 = __fmul_rn(sigmoidf_vk(x0[u]), obj0);                            // image_proc.py:135
+                const float p1 = __fmul_rn(sigmoidf_vk(x1[u]), obj1);
+                const bool ok = (al >> u) & 1u;
+                const bool f0 = ok && p0 > A.conf, f1 = ok && p1 > A.conf;                       // :141
+                const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+                // (the totals come from lane 31 by one shuffle, not from two more POPCs: see below)
+                const uint32_t r0 = __popc(b0 & lt), r1 = __popc(b1 & lt);
+                const uint32_t tot = __shfl_sync(0xffffffffu, (r0 + (uint32_t)f0) | ((r1 + (uint32_t)f1) << 16), 31);
+                const uint32_t n_b0 = run + (tot & 0xffffu);
+                st_pred_u2(out + (run + r0), __float_as_uint(p0), id0 + (uint32_t)(c0 + u), f0);
+                st_pred_u2(out + (n_b0 + r1), __float_as_uint(p1), id1 + (uint32_t)(c0 + u), f1);
+                run = n_b0 + (tot >> 16);
+                rows0 |= b0; rows1 |= b1;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float p0 = __fmul_rn(sigmoidf_vk(x0[u]), obj0);
+                const float p1 = __fmul_rn(sigmoidf_vk(x1[u]), obj1);
+                const bool ok = (al >> u) & 1u;
+                if (ok && p0 > bv0) { bv0 = p0; bj0 = c0 + u; }                                  // first max (:145)
+                if (ok && p1 > bv1) { bv1 = p1; bj1 = c0 + u; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { x0[u] = n0[u]; x1[u] = n1[u]; }
+    }
+    if (ML) {
+        any0 = (rows0 >> lane) & 1u; any1 = (rows1 >> lane) & 1u;
+    } else {
+        any0 = v0 && bj0 != 0x7fffffff && bv0 > A.conf && class_allowed(A.class_mask, bj0);      // :147,151
+        any1 = v1 && bj1 != 0x7fffffff && bv1 > A.conf && class_allowed(A.class_mask, bj1);
+        const unsigned b0 = __ballot_sync(0xffffffffu, any0), b1 = __ballot_sync(0xffffffffu, any1);
+        if (any0) out[__popc(b0 & lt)] = make_uint2(__float_as_uint(bv0), id0 + (uint32_t)bj0);
+        if (any1) out[__popc(b0) + __popc(b1 & lt)] = make_uint2(__float_as_uint(bv1), id1 + (uint32_t)bj1);
+        run = (uint32_t)(__popc(b0) + __popc(b1));
+    }
+    // boxes of the rows that produced candidates
+    if (run) {
+        const PlaneGeom geom{H.variant, H.nx[q.l], q.s0, H.stride[q.l], H.anchors[q.l][2 * q.a], H.anchors[q.l][2 * q.a + 1]};
+        float4* boxes = A.boxes + (size_t)q.b * A.rows + q.row0;
+        if (any0) {
+            const T* bp = base + lane;
+            boxes[lane] = geom.box(ld_elem(bp), ld_elem(bp + nynx), ld_elem(bp + 2 * (size_t)nynx), ld_elem(bp + 3 * (size_t)nynx), q.s0 + lane);
+        }
+        if (any1) {
+            const T* bp = base + lane + 32;
+            boxes[lane + 32] = geom.box(ld_elem(bp), ld_elem(bp + nynx), ld_elem(bp + 2 * (size_t)nynx), ld_elem(bp + 3 * (size_t)nynx), q.s0 + lane + 32);
+        }
+    }
+    if (lane == 0) {
+        A.seg_count[(size_t)q.b * A.segs + q.seg] = (int)run;
+        if (q.seg == 0) A.flags[q.b] = cand_flags(A);
+        if (run) atomicAdd(A.counts + q.b, (int)run);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Dense variant of filter_pred (the `nms(prediction)` drop-in at eval thresholds): the same
 // persistent pipeline and (row, class part) mapping as decode_filter_dense_kernel, reading an
 // existing (B, rows, no) prediction tensor.  A tile is 64 consecutive rows = one contiguous run of
@@ -1131,6 +1283,13 @@ static int launch_decode_filter_dense(const HeadDev& H, const FilterArgs& A, int
     return check_launch("decode_filter_dense_kernel");
 }
 
+template <class T, bool ML>
+static int launch_decode_filter_lanes(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
+    decode_filter_lanes_kernel<T, ML><<<ceil_div(total_tiles, kLaneWarps), 32 * kLaneWarps, 0, stream>>>(H, A, total_tiles);
+    count_launch();
+    return check_launch("decode_filter_lanes_kernel");
+}
+
 template <class T, int NK, bool ML>
 static int launch_decode_filter_rows(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
     int grid = ceil_div(total_tiles, kRowWarps);
@@ -1165,6 +1324,15 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels,
     const FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
     const int total_tiles = H.tiles * batch;
     const bool ml = A.multi_label != 0;
+#ifndef VK_DENSE_SMEM
+    if (pick_dense(kernel, conf_thres)) {
+#define VK_DL_T(T)                                                                                  \
+        return ml ? launch_decode_filter_lanes<T, true>(H, A, total_tiles, stream)                   \
+                  : launch_decode_filter_lanes<T, false>(H, A, total_tiles, stream)
+        VK_BY_DTYPE(dtype, VK_DL_T);
+#undef VK_DL_T
+    }
+#endif
     if (pick_dense(kernel, conf_thres) && H.nc <= 128) {
 #define VK_DF_T(T)                                                                                                   \
         do {                                                                                                          \

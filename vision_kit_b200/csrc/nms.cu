@@ -4,9 +4,10 @@
 //
 // Greedy NMS consumes candidates in descending score order and stops at max_det kept boxes
 // (image_proc.py:170 truncates afterwards), so the sorted order is only ever needed for a prefix.
-// Candidates carry the 64-bit key (ordered score << 32 | ~slot): slot order is the reference's
-// candidate order (include/vk_b200.h), so descending keys = the stable descending argsort the
-// reference's cut and torchvision's NMS are defined on, and keys are unique.
+// Candidates carry the 64-bit key (ordered score << 32 | ~id), id = row * nc + cls: ascending id is the
+// reference's candidate order (`nonzero` order, row then class), so descending keys = the stable descending
+// argsort the reference's cut and torchvision's NMS are defined on, and keys are unique.  The key is all a
+// candidate is: its box, class and score follow from it, whatever slot a filter kernel wrote it to.
 //
 //   nms_select_kernel   images with more candidates than their list holds (eval thresholds, ~240 k): a
 //                       sampled score histogram gives the largest bound whose estimated count fits half
@@ -26,7 +27,7 @@
 //       The stage source is the image's list (built by the select pass) while it lasts, then the
 //       segments of the candidate buffer; a small image (demo thresholds) is one stage read directly.  Because keys
 //       are unique the selection always terminates: a tie group of thousands of bit-identical
-//       scores is split by slot.  The exact cut at max_nms falls out of the order (the stage
+//       scores is split by candidate id.  The exact cut at max_nms falls out of the order (the stage
 //       crossing rank max_nms is truncated).
 //       Class-aware mode walks per-class hash lists (kept boxes and chunk boxes) so that only
 //       same-class pairs are ever tested.  That is exact while every coordinate seen so far
@@ -57,7 +58,7 @@ struct NmsArgs {
     int32_t* list_count;        // ctrl row 2
     int32_t* bound;             // ctrl row 3 (ordered score bits)
     const int32_t* seg_count;
-    ulonglong2* list;          // [batch][list_cap] {key, row * nc + cls}
+    uint64_t* list;            // [batch][list_cap] keys
     int cap, rows, segs, nc, list_cap;
     float iou_thr;  // largest float <= the double threshold
     int agnostic, max_nms, max_det;
@@ -130,7 +131,6 @@ nms_select_kernel(const NmsArgs A) {
     __shared__ int s_cnt[VK_MAX_SEGMENTS], s_pre[VK_MAX_SEGMENTS + 1], wsum[33];
     __shared__ int s_j;
     __shared__ unsigned long long s_stage[kSelThreads / 32][kSelStage];
-    __shared__ uint32_t s_stage_idx[kSelThreads / 32][kSelStage];
     __shared__ unsigned short s_item_seg[kItemTable];           // item -> segment (a binary search per item otherwise)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_cap = tile_slots_of(A.flags[b]);
@@ -196,9 +196,8 @@ nms_select_kernel(const NmsArgs A) {
     //      flushed with ONE reservation on the image's list counter per ~100 keys: a reservation per 32
     //      candidates would serialise thousands of same-address atomics per image.
     unsigned long long* stage = s_stage[warp];
-    uint32_t* stage_idx = s_stage_idx[warp];
     int staged = 0;                                               // warp-uniform
-    ulonglong2* list = A.list + (size_t)b * A.list_cap;
+    uint64_t* list = A.list + (size_t)b * A.list_cap;
     const unsigned lt = (1u << lane) - 1u;
     auto flush = [&]() {
         int base = 0;
@@ -206,7 +205,7 @@ nms_select_kernel(const NmsArgs A) {
         base = __shfl_sync(0xffffffffu, base, 0);
         __syncwarp();
         for (int i = lane; i < staged; i += 32)
-            if (base + i < A.list_cap) list[base + i] = make_ulonglong2(stage[i], (unsigned long long)stage_idx[i]);
+            if (base + i < A.list_cap) list[base + i] = stage[i];
         __syncwarp();
         staged = 0;
     };
@@ -239,10 +238,7 @@ nms_select_kernel(const NmsArgs A) {
                 const bool take = jj < cur.cnt && key >= bound;
                 const unsigned m = __ballot_sync(0xffffffffu, take);
                 if (m) {
-                    if (take) {
-                        stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~(cur.slot0 + (uint32_t)jj);
-                        stage_idx[staged + __popc(m & lt)] = sc[u].y;
-                    }
+                    if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~sc[u].y;
                     staged += __popc(m);
                     if (staged > kSelStage - 32) flush();
                 }
@@ -264,7 +260,7 @@ struct ScratchB {
     float4* kbox;      // [max_det] kept boxes (class-offset)
     uint32_t* pred;    // [kChunk][kChunkWords]
     uint32_t* kmeta;   // [max_det] cls << 16 | next kept slot of the bucket
-    uint32_t* kkeep;   // [max_det] rank (cut) or slot of the kept candidate
+    uint32_t* kkeep;   // [max_det] rank (cut) or id of the kept candidate
     int* khead;        // [kHash] newest kept slot per class bucket
     uint32_t* ccnt2;   // [kHash / 2] chunk members per class bucket, two 16-bit counts per word
     uint16_t* cstart;  // [kHash + 2] first member slot of each bucket (+ end)
@@ -583,14 +579,14 @@ nms_kernel(const NmsArgs A) {
     // which are skipped); -1 = none
     int list_n = -1, list_len = 0;
     uint32_t lbound = 0;
-    const ulonglong2* list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
+    const uint64_t* list = A.list ? A.list + (size_t)b * A.list_cap : nullptr;
     if (list != nullptr && (flags & VK_FLAG_LIST)) {
         const int lc = A.list_count[b];
         if (lc <= A.list_cap) {
             lbound = (uint32_t)A.bound[b];
             list_len = lc;
             int mine = 0;
-            for (int i = tid; i < lc; i += T) mine += (uint32_t)(list[i].x >> 32) >= lbound ? 1 : 0;
+            for (int i = tid; i < lc; i += T) mine += (uint32_t)(list[i] >> 32) >= lbound ? 1 : 0;
             if (tid == 0) s_cnt = 0;
             __syncthreads();
             mine = warp_incl_scan(mine, lane);
@@ -640,18 +636,18 @@ nms_kernel(const NmsArgs A) {
         const uint32_t row = idx / (uint32_t)A.nc;
         return (done[row >> 5] >> (row & 31)) & 1u;
     };
-    // every candidate of the current source: f(valid, key, row * nc + cls)
+    // every candidate of the current source: f(valid, key, id)
     const unsigned long long lfloor = (unsigned long long)lbound << 32;
     auto for_each_list = [&](auto&& f) {
         for (int i0 = 0; i0 < list_len; i0 += 4 * T) {
-            ulonglong2 e[4];
+            unsigned long long e[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * T + tid;
-                e[u] = (i < list_len) ? list[i] : make_ulonglong2(0ull, 0ull);
+                e[u] = (i < list_len) ? list[i] : 0ull;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) f(i0 + u * T + tid < list_len && e[u].x >= lfloor, e[u].x, (uint32_t)e[u].y);
+            for (int u = 0; u < 4; ++u) f(i0 + u * T + tid < list_len && e[u] >= lfloor, e[u], ~(uint32_t)e[u]);
         }
     };
     auto for_each_segment = [&](auto&& f) {
@@ -670,7 +666,7 @@ nms_kernel(const NmsArgs A) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + 32 * u + lane;
-                    f(j < cnt, ((unsigned long long)order_key(s[u].x) << 32) | (uint32_t)~(slot0 + (uint32_t)j), s[u].y);
+                    f(j < cnt, ((unsigned long long)order_key(s[u].x) << 32) | (uint32_t)~s[u].y, s[u].y);
                 }
             }
         }
@@ -755,8 +751,8 @@ nms_kernel(const NmsArgs A) {
                     const int mid = (lo + hi) >> 1;
                     if (segoff[mid] <= p) lo = mid; else hi = mid;
                 }
-                const uint32_t slot = (uint32_t)lo * (uint32_t)tile_cap + (uint32_t)(p - segoff[lo]);
-                keys[p] = ((unsigned long long)order_key(cand[slot].x) << 32) | (uint32_t)~slot;
+                const uint2 cd = cand[(size_t)lo * tile_cap + (p - segoff[lo])];
+                keys[p] = ((unsigned long long)order_key(cd.x) << 32) | (uint32_t)~cd.y;
             }
             if (tid == 0) { s_cnt = n; s_all = n; }
         } else {
@@ -854,12 +850,11 @@ nms_kernel(const NmsArgs A) {
             __syncthreads();
         }
         VK_STAMP(stamp + 2);
-        // ---- the stage's boxes, once: candidate slot -> (row, class) -> class-offset box
+        // ---- the stage's boxes, once: candidate id -> (row, class) -> class-offset box
         const int M = min(cnt, K - rank_base);             // truncated at rank max_nms (image_proc.py:161-163)
         bool ok = true;
         for (int p = tid; p < M; p += T) {
-            const uint32_t slot = ~(uint32_t)keys[p];
-            const uint32_t idx = cand[slot].y;
+            const uint32_t idx = ~(uint32_t)keys[p];
             const uint32_t row = idx / (uint32_t)A.nc;
             const uint32_t cls = idx - row * (uint32_t)A.nc;
             const float4 bx = boxes[row];
@@ -895,13 +890,40 @@ nms_kernel(const NmsArgs A) {
     for (int i = kept0 * 6 + tid; i < A.max_det * 6; i += T) dets[i] = 0.f;
     if (keep_out) {
         if (!cut && kept0 > 0) {
-            // torchvision's index = position in the reference's candidate list = candidates in earlier
-            // segments + position inside the segment
+            // torchvision's index = position in the reference's candidate list = number of candidates with a
+            // smaller id.  One pass over all candidates: a candidate with id x lies below every kept id > x, so it
+            // is tallied at b = #(kept ids <= x) and the ranks are the running sums of the tallies.
             if (!have_segoff) load_segoff();
+            uint32_t* sk = reinterpret_cast<uint32_t*>(sbox);           // kept ids, ascending     (stage arrays are free now)
+            int* tally = reinterpret_cast<int*>(sidx);                  // [kept0]
             for (int k = tid; k < kept0; k += T) {
-                const uint32_t slot = XB.kkeep[k];
-                const uint32_t seg = slot / (uint32_t)tile_cap;
-                keep_out[k] = (int64_t)segoff[seg] + (int64_t)(slot - seg * (uint32_t)tile_cap);
+                const uint32_t me = XB.kkeep[k];
+                int r = 0;
+                for (int j = 0; j < kept0; ++j) r += XB.kkeep[j] < me ? 1 : 0;
+                sk[r] = me;
+            }
+            for (int k = tid; k < kept0; k += T) tally[k] = 0;
+            __syncthreads();
+            for_each_segment([&](bool ok, unsigned long long, uint32_t idx) {
+                if (!ok) return;
+                int lo = 0, hi = kept0;                                 // first j with sk[j] > idx
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sk[mid] <= idx) lo = mid + 1; else hi = mid;
+                }
+                if (lo < kept0) atomicAdd(&tally[lo], 1);
+            });
+            __syncthreads();
+            for (int k = tid; k < kept0; k += T) {
+                const uint32_t me = XB.kkeep[k];
+                int lo = 0, hi = kept0;                                 // position of me in sk
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sk[mid] < me) lo = mid + 1; else hi = mid;
+                }
+                long long r = 0;
+                for (int j = 0; j <= lo; ++j) r += tally[j];
+                keep_out[k] = r;
             }
         } else {
             for (int k = tid; k < kept0; k += T) keep_out[k] = (int64_t)XB.kkeep[k];
@@ -960,7 +982,7 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, double iou_thres, i
     NmsArgs A;
     A.cand = c->cand; A.boxes = reinterpret_cast<const float4*>(c->boxes);
     A.counts = c->ctrl; A.flags = c->ctrl + (size_t)batch; A.list_count = c->ctrl + 2 * (size_t)batch; A.bound = c->ctrl + 3 * (size_t)batch;
-    A.seg_count = c->seg_count; A.list = reinterpret_cast<ulonglong2*>(c->list);
+    A.seg_count = c->seg_count; A.list = c->list;
     A.cap = c->cap; A.rows = c->rows; A.segs = c->segs; A.nc = c->nc; A.list_cap = c->list_cap;
     float thr = (float)iou_thres;                       // double compare == float compare against
     if ((double)thr > iou_thres) thr = nextafterf(thr, -INFINITY);  // the largest float <= threshold
@@ -984,12 +1006,15 @@ extern "C" int vk_nms_batched(const VkCandBuf* c, int batch, double iou_thres, i
         if (int rc = check_launch("nms_select_kernel")) return rc;
         return launch_nms<1024, 2048>(A, batch, c->segs, max_det, stream);
     }
+    // list-less buffers (demo thresholds, a few hundred candidates per image): 512 threads.  Measured inside the
+    // bench step, where this kernel runs beside the letterbox and the filter of the next batch: 115 us per step
+    // with 512 threads, 118.5 with 1024 (shorter alone, but it then takes a whole SM's registers), 141 with 256.
 #ifdef VK_NMS_TUNE
     if (const char* e = getenv("VK_NMS_T")) {              // tuning builds: CTA size of the list-less kernel
         const int t = atoi(e);
         if (t == 256) return launch_nms<256, 1024>(A, batch, c->segs, max_det, stream);
-        if (t == 512) return launch_nms<512, 1024>(A, batch, c->segs, max_det, stream);
+        if (t == 1024) return launch_nms<1024, 1024>(A, batch, c->segs, max_det, stream);
     }
 #endif
-    return launch_nms<1024, 1024>(A, batch, c->segs, max_det, stream);
+    return launch_nms<512, 1024>(A, batch, c->segs, max_det, stream);
 }

@@ -78,6 +78,11 @@ __device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
 __device__ __forceinline__ void st_stream_f32(void* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
+// predicated 8-byte store: the predicate guards the instruction, not a branch around it
+__device__ __forceinline__ void st_pred_u2(void* p, uint32_t a, uint32_t b, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.u32 [%0], {%1,%2};\n\t}"
+                 :: "l"(p), "r"(a), "r"(b), "r"((uint32_t)pred) : "memory");
+}
 __device__ __forceinline__ void st_stream_u2(void* p, uint2 v) {
     asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }

@@ -228,11 +228,11 @@ def detect_decode(cfg: VkHeadCfg, levels: Sequence[torch.Tensor], want_raw: bool
 @dataclass
 class CandBuf:
     """Caller-owned device buffers of one candidate set (include/vk_b200.h `VkCandBuf`)."""
-    cand: torch.Tensor       # int64 (B, cap): low 32 = score bits, high 32 = row*nc + cls; slot = seg * T + position
+    cand: torch.Tensor       # int64 (B, cap): low 32 = score bits, high 32 = row*nc + cls; segment s owns slots [s*T, (s+1)*T)
     boxes: torch.Tensor      # float32 (B, rows, 4)
     ctrl: torch.Tensor       # int32 (4 * B): counts | flags | list entries | bound
     seg_count: torch.Tensor  # int32 (B, segs)
-    list: Optional[torch.Tensor]   # int64 (B, list_cap, 2): {ordered score << 32 | ~slot, row*nc + cls}, unordered; None = no selection pass
+    list: Optional[torch.Tensor]   # int64 (B, list_cap): ordered score << 32 | ~(row*nc + cls), unordered; None = no selection pass
     cap: int
     rows: int
     segs: int
@@ -249,7 +249,7 @@ class CandBuf:
                        torch.empty((batch, rows, 4), dtype=torch.float32, device=device),
                        torch.zeros((VK_CTRL_WORDS * batch,), dtype=torch.int32, device=device),
                        torch.empty((batch, segs), dtype=torch.int32, device=device),
-                       torch.empty((batch, list_cap, 2), dtype=torch.int64, device=device) if list_cap > 0 else None,
+                       torch.empty((batch, list_cap), dtype=torch.int64, device=device) if list_cap > 0 else None,
                        int(cap), int(rows), int(segs), int(nc), list_cap)
 
     def c_struct(self) -> VkCandBuf:
