@@ -84,12 +84,9 @@ def test_shims_refuse_cpu_tensors(vk_lib):
         image_proc.nms(torch.zeros(1, 10, 85), iou_thres=2.0)
 
 
-def test_norm255_two_fma_division_is_correctly_rounded():
-    # lb_kernel's norm255(): q = v*r; e = fma(-q, 255, v); q' = fma(e, r, q) with r = RN(1/255).
+def test_norm255_split_reciprocal_is_correctly_rounded():
+    # letterbox.cu norm255(): fma(v, hi, fl(v * lo)) with hi = RN(1/255), lo = RN(1/255 - hi).
     # Exact rational arithmetic, each step rounded to float32 -> equals RN(v/255) for all 256 inputs.
-    def rn(x: Fraction) -> Fraction:
-        return Fraction(float(np.float32(float(x)))) if x != 0 else Fraction(0)
-
     def rn_exact(x: Fraction) -> Fraction:   # round-to-nearest-even of an exact rational to float32
         if x == 0:
             return Fraction(0)
@@ -98,13 +95,13 @@ def test_norm255_two_fma_division_is_correctly_rounded():
         best = min((abs(Fraction(float(c)) - x), i, c) for i, c in enumerate((f, lo, hi)))
         return Fraction(float(best[2]))
 
-    r = Fraction(float(np.float32(1.0) / np.float32(255.0)))
-    assert float(r) == float(np.float32(0.003921568859368563))
+    hi = Fraction(float(np.float32(1.0) / np.float32(255.0)))
+    assert float(hi) == float(np.float32(0.003921568859368563))
+    lo = rn_exact(Fraction(1, 255) - hi)
+    assert float(lo) == float(np.float32(-2.319175823606301e-10))
     for v in range(256):
-        q = rn_exact(Fraction(v) * r)
-        e = rn_exact(Fraction(v) - q * 255)
-        q2 = rn_exact(q + e * r)
-        assert float(q2) == float(np.float32(v) / np.float32(255.0)), v
+        q = rn_exact(Fraction(v) * hi + rn_exact(Fraction(v) * lo))
+        assert float(q) == float(np.float32(v) / np.float32(255.0)), v
 
 
 def test_iou_threshold_rounding_rule():

@@ -13,9 +13,10 @@
 namespace vk {
 
 // ---------------------------------------------------------------------------------------
-// coefficient tables: xtab[b][x] = {3*xs, 3*min(xs+1, sw-1), a0, a1}, ytab[b][y] =
-// {r0, r1, b0, b1} for interior coordinates.  float64/float32 chain with
-// every operation rounded separately, exactly as OpenCV's resize.cpp builds xofs/ialpha.
+// coefficient tables: xtab[b][x] = {3*xs, a0 | a1 << 16} (the second tap is the next pixel,
+// clamped to the last one, where OpenCV gives it weight 0), ytab[b][y] = {r0, r1, b0, b1} for
+// interior coordinates.  float64/float32 chain with every operation rounded
+// separately, exactly as OpenCV's resize.cpp builds xofs/ialpha.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void linear_coeff(int d, int dn, int sn, bool is_x, int* s_out,
                                              int* w0, int* w1) {
@@ -33,17 +34,17 @@ __device__ __forceinline__ void linear_coeff(int d, int dn, int sn, bool is_x, i
 }
 
 __global__ void __launch_bounds__(256)
-lb_tables_kernel(const VkLbDesc* __restrict__ descs, int4* __restrict__ xtab,
-                 int4* __restrict__ ytab, int out_h, int out_w) {
+lb_tables_kernel(const VkLbDesc* __restrict__ descs, int2* __restrict__ xtab,
+                 int4* __restrict__ ytab, int4* __restrict__ ttab, int out_h, int out_w, int tile_rows) {
     const int b = blockIdx.x;
     const VkLbDesc d = descs[b];
-    int4* xt = xtab + (size_t)b * out_w;
+    int2* xt = xtab + (size_t)b * out_w;
     int4* yt = ytab + (size_t)b * out_h;
     for (int i = threadIdx.x; i < d.new_w + d.new_h; i += blockDim.x) {
         int s, w0, w1;
         if (i < d.new_w) {
             linear_coeff(i, d.new_w, d.src_w, true, &s, &w0, &w1);
-            xt[i] = make_int4(3 * s, 3 * min(s + 1, d.src_w - 1), w0, w1);
+            xt[i] = make_int2(3 * s, w0 | (w1 << 16));
         } else {
             const int y = i - d.new_w;
             linear_coeff(y, d.new_h, d.src_h, false, &s, &w0, &w1);
@@ -51,15 +52,28 @@ lb_tables_kernel(const VkLbDesc* __restrict__ descs, int4* __restrict__ xtab,
                               w0, w1);
         }
     }
+    __syncthreads();
+    // ttab[b][g] = {first source row, number of source rows, first and one-past-last canvas row inside the image}
+    // of the tile of `tile_rows` canvas rows starting at g * tile_rows
+    const int tiles_y = (out_h + tile_rows - 1) / tile_rows;
+    for (int g = threadIdx.x; g < tiles_y; g += blockDim.x) {
+        const int y0 = g * tile_rows, y1 = min(y0 + tile_rows, out_h);
+        const int ys = max(y0, d.top), ye = min(y1, d.top + d.new_h);
+        int rlo = 0, nsrc = 0;
+        if (ys < ye) {
+            rlo = yt[ys - d.top].x;
+            nsrc = yt[ye - 1 - d.top].y - rlo + 1;
+        }
+        ttab[(size_t)b * tiles_y + g] = make_int4(rlo, nsrc, ys, ye);
+    }
 }
 
 // uint8 / 255 in float32, correctly rounded (== IEEE division for all 256 inputs;
-// tests/test_host_logic.py proves it exhaustively): q0 = v*r, one Newton correction.
+// tests/test_host_logic.py proves it exhaustively): 1/255 split in two floats, v*hi + fl(v*lo) in one FMA.
 __device__ __forceinline__ float norm255(float v) {
-    const float r = 0.003921568859368563f;  // RN(1/255)
-    const float q = __fmul_rn(v, r);
-    const float e = __fmaf_rn(-q, 255.0f, v);
-    return __fmaf_rn(e, r, q);
+    const float hi = 0.003921568859368563f;   // RN(1/255)
+    const float lo = -2.319175823606301e-10f;   // RN(1/255 - hi)
+    return __fmaf_rn(v, hi, __fmul_rn(v, lo));
 }
 
 template <int FMT> struct OutT;
@@ -106,12 +120,24 @@ __device__ __forceinline__ void taps_dp2a(uint32_t w0, uint32_t w1, uint32_t w2,
 constexpr int kLbRows = 8;        // canvas rows per block
 constexpr int kLbThreads = 320;   // 640-wide canvas = 2 columns per thread, no idle lanes
 #ifndef VK_GEN_ROWS
-#define VK_GEN_ROWS 4
+#define VK_GEN_ROWS 8
 #endif
-constexpr int kGenRows = VK_GEN_ROWS;       // canvas rows per block of the general kernel
-constexpr int kGenThreads = 160;  // 640-wide canvas = one 4-column group per thread
-constexpr int kGenWarps = kGenThreads / 32;
-constexpr int kLbMaxSrcRows = 2 * kGenRows + 4;  // staged source rows (down-scales up to ~2.2x)
+#ifndef VK_GEN_RING_KB
+#define VK_GEN_RING_KB 96
+#endif
+#ifndef VK_GEN_BPS
+#define VK_GEN_BPS 2
+#endif
+#ifndef VK_GEN_UNROLL
+#define VK_GEN_UNROLL 1
+#endif
+
+constexpr int kGenRows = VK_GEN_ROWS;           // canvas rows per tile of the general kernel
+constexpr int kGenCols = 160;                   // 4-column groups per pass: a 640-wide canvas row
+constexpr int kGenThreads = 2 * kGenCols;       // two row sets (even / odd rows of the tile)
+constexpr int kGenUnroll = VK_GEN_UNROLL;
+constexpr int kGenQ = 4;                        // tiles a block keeps in flight
+constexpr int kGenRing = VK_GEN_RING_KB * 1024; // staging ring per block (two blocks per SM)
 
 // ---------------------------------------------------------------------------------------
 // copy kernel: every image of the batch is a plain copy (no resize) with 4-pixel alignment.
@@ -196,183 +222,268 @@ lb_copy_kernel(const VkLbDesc* __restrict__ descs, int out_h, int out_w, int swa
 }
 
 // ---------------------------------------------------------------------------------------
-// general kernel: one block = kLbRows canvas rows of one image (any size, any alignment).
+// general kernel (any source size, alignment and pitch; images without resize use it with identity tables,
+// weights 2048/0 reproduce the source byte exactly).
 //
-//   1. the source rows the tile needs (a contiguous range, <= kLbMaxSrcRows) are staged in shared
-//      memory: one warp per row, 2 aligned 32-bit loads + a funnel shift per word, so that every
-//      staged row starts 4-byte aligned whatever the source pitch (3*w is rarely a multiple of 4).
-//      DRAM sees only coalesced word loads; nothing is read before the image's first aligned word
-//      or past its last byte.
-//   2. per canvas column the two horizontal taps are 6 consecutive bytes of a staged row: 2-3
-//      LDS.32, funnel shift, PRMT to pair the bytes, DP2A for P0*a0 + P1*a1.  Clamped taps at the
-//      right edge have weight 0 (OpenCV resets the fraction there), so every column takes this path.
-//   3. vertical pass with IMAD.HI on weights pre-shifted by 16, value/255 from a 256-entry
-//      table built with the correctly rounded two-FMA division.
+// Persistent blocks, each walking tiles of kGenRows canvas rows of one image (tile t = row group t / B of
+// image t % B, so that a block sees all the batch's sizes).  The source rows a tile needs are staged in a
+// shared-memory RING: a tile takes exactly the bytes it needs, and a block keeps issuing the asynchronous
+// copies of later tiles (up to kGenQ, as far as the ring has room) while it evaluates the oldest one.  What
+// bounds this kernel is the number of bytes in flight per SM; with one fixed worst-case staging buffer per
+// block (the round-1 kernel) a mixed batch kept ~27 KB per SM in flight and ran at 0.4-0.6 of the copy peak.
 //
-// Images without resize use the same code with identity tables (weights 2048/0 reproduce the
-// source byte exactly).  Tiles whose source span exceeds the staging capacity (down-scales
-// beyond ~2x) fall back to byte taps through L1.
+//   1. stage: 16-byte LDGSTS chunks; a staged row keeps its source alignment modulo 16 so that aligned
+//      global chunks are aligned shared chunks.  DRAM sees only coalesced loads; nothing is read before
+//      the image's first aligned word or past its last byte.
+//   2. per canvas column the two horizontal taps are 6 consecutive bytes of a staged row: 2-3 LDS.32, funnel
+//      shift, PRMT to pair the bytes, DP2A for P0*a0 + P1*a1.  Clamped taps at the right edge have weight 0
+//      (OpenCV resets the fraction there), so every column takes this path.
+//   3. vertical pass with IMAD.HI on weights pre-shifted by 16, value/255 by the two-FMA division.
+//
+// Tiles whose source span exceeds the ring (down-scales beyond ~2.5x of 1280-wide sources) take byte taps
+// through L1 instead.
 // ---------------------------------------------------------------------------------------
+struct GenTile {
+    int b, y_begin, nrows;
+    int ys, ye;            // canvas rows of the tile that intersect the image: [ys, ye)
+    int rlo, nsrc;         // source rows they touch: [rlo, rlo + nsrc)
+    int stride;            // bytes per staged row (multiple of 16)
+    int bytes;             // nsrc * stride
+    int off;               // ring offset of the first staged row, -1 = not staged (direct taps)
+    int acct;              // ring bytes the tile gives back (its own + the tail it skipped when wrapping)
+    int left, new_w;       // interior columns on the canvas: [left, left + new_w)
+};
+
 template <int FMT>
-__global__ void __launch_bounds__(kGenThreads)
-lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ xtab,
-                  const int4* __restrict__ ytab, int out_h, int out_w, int swap_rb, uint32_t pad_rgb,
-                  typename OutT<FMT>::type* __restrict__ dst_all, int row_words, int max_rows) {
+__global__ void __launch_bounds__(kGenThreads, VK_GEN_BPS)
+lb_general_kernel(const VkLbDesc* __restrict__ descs, const int2* __restrict__ xtab,
+                  const int4* __restrict__ ytab, const int4* __restrict__ ttab, int batch, int out_h, int out_w,
+                  int swap_rb, uint32_t pad_rgb, typename OutT<FMT>::type* __restrict__ dst_all) {
     using T = typename OutT<FMT>::type;
-    extern __shared__ uint32_t stage[];          // [max_rows][row_words]
+    extern __shared__ __align__(16) uint8_t ring[];
+    __shared__ GenTile s_q[kGenQ];
+    __shared__ int4 s_y[kGenQ][kGenRows];        // {ring byte offset of row r0's first pixel, of r1's, b0<<16, b1<<16}
     __shared__ float s_lut[256];
-    __shared__ int4 s_y[kGenRows];                // {stage word offset of row r0, of row r1, b0<<16, b1<<16}
-    __shared__ int s_span[2];
-    const int b = blockIdx.y;
-    const int y_begin = blockIdx.x * kGenRows;
-    const int y_end = min(y_begin + kGenRows, out_h);
-    const int nrows = y_end - y_begin;
-    const VkLbDesc d = descs[b];
+    const int tid = threadIdx.x;
+    const int tiles_y = (out_h + kGenRows - 1) / kGenRows, total = tiles_y * batch;
     const size_t plane = (size_t)out_h * out_w;
-    T* dst = dst_all + (size_t)b * 3 * plane;
     const int p0 = pad_rgb & 255, p1 = (pad_rgb >> 8) & 255, p2 = (pad_rgb >> 16) & 255;
     const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;  // source byte of output channel 0/2
-    const int4* xt = xtab + (size_t)b * out_w;
-    const int4* yt = ytab + (size_t)b * out_h;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pa = swap_rb ? p2 : p0, pc = swap_rb ? p0 : p2;                    // pad value per source byte
+    for (int i = tid; i < 256; i += kGenThreads) s_lut[i] = norm255((float)i);
 
-    // tile rows that intersect the image, and the source rows they touch
-    const int ys = max(y_begin, d.top), ye_ = min(y_end, d.top + d.new_h);   // [ys, ye_) valid canvas rows
-    for (int i = threadIdx.x; i < 256; i += kGenThreads) s_lut[i] = norm255((float)i);
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = -1;
-        if (ys < ye_) {
-            lo = __ldg(yt + (ys - d.top)).x;
-            hi = __ldg(yt + (ye_ - 1 - d.top)).y;
-        }
-        s_span[0] = lo; s_span[1] = hi;
-    }
-    __syncthreads();
-    const int rlo = s_span[0], nsrc = s_span[1] - s_span[0] + 1;
-    const bool staged = nsrc <= max_rows && 3 * d.src_w + 36 <= row_words * 4;
-
-    auto emit = [&](size_t off, int v0, int v1, int v2) {
-        if constexpr (FMT == VK_LB_F32_NCHW) {
-            st_stream_f32(dst + off, s_lut[v0]);
-            st_stream_f32(dst + off + plane, s_lut[v1]);
-            st_stream_f32(dst + off + 2 * plane, s_lut[v2]);
-        } else if constexpr (FMT == VK_LB_BF16_NCHW) {
-            dst[off] = __float2bfloat16_rn(s_lut[v0]);
-            dst[off + plane] = __float2bfloat16_rn(s_lut[v1]);
-            dst[off + 2 * plane] = __float2bfloat16_rn(s_lut[v2]);
-        } else {
-            dst[off * 3] = (uint8_t)v0; dst[off * 3 + 1] = (uint8_t)v1; dst[off * 3 + 2] = (uint8_t)v2;
-        }
+    // tile t = row group t % tiles_y of image t / tiles_y; its table entry and descriptor are loaded one tile ahead
+    auto describe = [&](int b, int g, const int4 ti, const VkLbDesc& d) {
+        GenTile q;
+        q.b = b;
+        q.y_begin = g * kGenRows;
+        q.nrows = min(kGenRows, out_h - q.y_begin);
+        q.rlo = ti.x; q.nsrc = ti.y; q.ys = ti.z; q.ye = ti.w;
+        q.stride = (3 * d.src_w + 36 + 15) & ~15;
+        q.bytes = q.nsrc * q.stride;
+        q.off = 0; q.acct = 0;
+        q.left = d.left; q.new_w = d.new_w;
+        return q;
     };
 
-    if (staged) {
-        // ---- 1. stage: warp per source row, asynchronous copies (LDGSTS): every load of the tile
-        // is in flight before anyone waits.  A staged row keeps its source alignment: the aligned
-        // global word i of the row lands in staging word (k + i), k = its word index mod 4, so that
-        // 16-byte global chunks are 16-byte chunks in shared memory too and move with one copy.
+    // asynchronous copies of a tile's source rows into the ring, and its row table
+    auto issue = [&](const GenTile& q, const VkLbDesc& d, int slot) {
+        if (tid == 0) s_q[slot] = q;
+        if (tid < kGenRows) {
+            const int y = q.y_begin + tid;
+            int4 e = make_int4(-1, -1, 0, 0);
+            if (q.off >= 0 && y >= q.ys && y < q.ye) {
+                const int4 yc = __ldg(ytab + (size_t)q.b * out_h + (y - d.top));
+                // byte position of a row's first pixel inside its staged row: its address mod 16
+                const int a0 = (int)(reinterpret_cast<uintptr_t>(d.src + (size_t)yc.x * d.pitch) & 15);
+                const int a1 = (int)(reinterpret_cast<uintptr_t>(d.src + (size_t)yc.y * d.pitch) & 15);
+                e = make_int4(q.off + (yc.x - q.rlo) * q.stride + a0, q.off + (yc.y - q.rlo) * q.stride + a1,
+                              yc.z << 16, yc.w << 16);
+            }
+            s_y[slot][tid] = e;
+        }
+        if (q.off < 0) return;
         const uint8_t* img_end = d.src + (size_t)(d.src_h - 1) * d.pitch + (size_t)3 * d.src_w;
-        for (int j = warp; j < nsrc; j += kGenWarps) {
-            const uint8_t* g = d.src + (size_t)(rlo + j) * d.pitch;
+        const int lane = tid & 31;
+        for (int j = tid >> 5; j < q.nsrc; j += kGenThreads / 32) {   // one warp per source row
+            const uint8_t* g = d.src + (size_t)(q.rlo + j) * d.pitch;
             const int a = (int)(reinterpret_cast<uintptr_t>(g) & 3);
             const uint8_t* ga = g - a;                                // first aligned word of the row
             const int k = (int)((reinterpret_cast<uintptr_t>(ga) >> 2) & 3);
-            const int nwj = (a + 3 * d.src_w + 3) >> 2;              // aligned words holding the row
-            uint32_t* srow = stage + j * row_words;                  // 16-byte aligned (row_words % 4 == 0)
-            const bool last_row = (rlo + j == d.src_h - 1);          // only there a word can cross img_end
-            for (int c = lane; 4 * c < k + nwj; c += 32) {           // 16-byte chunk c = staging words 4c..4c+3
-                const int i0 = 4 * c - k;                            // row word of the chunk's first slot
-                const uint8_t* gp = ga + 4 * i0;
-                if (i0 >= 0 && i0 + 4 <= nwj && !(last_row && gp + 16 > img_end)) {
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(srow + 4 * c);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gp) : "memory");
-                } else {
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u;
-                        if (i < 0 || i >= nwj) continue;
-                        const uint8_t* wp = ga + 4 * i;
-                        if (!last_row || wp + 4 <= img_end) {
-                            const unsigned sa = (unsigned)__cvta_generic_to_shared(srow + 4 * c + u);
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(wp) : "memory");
-                        } else {                                     // the image's very last word: no over-read
-                            uint32_t v = 0;
-                            for (int q = 0; q < 4 && wp + q < img_end; ++q) v |= (uint32_t)__ldg(wp + q) << (8 * q);
-                            srow[4 * c + u] = v;
+            const int nwj = (a + 3 * d.src_w + 3) >> 2;               // aligned words holding the row
+            uint32_t* srow = reinterpret_cast<uint32_t*>(ring + q.off + j * q.stride);
+            const bool last_row = (q.rlo + j == d.src_h - 1);         // only there a word can cross img_end
+            const uint8_t* gk = ga - 4 * k;                           // global address of staging word 0 (16-byte aligned)
+            const int c_first = k ? 1 : 0;                            // chunks [c_first, c_full) are whole and inside the row
+            int c_full = (k + nwj) >> 2;
+            if (last_row && c_full > c_first && gk + 16 * c_full > img_end) --c_full;
+            const unsigned sa0 = (unsigned)__cvta_generic_to_shared(srow);
+            for (int c = c_first + lane; c < c_full; c += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa0 + 16u * c), "l"(gk + 16 * c) : "memory");
+            // the ragged ends: words [k, 4) of chunk 0, the words after the last whole chunk, three zero words (taps read past the row)
+            if (lane < 11) {
+                int w;                                                // staging word index
+                if (lane < 4) w = lane;                               // head chunk
+                else w = 4 * c_full + (lane - 4);                     // up to 7 tail words (one dropped chunk + a partial one)
+                const bool head_ok = lane < 4 && k && w >= k && w < k + nwj;
+                const bool tail_ok = lane >= 4 && w >= k && w < k + nwj && (c_full >= c_first);
+                if (head_ok || tail_ok) {
+                    const uint8_t* wp = gk + 4 * w;
+                    if (!last_row || wp + 4 <= img_end) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa0 + 4u * w), "l"(wp) : "memory");
+                    } else {                                          // the image's very last word: no over-read
+                        uint32_t v = 0;
+                        for (int r = 0; r < 4 && wp + r < img_end; ++r) v |= (uint32_t)__ldg(wp + r) << (8 * r);
+                        srow[w] = v;
+                    }
+                }
+            } else if (lane < 14) {
+                srow[k + nwj + (lane - 11)] = 0u;
+            }
+        }
+    };
+
+    // (explicit 32-bit shared addresses: through generic pointers the compiler rebuilds the shared window base,
+    // an S2R, inside the row loop)
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    auto pixel = [&](const int4 ye, int tb, uint32_t a01, int& va, int& vb, int& vc) {
+        const uint32_t t0 = ring_s + (uint32_t)(ye.x + tb), t1 = ring_s + (uint32_t)(ye.y + tb);   // byte addresses of the taps
+        uint32_t u0, u1, u2, w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                     : "=r"(u0), "=r"(u1), "=r"(u2) : "r"(t0 & ~3u));
+        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(t1 & ~3u));
+        uint32_t h0[3], h1[3];
+        taps_dp2a(u0, u1, u2, (int)(t0 << 3), a01, h0);               // the funnel shift takes the amount modulo 32
+        taps_dp2a(w0, w1, w2, (int)(t1 << 3), a01, h1);
+        // ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
+        va = (int)((__umulhi((uint32_t)ye.z, h0[0] >> 4) + __umulhi((uint32_t)ye.w, h1[0] >> 4) + 2u) >> 2);
+        vb = (int)((__umulhi((uint32_t)ye.z, h0[1] >> 4) + __umulhi((uint32_t)ye.w, h1[1] >> 4) + 2u) >> 2);
+        vc = (int)((__umulhi((uint32_t)ye.z, h0[2] >> 4) + __umulhi((uint32_t)ye.w, h1[2] >> 4) + 2u) >> 2);
+    };
+    const uint32_t sy_s = (uint32_t)__cvta_generic_to_shared(&s_y[0][0]);
+    auto row_entry = [&](int slot, int r) {
+        int4 e;
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                     : "r"(sy_s + 16u * (uint32_t)(slot * kGenRows + r)));
+        return e;
+    };
+
+    const bool vec4 = ((out_w & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst_all) & 15) == 0);
+    // column coefficients of the thread's first 4-column group, kept across the tiles of one image
+    int cb = -1, ctb[4] = {0, 0, 0, 0};
+    uint32_t ca01[4] = {0, 0, 0, 0};
+    bool cin[4] = {false, false, false, false};
+    auto compute = [&](const GenTile& q, int slot) {
+        T* dst = dst_all + (size_t)q.b * 3 * plane;
+        const int2* xt = xtab + (size_t)q.b * out_w;
+        if (q.off < 0) {
+            const VkLbDesc d = descs[q.b];
+            // ---- byte taps through L1 (source span larger than the ring)
+            const int4* yt = ytab + (size_t)q.b * out_h;
+            for (int x = tid; x < out_w; x += kGenThreads) {
+                const int sx = x - d.left;
+                const bool in_x = sx >= 0 && sx < d.new_w;
+                const int2 xc = in_x ? __ldg(xt + sx) : make_int2(0, 0);
+                const int x0 = xc.x, x1 = min(xc.x + 3, 3 * (d.src_w - 1)), w0 = xc.y & 0xffff, w1 = (int)((uint32_t)xc.y >> 16);
+                for (int y = q.y_begin; y < q.y_begin + q.nrows; ++y) {
+                    const int sy = y - d.top;
+                    int v0 = p0, v1 = p1, v2 = p2;
+                    if (in_x && sy >= 0 && sy < d.new_h) {
+                        const int4 yc = __ldg(yt + sy);
+                        const uint8_t* r0 = d.src + (size_t)yc.x * d.pitch;
+                        const uint8_t* r1 = d.src + (size_t)yc.y * d.pitch;
+                        int v[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = (int)__ldg(r0 + x0 + c) * w0 + (int)__ldg(r0 + x1 + c) * w1;
+                            const int h1 = (int)__ldg(r1 + x0 + c) * w0 + (int)__ldg(r1 + x1 + c) * w1;
+                            v[c] = ((((yc.z * (h0 >> 4)) >> 16) + ((yc.w * (h1 >> 4)) >> 16) + 2) >> 2);
                         }
+                        v0 = v[c0]; v1 = v[1]; v2 = v[c2];
+                    }
+                    const size_t off = (size_t)y * out_w + x;
+                    if constexpr (FMT == VK_LB_F32_NCHW) {
+                        st_stream_f32(dst + off, s_lut[v0]);
+                        st_stream_f32(dst + off + plane, s_lut[v1]);
+                        st_stream_f32(dst + off + 2 * plane, s_lut[v2]);
+                    } else if constexpr (FMT == VK_LB_BF16_NCHW) {
+                        dst[off] = __float2bfloat16_rn(s_lut[v0]);
+                        dst[off + plane] = __float2bfloat16_rn(s_lut[v1]);
+                        dst[off + 2 * plane] = __float2bfloat16_rn(s_lut[v2]);
+                    } else {
+                        dst[off * 3] = (uint8_t)v0; dst[off * 3 + 1] = (uint8_t)v1; dst[off * 3 + 2] = (uint8_t)v2;
                     }
                 }
             }
-            if (lane < 3) srow[k + nwj + lane] = 0u;                 // taps may read past the row's words
+            return;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (threadIdx.x < kGenRows) {
-            const int y = y_begin + threadIdx.x;
-            int4 e = make_int4(-1, -1, 0, 0);
-            if (y >= ys && y < ye_) {
-                const int4 yc = __ldg(yt + (y - d.top));
-                // byte position of a row's first pixel inside its staging row: 4*k + a = address mod 16
-                const int a0 = (int)(reinterpret_cast<uintptr_t>(d.src + (size_t)yc.x * d.pitch) & 15);
-                const int a1 = (int)(reinterpret_cast<uintptr_t>(d.src + (size_t)yc.y * d.pitch) & 15);
-                // byte offsets into the staging buffer, source alignment included
-                e = make_int4((yc.x - rlo) * row_words * 4 + a0, (yc.y - rlo) * row_words * 4 + a1,
-                              yc.z << 16, yc.w << 16);
-            }
-            s_y[threadIdx.x] = e;
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        // ---- 2./3. taps from shared memory.  A thread owns 4 adjacent canvas columns and walks the
-        // tile's rows: the three plane stores of a row are 128 bits each and their address
-        // arithmetic is shared by 4 pixels.  BGR<->RGB is a swap of plane pointers, not of values.
-        const int pa = swap_rb ? p2 : p0, pc = swap_rb ? p0 : p2;                    // pad value per pointer
-        const uint8_t* const stage_b = reinterpret_cast<const uint8_t*>(stage);
-        auto pixel = [&](const int4 ye, int tb, uint32_t a01, int& va, int& vb, int& vc) {
-            const int t0 = ye.x + tb, t1 = ye.y + tb;                 // byte offsets of the taps in `stage`
-            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(stage_b + (t0 & ~3));
-            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(stage_b + (t1 & ~3));
-            uint32_t h0[3], h1[3];
-            taps_dp2a(q0[0], q0[1], q0[2], (t0 & 3) * 8, a01, h0);
-            taps_dp2a(q1[0], q1[1], q1[2], (t1 & 3) * 8, a01, h1);
-            // ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
-            va = (int)((__umulhi((uint32_t)ye.z, h0[0] >> 4) + __umulhi((uint32_t)ye.w, h1[0] >> 4) + 2u) >> 2);
-            vb = (int)((__umulhi((uint32_t)ye.z, h0[1] >> 4) + __umulhi((uint32_t)ye.w, h1[1] >> 4) + 2u) >> 2);
-            vc = (int)((__umulhi((uint32_t)ye.z, h0[2] >> 4) + __umulhi((uint32_t)ye.w, h1[2] >> 4) + 2u) >> 2);
-        };
-        const bool vec4 = ((out_w & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst_all) & 15) == 0);
+        // ---- taps from the ring.  A thread owns 4 adjacent canvas columns and every other row of the tile:
+        // the three plane stores of a row are 128 bits (64 for bf16) and their address arithmetic is shared by
+        // 4 pixels; the column coefficients are loaded once per tile.  BGR<->RGB is a swap of plane pointers.
         if (vec4) {
             const size_t oa = (FMT == VK_LB_U8_NHWC) ? 0 : (size_t)c0 * plane;       // plane of source byte 0
             const size_t ob = (FMT == VK_LB_U8_NHWC) ? 0 : plane;
             const size_t oc = (FMT == VK_LB_U8_NHWC) ? 0 : (size_t)c2 * plane;
-            for (int x4 = threadIdx.x * 4; x4 < out_w; x4 += kGenThreads * 4) {
+            const int rsel = tid / kGenCols, xfirst = (tid - rsel * kGenCols) * 4;
+            auto load_cols = [&](int x4, int* tb, uint32_t* a01, bool* in_x) {
+                const int sx0 = x4 - q.left;
+                if (sx0 >= 0 && sx0 + 3 < q.new_w && ((sx0 & 1) == 0)) {               // two 16-byte loads
+                    const int4 u = __ldg(reinterpret_cast<const int4*>(xt + sx0)), v = __ldg(reinterpret_cast<const int4*>(xt + sx0 + 2));
+                    tb[0] = u.x; a01[0] = (uint32_t)u.y; tb[1] = u.z; a01[1] = (uint32_t)u.w;
+                    tb[2] = v.x; a01[2] = (uint32_t)v.y; tb[3] = v.z; a01[3] = (uint32_t)v.w;
+                    in_x[0] = in_x[1] = in_x[2] = in_x[3] = true;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sx = sx0 + j;
+                        in_x[j] = sx >= 0 && sx < q.new_w;
+                        const int2 xc = in_x[j] ? __ldg(xt + sx) : make_int2(0, 0);
+                        tb[j] = xc.x;
+                        a01[j] = (uint32_t)xc.y;
+                    }
+                }
+            };
+            if (q.b != cb) {
+                cb = q.b;
+                if (xfirst < out_w) load_cols(xfirst, ctb, ca01, cin);
+            }
+            for (int x4 = xfirst; x4 < out_w; x4 += kGenCols * 4) {
                 int tb[4];
                 uint32_t a01[4];
                 bool in_x[4];
+                if (x4 == xfirst) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sx = x4 + j - d.left;
-                    in_x[j] = sx >= 0 && sx < d.new_w;
-                    const int4 xc = in_x[j] ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
-                    tb[j] = xc.x;
-                    a01[j] = (uint32_t)xc.z | ((uint32_t)xc.w << 16);
+                    for (int j = 0; j < 4; ++j) { tb[j] = ctb[j]; a01[j] = ca01[j]; in_x[j] = cin[j]; }
+                } else {
+                    load_cols(x4, tb, a01, in_x);
                 }
-                uint32_t idx = (uint32_t)(y_begin * out_w + x4);
-                for (int r = 0; r < nrows; ++r, idx += out_w) {
-                    const int4 ye = s_y[r];
+                const bool all_in = in_x[0] && in_x[1] && in_x[2] && in_x[3];
+                uint32_t idx = (uint32_t)((q.y_begin + rsel) * out_w + x4);
+#pragma unroll kGenUnroll
+                for (int r = rsel; r < q.nrows; r += 2, idx += 2 * out_w) {
+                    const int4 ye = row_entry(slot, r);
                     int va[4], vb[4], vc[4];
+                    if (all_in && ye.x >= 0) {                         // interior: no per-pixel predicates
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        va[j] = pa; vb[j] = p1; vc[j] = pc;
-                        if (in_x[j] && ye.x >= 0) pixel(ye, tb[j], a01[j], va[j], vb[j], vc[j]);
+                        for (int j = 0; j < 4; ++j) pixel(ye, tb[j], a01[j], va[j], vb[j], vc[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            va[j] = pa; vb[j] = p1; vc[j] = pc;
+                            if (in_x[j] && ye.x >= 0) pixel(ye, tb[j], a01[j], va[j], vb[j], vc[j]);
+                        }
                     }
                     if constexpr (FMT == VK_LB_F32_NCHW) {
                         // value/255 by arithmetic here: the table would cost 12 more shared-memory
-                        // wavefronts per thread-row, and this loop is already shared-memory bound
+                        // wavefronts per thread-row
                         st_stream_f4(dst + oa + idx, make_float4(norm255((float)va[0]), norm255((float)va[1]), norm255((float)va[2]), norm255((float)va[3])));
                         st_stream_f4(dst + ob + idx, make_float4(norm255((float)vb[0]), norm255((float)vb[1]), norm255((float)vb[2]), norm255((float)vb[3])));
                         st_stream_f4(dst + oc + idx, make_float4(norm255((float)vc[0]), norm255((float)vc[1]), norm255((float)vc[2]), norm255((float)vc[3])));
                     } else if constexpr (FMT == VK_LB_BF16_NCHW) {
                         auto pack = [&](const int* v) {
-                            __nv_bfloat162 lo = __floats2bfloat162_rn(s_lut[v[0]], s_lut[v[1]]);
-                            __nv_bfloat162 hi = __floats2bfloat162_rn(s_lut[v[2]], s_lut[v[3]]);
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(norm255((float)v[0]), norm255((float)v[1]));
+                            __nv_bfloat162 hi = __floats2bfloat162_rn(norm255((float)v[2]), norm255((float)v[3]));
                             uint2 u;
                             u.x = *reinterpret_cast<uint32_t*>(&lo);
                             u.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -398,16 +509,15 @@ lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ x
             T* const plane_a = dst + (FMT == VK_LB_U8_NHWC ? c0 : (size_t)c0 * plane);   // receives source byte 0
             T* const plane_b = dst + (FMT == VK_LB_U8_NHWC ? 1 : plane);
             T* const plane_c = dst + (FMT == VK_LB_U8_NHWC ? c2 : (size_t)c2 * plane);   // receives source byte 2
-            for (int x = threadIdx.x; x < out_w; x += kGenThreads) {
-                const int sx = x - d.left;
-                const bool in_x = sx >= 0 && sx < d.new_w;
-                const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
-                const uint32_t a01 = (uint32_t)xc.z | ((uint32_t)xc.w << 16);
-                uint32_t idx = (uint32_t)(y_begin * out_w + x);
-                for (int r = 0; r < nrows; ++r, idx += out_w) {
-                    const int4 ye = s_y[r];
+            for (int x = tid; x < out_w; x += kGenThreads) {
+                const int sx = x - q.left;
+                const bool in_x = sx >= 0 && sx < q.new_w;
+                const int2 xc = in_x ? __ldg(xt + sx) : make_int2(0, 0);
+                uint32_t idx = (uint32_t)(q.y_begin * out_w + x);
+                for (int r = 0; r < q.nrows; ++r, idx += out_w) {
+                    const int4 ye = row_entry(slot, r);
                     int va = pa, vb = p1, vc = pc;
-                    if (in_x && ye.x >= 0) pixel(ye, xc.x, a01, va, vb, vc);
+                    if (in_x && ye.x >= 0) pixel(ye, xc.x, (uint32_t)xc.y, va, vb, vc);
                     if constexpr (FMT == VK_LB_F32_NCHW) {
                         st_stream_f32(plane_a + idx, s_lut[va]);
                         st_stream_f32(plane_b + idx, s_lut[vb]);
@@ -422,32 +532,61 @@ lb_general_kernel(const VkLbDesc* __restrict__ descs, const int4* __restrict__ x
                 }
             }
         }
-        return;
-    }
+    };
 
-    // ---- fallback: byte taps through L1 (source span larger than the staging buffer)
-    for (int x = threadIdx.x; x < out_w; x += kGenThreads) {
-        const int sx = x - d.left;
-        const bool in_x = sx >= 0 && sx < d.new_w;
-        const int4 xc = in_x ? __ldg(xt + sx) : make_int4(0, 0, 0, 0);
-        for (int y = y_begin; y < y_end; ++y) {
-            const int sy = y - d.top;
-            int v0 = p0, v1 = p1, v2 = p2;
-            if (in_x && sy >= 0 && sy < d.new_h) {
-                const int4 yc = __ldg(yt + sy);
-                const uint8_t* r0 = d.src + (size_t)yc.x * d.pitch;
-                const uint8_t* r1 = d.src + (size_t)yc.y * d.pitch;
-                int v[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int h0 = (int)__ldg(r0 + xc.x + c) * xc.z + (int)__ldg(r0 + xc.y + c) * xc.w;
-                    const int h1 = (int)__ldg(r1 + xc.x + c) * xc.z + (int)__ldg(r1 + xc.y + c) * xc.w;
-                    v[c] = ((((yc.z * (h0 >> 4)) >> 16) + ((yc.w * (h1 >> 4)) >> 16) + 2) >> 2);
-                }
-                v0 = v[c0]; v1 = v[1]; v2 = v[c2];
+    // ---- the pipeline.  Tile t = row group t / B of image t % B, block k takes t = k, k + grid, ...: every block
+    // sees all the batch's sizes.  h = next tile to issue, c = next tile to evaluate.  One barrier per tile: the
+    // bytes of tile c - 1 go back to the ring after the barrier that precedes the evaluation of tile c.
+    const int t_begin = blockIdx.x, t_end = total, t_step = gridDim.x;
+    const int step_g = t_step / batch, step_b = t_step - step_g * batch;
+    int hg = t_begin / batch, hb = t_begin - hg * batch;               // row group and image of tile h
+    int h = t_begin, c = t_begin, nq = 0, qh = 0, qc = 0;
+    int wr = 0, room = kGenRing, pend = 0;                             // ring write offset, free bytes, bytes to give back
+    int4 nti = make_int4(0, 0, 0, 0);                                  // table entry and descriptor of tile h
+    VkLbDesc nd = {};
+    auto look_ahead = [&]() {
+        if (h < t_end) { nti = __ldg(ttab + (size_t)hb * tiles_y + hg); nd = descs[hb]; }
+    };
+    auto issue_some = [&]() {
+        while (h < t_end && nq < kGenQ) {
+            GenTile q = describe(hb, hg, nti, nd);
+            if (q.bytes > kGenRing) {
+                q.off = -1;
+            } else {
+                int off = wr, acct = q.bytes;
+                if (wr + q.bytes > kGenRing) { acct += kGenRing - wr; off = 0; }    // skip the tail, start over
+                if (acct > room) break;                                // wait for older tiles to leave
+                q.off = off; q.acct = acct;
+                wr = off + q.bytes; room -= acct;
             }
-            emit((size_t)y * out_w + x, v0, v1, v2);
+            issue(q, nd, qh);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            qh = (qh + 1) % kGenQ; ++nq; h += t_step;
+            hg += step_g; hb += step_b;
+            if (hb >= batch) { hb -= batch; ++hg; }
+            look_ahead();
         }
+    };
+    look_ahead();
+    while (c < t_end) {
+        if (nq == 0) {                                                 // nothing in flight: the ring starts over
+            __syncthreads();
+            room += pend; pend = 0; wr = 0;
+            issue_some();
+        }
+        switch (nq - 1) {                                              // groups newer than the oldest tile may stay pending
+            case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+            case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+            case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+            default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        }
+        __syncthreads();                                               // tile c has landed, everyone is done with tile c - 1
+        room += pend; pend = 0;
+        issue_some();
+        const GenTile q = s_q[qc];
+        compute(q, qc);
+        pend = q.acct;
+        qc = (qc + 1) % kGenQ; --nq; c += t_step;
     }
 }
 
@@ -531,7 +670,8 @@ static size_t lb_desc_bytes(int batch) { return align_up((size_t)batch * sizeof(
 
 extern "C" size_t vk_letterbox_workspace_bytes(int batch, int out_h, int out_w) {
     if (batch <= 0 || out_h <= 0 || out_w <= 0) return 0;
-    return lb_desc_bytes(batch) + (size_t)batch * ((size_t)out_w + out_h) * sizeof(int4);
+    return lb_desc_bytes(batch) + align_up((size_t)batch * out_w * sizeof(int2), 16) + (size_t)batch * out_h * sizeof(int4) +
+           (size_t)batch * ceil_div(out_h, kGenRows) * sizeof(int4);
 }
 
 extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* descs_dev, int batch,
@@ -548,7 +688,6 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
     const int px = (dst_fmt == VK_LB_BF16_NCHW) ? 8 : 4;     // pixels per 128-bit plane store of the copy kernel
     bool all_copy = (dst_fmt != VK_LB_U8_NHWC) && (out_w % px == 0) &&
                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    int max_w = 1, max_rows = 3;
     for (int i = 0; i < batch; ++i) {
         const VkLbDesc& d = descs_host[i];
         if (!d.src || d.src_h <= 0 || d.src_w <= 0 || d.new_h <= 0 || d.new_w <= 0 ||
@@ -558,12 +697,6 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
         const bool rs = !(d.new_h == d.src_h && d.new_w == d.src_w);
         all_copy &= !rs && (d.left % px == 0) && (d.new_w % px == 0) &&
                     ((reinterpret_cast<uintptr_t>(d.src) & 3) == 0) && ((d.pitch & 3) == 0);
-        // source rows one tile touches: kGenRows * (src_h / new_h) + 3, staged up to kLbMaxSrcRows
-        const int rows = (int)(((long long)kGenRows * d.src_h + d.new_h - 1) / d.new_h) + 3;
-        if (rows <= kLbMaxSrcRows) {
-            if (rows > max_rows) max_rows = rows;
-            if (d.src_w > max_w) max_w = d.src_w;
-        }
     }
     cudaStream_t stream = as_stream(stream_);
     char* w = static_cast<char*>(ws);
@@ -574,8 +707,9 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
         if (e != cudaSuccess) return fail_code((int)e, "vk_letterbox_batch: descriptor upload: %s", cudaGetErrorString(e));
         dd = reinterpret_cast<const VkLbDesc*>(w);
     }
-    int4* xtab = reinterpret_cast<int4*>(w + lb_desc_bytes(batch));
-    int4* ytab = xtab + (size_t)batch * out_w;
+    int2* xtab = reinterpret_cast<int2*>(w + lb_desc_bytes(batch));                  // 16-byte aligned rows when out_w is even
+    int4* ytab = reinterpret_cast<int4*>(w + lb_desc_bytes(batch) + align_up((size_t)batch * out_w * sizeof(int2), 16));
+    int4* ttab = ytab + (size_t)batch * out_h;
     dim3 grid(ceil_div(out_h, kLbRows), batch);
     if (all_copy) {
         if (dst_fmt == VK_LB_F32_NCHW)
@@ -585,20 +719,18 @@ extern "C" int vk_letterbox_batch(const VkLbDesc* descs_host, const VkLbDesc* de
         count_launch();
         return check_launch("lb_copy_kernel");
     }
-    grid = dim3(ceil_div(out_h, kGenRows), batch);
-    lb_tables_kernel<<<batch, 256, 0, stream>>>(dd, xtab, ytab, out_h, out_w);
+    lb_tables_kernel<<<batch, 256, 0, stream>>>(dd, xtab, ytab, ttab, out_h, out_w, kGenRows);
     count_launch();
     if (int rc = check_launch("lb_tables_kernel")) return rc;
-    // staging buffer: rows x (words of the widest staged source + 2); kept under ~100 KB so that
-    // two blocks fit an SM -- wider sources take the L1 fallback inside the kernel
-    int row_words = ((((3 * max_w + 3) >> 2) + 10) + 3) & ~3;
-    if ((size_t)max_rows * row_words * 4 > 100 * 1024) row_words = ((100 * 1024 / 4) / max_rows) & ~3;
-    const size_t smem = (size_t)max_rows * row_words * 4;
+    const int tiles = ceil_div(out_h, kGenRows) * batch;
 #define VK_LB_LAUNCH(FMT, T)                                                                              \
     do {                                                                                                   \
-        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&lb_general_kernel<FMT>), smem, "vk_letterbox_batch")) return rc; \
-        lb_general_kernel<FMT><<<grid, kGenThreads, smem, stream>>>(dd, xtab, ytab, out_h, out_w, swap_rb, pad_rgb, \
-                                                                    static_cast<T*>(dst), row_words, max_rows); \
+        const void* fn = reinterpret_cast<const void*>(&lb_general_kernel<FMT>);                           \
+        if (int rc = ensure_dyn_smem(fn, kGenRing, "vk_letterbox_batch")) return rc;                       \
+        const int bps = blocks_per_sm(fn, kGenThreads, kGenRing);                                          \
+        const int nblk = tiles < bps * kNumSMs ? tiles : bps * kNumSMs;                                   \
+        lb_general_kernel<FMT><<<nblk, kGenThreads, kGenRing, stream>>>(dd, xtab, ytab, ttab, batch, out_h, out_w, swap_rb, pad_rgb, \
+                                                                       static_cast<T*>(dst));              \
     } while (0)
     switch (dst_fmt) {
         case VK_LB_F32_NCHW: VK_LB_LAUNCH(VK_LB_F32_NCHW, float); break;
