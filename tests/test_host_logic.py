@@ -67,7 +67,7 @@ def test_argument_validation_without_gpu(vk_lib):
     cfg.nl = 9
     with pytest.raises(_lib.VkError):
         ops.head_rows(cfg)
-    assert vk_lib.vk_letterbox_workspace_bytes(64, 640, 640) == 3072 + 64 * 1280 * 16
+    assert vk_lib.vk_letterbox_workspace_bytes(64, 640, 640) == 3072 + 64 * (640 * 8 + 640 * 16 + 80 * 16)   # descs, xtab, ytab, tile table
     # null pointers / out-of-range thresholds are rejected before any launch
     assert vk_lib.vk_nms_batched(None, 1, 0.5, 0, 30000, 300, 7680.0, None, None, None, None, None) == -1
     assert vk_lib.vk_filter_pred(None, 0, 1, 100, 80, 0.25, 0, None, 0, None, None) == -1
