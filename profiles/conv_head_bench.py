@@ -8,8 +8,7 @@ import torch
 from vision_kit_b200 import ops
 from tests import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-from vision_kit_b200 import _lib
-_lib.lib().vk_set_conv_kernel(int(os.environ.get("VK_CONV_MODE", "1")))   # 1 = persistent warp-specialised kernel (default), 0 = tile kernel
+PERSISTENT = os.environ.get("VK_CONV_MODE", "1") == "1"   # 1 = persistent warp-specialised kernel (default), 0 = tile kernel
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]
 res = {}
@@ -42,8 +41,8 @@ for name, cins in (("yolov5s", (128, 256, 512)), ("yolov5x", (320, 640, 1280))):
     in_bytes = sum(f.numel() * 4 for f in feats)
     flops = 2 * 255 * sum(f.numel() for f in feats)
     for mode, conf, ml in (("demo", 0.25, False), ("eval", 0.001, True)):
-        buf = ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
-        t_fused = timeit(lambda: ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml, buf=buf))
+        buf = ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml, persistent=PERSISTENT)
+        t_fused = timeit(lambda: ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml, buf=buf, persistent=PERSISTENT))
         row = {"fused_us": round(t_fused, 1), "candidates_per_img": int(buf.counts.sum()) // B,
                "in_MB": round(in_bytes / 1e6, 1), "GFLOP": round(flops / 1e9, 2),
                "fused_TFLOPs": round(flops / t_fused / 1e6, 1), "fused_in_GBps": round(in_bytes / t_fused / 1e3, 1)}

@@ -13,15 +13,16 @@
 //   whole prediction rows (one per anchor) and runs the dense filter's per-row logic straight
 //   from tcgen05.ld -- no shared-memory round trip of the logits.
 //
-//   Operands: both K-major, 128-byte swizzled (rows of 32 tf32 = 128 B, 8-row atoms of 1024 B).
-//   W[co][ci] is K-major as stored: 16-byte cp.async copies land directly in the swizzled tile.
-//   X is [ci][s] (s contiguous = MN-major; tcgen05 returned zeros for MN-major TF32 operands on
-//   this part -- profiles/micro/umma_tf32.cu -- so X is transposed on chip): 16-byte cp.async into
-//   a raw [k][128] staging tile, then thread s reads its column (conflict-free LDS.32) and writes
-//   row s of the A tile with 128-bit stores (the swizzle makes them conflict-free).
-//   Pipeline per 32-channel block: the copies of block k+1 (X and W) are in flight while block k is
-//   transposed and multiplied; the A tile is single-buffered behind the MMA-completion mbarrier.
-//   128 threads, 256 TMEM columns, 112 KB shared memory and no static allocation -> 2 CTAs per SM.
+//   Operands, both straight from global memory by 16-byte cp.async copies:
+//     W[co][ci] is K-major as stored: rows of 32 tf32 = 128 B, 8-row atoms of 1024 B, SWIZZLE_128B.
+//     X is [ci][s], s contiguous = MN-major for the A operand.  tcgen05 takes MN-major TF32 only in the
+//     SWIZZLE_128B_BASE32B layout (layout type 1; every other layout type yields zeros or an illegal instruction --
+//     profiles/micro/umma_probe.cu reads the mapping back from the tensor core): atoms of 4 k-rows x 32 positions
+//     (4 x 128 B), the 32-byte chunks of row k at position chunk ^ (k & 3); position blocks LBO apart, k-groups SBO
+//     apart.  A 16-byte copy of X[k][m..m+3] lands where the MMA expects it: no transposition on chip.
+//   Pipeline per 32-channel block: the copies of block k+1 (X and W) are in flight while block k is multiplied; both
+//   operand tiles are double-buffered behind the MMA-completion mbarrier.
+//   128 threads, 256 TMEM columns, 96 KB shared memory and no static allocation -> 2 CTAs per SM.
 //
 //   Candidates, boxes, segment table: exactly vk_decode_filter's format (same VkCandBuf), so
 //   vk_nms_batched consumes it unchanged.  Results equal conv-then-vk_decode_filter up to TF32
@@ -30,11 +31,11 @@
 namespace vk {
 
 constexpr int kChM = 128, kChN = 256, kChKB = 32, kChThreads = 128;
-constexpr int kChStageBytes = kChKB * kChM * 4;       // 16 KB raw X block [k][m]
-constexpr int kChABytes = kChM * 128;                 // 16 KB
+constexpr int kChABytes = kChM * 128;                 // 16 KB: [8 k-groups][4 position blocks][4 k x 128 B]
 constexpr int kChBBytes = kChN * 128;                 // 32 KB
 constexpr int kChTail = 64;                           // mbarrier, TMEM base, warp totals
-constexpr int kChSmem = 2 * kChStageBytes + kChABytes + 2 * kChBBytes + kChTail;   // 112 KB + 64 B, no static shared memory: 2 CTAs per SM
+constexpr int kChSmem = 2 * kChABytes + 2 * kChBBytes + kChTail;   // 96 KB + 64 B, no static shared memory: 2 CTAs per SM
+constexpr uint32_t kChALbo = 512, kChASbo = 2048;     // A tile: position blocks 512 B apart, k-groups (4 channels) 2048 B apart
 
 struct ConvHead {
     const float* x[VK_MAX_LEVELS];      // (B, cin, ny, nx)
@@ -58,6 +59,30 @@ __device__ __forceinline__ uint64_t ch_desc(uint32_t saddr) {
     d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
     d |= (uint64_t)2 << 61;              // SWIZZLE_128B
     return d;
+}
+// MN-major SW128_BASE32B tile of A: element (m, k) of a 32-channel block
+__device__ __forceinline__ uint32_t ch_aoff(int m, int k) {
+    return (uint32_t)((m >> 5) * kChALbo + (k >> 2) * kChASbo + (k & 3) * 128 + ((((m & 31) >> 2) ^ ((k & 3) << 1)) << 4) + (m & 3) * 4);
+}
+__device__ __forceinline__ uint64_t ch_desc_a(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(kChALbo >> 4) << 16;
+    d |= (uint64_t)(kChASbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+    d |= (uint64_t)1 << 61;              // SWIZZLE_128B_BASE32B
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, A MN-major, B K-major, N = 256, M = 128
+constexpr uint32_t kChIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
+// A tile of the bias step (K = 8): A[m][0] = A[m][1] = 1, everything else 0 (rows of equal values: the swizzle does not move them)
+__device__ __forceinline__ void ch_bias_a(uint8_t* a_tile, int t128) {
+#pragma unroll
+    for (int e = t128; e < 256; e += 128) {                // 2 k-groups x 4 position blocks x 4 rows x 8 float4
+        const int g = e >> 7, k = (e >> 3) & 3;
+        const float v = (g == 0 && k < 2) ? 1.0f : 0.0f;
+        *reinterpret_cast<float4*>(a_tile + g * kChASbo + ((e >> 5) & 3) * kChALbo + (e & 31) * 16) = make_float4(v, v, v, v);
+    }
 }
 __device__ __forceinline__ void ch_cp16(uint32_t dst, const void* src, bool valid) {
     const int n = valid ? 16 : 0;        // src-size 0: the 16 bytes are zero-filled
@@ -211,11 +236,10 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
 __global__ void __launch_bounds__(kChThreads, 2)
 conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int* __restrict__ fault) {
     // no static shared memory: the dynamic window then starts 1024-byte aligned (the swizzled tiles need it)
-    // and 2 x (112 KB + 64 B + 1 KB reserved) fits one SM
+    // and 2 x (96 KB + 64 B + 1 KB reserved) fits one SM
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sStage = smem;                                  // 2 x 16 KB
-    uint8_t* sA = smem + 2 * kChStageBytes;                  // 16 KB
-    uint8_t* sB = sA + kChABytes;                            // 2 x 32 KB
+    uint8_t* sA = smem;                                      // 2 x 16 KB
+    uint8_t* sB = sA + 2 * kChABytes;                        // 2 x 32 KB
     uint64_t& s_bar = *reinterpret_cast<uint64_t*>(sB + 2 * kChBBytes);
     uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(sB + 2 * kChBBytes + 8);
     int* s_wtot = reinterpret_cast<int*>(sB + 2 * kChBBytes + 16);
@@ -246,15 +270,15 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     const int xk0 = tid >> 5, xm4 = (tid & 31) << 2;                       // X: channel xk0 + 4 i, positions xm4..+3
     const bool xvalid = xm4 < nvalid;
     const float* const xsrc0 = X + (size_t)xk0 * nynx + (xvalid ? xm4 : 0);
-    const uint32_t xdst0 = (uint32_t)(xk0 * kChM + xm4) * 4;
+    const uint32_t xdst0 = ch_aoff(xm4, xk0);                              // + i * kChASbo: channel xk0 + 4 i is row xk0 of k-group i
     const int wn0 = tid >> 3, wc = tid & 7;                                // W: row wn0 + 16 i, chunk wc
     const uint32_t wdst0 = ch_koff(wn0, wc);                               // (n & 7) does not change with i: + i * 2048
     auto issue_x = [&](int kb) {
-        // X block: 32 channels x 32 chunks of 4 positions (raw [k][128]); positions past the plane are zeros
-        const uint32_t st = ch_smem(sStage + (kb & 1) * kChStageBytes) + xdst0;
+        // X block: 32 channels x 32 chunks of 4 positions, straight into the MN-major tile; positions past the plane are zeros
+        const uint32_t sa = ch_smem(sA + (kb & 1) * kChABytes) + xdst0;
         const float* src = xsrc0 + (size_t)kb * kChKB * nynx;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ch_cp16(st + i * (4 * kChM * 4), src + (size_t)(4 * i) * nynx, xvalid);
+        for (int i = 0; i < 8; ++i) ch_cp16(sa + i * kChASbo, src + (size_t)(4 * i) * nynx, xvalid);
     };
     auto issue_w = [&](int kb) {
         // W block: 256 rows x 8 chunks of 4 channels, straight into the swizzled K-major tile
@@ -273,13 +297,10 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
-    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
     bool ok = true;
     // one copy group per block (X then W): at block kb everything but the newest group must have landed
     for (int kb = 0; kb < nkb; ++kb) {
-        // the MMAs of block kb-1 read the A tile (single-buffered) and the W buffer that block kb+1 reuses;
-        // the staging buffer of block kb+1 was drained by the transposition of block kb-1
+        // the MMAs of block kb-1 read the operand buffers that block kb+1 reuses
         if (kb > 0) ok &= ch_wait(ch_smem(&s_bar), (uint32_t)((kb - 1) & 1));
         if (kb + 1 < nkb) {
             issue_x(kb + 1);
@@ -288,43 +309,33 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        __syncthreads();                                      // block kb landed (staging + W tile)
-        {   // transpose: thread = spatial position; 8 chunks of 4 channels -> row `tid` of the A tile
-            const float* st = reinterpret_cast<const float*>(sStage + (kb & 1) * kChStageBytes) + tid;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
-                *reinterpret_cast<float4*>(sA + ch_koff(tid, c)) = v;
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes (cp.async W, stores A) -> async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (cp.async) -> async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        __syncthreads();                                      // block kb landed for everyone
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = ch_smem(sA), b0 = ch_smem(sB + (kb & 1) * kChBBytes);
+            const uint32_t a0 = ch_smem(sA + (kb & 1) * kChABytes), b0 = ch_smem(sB + (kb & 1) * kChBBytes);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte row
+            for (int ks = 0; ks < 4; ++ks) {                  // UMMA_K = 8 tf32: two k-groups of A, 32 bytes inside W's 128-byte rows
                 const uint32_t acc = (kb | ks) ? 1u : 0u;
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             :: "r"(tmem), "l"(ch_desc(a0 + ks * 32)), "l"(ch_desc(b0 + ks * 32)), "r"(idesc), "r"(acc) : "memory");
+                             :: "r"(tmem), "l"(ch_desc_a(a0 + ks * 2 * kChASbo)), "l"(ch_desc(b0 + ks * 32)), "r"(kChIdesc), "r"(acc) : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
         }
     }
     // The bias rides on the tensor cores as one more K = 8 step: A gets the columns [1, 1, 0, ...], W the
     // columns [hi, lo, 0, ...] with bias = hi + lo split into two TF32 values (fp32-accurate sum), built in
-    // the staging / W buffers that block nkb would use (both free: their last readers have completed).
+    // the operand buffers that block nkb would use (both free: their last readers have completed).
     int last_phase = (nkb - 1) & 1;
     if (bias != nullptr) {
         // a parity wait only distinguishes adjacent phases: pass the last block's phase before the
         // bias step can complete the next one
         ok &= ch_wait(ch_smem(&s_bar), (uint32_t)last_phase);
-        uint8_t* ea = sStage + (nkb & 1) * kChStageBytes;
+        uint8_t* ea = sA + (nkb & 1) * kChABytes;
         uint8_t* eb = sB + (nkb & 1) * kChBBytes;
-        *reinterpret_cast<float4*>(ea + ch_koff(tid, 0)) = make_float4(1.f, 1.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(ea + ch_koff(tid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        ch_bias_a(ea, tid);
         for (int n = tid; n < kChN; n += kChThreads) {
             const float v = n < cout ? __ldg(bias + n) : 0.0f;
             const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -338,7 +349,7 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                         :: "r"(tmem), "l"(ch_desc(ch_smem(ea))), "l"(ch_desc(ch_smem(eb))), "r"(idesc), "r"(1u) : "memory");
+                         :: "r"(tmem), "l"(ch_desc_a(ch_smem(ea))), "l"(ch_desc(ch_smem(eb))), "r"(kChIdesc), "r"(1u) : "memory");
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(ch_smem(&s_bar)) : "memory");
         }
         last_phase = nkb & 1;
@@ -367,10 +378,9 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 // n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
 // ---------------------------------------------------------------------------------------
 constexpr int kWsThreads = 17 * 32;
-constexpr int kWsStage = 4, kWsASlots = 2, kWsBSlots = 4;            // staging / A tile / W tile ring depths
-constexpr int kWsOffA = kWsStage * kChStageBytes;                    // 64 KB
-constexpr int kWsOffB = kWsOffA + kWsASlots * kChABytes;             // 96 KB
-constexpr int kWsOffBar = kWsOffB + kWsBSlots * kChBBytes;           // 224 KB
+constexpr int kWsASlots = 4, kWsBSlots = 4;                          // A tile / W tile ring depths
+constexpr int kWsOffB = kWsASlots * kChABytes;                       // 64 KB
+constexpr int kWsOffBar = kWsOffB + kWsBSlots * kChBBytes;           // 192 KB
 constexpr int kWsSmem = kWsOffBar + 256;
 
 struct WsTile {
@@ -419,8 +429,7 @@ __device__ __forceinline__ bool ws_wait(uint32_t bar, uint32_t parity, volatile 
 __global__ void __launch_bounds__(kWsThreads, 1)
 conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int total_tiles, int* __restrict__ fault) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sStage = smem;
-    uint8_t* sA = smem + kWsOffA;
+    uint8_t* sA = smem;
     uint8_t* sB = smem + kWsOffB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[4] done[4] tfull[2] tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 112);
@@ -451,7 +460,6 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(kChM >> 4) << 24);
 
     if (warp >= 8 && warp < 16) {
         // ------------------------------------------------------------------ producers: two teams of 4 warps,
@@ -474,9 +482,9 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 const int nynx = H.nynx[it.q.l], cin = C.cin[it.q.l];
                 const bool xvalid = xm4 < it.q.nvalid;
                 const float* xsrc = C.x[it.q.l] + (size_t)it.q.b * cin * nynx + it.q.s0 + (size_t)(it.kb * kChKB + xk0) * nynx + (xvalid ? xm4 : 0);
-                const uint32_t st = ch_smem(sStage + (j % kWsStage) * kChStageBytes) + (uint32_t)(xk0 * kChM + xm4) * 4;
+                const uint32_t sa = ch_smem(sA + (j % kWsASlots) * kChABytes) + ch_aoff(xm4, xk0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ch_cp16(st + i * (4 * kChM * 4), xsrc + (size_t)(4 * i) * nynx, xvalid);
+                for (int i = 0; i < 8; ++i) ch_cp16(sa + i * kChASbo, xsrc + (size_t)(4 * i) * nynx, xvalid);
                 const float* wsrc = C.w[it.q.l] + it.kb * kChKB + 4 * wc;
                 const uint32_t sb = ch_smem(sB + (j % kWsBSlots) * kChBBytes) + wdst0;
 #pragma unroll
@@ -495,21 +503,12 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
             // are two blocks behind the newest, so this wait rarely stalls
             if (j >= 2) ok &= ws_wait<false>(DONE((j - 2) % kWsBSlots), (uint32_t)(((j - 2) / kWsBSlots) & 1), s_abort);
             issue_block(j + 2);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");    // block j landed for the whole team
-            uint8_t* a_tile = sA + (j % kWsASlots) * kChABytes;
-            if (pr.kb < pr.q.nkb) {
-                const float* st = reinterpret_cast<const float*>(sStage + (j % kWsStage) * kChStageBytes) + ptid;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v = make_float4(st[(4 * c + 0) * kChM], st[(4 * c + 1) * kChM], st[(4 * c + 2) * kChM], st[(4 * c + 3) * kChM]);
-                    *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, c)) = v;
-                }
-            } else {                                   // bias block: A = [1, 1, 0...], W = [hi, lo, 0...]
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this thread's copies of block j landed
+            if (pr.kb >= pr.q.nkb) {                   // bias block: A = [1, 1, 0...], W = [hi, lo, 0...]
+                uint8_t* a_tile = sA + (j % kWsASlots) * kChABytes;
                 uint8_t* b_tile = sB + (j % kWsBSlots) * kChBBytes;
                 const float* bias = C.bias[pr.q.l];
-                *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, 0)) = make_float4(1.f, 1.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(a_tile + ch_koff(ptid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                ch_bias_a(a_tile, ptid);
                 for (int n = ptid; n < kChN; n += 128) {
                     const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
                     const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -545,7 +544,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                         const uint32_t acc = (kb | ks) ? 1u : 0u;
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                     :: "r"(acc_addr), "l"(ch_desc(a0 + ks * 32)), "l"(ch_desc(b0 + ks * 32)), "r"(idesc), "r"(acc) : "memory");
+                                     :: "r"(acc_addr), "l"(ch_desc_a(a0 + ks * 2 * kChASbo)), "l"(ch_desc(b0 + ks * 32)), "r"(kChIdesc), "r"(acc) : "memory");
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(DONE(s)) : "memory");
                 }

@@ -643,235 +643,6 @@ filter_pred_rows_kernel(const T* __restrict__ pred, int no, const FilterArgs A, 
 }
 
 // ---------------------------------------------------------------------------------------
-// Dense variant of the fused filter (eval thresholds: most rows survive, every tile is read
-// whole).  Same persistent two-deep pipeline and tile layout as detect_decode_kernel: 16-byte
-// async copies keep a full tile of reads in flight per block while the previous tile is
-// evaluated.  Thread = (class part qd = tid / 64, row = tid % 64): lanes run over rows
-// (conflict-free scalar reads of the chunk-swizzled tile), every thread walks its own CPP
-// consecutive classes and keeps the products in registers, so there is no second pass over
-// shared memory.  One scan over the 256 (row, part) counts in canonical order gives every
-// thread its first slot inside the range the tile owns.
-// ML = multi_label, T = element type of the conv outputs.  Results are bit-identical to
-// decode_filter_rows_kernel (same sigmoid, same product, same order).
-// ---------------------------------------------------------------------------------------
-constexpr int kParts = kDecThreads / kTileS;   // 4 class parts per row
-
-// How a staged tile [no][kTileS] of element type T is laid out, filled and read.
-//   float       chunk-swizzled (the layout detect_decode_kernel needs for its transposed reads)
-//   half types  plain [c][64]: lanes over rows read 64 contiguous bytes, 16-byte copies of 8 rows
-template <class T>
-struct DenseTile {
-    static __device__ __forceinline__ int offset(int c, int s) { return c * kTileS + s; }        // in elements
-    static __device__ __forceinline__ void prefetch(const DecTile& d, void* tile, int no) {
-        const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
-        const T* const tsrc = static_cast<const T*>(d.src);
-        if (d.vec) {
-            const int q = threadIdx.x & 7, c0 = threadIdx.x >> 3;      // 8 chunks of 8 rows per channel, 32 channels per pass
-            if (8 * q < d.nvalid)
-                for (int c = c0; c < no; c += kDecThreads / 8)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                 :: "r"(base + 2u * (uint32_t)(c * kTileS + 8 * q)), "l"(tsrc + (size_t)c * d.nynx + 8 * q) : "memory");
-        } else {                                                       // unaligned planes: plain 2-byte loads
-            T* const t = static_cast<T*>(tile);
-            for (int e = threadIdx.x; e < no * kTileS; e += kDecThreads) {
-                const int c = e >> 6, r = e & 63;
-                if (r < d.nvalid) t[e] = tsrc[(size_t)c * d.nynx + r];
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    static __device__ __forceinline__ float elem(const void* tile, int c, int s) {
-        return to_f32(static_cast<const T*>(tile)[c * kTileS + s]);
-    }
-};
-template <>
-struct DenseTile<float> {
-    static __device__ __forceinline__ void prefetch(const DecTile& d, void* tile, int no) {
-        decode_prefetch(d, static_cast<float*>(tile), no);
-    }
-    static __device__ __forceinline__ float elem(const void* tile, int c, int s) {
-        return static_cast<const float*>(tile)[swz(c, s)];
-    }
-};
-
-// p[I] = sigmoid(logit of the thread's I-th class) * obj, the logit read with an immediate offset
-// (compile-time recursion: the offset must be a constant).  float tiles: the 16-byte chunk of
-// channel ch0 + I sits at position (row/4 ^ channel) & 7, which repeats with period 8 in I -- eight
-// base addresses; half tiles: one base address, channels 128 bytes apart.
-template <class T, int I, int N>
-struct ClassProducts {
-    static __device__ __forceinline__ void run(float* p, const uint32_t* tq, float obj) {
-        unsigned short h;
-        asm("ld.shared.u16 %0, [%1+%2];" : "=h"(h) : "r"(tq[0]), "n"(I * kTileS * 2));
-        float x;
-        x = to_f32(*reinterpret_cast<const T*>(&h));
-        p[I] = __fmul_rn(sigmoidf_vk(x), obj);                                                    // image_proc.py:135
-        ClassProducts<T, I + 1, N>::run(p, tq, obj);
-    }
-};
-template <int I, int N>
-struct ClassProducts<float, I, N> {
-    static __device__ __forceinline__ void run(float* p, const uint32_t* tq, float obj) {
-        float x;
-        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(tq[I & 7]), "n"(I * kTileS * 4));
-        p[I] = __fmul_rn(sigmoidf_vk(x), obj);                                                    // image_proc.py:135
-        ClassProducts<float, I + 1, N>::run(p, tq, obj);
-    }
-};
-template <class T, int N>
-struct ClassProducts<T, N, N> {
-    static __device__ __forceinline__ void run(float*, const uint32_t*, float) {}
-};
-template <int N>
-struct ClassProducts<float, N, N> {
-    static __device__ __forceinline__ void run(float*, const uint32_t*, float) {}
-};
-
-template <class T, int CPP, bool ML>
-__global__ void __launch_bounds__(kDecThreads, VK_DENSE_BPS)
-decode_filter_dense_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
-    extern __shared__ __align__(16) unsigned char tiles_sm[];  // 2 x [no][kTileS] logits of type T (DenseTile<T> layout)
-    __shared__ DecTile s_dt[3];
-    __shared__ TilePos s_pos[3];
-    __shared__ int s_cnt[kDecThreads];      // counts, slot = row * kParts + part (canonical order)
-    __shared__ int s_off[kDecThreads + 1];  // exclusive offsets inside each warp's 32 slots
-    __shared__ int s_wsum[kWarps];
-    __shared__ float s_bv[kDecThreads];     // best-class partials
-    __shared__ int s_bj[kDecThreads];
-    const int no = H.no, nc = A.nc;
-    const int tile_bytes = kTileS * no * (int)sizeof(T);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int row = threadIdx.x & (kTileS - 1), qd = threadIdx.x >> 6;
-    const int cpp = (nc + kParts - 1) / kParts;            // <= CPP
-    const int c_lo = min(nc, qd * cpp), c_hi = min(nc, c_lo + cpp);
-    const int slot = row * kParts + qd;
-    // classes this thread may emit (class filter, :151): bit i <-> class c_lo + i
-    uint32_t allowed = 0;
-    for (int i = 0; i < c_hi - c_lo; ++i)
-        if (class_allowed(A.class_mask, c_lo + i)) allowed |= 1u << i;
-    int t = blockIdx.x;
-    if (t >= total_tiles) return;
-    __shared__ DecCursor cur;                       // thread 0 only (shared: keeps it out of everyone's registers)
-    if (threadIdx.x == 0) {
-        cur = cursor_begin(H, t, gridDim.x);
-        decode_tile_at<T>(H, nullptr, cur, &s_dt[0], &s_pos[0]);
-        cursor_next(H, cur);
-        if (cur.t < total_tiles) decode_tile_at<T>(H, nullptr, cur, &s_dt[1], &s_pos[1]);
-        cursor_next(H, cur);
-    }
-    __syncthreads();
-    DenseTile<T>::prefetch(s_dt[0], tiles_sm, no);
-    for (int k = 0; t < total_tiles; ++k, t += gridDim.x) {
-        const unsigned char* tile = tiles_sm + (k & 1) * tile_bytes;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                      // tile k landed; everyone is done with the other buffer and the scratch arrays
-        const int slot3 = k % 3;
-        if (t + (int)gridDim.x < total_tiles)
-            DenseTile<T>::prefetch(s_dt[slot3 == 2 ? 0 : slot3 + 1], tiles_sm + ((k + 1) & 1) * tile_bytes, no);
-        if (threadIdx.x == 0) {
-            if (cur.t < total_tiles) decode_tile_at<T>(H, nullptr, cur, &s_dt[slot3 == 0 ? 2 : slot3 - 1], &s_pos[slot3 == 0 ? 2 : slot3 - 1]);
-            cursor_next(H, cur);
-        }
-        const DecTile& d = s_dt[slot3];
-        const TilePos& tp = s_pos[slot3];
-
-        // ---- products of this thread's classes (registers), flags as a bit mask.
-        const float o = sigmoidf_vk(DenseTile<T>::elem(tile, 4, row));
-        const float obj = (row < d.nvalid && o > A.conf) ? o : 0.0f;  // image_proc.py:99 (dead rows: products 0)
-        const int ch0 = 5 + c_lo;
-        uint32_t tq[8];
-        if (sizeof(T) == 4) {
-            // element i of the thread is channel ch0 + i of its row; its 16-byte chunk sits at position
-            // (row/4 ^ channel) & 7, which repeats with period 8 in i: eight base pointers, immediate offsets
-            const float* trow = reinterpret_cast<const float*>(tile) + ((row & 32) | (row & 3));
-            const int rq = row >> 2;
-            const uint32_t trow_s = (uint32_t)__cvta_generic_to_shared(trow + ch0 * kTileS);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tq[j] = trow_s + ((((uint32_t)(rq ^ (ch0 + j))) & 7u) << 4);
-        } else {
-            tq[0] = (uint32_t)__cvta_generic_to_shared(tile) + 2u * (uint32_t)(ch0 * kTileS + row);
-        }
-        float p[CPP];
-        ClassProducts<T, 0, CPP>::run(p, tq, obj);   // reads past the thread's last class stay inside the (padded) buffer
-        uint32_t flags = 0;
-        float bv = -INFINITY;
-        int bj = 0x7fffffff;
-        if (ML) {
-#pragma unroll
-            for (int i = 0; i < CPP; ++i)
-                if (p[i] > A.conf) flags |= 1u << i;                                              // :141
-        } else {
-            const int ncls = c_hi - c_lo;
-#pragma unroll
-            for (int i = 0; i < CPP; ++i)
-                if (i < ncls && p[i] > bv) { bv = p[i]; bj = c_lo + i; }                          // first max (:145)
-        }
-        int count;
-        if (ML) {
-            flags &= allowed;
-            count = __popc(flags);
-        } else {
-            s_bv[slot] = bv; s_bj[slot] = bj;
-            __syncthreads();
-            count = 0;
-            if (qd == 0) {                                          // first max across the parts
-#pragma unroll
-                for (int q2 = 1; q2 < kParts; ++q2)
-                    if (s_bv[slot + q2] > bv) { bv = s_bv[slot + q2]; bj = s_bj[slot + q2]; }
-                count = (bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;   // :147,151
-            }
-        }
-        s_cnt[slot] = count;
-        __syncthreads();
-        {   // scan in slot order: thread tid owns slot tid
-            const int v = s_cnt[threadIdx.x];
-            const int inc = warp_incl_scan(v, lane);
-            s_off[threadIdx.x] = inc - v;
-            if (lane == 31) s_wsum[w] = inc;
-        }
-        __syncthreads();
-        int wbase = 0, total = 0;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) {
-            const int x = s_wsum[i];
-            if (i < (slot >> 5)) wbase += x;
-            total += x;
-        }
-        const int tile_base = tp.seg * A.tile_cap;
-        if (count) {
-            uint2* const wp = reinterpret_cast<uint2*>(A.cand + (size_t)tp.b * A.cap) + tile_base + wbase + s_off[slot];
-            const uint32_t idx0 = (uint32_t)((tp.row0 + row) * nc + c_lo);
-            if (ML) {
-                uint32_t pos = 0;
-#pragma unroll
-                for (int i = 0; i < CPP; ++i) {
-                    const bool f = (flags & (1u << i)) != 0;
-                    if (f) wp[pos] = make_uint2(__float_as_uint(p[i]), idx0 + (uint32_t)i);
-                    pos += f;
-                }
-            } else {
-                *wp = make_uint2(__float_as_uint(bv), (uint32_t)((tp.row0 + row) * nc + bj));
-            }
-        }
-        // ---- box of the row if any of its parts produced a candidate
-        if (qd == 0) {
-            const int n = s_cnt[slot] + s_cnt[slot + 1] + s_cnt[slot + 2] + s_cnt[slot + 3];
-            if (n > 0) {
-                const PlaneGeom geom{H.variant, d.nx, tp.s0, d.stride, d.aw, d.ah};
-                A.boxes[(size_t)tp.b * A.rows + tp.row0 + row] =
-                    geom.box(DenseTile<T>::elem(tile, 0, row), DenseTile<T>::elem(tile, 1, row), DenseTile<T>::elem(tile, 2, row),
-                             DenseTile<T>::elem(tile, 3, row), tp.s0 + row);
-            }
-        }
-        if (threadIdx.x == 0) {
-            A.seg_count[(size_t)tp.b * A.segs + tp.seg] = total;
-            if (tp.seg == 0) A.flags[tp.b] = cand_flags(A);
-            if (total) atomicAdd(A.counts + tp.b, total);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
 // Dense fused filter without shared memory or barriers ("lanes = rows"), the default at eval thresholds.
 // NCHW conv outputs are already laid out the way a warp wants to read them: the 64 rows of a tile are contiguous
 // inside every channel plane, so lane j reading rows j and j + 32 of one channel is two coalesced 128-byte
@@ -1030,6 +801,8 @@ decode_filter_lanes_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
 // 64*no floats, copied as it is ([row][no], odd pitch: lanes over rows are conflict-free); the
 // values are probabilities already, boxes are cxcywh.
 // ---------------------------------------------------------------------------------------
+constexpr int kParts = kDecThreads / kTileS;   // 4 class parts per row
+
 template <class T, int I, int N>
 struct PredProducts {
     static __device__ __forceinline__ void run(float* p, uint32_t base, float obj) {
@@ -1268,21 +1041,6 @@ static bool pick_dense(int kernel, float conf_thres) {
     return kernel == VK_FILTER_DENSE || (kernel == VK_FILTER_AUTO && conf_thres < 0.05f);
 }
 
-template <class T, int CPP, bool ML>
-static int launch_decode_filter_dense(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
-    // + one part's worth of rows: the unrolled class loop may read past channel no-1
-    const size_t dsmem = (2 * (size_t)kTileS * H.no + (size_t)kTileS * CPP) * sizeof(T);
-    if (dsmem > 200 * 1024) return fail_code(VK_E_LIMIT, "vk_decode_filter: nc=%d needs %zu B of shared memory", H.nc, dsmem);
-    const void* fn = reinterpret_cast<const void*>(&decode_filter_dense_kernel<T, CPP, ML>);
-    if (int rc = ensure_dyn_smem(fn, dsmem, "vk_decode_filter")) return rc;
-    int per_sm = blocks_per_sm(fn, kDecThreads, dsmem);
-    if (per_sm > VK_DENSE_BPS) per_sm = VK_DENSE_BPS;
-    const int grid = total_tiles < per_sm * kNumSMs ? total_tiles : per_sm * kNumSMs;
-    decode_filter_dense_kernel<T, CPP, ML><<<grid, kDecThreads, dsmem, stream>>>(H, A, total_tiles);
-    count_launch();
-    return check_launch("decode_filter_dense_kernel");
-}
-
 template <class T, bool ML>
 static int launch_decode_filter_lanes(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
     decode_filter_lanes_kernel<T, ML><<<ceil_div(total_tiles, kLaneWarps), 32 * kLaneWarps, 0, stream>>>(H, A, total_tiles);
@@ -1324,27 +1082,12 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels,
     const FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
     const int total_tiles = H.tiles * batch;
     const bool ml = A.multi_label != 0;
-#ifndef VK_DENSE_SMEM
     if (pick_dense(kernel, conf_thres)) {
 #define VK_DL_T(T)                                                                                  \
         return ml ? launch_decode_filter_lanes<T, true>(H, A, total_tiles, stream)                   \
                   : launch_decode_filter_lanes<T, false>(H, A, total_tiles, stream)
         VK_BY_DTYPE(dtype, VK_DL_T);
 #undef VK_DL_T
-    }
-#endif
-    if (pick_dense(kernel, conf_thres) && H.nc <= 128) {
-#define VK_DF_T(T)                                                                                                   \
-        do {                                                                                                          \
-            if (H.nc <= 32) return ml ? launch_decode_filter_dense<T, 8, true>(H, A, total_tiles, stream)            \
-                                      : launch_decode_filter_dense<T, 8, false>(H, A, total_tiles, stream);          \
-            if (H.nc <= 80) return ml ? launch_decode_filter_dense<T, 20, true>(H, A, total_tiles, stream)           \
-                                      : launch_decode_filter_dense<T, 20, false>(H, A, total_tiles, stream);         \
-            return ml ? launch_decode_filter_dense<T, 32, true>(H, A, total_tiles, stream)                           \
-                      : launch_decode_filter_dense<T, 32, false>(H, A, total_tiles, stream);                         \
-        } while (0)
-        VK_BY_DTYPE(dtype, VK_DF_T);
-#undef VK_DF_T
     }
 #define VK_DR_NK(T, NK) return ml ? launch_decode_filter_rows<T, NK, true>(H, A, total_tiles, stream) \
                                   : launch_decode_filter_rows<T, NK, false>(H, A, total_tiles, stream)
