@@ -865,7 +865,7 @@ def test_conv_head_matches_conv_then_filter(variant, conf, ml, cins, B, vk, cuda
         torch.backends.cudnn.allow_tf32 = old
     ref = vk.ops.decode_filter(cfg, logits, conf, ml)
     got = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml)
-    # the one-tile-per-CTA variant must produce the very same bits as the (default) persistent kernel
+    # the one-tile-per-CTA variant must produce the very same bits as the (default) persistent CTA-pair kernel
     got2 = vk.ops.conv_decode_filter(cfg, feats, ws, bs, conf, ml, persistent=False)
     torch.cuda.synchronize()
     assert int(got.fault.item()) == 0 and int(got2.fault.item()) == 0

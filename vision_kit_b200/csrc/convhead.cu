@@ -44,6 +44,8 @@ struct ConvHead {
     int cin[VK_MAX_LEVELS];
     int mtile_start[VK_MAX_LEVELS + 1]; // first 128-row tile of each level inside an image
     int mtiles;                         // per image
+    int ptile_start[VK_MAX_LEVELS + 1]; // the same in 256-position pair tiles (persistent kernel)
+    int ptiles;
 };
 
 __device__ __forceinline__ uint32_t ch_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +108,18 @@ __device__ __forceinline__ bool ch_wait(uint32_t bar, uint32_t parity) {
                  : "r"(taddr));                                                                                    \
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
+// 32 / 64 consecutive columns of the calling warp's 32 lanes (no wait: the caller waits once for all its loads)
+__device__ __forceinline__ void ch_tmem_ld32(uint32_t* r, uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ch_tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Epilogue of one 128-position tile whose accumulator sits in 256 TMEM columns at `trow` (lane
 // offset of the calling warp included): thread `tid` (0..127) = spatial position s0 + tid = TMEM
 // lane, one prediction row per anchor.  `bar_id` names a 128-thread barrier shared by the 4 warps
@@ -162,26 +176,64 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
                     }
                 }
             } else {
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+                // Best class = first maximum of the PRODUCTS p = sigmoid(x) * obj (image_proc.py:145).  ONE sweep over
+                // the 80 class logits (three 32-column loads: the epilogue is bound by TMEM round trips) keeps
+                // the two largest logits and the first index of the largest.  Runner-up more than 1e-3 below (almost
+                // always): the arg-max of the logits is the answer and only its product is evaluated.  Otherwise,
+                // anywhere in the warp (tcgen05.ld is warp-collective): the products of all classes within 1e-3 of the
+                // maximum are compared, as before.
+                float m1 = -INFINITY, m2 = -INFINITY;
+                {
+                    // columns cb+5 .. cb+84 in chunks [0,32) [32,64) [48,80): the last one overlaps (class 79 is the
+                    // anchor's last column; reading 32 more from class 64 on would leave the accumulator for a = 2).
+                    // One chunk at a time: 96 live registers spill in the 17-warp kernel.
+                    uint32_t q[32];
+                    auto take = [&](uint32_t u, int c) {
+                        const float x = __uint_as_float(u);
+                        m2 = fmaxf(m2, fminf(m1, x));
+                        bj = x > m1 ? c : bj;
+                        m1 = fmaxf(m1, x);
+                    };
+                    auto sweep = [&](const uint32_t* q, int first, int lo, int hi) {   // classes first + j inside [lo, hi)
+                        if (first >= lo && first + 32 <= hi) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < nc) mx = fmaxf(mx, __uint_as_float(q[j]));
+                            for (int j = 0; j < 32; ++j) take(q[j], first + j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (first + j >= lo && first + j < hi) take(q[j], first + j);
+                        }
+                    };
+                    ch_tmem_ld32(q, trow + cb + 5);
+                    ch_tmem_wait();
+                    sweep(q, 0, 0, nc);
+                    if (nc > 32) {
+                        ch_tmem_ld32(q, trow + cb + 5 + 32);
+                        ch_tmem_wait();
+                        sweep(q, 32, 32, nc);
+                    }
+                    if (nc > 64) {
+                        ch_tmem_ld32(q, trow + cb + 5 + nc - 32);
+                        ch_tmem_wait();
+                        sweep(q, nc - 32, 64, nc);
+                    }
                 }
-                const float near = mx - 1e-3f;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
-                    uint32_t q[16];
-                    VK_TMEM_LD16(q, trow + cb + 5 + c0);
+                const float near = m1 - 1e-3f;
+                if (__any_sync(0xffffffffu, alive && m2 >= near)) {
+                    bj = 0x7fffffff;
+                    for (int c0 = 0; c0 < nc; c0 += 16) {
+                        uint32_t q[16];
+                        VK_TMEM_LD16(q, trow + cb + 5 + c0);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float x = __uint_as_float(q[j]);
-                        if (c0 + j < nc && x >= near) {
-                            const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
-                            if (p > bv) { bv = p; bj = c0 + j; }                                        // :145
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = __uint_as_float(q[j]);
+                            if (c0 + j < nc && x >= near) {
+                                const float p = __fmul_rn(sigmoidf_vk(x), obj);                            // :135
+                                if (p > bv) { bv = p; bj = c0 + j; }                                        // :145
+                            }
                         }
                     }
+                } else {
+                    bv = __fmul_rn(sigmoidf_vk(m1), obj);                                                  // :135
                 }
                 count = (alive && bj != 0x7fffffff && bv > A.conf && class_allowed(A.class_mask, bj)) ? 1 : 0;
             }
@@ -366,46 +418,68 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-specialised persistent variant: one CTA per SM, 17 warps.
-//   warps 8-15  two producer teams taking alternate k-blocks: cp.async of the X and W blocks two blocks
-//               ahead (4 staging slots, 2 A slots, 4 W slots), transposition of X into the A tile, bias
-//               block at the end of a tile
-//   warp 16     MMA issuer (one lane): tcgen05.mma into one of TWO 256-column accumulators,
-//               tcgen05.commit -> "slot free" and "accumulator full" mbarriers
-//   warps 0-7   two epilogue groups (one per accumulator) draining tile i while the mainloop
-//               of tile i+1 runs
+// Warp-specialised persistent variant on CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one CTA per SM, 17 warps.
+// What bounds this kernel is the traffic that fills shared memory: every 128-position tile needs all of W
+// (256 x cin), twice the bytes of its own X block.  A pair computes two tiles with one M = 256 instruction stream:
+// each CTA stages the X block of ITS tile and only ITS HALF of W (128 of the 256 output channels); the tensor cores
+// of both SMs read both halves.  W traffic per tile is halved.
+//   warps 8-15  two producer teams taking alternate k-blocks: cp.async of the X block and the W half two blocks
+//               ahead (4-slot rings), bias block at the end of a tile; READY is signalled on the LEADER's barrier
+//   warp 16     (leader CTA only) MMA issuer, one lane: tcgen05.mma.cta_group::2 into one of TWO 256-column
+//               accumulators (each CTA's TMEM receives its own tile's 128 rows); tcgen05.commit multicast to both
+//               CTAs -> "slot free" and "accumulator full" mbarriers
+//   warps 0-7   two epilogue groups (one per accumulator) draining tile i while the mainloop of tile i+1 runs;
+//               "accumulator empty" is signalled on the leader's barrier by both CTAs
+// A pair's two tiles are the two halves of 256 consecutive positions of one level (the last pair of a level may have
+// an empty second half: its X is zeros and its epilogue writes nothing).
 // Every mbarrier phase is waited in order by its consumer (a parity wait cannot tell phase n from
 // n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
 // ---------------------------------------------------------------------------------------
 constexpr int kWsThreads = 17 * 32;
-constexpr int kWsASlots = 4, kWsBSlots = 4;                          // A tile / W tile ring depths
-constexpr int kWsOffB = kWsASlots * kChABytes;                       // 64 KB
-constexpr int kWsOffBar = kWsOffB + kWsBSlots * kChBBytes;           // 192 KB
+constexpr int kWsSlots = 6;                                          // ring depth of the operand tiles (each team keeps two blocks ahead in flight)
+constexpr int kWsBBytes = 128 * 128;                                 // this CTA's half of a W block: 128 rows x 128 B
+constexpr int kWsOffB = kWsSlots * kChABytes;                        // 96 KB
+constexpr int kWsOffBar = kWsOffB + kWsSlots * kWsBBytes;            // 192 KB
 constexpr int kWsSmem = kWsOffBar + 256;
+// instruction descriptor of the pair: M = 256 (128 rows per CTA), N = 256, A MN-major, B K-major
+constexpr uint32_t kWsIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 struct WsTile {
     int valid, b, l, s0, nvalid, nkb;
 };
 
-__device__ __forceinline__ WsTile ws_tile(const HeadDev& H, const ConvHead& C, int t, int total) {
+// pair-tile tp (256 positions of one level of one image), this CTA's half
+__device__ __forceinline__ WsTile ws_tile(const HeadDev& H, const ConvHead& C, int tp, int total, int rank) {
     WsTile q;
-    q.valid = t < total;
+    q.valid = tp < total;
     if (!q.valid) { q.b = q.l = q.s0 = q.nvalid = q.nkb = 0; return q; }
-    q.b = t / C.mtiles;
-    const int mt = t - q.b * C.mtiles;
+    q.b = tp / C.ptiles;
+    const int pt = tp - q.b * C.ptiles;
     int l = 0;
 #pragma unroll
     for (int i = 1; i < VK_MAX_LEVELS; ++i)
-        if (i < H.nl && mt >= C.mtile_start[i]) l = i;
+        if (i < H.nl && pt >= C.ptile_start[i]) l = i;
     q.l = l;
-    q.s0 = (mt - C.mtile_start[l]) * kChM;
-    q.nvalid = min(kChM, H.nynx[l] - q.s0);
+    q.s0 = ((pt - C.ptile_start[l]) * 2 + rank) * kChM;
+    q.nvalid = max(0, min(kChM, H.nynx[l] - q.s0));
     q.nkb = C.cin[l] / kChKB;
     return q;
 }
 
 __device__ __forceinline__ void ws_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in the leader CTA (rank 0) of the pair.  Default (CTA-scope) semantics on
+// both sides, as CUTLASS's ClusterBarrier does: the operands are read by the tensor cores through the async proxy
+// (fence.proxy.async precedes the arrive), never through the leader's L1; cluster-scope acquire / release compiled to
+// CCTL.IVALL + MEMBAR.ALL.GPU on every wait and arrive.
+__device__ __forceinline__ void ws_arrive_leader(uint32_t bar) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(0));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+}
+__device__ __forceinline__ void ws_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // POLL = true: mbarrier.test_wait in a tight loop (the single MMA-issuing lane: its hand-offs happen once
 // per 0.3 us k-block); false: try_wait, which lets the hardware suspend the (many) waiting threads.
@@ -426,70 +500,78 @@ __device__ __forceinline__ bool ws_wait(uint32_t bar, uint32_t parity, volatile 
     return false;
 }
 
-__global__ void __launch_bounds__(kWsThreads, 1)
-conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int total_tiles, int* __restrict__ fault) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWsThreads, 1)
+conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int total_pairs, int* __restrict__ fault) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + kWsOffB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[4] done[4] tfull[2] tempty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 112);
-    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 116);
-    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 128);     // [2][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[S] done[S] tfull[2] tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 144);
+    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 148);
+    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 160);     // [2][4]
     const uint32_t bar0 = ch_smem(bars);
-    auto READY = [&](int s) { return bar0 + 8u * s; };
-    auto DONE = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto TFULL = [&](int g) { return bar0 + 8u * (8 + g); };
-    auto TEMPTY = [&](int g) { return bar0 + 8u * (10 + g); };
+    auto READY = [&](int s) { return bar0 + 8u * s; };                 // leader: both CTAs' operands of the slot landed
+    auto DONE = [&](int s) { return bar0 + 8u * (kWsSlots + s); };     // both: the MMAs reading the slot completed
+    auto TFULL = [&](int g) { return bar0 + 8u * (2 * kWsSlots + g); };        // both: accumulator g holds a finished tile
+    auto TEMPTY = [&](int g) { return bar0 + 8u * (2 * kWsSlots + 2 + g); };   // leader: both CTAs drained accumulator g
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int no = H.no, cout = H.na * no;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (warp == 16) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(s_tmem)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar0 + 8u * i), "r"(1));
+        for (int i = 0; i < kWsSlots; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(READY(i)), "r"(2));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(DONE(i)), "r"(1));
+        }
         for (int g = 0; g < 2; ++g) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TFULL(g)), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TEMPTY(g)), "r"(4));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TEMPTY(g)), "r"(8));
         }
         *s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    ws_cluster_sync();                                                 // the peer's barriers exist before anyone arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
 
     if (warp >= 8 && warp < 16) {
         // ------------------------------------------------------------------ producers: two teams of 4 warps,
-        // team T owns the blocks j = T, T+2, T+4, ... (copies of block j+2 in flight while block j is transposed)
+        // team T owns the blocks j = T, T+2, T+4, ... (copies of block j+2 in flight while block j is handed over)
         const int team = (warp - 8) >> 2;
         const int ptid = (tid - 256) & 127;
         const int xk0 = ptid >> 5, xm4 = (ptid & 31) << 2;
         const int wn0 = ptid >> 3, wc = ptid & 7;
         const uint32_t wdst0 = ch_koff(wn0, wc);
-        // cursors over the CTA's tiles; a tile has nkb data blocks + one bias block
+        const int nbase = (int)rank * 128;             // first output channel of this CTA's half of W
+        // cursors over the pair's tiles; a tile has nkb data blocks + one bias block
         struct Cursor { int i, kb; WsTile q; };
         auto advance = [&](Cursor& c) {                // one block forward
-            if (c.q.valid && ++c.kb > c.q.nkb) { c.kb = 0; ++c.i; c.q = ws_tile(H, C, blockIdx.x + c.i * gridDim.x, total_tiles); }
+            if (c.q.valid && ++c.kb > c.q.nkb) { c.kb = 0; ++c.i; c.q = ws_tile(H, C, pair0 + c.i * npairs, total_pairs, (int)rank); }
         };
-        Cursor it{0, 0, ws_tile(H, C, blockIdx.x, total_tiles)};
+        Cursor it{0, 0, ws_tile(H, C, pair0, total_pairs, (int)rank)};
         if (team) advance(it);
         Cursor pr = it;
         auto issue_block = [&](int j) {                // copies of the block at the issue cursor into the rings at j
             if (it.q.valid && it.kb < it.q.nkb) {
                 const int nynx = H.nynx[it.q.l], cin = C.cin[it.q.l];
                 const bool xvalid = xm4 < it.q.nvalid;
-                const float* xsrc = C.x[it.q.l] + (size_t)it.q.b * cin * nynx + it.q.s0 + (size_t)(it.kb * kChKB + xk0) * nynx + (xvalid ? xm4 : 0);
-                const uint32_t sa = ch_smem(sA + (j % kWsASlots) * kChABytes) + ch_aoff(xm4, xk0);
+                const float* xsrc = C.x[it.q.l] + (size_t)it.q.b * cin * nynx + (size_t)(it.kb * kChKB + xk0) * nynx + (xvalid ? it.q.s0 + xm4 : 0);
+                const uint32_t sa = ch_smem(sA + (j % kWsSlots) * kChABytes) + ch_aoff(xm4, xk0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ch_cp16(sa + i * kChASbo, xsrc + (size_t)(4 * i) * nynx, xvalid);
                 const float* wsrc = C.w[it.q.l] + it.kb * kChKB + 4 * wc;
-                const uint32_t sb = ch_smem(sB + (j % kWsBSlots) * kChBBytes) + wdst0;
+                const uint32_t sb = ch_smem(sB + (j % kWsSlots) * kWsBBytes) + wdst0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int n = wn0 + 16 * i;
+                for (int i = 0; i < 8; ++i) {
+                    const int n = nbase + wn0 + 16 * i;
                     ch_cp16(sb + i * 2048, wsrc + (size_t)(n < cout ? n : 0) * cin, n < cout);
                 }
             }
@@ -498,57 +580,58 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
         };
         bool ok = true;
         issue_block(team);
+        issue_block(team + 2);
         for (int j = team; pr.q.valid && ok; j += 2) {
-            // ring slots of block j+2 (staging, W) and of block j (A) were last used by block j-2: its MMAs
-            // are two blocks behind the newest, so this wait rarely stalls
-            if (j >= 2) ok &= ws_wait<false>(DONE((j - 2) % kWsBSlots), (uint32_t)(((j - 2) / kWsBSlots) & 1), s_abort);
-            issue_block(j + 2);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this thread's copies of block j landed
+            // the ring slots of block j+4 were last used by block j-2: its MMAs are well behind the newest copies,
+            // so this wait rarely stalls
+            if (j >= 2) ok &= ws_wait<false>(DONE((j - 2) % kWsSlots), (uint32_t)(((j - 2) / kWsSlots) & 1), s_abort);
+            issue_block(j + 4);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");               // this thread's copies of block j landed
             if (pr.kb >= pr.q.nkb) {                   // bias block: A = [1, 1, 0...], W = [hi, lo, 0...]
-                uint8_t* a_tile = sA + (j % kWsASlots) * kChABytes;
-                uint8_t* b_tile = sB + (j % kWsBSlots) * kChBBytes;
+                uint8_t* b_tile = sB + (j % kWsSlots) * kWsBBytes;
                 const float* bias = C.bias[pr.q.l];
-                ch_bias_a(a_tile, ptid);
-                for (int n = ptid; n < kChN; n += 128) {
-                    const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
-                    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                    *reinterpret_cast<float4*>(b_tile + ch_koff(n, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
-                    *reinterpret_cast<float4*>(b_tile + ch_koff(n, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                ch_bias_a(sA + (j % kWsSlots) * kChABytes, ptid);
+                const int n = nbase + ptid;
+                const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
+                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                *reinterpret_cast<float4*>(b_tile + ch_koff(ptid, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
+                *reinterpret_cast<float4*>(b_tile + ch_koff(ptid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");
-            if (ptid == 0) ws_arrive(READY(j % kWsBSlots));
+            if (ptid == 0) ws_arrive_leader(READY(j % kWsSlots));
             advance(pr); advance(pr);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == 16) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA)
+        if (lane == 0 && rank == 0) {
             bool ok = true;
             int j = 0;
             for (int i = 0; ok; ++i) {
-                const WsTile q = ws_tile(H, C, blockIdx.x + i * gridDim.x, total_tiles);
+                const WsTile q = ws_tile(H, C, pair0 + i * npairs, total_pairs, 0);
                 if (!q.valid) break;
                 const int g = i & 1;
-                if (i >= 2) ok &= ws_wait<true>(TEMPTY(g), (uint32_t)(((i - 2) >> 1) & 1), s_abort);   // epilogue drained tile i-2
+                if (i >= 2) ok &= ws_wait<true>(TEMPTY(g), (uint32_t)(((i - 2) >> 1) & 1), s_abort);   // both epilogues drained tile i-2
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_addr = tmem + (uint32_t)(g * kChN);
                 for (int kb = 0; kb <= q.nkb && ok; ++kb, ++j) {
-                    const int s = j % kWsBSlots;
-                    ok &= ws_wait<true>(READY(s), (uint32_t)((j / kWsBSlots) & 1), s_abort);
+                    const int s = j % kWsSlots;
+                    ok &= ws_wait<true>(READY(s), (uint32_t)((j / kWsSlots) & 1), s_abort);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a0 = ch_smem(sA + (j % kWsASlots) * kChABytes), b0 = ch_smem(sB + s * kChBBytes);
+                    const uint32_t a0 = ch_smem(sA + s * kChABytes), b0 = ch_smem(sB + s * kWsBBytes);
                     const int nks = (kb < q.nkb) ? 4 : 1;                      // the bias block is one K = 8 step
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t acc = (kb | ks) ? 1u : 0u;
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                     :: "r"(acc_addr), "l"(ch_desc_a(a0 + ks * 2 * kChASbo)), "l"(ch_desc(b0 + ks * 32)), "r"(kChIdesc), "r"(acc) : "memory");
+                                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                     :: "r"(acc_addr), "l"(ch_desc_a(a0 + ks * 2 * kChASbo)), "l"(ch_desc(b0 + ks * 32)), "r"(kWsIdesc), "r"(acc) : "memory");
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(DONE(s)) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 :: "r"(DONE(s)), "h"((uint16_t)3) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(TFULL(g)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                             :: "r"(TFULL(g)), "h"((uint16_t)3) : "memory");
             }
         }
     } else {
@@ -556,7 +639,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
         const int g = warp >> 2, etid = tid & 127, ewarp = warp & 3;
         bool ok = true;
         for (int i = g; ; i += 2) {
-            const WsTile q = ws_tile(H, C, blockIdx.x + i * gridDim.x, total_tiles);
+            const WsTile q = ws_tile(H, C, pair0 + i * npairs, total_pairs, (int)rank);
             if (!q.valid) break;
             ok &= ws_wait<false>(TFULL(g), (uint32_t)((i >> 1) & 1), s_abort);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -564,13 +647,14 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                           etid, s_wtot + 4 * g, 3 + g, ok);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) ws_arrive(TEMPTY(g));
+            if (lane == 0) ws_arrive_leader(TEMPTY(g));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0 && *s_abort) atomicExch(fault, 1);
-    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
+    ws_cluster_sync();                                                 // neither CTA leaves while the other may still read its shared memory
+    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
 }
 
 }  // namespace vk
@@ -588,12 +672,13 @@ extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* f
     if (kernel != VK_CONV_TILE && kernel != VK_CONV_PERSISTENT) return fail_arg("vk_conv_decode_filter: kernel %d", kernel);
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_conv_decode_filter: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: batch %d > 65535", batch);
-    if (H.na * H.no > kChN || (H.na - 1) * H.no + 5 + 16 * ceil_div(H.nc, 16) > kChN)
+    if (H.na * H.no > kChN || (H.na - 1) * H.no + 5 + 16 * ceil_div(H.nc, 16) > kChN ||
+        (H.nc <= 64 && (H.na - 1) * H.no + 5 + 64 > kChN))            // the epilogue's 32-column loads stay inside the accumulator
         return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: %d output channels do not fit %d TMEM columns", H.na * H.no, kChN);
     if (int rc = check_cand(out, H.rows, H.tiles, H.nc, multi_label, "vk_conv_decode_filter")) return rc;
     ConvHead C;
     memset(&C, 0, sizeof(C));
-    int mt = 0;
+    int mt = 0, pt = 0;
     for (int l = 0; l < H.nl; ++l) {
         if (!feats[l] || !weights[l]) return fail_arg("vk_conv_decode_filter: level %d is NULL", l);
         if (cin[l] <= 0 || cin[l] % kChKB) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: cin[%d] = %d is not a multiple of %d", l, cin[l], kChKB);
@@ -601,19 +686,23 @@ extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* f
             return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: level %d needs ny*nx %% 4 == 0 and 16-byte aligned tensors", l);
         C.x[l] = feats[l]; C.w[l] = weights[l]; C.bias[l] = biases ? biases[l] : nullptr; C.cin[l] = cin[l];
         C.mtile_start[l] = mt;
+        C.ptile_start[l] = pt;
         mt += ceil_div(H.nynx[l], kChM);
+        pt += ceil_div(H.nynx[l], 2 * kChM);
     }
-    for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) C.mtile_start[l] = mt;
+    for (int l = H.nl; l <= VK_MAX_LEVELS; ++l) { C.mtile_start[l] = mt; C.ptile_start[l] = pt; }
     C.mtiles = mt;
+    C.ptiles = pt;
     cudaStream_t stream = as_stream(stream_);
     if (int rc = reset_cand(out, batch, "vk_conv_decode_filter", stream)) return rc;
     cudaError_t e = cudaMemsetAsync(fault, 0, sizeof(int32_t), stream);
     if (e != cudaSuccess) return fail_code((int)e, "vk_conv_decode_filter: memset: %s", cudaGetErrorString(e));
     FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
     if (kernel == VK_CONV_PERSISTENT) {
-        const int total = mt * batch;
+        const int total = pt * batch;                                  // pair tiles
         if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv_decode_filter_ws_kernel), kWsSmem, "vk_conv_decode_filter")) return rc;
-        conv_decode_filter_ws_kernel<<<total < kNumSMs ? total : kNumSMs, kWsThreads, kWsSmem, stream>>>(H, C, A, total, fault);
+        const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
+        conv_decode_filter_ws_kernel<<<2 * pairs, kWsThreads, kWsSmem, stream>>>(H, C, A, total, fault);
         count_launch();
         return check_launch("conv_decode_filter_ws_kernel");
     }
