@@ -389,7 +389,7 @@ def main():
     # stream it runs on), which is where the per-kernel durations of the roofline come from.
     K = args.steps
     EV = 8
-    sampled = [k for k in range(K) if k % EV == EV - 1]
+    sampled = [k for k in range(K) if k % EV == EV - 1] or [K - 1]      # short runs: the last step is the event step
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(5)] for k in sampled}
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -405,6 +405,24 @@ def main():
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
     kern_ms = [sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in sampled) / max(len(sampled), 1) for i in (0, 1, 3)]
+
+    # ---- outside the timed region: the same three kernels one after the other on one stream (no overlap), the
+    # arrangement the committed ncu launch list (profiles/) sees; its shares are comparable with these.
+    def serial_times(reps=8):
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
+        for e in evs:
+            e[0].record(main_stream)
+            _lib.check("vk_letterbox_batch", L.vk_letterbox_batch(*pipe._lb_args, sptr(main_stream)))
+            e[1].record(main_stream)
+            _lib.check("vk_decode_filter", L.vk_decode_filter(pipe._cfg_ref, C.cast(pipe._lv_arr, C.c_void_p), pipe._lv_dt,
+                                                                BATCH, pipe._conf, pipe._ml, pipe._mask_p, pipe._kernel,
+                                                                C.byref(pipe._cs[0]), sptr(main_stream)))
+            e[2].record(main_stream)
+            _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[0], sptr(main_stream)))
+            e[3].record(main_stream)
+        torch.cuda.synchronize()
+        return [sum(e[i].elapsed_time(e[i + 1]) for e in evs[1:]) / (reps - 1) for i in range(3)]
+    serial_ms = serial_times()
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -480,7 +498,8 @@ def main():
     kernels = {}
     for i, n_ in enumerate(names):
         kernels[n_] = {"ms": kern_ms[i], "algorithmic_bytes": alg[n_],
-                       "algorithmic_gbs": alg[n_] / (kern_ms[i] * 1e-3) / 1e9}
+                       "algorithmic_gbs": alg[n_] / (kern_ms[i] * 1e-3) / 1e9,
+                       "ms_serial": serial_ms[i], "share_serial": serial_ms[i] / sum(serial_ms)}
         tr = traffic_all.get(n_)
         if tr:                                               # DRAM bytes per launch from the committed ncu capture
             kernels[n_]["dram_bytes_ncu"] = tr
@@ -495,7 +514,8 @@ def main():
                 "unit": "GB/s", "frac": kernels[dom]["algorithmic_gbs"] / peak, "traffic": traffic_all.get(dom),
                 "peak_kind": f"of {peak_kind}",
                 "note": ("duration measured inside the step: the NMS of the previous batch runs beside it on the side "
-                         "stream and shares the SMs; the same kernel timed alone is in profiles/ (kernel_bench)"
+                         "stream and shares the SMs; kernels[*].ms_serial / share_serial are the same kernels issued one "
+                         "after the other (the arrangement of the ncu launch list in profiles/)"
                          if overlap else "")}
 
     if rank != 0:
