@@ -1,6 +1,8 @@
 // Fused Detect conv head: vk_conv_decode_filter and its tcgen05 kernels.
 #include "decode_common.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 // =======================================================================================
 // Fused Detect head: 1x1 conv (tensor cores) + decode + confidence filter  
 //
@@ -418,16 +420,20 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-specialised persistent variant on CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one CTA per SM, 17 warps.
+// Warp-specialised persistent variant on CTA PAIRS (cluster of 2, tcgen05 cta_group::2), operands by TMA.
 // What bounds this kernel is the traffic that fills shared memory: every 128-position tile needs all of W
 // (256 x cin), twice the bytes of its own X block.  A pair computes two tiles with one M = 256 instruction stream:
 // each CTA stages the X block of ITS tile and only ITS HALF of W (128 of the 256 output channels); the tensor cores
 // of both SMs read both halves.  W traffic per tile is halved.
-//   warps 8-15  two producer teams taking alternate k-blocks: cp.async of the X block and the W half two blocks
-//               ahead (4-slot rings), bias block at the end of a tile; READY is signalled on the LEADER's barrier
-//   warp 16     (leader CTA only) MMA issuer, one lane: tcgen05.mma.cta_group::2 into one of TWO 256-column
-//               accumulators (each CTA's TMEM receives its own tile's 128 rows); tcgen05.commit multicast to both
-//               CTAs -> "slot free" and "accumulator full" mbarriers
+//   warp 8      producer, one lane: per 32-channel block four cp.async.bulk.tensor boxes of X ([32 k][32 s], swizzle
+//               128B_ATOM_32B = the MN-major BASE32B operand layout, profiles/micro/tma_probe.cu) and one of W
+//               ([128 n][32 k], swizzle 128B), 32 KB on one transaction barrier; kWsSlots-deep ring; positions past
+//               a plane and output channels past na*no arrive as zeros (TMA out-of-bounds fill)
+//   warp 9      forwarder, one lane: "this CTA's block landed" -> arrive on the LEADER's READY barrier
+//   warp 10     (leader CTA only) MMA issuer, one lane: tcgen05.mma.cta_group::2 into one of TWO 256-column
+//               accumulators (each CTA's TMEM receives its own tile's 128 rows); the bias as one more K = 8 step from
+//               constant tiles built at kernel start; tcgen05.commit multicast to both CTAs -> "slot free" and
+//               "accumulator full" mbarriers
 //   warps 0-7   two epilogue groups (one per accumulator) draining tile i while the mainloop of tile i+1 runs;
 //               "accumulator empty" is signalled on the leader's barrier by both CTAs
 // A pair's two tiles are the two halves of 256 consecutive positions of one level (the last pair of a level may have
@@ -435,14 +441,31 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 // Every mbarrier phase is waited in order by its consumer (a parity wait cannot tell phase n from
 // n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
 // ---------------------------------------------------------------------------------------
-constexpr int kWsThreads = 17 * 32;
-constexpr int kWsSlots = 6;                                          // ring depth of the operand tiles (each team keeps two blocks ahead in flight)
+constexpr int kWsThreads = 11 * 32;
+constexpr int kWsSlots = 4;                                          // ring depth of the operand tiles
 constexpr int kWsBBytes = 128 * 128;                                 // this CTA's half of a W block: 128 rows x 128 B
-constexpr int kWsOffB = kWsSlots * kChABytes;                        // 96 KB
-constexpr int kWsOffBar = kWsOffB + kWsSlots * kWsBBytes;            // 192 KB
+constexpr int kWsOffB = kWsSlots * kChABytes;                        // 64 KB
+constexpr int kWsOffBiasA = kWsOffB + kWsSlots * kWsBBytes;          // 128 KB: A tile of the bias step (4 KB)
+constexpr int kWsOffBiasB = kWsOffBiasA + 4096;                      // W tiles of the bias step, one per level (16 KB each)
+constexpr int kWsOffBar = kWsOffBiasB + VK_MAX_LEVELS * kWsBBytes;
 constexpr int kWsSmem = kWsOffBar + 256;
+constexpr uint32_t kWsStageTx = kChABytes + kWsBBytes;               // bytes one block brings: 4 X boxes + 1 W box
 // instruction descriptor of the pair: M = 256 (128 rows per CTA), N = 256, A MN-major, B K-major
 constexpr uint32_t kWsIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+// A tile as TMA writes it: one box = 32 positions x 32 channels = 8 k-groups of 512 B; the 4 position blocks 4096 B apart
+__device__ __forceinline__ uint64_t ch_desc_a_tma(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(4096 >> 4) << 16;    // leading byte offset: position blocks
+    d |= (uint64_t)(512 >> 4) << 32;     // stride byte offset: k-groups
+    d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+    d |= (uint64_t)1 << 61;              // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+struct ConvMaps {                        // one tensor map per level: X as (s, b * cin + ci), W as (ci, co)
+    CUtensorMap x[VK_MAX_LEVELS], w[VK_MAX_LEVELS];
+};
 
 struct WsTile {
     int valid, b, l, s0, nvalid, nkb;
@@ -466,13 +489,10 @@ __device__ __forceinline__ WsTile ws_tile(const HeadDev& H, const ConvHead& C, i
     return q;
 }
 
-__device__ __forceinline__ void ws_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
 // arrive on the barrier at the same offset in the leader CTA (rank 0) of the pair.  Default (CTA-scope) semantics on
-// both sides, as CUTLASS's ClusterBarrier does: the operands are read by the tensor cores through the async proxy
-// (fence.proxy.async precedes the arrive), never through the leader's L1; cluster-scope acquire / release compiled to
-// CCTL.IVALL + MEMBAR.ALL.GPU on every wait and arrive.
+// both sides, as CUTLASS's ClusterBarrier does: the operands are read by the tensor cores through the async proxy,
+// never through the leader's L1; cluster-scope acquire / release compiled to CCTL.IVALL + MEMBAR.ALL.GPU on every
+// wait and arrive (225 -> 172 us per 64 images in the LDGSTS version of this kernel).
 __device__ __forceinline__ void ws_arrive_leader(uint32_t bar) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(0));
@@ -481,8 +501,8 @@ __device__ __forceinline__ void ws_arrive_leader(uint32_t bar) {
 __device__ __forceinline__ void ws_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// POLL = true: mbarrier.test_wait in a tight loop (the single MMA-issuing lane: its hand-offs happen once
-// per 0.3 us k-block); false: try_wait, which lets the hardware suspend the (many) waiting threads.
+// POLL = true: mbarrier.test_wait in a tight loop (single lanes whose hand-offs happen once per 0.3 us k-block);
+// false: try_wait, which lets the hardware suspend the (many) waiting threads.
 template <bool POLL>
 __device__ __forceinline__ bool ws_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
     for (int spin = 0; spin < (POLL ? (1 << 26) : (1 << 22)); ++spin) {
@@ -499,33 +519,43 @@ __device__ __forceinline__ bool ws_wait(uint32_t bar, uint32_t parity, volatile 
     *abort_flag = 1;
     return false;
 }
+__device__ __forceinline__ void ws_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWsThreads, 1)
-conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, int total_pairs, int* __restrict__ fault) {
+conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs A, const __grid_constant__ ConvMaps M,
+                             int total_pairs, int* __restrict__ fault) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + kWsOffB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // ready[S] done[S] tfull[2] tempty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 144);
-    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 148);
-    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 160);     // [2][4]
+    uint8_t* sBiasA = smem + kWsOffBiasA;
+    uint8_t* sBiasB = smem + kWsOffBiasB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // full[S] ready[S] done[S] tfull[2] tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 192);
+    volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 196);
+    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 208);     // [2][4]
     const uint32_t bar0 = ch_smem(bars);
-    auto READY = [&](int s) { return bar0 + 8u * s; };                 // leader: both CTAs' operands of the slot landed
-    auto DONE = [&](int s) { return bar0 + 8u * (kWsSlots + s); };     // both: the MMAs reading the slot completed
-    auto TFULL = [&](int g) { return bar0 + 8u * (2 * kWsSlots + g); };        // both: accumulator g holds a finished tile
-    auto TEMPTY = [&](int g) { return bar0 + 8u * (2 * kWsSlots + 2 + g); };   // leader: both CTAs drained accumulator g
+    auto FULL = [&](int s) { return bar0 + 8u * s; };                  // own: this CTA's copies of the slot landed (transaction count)
+    auto READY = [&](int s) { return bar0 + 8u * (kWsSlots + s); };    // leader: both CTAs' operands of the slot landed
+    auto DONE = [&](int s) { return bar0 + 8u * (2 * kWsSlots + s); }; // both: the MMAs reading the slot completed
+    auto TFULL = [&](int g) { return bar0 + 8u * (3 * kWsSlots + g); };        // both: accumulator g holds a finished tile
+    auto TEMPTY = [&](int g) { return bar0 + 8u * (3 * kWsSlots + 2 + g); };   // leader: both CTAs drained accumulator g
+    static_assert(8 * (3 * kWsSlots + 4) <= 192, "barrier block");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int no = H.no, cout = H.na * no;
+    const int cout = H.na * H.no;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-    if (warp == 16) {
+    if (warp == 10) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(s_tmem)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     if (tid == 0) {
         for (int i = 0; i < kWsSlots; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(FULL(i)), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(READY(i)), "r"(2));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(DONE(i)), "r"(1));
         }
@@ -536,74 +566,64 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
         *s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // The bias rides on the tensor cores as one more K = 8 step per tile: A = [1, 1, 0...], W = [hi, lo, 0...] with
+    // bias = hi + lo split into two TF32 values (fp32-accurate sum).  Constant tiles, built once.
+    if (tid < 128) {
+        ch_bias_a(sBiasA, tid);
+        for (int l = 0; l < H.nl; ++l) {
+            const float* bias = C.bias[l];
+            const int n = (int)rank * 128 + tid;
+            const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            uint8_t* b_tile = sBiasB + l * kWsBBytes;
+            *reinterpret_cast<float4*>(b_tile + ch_koff(tid, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
+            *reinterpret_cast<float4*>(b_tile + ch_koff(tid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    ws_cluster_sync();                                                 // the peer's barriers exist before anyone arrives on them
+    ws_cluster_sync();                                                 // the peer's barriers and bias tiles exist before anyone uses them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
 
-    if (warp >= 8 && warp < 16) {
-        // ------------------------------------------------------------------ producers: two teams of 4 warps,
-        // team T owns the blocks j = T, T+2, T+4, ... (copies of block j+2 in flight while block j is handed over)
-        const int team = (warp - 8) >> 2;
-        const int ptid = (tid - 256) & 127;
-        const int xk0 = ptid >> 5, xm4 = (ptid & 31) << 2;
-        const int wn0 = ptid >> 3, wc = ptid & 7;
-        const uint32_t wdst0 = ch_koff(wn0, wc);
-        const int nbase = (int)rank * 128;             // first output channel of this CTA's half of W
-        // cursors over the pair's tiles; a tile has nkb data blocks + one bias block
-        struct Cursor { int i, kb; WsTile q; };
-        auto advance = [&](Cursor& c) {                // one block forward
-            if (c.q.valid && ++c.kb > c.q.nkb) { c.kb = 0; ++c.i; c.q = ws_tile(H, C, pair0 + c.i * npairs, total_pairs, (int)rank); }
-        };
-        Cursor it{0, 0, ws_tile(H, C, pair0, total_pairs, (int)rank)};
-        if (team) advance(it);
-        Cursor pr = it;
-        auto issue_block = [&](int j) {                // copies of the block at the issue cursor into the rings at j
-            if (it.q.valid && it.kb < it.q.nkb) {
-                const int nynx = H.nynx[it.q.l], cin = C.cin[it.q.l];
-                const bool xvalid = xm4 < it.q.nvalid;
-                const float* xsrc = C.x[it.q.l] + (size_t)it.q.b * cin * nynx + (size_t)(it.kb * kChKB + xk0) * nynx + (xvalid ? it.q.s0 + xm4 : 0);
-                const uint32_t sa = ch_smem(sA + (j % kWsSlots) * kChABytes) + ch_aoff(xm4, xk0);
+    if (warp == 8) {
+        // ------------------------------------------------------------------ producer (one lane)
+        if (lane == 0) {
+            bool ok = true;
+            int j = 0;
+            for (int i = 0; ok; ++i) {
+                const WsTile q = ws_tile(H, C, pair0 + i * npairs, total_pairs, (int)rank);
+                if (!q.valid) break;
+                const int row0 = q.b * C.cin[q.l];                     // first row of the image in the (s, b*cin + ci) view
+                for (int kb = 0; kb < q.nkb && ok; ++kb, ++j) {
+                    const int s = j % kWsSlots;
+                    if (j >= kWsSlots) ok &= ws_wait<true>(DONE(s), (uint32_t)((j / kWsSlots - 1) & 1), s_abort);   // the slot's last readers completed
+                    if (!ok) break;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(FULL(s)), "r"(kWsStageTx) : "memory");
+                    const uint32_t a0 = ch_smem(sA + s * kChABytes);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ch_cp16(sa + i * kChASbo, xsrc + (size_t)(4 * i) * nynx, xvalid);
-                const float* wsrc = C.w[it.q.l] + it.kb * kChKB + 4 * wc;
-                const uint32_t sb = ch_smem(sB + (j % kWsSlots) * kWsBBytes) + wdst0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = nbase + wn0 + 16 * i;
-                    ch_cp16(sb + i * 2048, wsrc + (size_t)(n < cout ? n : 0) * cin, n < cout);
+                    for (int mb = 0; mb < 4; ++mb) ws_tma_2d(a0 + mb * 4096, &M.x[q.l], q.s0 + 32 * mb, row0 + kb * kChKB, FULL(s));
+                    ws_tma_2d(ch_smem(sB + s * kWsBBytes), &M.w[q.l], kb * kChKB, (int)rank * 128, FULL(s));
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            advance(it); advance(it);
-        };
-        bool ok = true;
-        issue_block(team);
-        issue_block(team + 2);
-        for (int j = team; pr.q.valid && ok; j += 2) {
-            // the ring slots of block j+4 were last used by block j-2: its MMAs are well behind the newest copies,
-            // so this wait rarely stalls
-            if (j >= 2) ok &= ws_wait<false>(DONE((j - 2) % kWsSlots), (uint32_t)(((j - 2) / kWsSlots) & 1), s_abort);
-            issue_block(j + 4);
-            asm volatile("cp.async.wait_group 2;" ::: "memory");               // this thread's copies of block j landed
-            if (pr.kb >= pr.q.nkb) {                   // bias block: A = [1, 1, 0...], W = [hi, lo, 0...]
-                uint8_t* b_tile = sB + (j % kWsSlots) * kWsBBytes;
-                const float* bias = C.bias[pr.q.l];
-                ch_bias_a(sA + (j % kWsSlots) * kChABytes, ptid);
-                const int n = nbase + ptid;
-                const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                *reinterpret_cast<float4*>(b_tile + ch_koff(ptid, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
-                *reinterpret_cast<float4*>(b_tile + ch_koff(ptid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");
-            if (ptid == 0) ws_arrive_leader(READY(j % kWsSlots));
-            advance(pr); advance(pr);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == 16) {
+    } else if (warp == 9) {
+        // ------------------------------------------------------------------ forwarder (one lane)
+        if (lane == 0) {
+            bool ok = true;
+            int j = 0;
+            for (int i = 0; ok; ++i) {
+                const WsTile q = ws_tile(H, C, pair0 + i * npairs, total_pairs, (int)rank);
+                if (!q.valid) break;
+                for (int kb = 0; kb < q.nkb && ok; ++kb, ++j) {
+                    const int s = j % kWsSlots;
+                    ok &= ws_wait<true>(FULL(s), (uint32_t)((j / kWsSlots) & 1), s_abort);
+                    if (ok) ws_arrive_leader(READY(s));
+                }
+            }
+        }
+    } else if (warp == 10) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA)
         if (lane == 0 && rank == 0) {
             bool ok = true;
@@ -615,26 +635,32 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 if (i >= 2) ok &= ws_wait<true>(TEMPTY(g), (uint32_t)(((i - 2) >> 1) & 1), s_abort);   // both epilogues drained tile i-2
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc_addr = tmem + (uint32_t)(g * kChN);
-                for (int kb = 0; kb <= q.nkb && ok; ++kb, ++j) {
+                for (int kb = 0; kb < q.nkb && ok; ++kb, ++j) {
                     const int s = j % kWsSlots;
                     ok &= ws_wait<true>(READY(s), (uint32_t)((j / kWsSlots) & 1), s_abort);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = ch_smem(sA + s * kChABytes), b0 = ch_smem(sB + s * kWsBBytes);
-                    const int nks = (kb < q.nkb) ? 4 : 1;                      // the bias block is one K = 8 step
-                    for (int ks = 0; ks < nks; ++ks) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {                           // K = 8: two k-groups (512 B each) of A, 32 B of W's rows
                         const uint32_t acc = (kb | ks) ? 1u : 0u;
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                     :: "r"(acc_addr), "l"(ch_desc_a(a0 + ks * 2 * kChASbo)), "l"(ch_desc(b0 + ks * 32)), "r"(kWsIdesc), "r"(acc) : "memory");
+                                     :: "r"(acc_addr), "l"(ch_desc_a_tma(a0 + ks * 1024)), "l"(ch_desc(b0 + ks * 32)), "r"(kWsIdesc), "r"(acc) : "memory");
                     }
                     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                                  :: "r"(DONE(s)), "h"((uint16_t)3) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                             :: "r"(TFULL(g)), "h"((uint16_t)3) : "memory");
+                if (ok) {                                                      // bias step, then the tile is complete
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 :: "r"(acc_addr), "l"(ch_desc_a(ch_smem(sBiasA))), "l"(ch_desc(ch_smem(sBiasB + q.l * kWsBBytes))),
+                                    "r"(kWsIdesc), "r"(1u) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 :: "r"(TFULL(g)), "h"((uint16_t)3) : "memory");
+                }
             }
         }
-    } else {
+    } else if (warp < 8) {
         // ------------------------------------------------------------------ epilogue groups
         const int g = warp >> 2, etid = tid & 127, ewarp = warp & 3;
         bool ok = true;
@@ -654,12 +680,47 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     __syncthreads();
     if (tid == 0 && *s_abort) atomicExch(fault, 1);
     ws_cluster_sync();                                                 // neither CTA leaves while the other may still read its shared memory
-    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
+    if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
 }
 
 }  // namespace vk
 
 using namespace vk;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*VkEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_conv_maps(const HeadDev& H, const ConvHead& C, int batch, ConvMaps* maps) {
+    static VkEncodeTiled enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+            return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: the driver has no cuTensorMapEncodeTiled");
+        enc = reinterpret_cast<VkEncodeTiled>(fn);
+    }
+    memset(maps, 0, sizeof(*maps));
+    const cuuint32_t ones[2] = {1, 1};
+    for (int l = 0; l < H.nl; ++l) {
+        // X: element (s, r) of the (nynx, B * cin) view = X[b][ci][s], r = b * cin + ci; box = 32 positions x 32 channels,
+        // written in the MN-major operand layout (32-byte swizzle atoms); positions past the plane are zeros
+        const cuuint64_t xd[2] = {(cuuint64_t)H.nynx[l], (cuuint64_t)batch * C.cin[l]}, xs[1] = {(cuuint64_t)H.nynx[l] * 4};
+        const cuuint32_t xb[2] = {32, 32};
+        CUresult r = enc(&maps->x[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(C.x[l]), xd, xs, xb, ones,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: tensor map of the level-%d features: CUresult %d", l, (int)r);
+        // W: element (ci, co); box = 32 channels x 128 output channels, K-major 128-byte swizzle; rows past na*no are zeros
+        const cuuint64_t wd[2] = {(cuuint64_t)C.cin[l], (cuuint64_t)(H.na * H.no)}, ws[1] = {(cuuint64_t)C.cin[l] * 4};
+        const cuuint32_t wb[2] = {32, 128};
+        r = enc(&maps->w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(C.w[l]), wd, ws, wb, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail_code(VK_E_LIMIT, "vk_conv_decode_filter: tensor map of the level-%d weights: CUresult %d", l, (int)r);
+    }
+    return VK_OK;
+}
 
 extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* feats, const int32_t* cin,
                                      const float* const* weights, const float* const* biases, int batch,
@@ -700,9 +761,11 @@ extern "C" int vk_conv_decode_filter(const VkHeadCfg* cfg, const float* const* f
     FilterArgs A = make_filter_args(out, batch, conf_thres, multi_label, class_mask);
     if (kernel == VK_CONV_PERSISTENT) {
         const int total = pt * batch;                                  // pair tiles
+        ConvMaps maps;
+        if (int rc = make_conv_maps(H, C, batch, &maps)) return rc;
         if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv_decode_filter_ws_kernel), kWsSmem, "vk_conv_decode_filter")) return rc;
         const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
-        conv_decode_filter_ws_kernel<<<2 * pairs, kWsThreads, kWsSmem, stream>>>(H, C, A, total, fault);
+        conv_decode_filter_ws_kernel<<<2 * pairs, kWsThreads, kWsSmem, stream>>>(H, C, A, maps, total, fault);
         count_launch();
         return check_launch("conv_decode_filter_ws_kernel");
     }
