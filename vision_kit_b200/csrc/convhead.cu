@@ -184,25 +184,28 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
                 // always): the arg-max of the logits is the answer and only its product is evaluated.  Otherwise,
                 // anywhere in the warp (tcgen05.ld is warp-collective): the products of all classes within 1e-3 of the
                 // maximum are compared, as before.
-                float m1 = -INFINITY, m2 = -INFINITY;
+                // (four independent accumulators over interleaved classes, merged at the end)
+                float m1, m2;
                 {
+                    float a1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, a2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    int aj[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
                     // columns cb+5 .. cb+84 in chunks [0,32) [32,64) [48,80): the last one overlaps (class 79 is the
                     // anchor's last column; reading 32 more from class 64 on would leave the accumulator for a = 2).
-                    // One chunk at a time: 96 live registers spill in the 17-warp kernel.
+                    // One chunk at a time: 96 live registers spill in this kernel.
                     uint32_t q[32];
-                    auto take = [&](uint32_t u, int c) {
+                    auto take = [&](uint32_t u, int c, int k) {
                         const float x = __uint_as_float(u);
-                        m2 = fmaxf(m2, fminf(m1, x));
-                        bj = x > m1 ? c : bj;
-                        m1 = fmaxf(m1, x);
+                        a2[k] = fmaxf(a2[k], fminf(a1[k], x));
+                        aj[k] = x > a1[k] ? c : aj[k];
+                        a1[k] = fmaxf(a1[k], x);
                     };
                     auto sweep = [&](const uint32_t* q, int first, int lo, int hi) {   // classes first + j inside [lo, hi)
                         if (first >= lo && first + 32 <= hi) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) take(q[j], first + j);
+                            for (int j = 0; j < 32; ++j) take(q[j], first + j, j & 3);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (first + j >= lo && first + j < hi) take(q[j], first + j);
+                            for (int j = 0; j < 32; ++j) if (first + j >= lo && first + j < hi) take(q[j], first + j, j & 3);
                         }
                     };
                     ch_tmem_ld32(q, trow + cb + 5);
@@ -218,6 +221,14 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
                         ch_tmem_wait();
                         sweep(q, nc - 32, 64, nc);
                     }
+                    // merge: largest, runner-up (the smaller of two maxima is a runner-up candidate), index of the largest
+                    auto merge = [&](int x, int y) {
+                        a2[x] = fmaxf(fmaxf(a2[x], a2[y]), fminf(a1[x], a1[y]));
+                        aj[x] = a1[y] > a1[x] ? aj[y] : aj[x];
+                        a1[x] = fmaxf(a1[x], a1[y]);
+                    };
+                    merge(0, 1); merge(2, 3); merge(0, 2);
+                    m1 = a1[0]; m2 = a2[0]; bj = aj[0];
                 }
                 const float near = m1 - 1e-3f;
                 if (__any_sync(0xffffffffu, alive && m2 >= near)) {
@@ -442,12 +453,13 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 // n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
 // ---------------------------------------------------------------------------------------
 constexpr int kWsThreads = 11 * 32;
-constexpr int kWsSlots = 4;                                          // ring depth of the operand tiles
+constexpr int kWsSlots = 6;                                          // ring depth of the operand tiles
 constexpr int kWsBBytes = 128 * 128;                                 // this CTA's half of a W block: 128 rows x 128 B
-constexpr int kWsOffB = kWsSlots * kChABytes;                        // 64 KB
-constexpr int kWsOffBiasA = kWsOffB + kWsSlots * kWsBBytes;          // 128 KB: A tile of the bias step (4 KB)
-constexpr int kWsOffBiasB = kWsOffBiasA + 4096;                      // W tiles of the bias step, one per level (16 KB each)
-constexpr int kWsOffBar = kWsOffBiasB + VK_MAX_LEVELS * kWsBBytes;
+constexpr int kWsOffB = kWsSlots * kChABytes;                        // 96 KB
+constexpr int kWsOffBiasA = kWsOffB + kWsSlots * kWsBBytes;          // 192 KB: A tile of the bias step (4 KB)
+constexpr int kWsOffBiasB = kWsOffBiasA + 4096;                      // W tile of the bias step: level l in the columns 8 l .. 8 l + 7
+constexpr int kWsOffBar = kWsOffBiasB + kWsBBytes;
+static_assert(VK_MAX_LEVELS * 8 <= kChKB, "bias columns of all levels fit one 32-column tile");
 constexpr int kWsSmem = kWsOffBar + 256;
 constexpr uint32_t kWsStageTx = kChABytes + kWsBBytes;               // bytes one block brings: 4 X boxes + 1 W box
 // instruction descriptor of the pair: M = 256 (128 rows per CTA), N = 256, A MN-major, B K-major
@@ -575,9 +587,8 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
             const int n = (int)rank * 128 + tid;
             const float v = (bias && n < cout) ? __ldg(bias + n) : 0.0f;
             const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            uint8_t* b_tile = sBiasB + l * kWsBBytes;
-            *reinterpret_cast<float4*>(b_tile + ch_koff(tid, 0)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
-            *reinterpret_cast<float4*>(b_tile + ch_koff(tid, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(sBiasB + ch_koff(tid, 2 * l)) = make_float4(hi, __fsub_rn(v, hi), 0.f, 0.f);
+            *reinterpret_cast<float4*>(sBiasB + ch_koff(tid, 2 * l + 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -653,7 +664,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 if (ok) {                                                      // bias step, then the tile is complete
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                  "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                 :: "r"(acc_addr), "l"(ch_desc_a(ch_smem(sBiasA))), "l"(ch_desc(ch_smem(sBiasB + q.l * kWsBBytes))),
+                                 :: "r"(acc_addr), "l"(ch_desc_a(ch_smem(sBiasA))), "l"(ch_desc(ch_smem(sBiasB) + q.l * 32)),
                                     "r"(kWsIdesc), "r"(1u) : "memory");
                     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                                  :: "r"(TFULL(g)), "h"((uint16_t)3) : "memory");
@@ -669,8 +680,10 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
             if (!q.valid) break;
             ok &= ws_wait<false>(TFULL(g), (uint32_t)((i >> 1) & 1), s_abort);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifndef VK_CONV_NO_EPILOGUE      // (tuning builds: how long the mainloop alone takes)
             conv_epilogue(H, A, tmem + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(g * kChN), q.l, q.b, q.s0, q.nvalid,
                           etid, s_wtot + 4 * g, 3 + g, ok);
+#endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) ws_arrive_leader(TEMPTY(g));
