@@ -125,11 +125,12 @@ __device__ __forceinline__ void ch_tmem_wait() { asm volatile("tcgen05.wait::ld.
 // Epilogue of one 128-position tile whose accumulator sits in 256 TMEM columns at `trow` (lane
 // offset of the calling warp included): thread `tid` (0..127) = spatial position s0 + tid = TMEM
 // lane, one prediction row per anchor.  `bar_id` names a 128-thread barrier shared by the 4 warps
-// that run it, `s_wtot` 4 ints of their scratch.
+// that run it, `s_wtot` 4 ints of their scratch.  Anchors a_first, a_first + a_step, ... are handled.
 __device__ __forceinline__ void ch_bar_sync(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
 
 __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs& A, uint32_t trow, int l, int b, int s0,
-                                              int nvalid, int tid, int* s_wtot, int bar_id, bool ok) {
+                                              int nvalid, int tid, int* s_wtot, int bar_id, bool ok,
+                                              int a_first = 0, int a_step = 1) {
     const int lane = tid & 31, warp = tid >> 5;
     const int nynx = H.nynx[l], no = H.no;
     const int nc = A.nc;
@@ -137,7 +138,7 @@ __device__ __forceinline__ void conv_epilogue(const HeadDev& H, const FilterArgs
     const int half = tid >> 6;                                 // 64-row segment of the thread inside the tile
     const bool seg_exists = s0 + 64 * half < nynx;
     struct { int variant, nx; float stride; } const gbase{H.variant, H.nx[l], H.stride[l]};
-    for (int a = 0; a < H.na; ++a) {
+    for (int a = a_first; a < H.na; a += a_step) {            // (the persistent kernel splits the anchors over two teams)
         const int cb = a * no;
         uint32_t r[16];
         VK_TMEM_LD16(r, trow + cb);                            // x, y, w, h, obj, first 11 classes
@@ -436,23 +437,23 @@ conv_decode_filter_kernel(const HeadDev H, const ConvHead C, const FilterArgs A,
 // (256 x cin), twice the bytes of its own X block.  A pair computes two tiles with one M = 256 instruction stream:
 // each CTA stages the X block of ITS tile and only ITS HALF of W (128 of the 256 output channels); the tensor cores
 // of both SMs read both halves.  W traffic per tile is halved.
-//   warp 8      producer, one lane: per 32-channel block four cp.async.bulk.tensor boxes of X ([32 k][32 s], swizzle
+//   warp 16     producer, one lane: per 32-channel block four cp.async.bulk.tensor boxes of X ([32 k][32 s], swizzle
 //               128B_ATOM_32B = the MN-major BASE32B operand layout, profiles/micro/tma_probe.cu) and one of W
 //               ([128 n][32 k], swizzle 128B), 32 KB on one transaction barrier; kWsSlots-deep ring; positions past
 //               a plane and output channels past na*no arrive as zeros (TMA out-of-bounds fill)
-//   warp 9      forwarder, one lane: "this CTA's block landed" -> arrive on the LEADER's READY barrier
-//   warp 10     (leader CTA only) MMA issuer, one lane: tcgen05.mma.cta_group::2 into one of TWO 256-column
+//   warp 17     forwarder, one lane: "this CTA's block landed" -> arrive on the LEADER's READY barrier
+//   warp 18     (leader CTA only) MMA issuer, one lane: tcgen05.mma.cta_group::2 into one of TWO 256-column
 //               accumulators (each CTA's TMEM receives its own tile's 128 rows); the bias as one more K = 8 step from
 //               constant tiles built at kernel start; tcgen05.commit multicast to both CTAs -> "slot free" and
 //               "accumulator full" mbarriers
-//   warps 0-7   two epilogue groups (one per accumulator) draining tile i while the mainloop of tile i+1 runs;
-//               "accumulator empty" is signalled on the leader's barrier by both CTAs
+//   warps 0-15  two epilogue groups (one per accumulator) of two 4-warp teams (alternate anchors) draining tile i while
+//               the mainloop of tile i+1 runs; "accumulator empty" is signalled on the leader's barrier by both CTAs
 // A pair's two tiles are the two halves of 256 consecutive positions of one level (the last pair of a level may have
 // an empty second half: its X is zeros and its epilogue writes nothing).
 // Every mbarrier phase is waited in order by its consumer (a parity wait cannot tell phase n from
 // n + 2); every wait is bounded and an abort flag stops all roles if one ever times out.
 // ---------------------------------------------------------------------------------------
-constexpr int kWsThreads = 11 * 32;
+constexpr int kWsThreads = 19 * 32;
 constexpr int kWsSlots = 6;                                          // ring depth of the operand tiles
 constexpr int kWsBBytes = 128 * 128;                                 // this CTA's half of a W block: 128 rows x 128 B
 constexpr int kWsOffB = kWsSlots * kChABytes;                        // 96 KB
@@ -460,7 +461,7 @@ constexpr int kWsOffBiasA = kWsOffB + kWsSlots * kWsBBytes;          // 192 KB: 
 constexpr int kWsOffBiasB = kWsOffBiasA + 4096;                      // W tile of the bias step: level l in the columns 8 l .. 8 l + 7
 constexpr int kWsOffBar = kWsOffBiasB + kWsBBytes;
 static_assert(VK_MAX_LEVELS * 8 <= kChKB, "bias columns of all levels fit one 32-column tile");
-constexpr int kWsSmem = kWsOffBar + 256;
+constexpr int kWsSmem = kWsOffBar + 320;                               // barriers (192 B), TMEM base, abort flag, 64 B of scan scratch
 constexpr uint32_t kWsStageTx = kChABytes + kWsBBytes;               // bytes one block brings: 4 X boxes + 1 W box
 // instruction descriptor of the pair: M = 256 (128 rows per CTA), N = 256, A MN-major, B K-major
 constexpr uint32_t kWsIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(kChN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -547,7 +548,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWsOffBar);   // full[S] ready[S] done[S] tfull[2] tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 192);
     volatile int* s_abort = reinterpret_cast<volatile int*>(smem + kWsOffBar + 196);
-    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 208);     // [2][4]
+    int* s_wtot = reinterpret_cast<int*>(smem + kWsOffBar + 208);     // [2 accumulators][2 teams][4]
     const uint32_t bar0 = ch_smem(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };                  // own: this CTA's copies of the slot landed (transaction count)
     auto READY = [&](int s) { return bar0 + 8u * (kWsSlots + s); };    // leader: both CTAs' operands of the slot landed
@@ -561,7 +562,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-    if (warp == 10) {
+    if (warp == 18) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(ch_smem(s_tmem)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
@@ -573,7 +574,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
         }
         for (int g = 0; g < 2; ++g) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TFULL(g)), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TEMPTY(g)), "r"(8));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(TEMPTY(g)), "r"(16));
         }
         *s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -598,7 +599,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ------------------------------------------------------------------ producer (one lane)
         if (lane == 0) {
             bool ok = true;
@@ -619,7 +620,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // ------------------------------------------------------------------ forwarder (one lane)
         if (lane == 0) {
             bool ok = true;
@@ -634,7 +635,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 18) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA)
         if (lane == 0 && rank == 0) {
             bool ok = true;
@@ -671,9 +672,12 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
                 }
             }
         }
-    } else if (warp < 8) {
-        // ------------------------------------------------------------------ epilogue groups
-        const int g = warp >> 2, etid = tid & 127, ewarp = warp & 3;
+    } else if (warp < 16) {
+        // ------------------------------------------------------------------ epilogue: accumulator g = warps 8g .. 8g+7, two
+        // teams of 4 warps (one per 32-lane quarter of TMEM) taking alternate anchors.  An accumulator is refilled only
+        // after its previous tile is drained, so a tile costs (mainloop + epilogue) / 2 whenever the epilogue is the
+        // longer of the two: the epilogue's LATENCY counts, and two teams cut it by a third (three anchors).
+        const int g = warp >> 3, team = (warp >> 2) & 1, ewarp = warp & 3, etid = ewarp * 32 + lane;
         bool ok = true;
         for (int i = g; ; i += 2) {
             const WsTile q = ws_tile(H, C, pair0 + i * npairs, total_pairs, (int)rank);
@@ -682,7 +686,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifndef VK_CONV_NO_EPILOGUE      // (tuning builds: how long the mainloop alone takes)
             conv_epilogue(H, A, tmem + ((uint32_t)(ewarp * 32) << 16) + (uint32_t)(g * kChN), q.l, q.b, q.s0, q.nvalid,
-                          etid, s_wtot + 4 * g, 3 + g, ok);
+                          etid, s_wtot + 4 * (2 * g + team), 3 + 2 * g + team, ok, team, 2);
 #endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -693,7 +697,7 @@ conv_decode_filter_ws_kernel(const HeadDev H, const ConvHead C, const FilterArgs
     __syncthreads();
     if (tid == 0 && *s_abort) atomicExch(fault, 1);
     ws_cluster_sync();                                                 // neither CTA leaves while the other may still read its shared memory
-    if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
+    if (warp == 18) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512));
 }
 
 }  // namespace vk
