@@ -350,15 +350,21 @@ def main():
         """The captured step issued call by call, with CUDA events on the stream of each kernel:
         [NMS of the previous batch] on the side stream beside [letterbox, filter of this batch]."""
         s = pipe._graph_step & 1 if overlap else 0
-        if overlap:
+        late = overlap and pipe.nms_fork == "after_preprocess"     # the NMS branch forks after the letterbox (as captured)
+
+        def side_nms():
             pipe._graph_step += 1
             side.wait_stream(main_stream)
             if ev: ev[3].record(side)
             _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[s ^ 1], sptr(side)))
             if ev: ev[4].record(side)
+        if overlap and not late:
+            side_nms()
         if ev: ev[0].record(main_stream)
         _lib.check("vk_letterbox_batch", L.vk_letterbox_batch(*pipe._lb_args, sptr(main_stream)))
         if ev: ev[1].record(main_stream)
+        if late:
+            side_nms()
         _lib.check("vk_decode_filter", L.vk_decode_filter(pipe._cfg_ref, C.cast(pipe._lv_arr, C.c_void_p), pipe._lv_dt,
                                                             BATCH, pipe._conf, pipe._ml, pipe._mask_p, pipe._kernel,
                                                             C.byref(pipe._cs[s]), sptr(main_stream)))

@@ -35,7 +35,7 @@ class DetectPipeline:
                  anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
                  swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False,
                  overlap: bool = False, filter_kernel="auto", list_cap: int = ops.LIST_CAP,
-                 fork_preprocess: bool = False, nvtx: bool = False):
+                 fork_preprocess: bool = False, nvtx: bool = False, nms_fork: str = "auto"):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
@@ -59,6 +59,15 @@ class DetectPipeline:
         self.overlap = bool(overlap)
         # captured graphs only: the letterbox on a third branch, beside the filter (they share no data)
         self.fork_preprocess = bool(fork_preprocess)
+        # captured overlapped graphs: where the NMS branch of the previous batch forks off.  "start": beside the letterbox
+        # and the filter; "after_preprocess": beside the filter only.  The copy-peak letterbox loses more to NMS CTAs on
+        # its SMs than the sector-rate-bound sparse filter does (config 2: 117.6 -> 113.4 us per step), while the eval
+        # NMS's select pass is better started early (config 3: 271 vs 292 us).
+        if nms_fork not in ("auto", "start", "after_preprocess"):
+            raise ValueError(f"nms_fork={nms_fork!r}")
+        if nms_fork == "auto":
+            nms_fork = "start" if ops.expects_dense(filter_kernel, conf_thres) else "after_preprocess"
+        self.nms_fork = nms_fork
         nsets = 2 if self.overlap else 1
         if agnostic and list_cap == ops.LIST_CAP:
             list_cap *= 2        # agnostic NMS goes deeper: most candidates it meets are other classes of rows already decided
@@ -227,11 +236,16 @@ class DetectPipeline:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     main = torch.cuda.current_stream()
+                    late = with_preprocess and not self.fork_preprocess and self.nms_fork == "after_preprocess"
+                    if late:
+                        self.preprocess()
                     self.side.wait_stream(main)
                     rc = self._lib.vk_nms_batched(*self._nms_args[s ^ 1], C.c_void_p(self.side.cuda_stream))
                     if rc:
                         _lib.check("vk_nms_batched", rc)
-                    if with_preprocess and self.fork_preprocess:
+                    if late:
+                        pass
+                    elif with_preprocess and self.fork_preprocess:
                         self.pre_stream.wait_stream(main)
                         rc = self._lib.vk_letterbox_batch(*self._lb_args, C.c_void_p(self.pre_stream.cuda_stream))
                         if rc:
