@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""Launches the eval-mode fused filter (dense kernel) a few times, for ncu captures: python profiles/run_dense.py [batch]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vision_kit_b200 import ops
+from tests import synth
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+dev = torch.device("cuda:0")
+grids = [(640 // s, 640 // s) for s in synth.STRIDES]
+cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)
+lv = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
+buf = ops.decode_filter(cfg, lv, 0.001, True, kernel="dense")
+for _ in range(3):
+    ops.decode_filter(cfg, lv, 0.001, True, buf=buf, kernel="dense")
+torch.cuda.synchronize()
+print("ok", int(buf.counts.sum()))

@@ -1,5 +1,8 @@
+#!/usr/bin/env python
+"""Captured-step variants of configs 2 and 3 on one GPU (where the NMS branch forks, priority of the side stream):
+python profiles/step_variants.py"""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tests import synth
 from vision_kit_b200.pipeline import DetectPipeline
@@ -7,13 +10,17 @@ dev = torch.device("cuda:0")
 B = 64
 ident = list(torch.from_numpy(synth.images_u8(B, 640, 640, seed=0)).to(dev))
 lv2 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
-for overlap, fork in ((True, False), (True, True), (False, False)):
-    pipe = DetectPipeline("v5", batch=B, device=dev, overlap=overlap, fork_preprocess=fork)
-    pipe.plan_sources(ident); pipe.capture(lv2)
-    for _ in range(10): pipe.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(200): pipe.replay()
-    e1.record(); torch.cuda.synchronize()
-    print(f"VK_NMS_T={os.environ.get('VK_NMS_T','-')} overlap={overlap} fork={fork}: {e0.elapsed_time(e1)/200*1e3:.1f} us/step")
+EVAL = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)
+for name, kw in (("config 2", {}), ("config 3", EVAL)):
+    for fork in ("start", "after_preprocess"):
+        for prio in (0, -1):
+            pipe = DetectPipeline("v5", batch=B, device=dev, overlap=True, nms_fork=fork, side_priority=prio, **kw)
+            pipe.plan_sources(ident); pipe.capture(lv2)
+            for _ in range(10): pipe.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(200): pipe.replay()
+            e1.record(); torch.cuda.synchronize()
+            print(f"{name} nms_fork={fork:16s} side_priority={prio:2d}: {e0.elapsed_time(e1)/200*1e3:.1f} us/step", flush=True)
+            del pipe

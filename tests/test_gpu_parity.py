@@ -434,6 +434,49 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
         assert torch.equal(op.counts, oa.counts) and torch.equal(op.dets, oa.dets) and torch.equal(op.keep, oa.keep)
 
 
+@pytest.mark.parametrize("conf", [0.001, 0.05, 0.5, 0.0])
+def test_dense_filter_pretest_is_a_superset_at_the_threshold(conf, vk, cuda):
+    """The multi-label dense kernel (decode_filter_pairs_kernel) pre-tests logits against logit(conf / obj) - margin
+    and runs the exact `sigmoid(x) * obj > conf` only on the survivors.  Class logits are planted within a few 1e-7
+    (relative) of the exact threshold of their row, for objectness values from barely above conf to ~1 (and rows that
+    fail :99, and -inf / +inf / NaN logits): the candidates must be the sparse kernel's, bit for bit."""
+    nc, img = 80, 320
+    cfg, _ = _cfg(vk, "v5", img=img, nc=nc)
+    rng = np.random.default_rng(1234)
+    lv = []
+    for x in synth.head_logits(2, seed=9, img=img, nc=nc, clusters=0):
+        x = x.copy()                                          # (B, na * no, ny, nx)
+        B, _, ny, nx = x.shape
+        v = x.reshape(B, 3, nc + 5, ny, nx)
+        # objectness: log-uniform in probability from just above conf to 1, a tenth of the rows under conf
+        lo = max(conf, 1e-6)
+        pobj = lo * (1.0 / lo) ** rng.random((B, 3, ny, nx))
+        pobj *= 1.0 + 10.0 ** rng.uniform(-7, -1, pobj.shape)
+        pobj = np.where(rng.random(pobj.shape) < 0.1, lo * 0.9, np.minimum(pobj, 1 - 1e-7))
+        v[:, :, 4] = np.log(pobj / (1 - pobj)).astype(np.float32)
+        # class logits: the threshold logit of the row, displaced by up to +-64 float32 ulps of itself (plus exact 0)
+        s = np.clip(lo / pobj, 1e-30, 1 - 1e-9)[:, :, None]
+        t = np.log(s / (1 - s))
+        k = rng.integers(-64, 65, size=(B, 3, nc, ny, nx))
+        planted = (t * (1.0 + k * 2.0 ** -23)).astype(np.float32)
+        take = rng.random(planted.shape) < 0.5
+        v[:, :, 5:] = np.where(take, planted, v[:, :, 5:])
+        special = rng.random(planted.shape)
+        v[:, :, 5:][special < 0.001] = -np.inf
+        v[:, :, 5:][(special >= 0.001) & (special < 0.002)] = np.inf
+        v[:, :, 5:][(special >= 0.002) & (special < 0.003)] = np.nan
+        lv.append(torch.from_numpy(x).to(cuda))
+    a = vk.ops.decode_filter(cfg, lv, conf, True, kernel="sparse")
+    b = vk.ops.decode_filter(cfg, lv, conf, True, kernel="dense")
+    torch.cuda.synchronize()
+    assert torch.equal(a.counts, b.counts) and int(a.counts.sum()) > 1000
+    for (la, ra, ba), (lb, rb, bb) in zip(_canonical(a), _canonical(b)):
+        assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb, equal_nan=True)
+    # the planted logits really straddle the cut: some pass and some fail on both sides of the true threshold
+    n_all = 2 * 3 * nc * sum((img // st) ** 2 for st in synth.STRIDES)
+    assert 0.05 * n_all < int(a.counts.sum()) < (0.95 if conf > 0 else 1.0) * n_all
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("variant,nc,img,conf,ml", [
     ("v5", 80, 640, 0.25, False),

@@ -795,6 +795,205 @@ decode_filter_lanes_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
 }
 
 // ---------------------------------------------------------------------------------------
+// Multi-label dense filter, two phases ("pairs" kernel; the default at eval thresholds when every plane has an even
+// number of rows and the level pointers are aligned for two-element loads -- the lanes kernel above otherwise).
+// The one-phase loop spends two MUFUs and two POPCs per (row, class) pair although only ~1 pair in 8 becomes a
+// candidate at eval thresholds (XU pipe 61% busy, 4900 issue slots per tile).  Here the transcendentals run on
+// candidates only:
+//   (1) lane j owns rows 2j and 2j+1 of the tile (one 8-byte load per class plane).  Every logit takes a conservative
+//       pre-test in the logit domain, !(x <= logit(conf / obj) - margin): one FSET + one LOP3 into a 16-bit mask per
+//       8 classes, threshold computed once per row (`logit_floor`).  Survivors go to a per-warp shared-memory list
+//       (logit, class << 6 | row) in lane-private runs: one POPC and one warp scan per 8 classes.
+//   (2) while the list holds 32 entries, a dense round takes the last 32: every lane computes the exact
+//       p = sigmoid(x) * obj > conf of image_proc.py:135,141 for one entry and one ballot gives the passing lanes their
+//       slots.  The order of a tile's candidates is free (include/vk_b200.h: consumers order by id).
+// Every stored bit comes from the same `sigmoidf_vk` as in the other kernels; the pre-test only has to be a superset
+// of the exact test.
+// ---------------------------------------------------------------------------------------
+#ifndef VK_PAIRS_BPS
+#define VK_PAIRS_BPS 8
+#endif
+constexpr int kPairList = 16 * 32 + 32;       // one 8-class step appends at most 512 entries to at most 31 left over
+
+// Largest logit that certainly fails `fl(sigmoidf_vk(x) * obj) > conf`, minus a margin (needs obj > conf > 0).
+//   pass  =>  sigma(x) (1 + d) obj (1 + 2^-24) > conf with |d| <= 4e-7 (vk_common.cuh)  =>  sigma(x) > (conf / obj)(1 - 5e-7)
+//         =>  sigma(x) > s := min(fl(fl(conf / obj) * 0.999996f), 0.999f)  =>  x > logit(s) = -ln(1 / s - 1).
+// Computed value: u = fl(1 / s) - 1 >= 1.001e-3 carries a relative error <= 6e-8 / (1 - s) + 6e-8 <= 6.1e-5, lg2.approx
+// adds <= 2^-22 absolute and the product with ln 2 a relative 6e-8 (|logit| <= 104): the computed logit is within
+// 1.1e-4 of the true one; the margin is 1e-3.  s == 0 (conf / obj underflows) gives u = +inf and a floor of -inf:
+// every logit goes on to the exact test.
+__device__ __forceinline__ float logit_floor(float conf, float obj) {
+    const float s = fminf(__fmul_rn(__fdiv_rn(conf, obj), 0.999996f), 0.999f);
+    const float u = __fsub_rn(__fdiv_rn(1.0f, s), 1.0f);
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+    return __fsub_rn(__fmul_rn(l, -0.6931471805599453f), 1e-3f);
+}
+// m | (!(x <= thr) ? bit : 0) as FSETP + predicated LOP3 (a NaN threshold passes every logit, a NaN logit goes on
+// to the exact test and fails it there)
+__device__ __forceinline__ void pretest_bit(float x, float thr, uint32_t bit, uint32_t& m) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gtu.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(x), "f"(thr), "r"(bit));
+}
+// inclusive warp scan, two instructions per level (the shuffle's own predicate guards the add)
+__device__ __forceinline__ int warp_incl_scan_p(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        asm("{\n\t.reg .s32 t;\n\t.reg .pred p;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.s32 %0, %0, t;\n\t}"
+            : "+r"(v) : "r"(o));
+    return v;
+}
+template <class T> struct Pair;
+template <> struct Pair<float> {
+    typedef float2 type;
+    static __device__ __forceinline__ float2 ld(const float2* p) { return __ldg(p); }
+};
+template <> struct Pair<__half> {
+    typedef __half2 type;
+    static __device__ __forceinline__ float2 ld(const __half2* p) { return __half22float2(__ldg(p)); }
+};
+template <> struct Pair<__nv_bfloat16> {
+    typedef __nv_bfloat162 type;
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat162* p) { return __bfloat1622float2(__ldg(p)); }
+};
+
+template <class T>
+__global__ void __launch_bounds__(32 * kLaneWarps, VK_PAIRS_BPS)
+decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
+    typedef typename Pair<T>::type T2;
+    // logits that passed the pre-test [0] and their class << 6 | row of the tile [1]
+    __shared__ uint32_t s_list[kLaneWarps][2][kPairList];
+    __shared__ __align__(8) float s_obj[kLaneWarps][kTileS];
+    __shared__ __align__(4) uint8_t s_hit[kLaneWarps][kTileS];          // rows that produced a candidate
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int t = blockIdx.x * kLaneWarps + warp;
+    if (t >= total_tiles) return;
+    const LogitLocator<T> L{H};
+    const LogitTileRef<T> q = L.locate(t);
+    const int nc = A.nc;
+    const int np = q.nynx >> 1;                           // pairs per plane (nynx is even: checked by the host)
+    const bool v = 2 * lane < q.nvalid;                   // nvalid is even as well: a pair is inside or outside
+    // Pairs past the end of a ragged tile read pair 0 instead (no per-load predicate) and carry obj = NaN.
+    const T2* const base = reinterpret_cast<const T2*>(q.base) + (v ? lane : 0);        // channel 0, the lane's pair
+    uint32_t* const list = s_list[warp][0];
+    float* const sobj = s_obj[warp];
+    uint8_t* const shit = s_hit[warp];
+    // objectness (image_proc.py:99); rows at or under the threshold keep obj = 0 and never pass
+    const float2 o = Pair<T>::ld(base + (size_t)4 * np);
+    const float oa = sigmoidf_vk(o.x), ob = sigmoidf_vk(o.y);
+    const float obj0 = v ? (oa > A.conf ? oa : 0.0f) : __int_as_float(0x7fc00000);
+    const float obj1 = v ? (ob > A.conf ? ob : 0.0f) : __int_as_float(0x7fc00000);
+    if (!__any_sync(0xffffffffu, obj0 > 0.0f || obj1 > 0.0f) && A.conf >= 0.0f) {         // no row passes :99
+        if (lane == 0) {
+            A.seg_count[(size_t)q.b * A.segs + q.seg] = 0;
+            if (q.seg == 0) A.flags[q.b] = cand_flags(A);
+        }
+        return;
+    }
+    float thr0 = INFINITY, thr1 = INFINITY;               // rows that failed :99 (or lie past the tile) never pass
+    if (A.conf > 0.0f) {
+        if (obj0 > 0.0f) thr0 = logit_floor(A.conf, obj0);
+        if (obj1 > 0.0f) thr1 = logit_floor(A.conf, obj1);
+    } else if (v) {                                       // conf <= 0: even a product of 0 may pass, test every logit
+        thr0 = thr1 = __int_as_float(0x7fc00000);
+    }
+    *reinterpret_cast<float2*>(sobj + 2 * lane) = make_float2(obj0, obj1);
+    *reinterpret_cast<uint16_t*>(shit + 2 * lane) = 0;
+    __syncwarp();
+    uint2* out = reinterpret_cast<uint2*>(A.cand + (size_t)q.b * A.cap) + (size_t)q.seg * A.tile_cap;
+    asm volatile("" : "+l"(out));                         // one base register (not re-derived per store)
+    const uint32_t id0 = (uint32_t)q.row0 * (uint32_t)nc;
+    uint32_t run = 0;                                     // candidates of the tile so far (warp-uniform)
+    int fill = 0;                                         // entries waiting in the list (warp-uniform)
+    // one dense round over list entries [at, at + 32)
+    auto settle = [&](int at, bool active) {
+        const uint32_t* e = list + at + lane;
+        const float x = active ? __uint_as_float(e[0]) : 0.0f;
+        const uint32_t code = active ? e[kPairList] : 0u;
+        const uint32_t r = code & 63u;
+        const float p = __fmul_rn(sigmoidf_vk(x), sobj[r]);                                      // image_proc.py:135
+        const bool f = active && p > A.conf;                                                     // :141
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (f) {
+            out[run + (uint32_t)__popc(b & lt)] = make_uint2(__float_as_uint(p), id0 + r * (uint32_t)nc + (code >> 6));
+            shit[r] = 1;
+        }
+        run += __popc(b);
+    };
+    const T2* src = base + (size_t)5 * np;                // class plane being fetched
+    float2 x[8];
+    auto fetch = [&](int c0, float2* a) {
+        if (c0 + 8 <= nc) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a[u] = Pair<T>::ld(src); src += np; }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a[u] = c0 + u < nc ? Pair<T>::ld(src) : make_float2(0.0f, 0.0f);
+                src += np;
+            }
+        }
+    };
+    // one step: the next 8 planes are requested, the current 8 tested, their survivors listed, full rounds settled
+    auto step = [&](int c0, const float2* cur, float2* nxt) {
+        fetch(c0 + 8, nxt);
+        uint32_t m = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            pretest_bit(cur[u].x, thr0, 1u << (2 * u), m);
+            pretest_bit(cur[u].y, thr1, 2u << (2 * u), m);
+        }
+        if (A.class_mask != nullptr || c0 + 8 > nc) {     // class filter (:151) and the classes past nc: two bits each
+            uint32_t al = A.class_mask ? (__ldg(A.class_mask + (c0 >> 5)) >> (c0 & 31)) & 0xffu : 0xffu;
+            if (nc - c0 < 8) al &= (1u << (nc - c0)) - 1u;
+            al = (al | (al << 4)) & 0x0f0fu;
+            al = (al | (al << 2)) & 0x3333u;
+            al = (al | (al << 1)) & 0x5555u;
+            m &= al | (al << 1);
+        }
+        const int cnt = __popc(m);
+        const int incl = warp_incl_scan_p(cnt);
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot) {
+            uint32_t* w = list + (fill + incl - cnt);
+            const uint32_t cb = ((uint32_t)c0 << 6) | (uint32_t)(2 * lane);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (m & (1u << (2 * u))) { w[0] = __float_as_uint(cur[u].x); w[kPairList] = cb + (uint32_t)(u << 6); ++w; }
+                if (m & (2u << (2 * u))) { w[0] = __float_as_uint(cur[u].y); w[kPairList] = cb + (uint32_t)(u << 6) + 1u; ++w; }
+            }
+            fill += tot;
+            __syncwarp();
+            while (fill >= 32) { fill -= 32; settle(fill, true); }      // the last 32: what stays needs no move
+            __syncwarp();
+        }
+    };
+    float2 y[8];
+    fetch(0, x);
+    for (int c0 = 0; c0 < nc; c0 += 16) {                 // (two steps per trip: the buffers swap without copies)
+        step(c0, x, y);
+        if (c0 + 8 < nc) step(c0 + 8, y, x);
+    }
+    if (fill) settle(0, lane < fill);
+    __syncwarp();
+    const uint32_t hit = *reinterpret_cast<const uint16_t*>(shit + 2 * lane);
+    // boxes of the rows that produced candidates
+    if (hit) {
+        const PlaneGeom geom{H.variant, H.nx[q.l], q.s0, H.stride[q.l], H.anchors[q.l][2 * q.a], H.anchors[q.l][2 * q.a + 1]};
+        float4* boxes = A.boxes + (size_t)q.b * A.rows + q.row0 + 2 * lane;
+        const float2 l0 = Pair<T>::ld(base), l1 = Pair<T>::ld(base + np), l2 = Pair<T>::ld(base + 2 * (size_t)np),
+                     l3 = Pair<T>::ld(base + 3 * (size_t)np);
+        if (hit & 0xffu) boxes[0] = geom.box(l0.x, l1.x, l2.x, l3.x, q.s0 + 2 * lane);
+        if (hit >> 8) boxes[1] = geom.box(l0.y, l1.y, l2.y, l3.y, q.s0 + 2 * lane + 1);
+    }
+    if (lane == 0) {
+        A.seg_count[(size_t)q.b * A.segs + q.seg] = (int)run;
+        if (q.seg == 0) A.flags[q.b] = cand_flags(A);
+        if (run) atomicAdd(A.counts + q.b, (int)run);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Dense variant of filter_pred (the `nms(prediction)` drop-in at eval thresholds): the same
 // persistent pipeline and (row, class part) mapping as decode_filter_dense_kernel, reading an
 // existing (B, rows, no) prediction tensor.  A tile is 64 consecutive rows = one contiguous run of
@@ -1048,6 +1247,19 @@ static int launch_decode_filter_lanes(const HeadDev& H, const FilterArgs& A, int
     return check_launch("decode_filter_lanes_kernel");
 }
 
+// The pairs kernel loads two rows at once: every plane needs an even number of rows and 2-element alignment.
+static bool pairs_ok(const HeadDev& H, size_t elem) {
+    for (int l = 0; l < H.nl; ++l)
+        if ((H.nynx[l] & 1) || (reinterpret_cast<uintptr_t>(H.lv[l]) & (2 * elem - 1))) return false;
+    return true;
+}
+template <class T>
+static int launch_decode_filter_pairs(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
+    decode_filter_pairs_kernel<T><<<ceil_div(total_tiles, kLaneWarps), 32 * kLaneWarps, 0, stream>>>(H, A, total_tiles);
+    count_launch();
+    return check_launch("decode_filter_pairs_kernel");
+}
+
 template <class T, int NK, bool ML>
 static int launch_decode_filter_rows(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
     int grid = ceil_div(total_tiles, kRowWarps);
@@ -1084,6 +1296,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels,
     const bool ml = A.multi_label != 0;
     if (pick_dense(kernel, conf_thres)) {
 #define VK_DL_T(T)                                                                                  \
+        if (ml && pairs_ok(H, sizeof(T)) && !getenv("VK_NO_PAIRS")) return launch_decode_filter_pairs<T>(H, A, total_tiles, stream); \
         return ml ? launch_decode_filter_lanes<T, true>(H, A, total_tiles, stream)                   \
                   : launch_decode_filter_lanes<T, false>(H, A, total_tiles, stream)
         VK_BY_DTYPE(dtype, VK_DL_T);

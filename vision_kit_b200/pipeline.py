@@ -35,7 +35,8 @@ class DetectPipeline:
                  anchors=None, strides=(8, 16, 32), dtype=torch.float32, color=(114, 114, 114),
                  swap_rb: bool = True, device=None, cand_cap: Optional[int] = None, want_keep: bool = False,
                  overlap: bool = False, filter_kernel="auto", list_cap: int = ops.LIST_CAP,
-                 fork_preprocess: bool = False, nvtx: bool = False, nms_fork: str = "auto"):
+                 fork_preprocess: bool = False, nvtx: bool = False, nms_fork: str = "auto",
+                 side_priority: int = 0):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if isinstance(img_sz, int):
             img_sz = (img_sz, img_sz)
@@ -83,7 +84,7 @@ class DetectPipeline:
         if self.fork_preprocess:
             self.pre_stream = torch.cuda.Stream(device=self.device)
         if self.overlap:
-            self.side = torch.cuda.Stream(device=self.device)
+            self.side = torch.cuda.Stream(device=self.device, priority=int(side_priority))
             self._ev_filter = [torch.cuda.Event() for _ in range(2)]
             self._ev_nms = [torch.cuda.Event() for _ in range(2)]
             self._nms_pending = [False, False]
