@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Captured-step variants of configs 2 and 3 on one GPU (where the NMS branch forks, priority of the side stream):
+"""Captured-step variants of config 3 on one GPU (tuning knobs read from the environment at capture time):
 python profiles/step_variants.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,20 +7,18 @@ import torch
 from tests import synth
 from vision_kit_b200.pipeline import DetectPipeline
 dev = torch.device("cuda:0")
-B = 64
+B = int(os.environ.get("VK_BATCH", "64"))
 ident = list(torch.from_numpy(synth.images_u8(B, 640, 640, seed=0)).to(dev))
 lv2 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
 EVAL = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)
-for name, kw in (("config 2", {}), ("config 3", EVAL)):
-    for fork in ("start", "after_preprocess"):
-        for prio in (0, -1):
-            pipe = DetectPipeline("v5", batch=B, device=dev, overlap=True, nms_fork=fork, side_priority=prio, **kw)
-            pipe.plan_sources(ident); pipe.capture(lv2)
-            for _ in range(10): pipe.replay()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(200): pipe.replay()
-            e1.record(); torch.cuda.synchronize()
-            print(f"{name} nms_fork={fork:16s} side_priority={prio:2d}: {e0.elapsed_time(e1)/200*1e3:.1f} us/step", flush=True)
-            del pipe
+for fork in ("start", "after_preprocess"):
+    pipe = DetectPipeline("v5", batch=B, device=dev, overlap=True, nms_fork=fork, **EVAL)
+    pipe.plan_sources(ident); pipe.capture(lv2)
+    for _ in range(10): pipe.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200): pipe.replay()
+    e1.record(); torch.cuda.synchronize()
+    print(f"config 3 B={B} SEL_PER_SM={os.environ.get('VK_SEL_PER_SM','-')} NMS_LIST_T={os.environ.get('VK_NMS_LIST_T','-')} nms_fork={fork:16s}: {e0.elapsed_time(e1)/200*1e3:.1f} us/step", flush=True)
+    del pipe

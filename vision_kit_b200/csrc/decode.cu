@@ -856,14 +856,25 @@ template <> struct Pair<__nv_bfloat16> {
     static __device__ __forceinline__ float2 ld(const __nv_bfloat162* p) { return __bfloat1622float2(__ldg(p)); }
 };
 
+// shared memory of one warp of the pairs kernel, addressed with explicit 32-bit shared addresses (through generic
+// pointers the compiler rebuilds the shared window base, an S2R + LEA, inside the loops)
+constexpr int kPairX = 0;                                  // logits that passed the pre-test
+constexpr int kPairC = kPairX + 4 * kPairList;             // ... their class << 6 | row of the tile
+constexpr int kPairObj = kPairC + 4 * kPairList;           // objectness of the 64 rows (0: failed :99, NaN: past the tile)
+constexpr int kPairHit = kPairObj + 4 * kTileS;            // rows that produced a candidate (bytes)
+constexpr int kPairBytes = kPairHit + kTileS;
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
 template <class T>
 __global__ void __launch_bounds__(32 * kLaneWarps, VK_PAIRS_BPS)
 decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
     typedef typename Pair<T>::type T2;
-    // logits that passed the pre-test [0] and their class << 6 | row of the tile [1]
-    __shared__ uint32_t s_list[kLaneWarps][2][kPairList];
-    __shared__ __align__(8) float s_obj[kLaneWarps][kTileS];
-    __shared__ __align__(4) uint8_t s_hit[kLaneWarps][kTileS];          // rows that produced a candidate
+    __shared__ __align__(16) uint8_t s_warp[kLaneWarps][kPairBytes];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int t = blockIdx.x * kLaneWarps + warp;
@@ -875,9 +886,8 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     const bool v = 2 * lane < q.nvalid;                   // nvalid is even as well: a pair is inside or outside
     // Pairs past the end of a ragged tile read pair 0 instead (no per-load predicate) and carry obj = NaN.
     const T2* const base = reinterpret_cast<const T2*>(q.base) + (v ? lane : 0);        // channel 0, the lane's pair
-    uint32_t* const list = s_list[warp][0];
-    float* const sobj = s_obj[warp];
-    uint8_t* const shit = s_hit[warp];
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_warp[warp]);
+    asm volatile("" : "+r"(sb));                          // one register, not re-derived
     // objectness (image_proc.py:99); rows at or under the threshold keep obj = 0 and never pass
     const float2 o = Pair<T>::ld(base + (size_t)4 * np);
     const float oa = sigmoidf_vk(o.x), ob = sigmoidf_vk(o.y);
@@ -897,26 +907,28 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     } else if (v) {                                       // conf <= 0: even a product of 0 may pass, test every logit
         thr0 = thr1 = __int_as_float(0x7fc00000);
     }
-    *reinterpret_cast<float2*>(sobj + 2 * lane) = make_float2(obj0, obj1);
-    *reinterpret_cast<uint16_t*>(shit + 2 * lane) = 0;
+    sts32(sb + kPairObj + 8 * lane, __float_as_uint(obj0));
+    sts32(sb + kPairObj + 8 * lane + 4, __float_as_uint(obj1));
+    if (lane < kTileS / 4) sts32(sb + kPairHit + 4 * lane, 0u);
     __syncwarp();
     uint2* out = reinterpret_cast<uint2*>(A.cand + (size_t)q.b * A.cap) + (size_t)q.seg * A.tile_cap;
     asm volatile("" : "+l"(out));                         // one base register (not re-derived per store)
-    const uint32_t id0 = (uint32_t)q.row0 * (uint32_t)nc;
+    uint32_t id0 = (uint32_t)q.row0 * (uint32_t)nc;
+    asm volatile("" : "+r"(id0));
     uint32_t run = 0;                                     // candidates of the tile so far (warp-uniform)
     int fill = 0;                                         // entries waiting in the list (warp-uniform)
     // one dense round over list entries [at, at + 32)
     auto settle = [&](int at, bool active) {
-        const uint32_t* e = list + at + lane;
-        const float x = active ? __uint_as_float(e[0]) : 0.0f;
-        const uint32_t code = active ? e[kPairList] : 0u;
+        const uint32_t e = sb + 4u * (uint32_t)(at + lane);
+        const float x = active ? __uint_as_float(lds32(e + kPairX)) : 0.0f;
+        const uint32_t code = active ? lds32(e + kPairC) : 0u;
         const uint32_t r = code & 63u;
-        const float p = __fmul_rn(sigmoidf_vk(x), sobj[r]);                                      // image_proc.py:135
+        const float p = __fmul_rn(sigmoidf_vk(x), __uint_as_float(lds32(sb + kPairObj + 4u * r)));      // image_proc.py:135
         const bool f = active && p > A.conf;                                                     // :141
         const unsigned b = __ballot_sync(0xffffffffu, f);
         if (f) {
             out[run + (uint32_t)__popc(b & lt)] = make_uint2(__float_as_uint(p), id0 + r * (uint32_t)nc + (code >> 6));
-            shit[r] = 1;
+            asm volatile("st.shared.u8 [%0], %1;" :: "r"(sb + kPairHit + r), "r"(1u) : "memory");
         }
         run += __popc(b);
     };
@@ -955,12 +967,13 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
         const int incl = warp_incl_scan_p(cnt);
         const int tot = __shfl_sync(0xffffffffu, incl, 31);
         if (tot) {
-            uint32_t* w = list + (fill + incl - cnt);
-            const uint32_t cb = ((uint32_t)c0 << 6) | (uint32_t)(2 * lane);
+            uint32_t w = sb + 4u * (uint32_t)(fill + incl - cnt);
+            uint32_t cb = ((uint32_t)c0 << 6) | (uint32_t)(2 * lane);
+            asm volatile("" : "+r"(cb));                  // (the compiler re-derives it from %tid per entry otherwise)
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (m & (1u << (2 * u))) { w[0] = __float_as_uint(cur[u].x); w[kPairList] = cb + (uint32_t)(u << 6); ++w; }
-                if (m & (2u << (2 * u))) { w[0] = __float_as_uint(cur[u].y); w[kPairList] = cb + (uint32_t)(u << 6) + 1u; ++w; }
+                if (m & (1u << (2 * u))) { sts32(w + kPairX, __float_as_uint(cur[u].x)); sts32(w + kPairC, cb + (uint32_t)(u << 6)); w += 4; }
+                if (m & (2u << (2 * u))) { sts32(w + kPairX, __float_as_uint(cur[u].y)); sts32(w + kPairC, cb + (uint32_t)(u << 6) + 1u); w += 4; }
             }
             fill += tot;
             __syncwarp();
@@ -976,7 +989,8 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     }
     if (fill) settle(0, lane < fill);
     __syncwarp();
-    const uint32_t hit = *reinterpret_cast<const uint16_t*>(shit + 2 * lane);
+    uint32_t hit;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(hit) : "r"(sb + kPairHit + 2 * lane) : "memory");
     // boxes of the rows that produced candidates
     if (hit) {
         const PlaneGeom geom{H.variant, H.nx[q.l], q.s0, H.stride[q.l], H.anchors[q.l][2 * q.a], H.anchors[q.l][2 * q.a + 1]};
