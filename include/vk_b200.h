@@ -166,7 +166,8 @@ int vk_decode_filter_segments(const VkHeadCfg* cfg); /* for vk_decode_filter */
 
 /* Which kernel a filter call uses (per call; both produce identical candidates, boxes and counts):
  * AUTO picks from the threshold (conf < 0.05, where most rows survive: DENSE); SPARSE = one warp per
- * 64-row tile gathering only the rows with obj > conf; DENSE = persistent, whole tiles staged in shared memory. */
+ * 64-row tile gathering only the rows with obj > conf; DENSE = every logit of every tile is read once, coalesced
+ * (multi-label: a logit-domain pre-test, then the exact test on the survivors only). */
 #define VK_FILTER_AUTO 0
 #define VK_FILTER_SPARSE 1
 #define VK_FILTER_DENSE 2

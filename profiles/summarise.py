@@ -74,6 +74,21 @@ if os.path.exists(rp):
             pass
         out.append("")
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
+    pipes = [("ALU %", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+             ("FMA %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+             ("XU %", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+             ("LSU %", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+             ("issue active %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+             ("warp instructions", "smsp__inst_executed.sum"),
+             ("long-scoreboard stall (warps per issue)", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio")]
+    pipes = [(n, h.index(m)) for n, m in pipes if m in h]
+    if pipes:
+        out += ["## Pipe utilisation (same capture)", "", "| kernel | " + " | ".join(n for n, _ in pipes) + " |",
+                "|---|" + "---|" * len(pipes)]
+        for r in rows[2:]:
+            name = r[kn].split("(")[0].replace("void ", "")
+            out.append(f"| `{name}` | " + " | ".join(r[i] for _, i in pipes) + " |")
+        out.append("")
 
 open(os.path.join(ROOT, "profiles", f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
