@@ -1,17 +1,15 @@
 #!/usr/bin/env python
-"""Device time of the eval-mode (dense) fused filter of whichever library VK_B200_LIB names (tuning builds)."""
+"""Device time of the eval-mode NMS (select pass + per-image kernel) of whichever library VK_B200_LIB names:
+python profiles/nms_bench.py [tag]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vision_kit_b200 import ops
 from tests import synth
 tag = sys.argv[1] if len(sys.argv) > 1 else os.path.basename(os.environ.get("VK_B200_LIB", "default"))
-B = 64
 dev = torch.device("cuda:0")
 grids = [(640 // s, 640 // s) for s in synth.STRIDES]
 cfg = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids)
-lv = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
-lvh = [t.half() for t in lv]
 
 
 def timeit(fn, iters=10):
@@ -31,8 +29,11 @@ def timeit(fn, iters=10):
 
 
 out = []
-for name, levels, conf, ml, k in (("eval ML f32", lv, 0.001, True, "dense"), ("eval ML f16", lvh, 0.001, True, "dense"),
-                                  ("eval ML f32 one-pass", lv, 0.001, True, "dense_onepass"), ("best-class dense f32", lv, 0.01, False, "dense")):
-    buf = ops.decode_filter(cfg, levels, conf, ml, kernel=k)
-    out.append(f"{name} {timeit(lambda: ops.decode_filter(cfg, levels, conf, ml, buf=buf, kernel=k)):7.1f} us")
-print(f"{tag:24s} " + "   ".join(out) + f"   ({int(buf.counts.sum())} cand)")
+for B in (32, 64, 256):
+    lv = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20)]
+    buf = ops.decode_filter(cfg, lv, 0.001, True)
+    for agn in (False, True):
+        o = ops.nms_batched(buf, 0.6, agnostic=agn)
+        out.append(f"B={B}{' agnostic' if agn else ''} {timeit(lambda: ops.nms_batched(buf, 0.6, agnostic=agn, out=o)):7.1f} us")
+    del lv, buf
+print(f"{tag:16s} nms eval: " + "   ".join(out))

@@ -411,7 +411,7 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
     lv = [torch.from_numpy(x).to(cuda) for x in synth.head_logits(3, seed=77 + nc, img=img, nc=nc, clusters=12)]
     res, resp = {}, {}
     pred = vk.ops.detect_decode(cfg, lv)
-    for mode, kernel in ((1, "sparse"), (2, "dense")):
+    for mode, kernel in ((1, "sparse"), (2, "dense"), (3, "dense_onepass")):
         buf = vk.ops.decode_filter(cfg, lv, conf, ml, classes=classes, kernel=kernel)
         out = vk.ops.nms_batched(buf, 0.6, want_keep=True)
         bufp = vk.ops.filter_pred(pred, conf, ml, classes=classes, kernel=kernel)      # the nms(prediction) drop-in path
@@ -419,14 +419,16 @@ def test_dense_and_sparse_filter_kernels_are_bit_identical(variant, nc, img, con
         torch.cuda.synchronize()
         res[mode] = (_canonical(buf), buf.counts.cpu().numpy(), out)
         resp[mode] = (_canonical(bufp), bufp.counts.cpu().numpy(), outp)
-    (ca, na, oa), (cb, nb, ob) = res[1], res[2]
-    assert np.array_equal(na, nb)
+    ca, na, oa = res[1]
     assert na.sum() > 0 or conf >= 0.25
-    for (la, ra, ba), (lb, rb, bb) in zip(ca, cb):
-        assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
-    assert torch.equal(oa.counts, ob.counts) and torch.equal(oa.dets, ob.dets) and torch.equal(oa.keep, ob.keep)
+    for m in (2, 3):                     # the two-phase and the one-pass dense kernels against the sparse kernel
+        cb, nb, ob = res[m]
+        assert np.array_equal(na, nb)
+        for (la, ra, ba), (lb, rb, bb) in zip(ca, cb):
+            assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb)
+        assert torch.equal(oa.counts, ob.counts) and torch.equal(oa.dets, ob.dets) and torch.equal(oa.keep, ob.keep)
     # filter_pred: dense == sparse == the fused path (same sigmoid bits, same order)
-    for m in (1, 2):
+    for m in (1, 2, 3):
         assert np.array_equal(resp[m][1], na)
         for (lp, rp, bp), (la, ra, ba) in zip(resp[m][0], ca):
             assert np.array_equal(lp, la) and np.array_equal(rp, ra) and np.array_equal(bp, ba)
@@ -468,10 +470,12 @@ def test_dense_filter_pretest_is_a_superset_at_the_threshold(conf, vk, cuda):
         lv.append(torch.from_numpy(x).to(cuda))
     a = vk.ops.decode_filter(cfg, lv, conf, True, kernel="sparse")
     b = vk.ops.decode_filter(cfg, lv, conf, True, kernel="dense")
+    c = vk.ops.decode_filter(cfg, lv, conf, True, kernel="dense_onepass")
     torch.cuda.synchronize()
-    assert torch.equal(a.counts, b.counts) and int(a.counts.sum()) > 1000
-    for (la, ra, ba), (lb, rb, bb) in zip(_canonical(a), _canonical(b)):
+    assert torch.equal(a.counts, b.counts) and torch.equal(a.counts, c.counts) and int(a.counts.sum()) > 1000
+    for (la, ra, ba), (lb, rb, bb), (lc, rc, bc) in zip(_canonical(a), _canonical(b), _canonical(c)):
         assert np.array_equal(la, lb) and np.array_equal(ra, rb) and np.array_equal(ba, bb, equal_nan=True)
+        assert np.array_equal(la, lc) and np.array_equal(ra, rc) and np.array_equal(ba, bc, equal_nan=True)
     # the planted logits really straddle the cut: some pass and some fail on both sides of the true threshold
     n_all = 2 * 3 * nc * sum((img // st) ** 2 for st in synth.STRIDES)
     assert 0.05 * n_all < int(a.counts.sum()) < (0.95 if conf > 0 else 1.0) * n_all

@@ -20,7 +20,7 @@ VK_MAX_SEGMENTS = 2048
 VK_LB_F32_NCHW, VK_LB_BF16_NCHW, VK_LB_U8_NHWC = 0, 1, 2
 VK_HEAD_V5, VK_HEAD_V7 = 0, 1
 VK_F32, VK_F16, VK_BF16 = 0, 1, 2
-VK_FILTER_AUTO, VK_FILTER_SPARSE, VK_FILTER_DENSE = 0, 1, 2
+VK_FILTER_AUTO, VK_FILTER_SPARSE, VK_FILTER_DENSE, VK_FILTER_DENSE_ONEPASS = 0, 1, 2, 3
 VK_CONV_TILE, VK_CONV_PERSISTENT = 0, 1
 VK_HIST_BINS = 1024
 VK_CTRL_WORDS = 4

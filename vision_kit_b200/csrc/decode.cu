@@ -1251,7 +1251,7 @@ extern "C" int vk_detect_decode(const VkHeadCfg* cfg, const void* const* levels,
 
 // ---- filter launches.  `dense` = whole tiles staged in shared memory (persistent); else one warp per tile.
 static bool pick_dense(int kernel, float conf_thres) {
-    return kernel == VK_FILTER_DENSE || (kernel == VK_FILTER_AUTO && conf_thres < 0.05f);
+    return kernel == VK_FILTER_DENSE || kernel == VK_FILTER_DENSE_ONEPASS || (kernel == VK_FILTER_AUTO && conf_thres < 0.05f);
 }
 
 template <class T, bool ML>
@@ -1293,7 +1293,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels,
     if (batch == 0) return VK_OK;
     if (!levels || batch < 0) return fail_arg("vk_decode_filter: null/negative argument");
     if (bad_dtype(dtype)) return fail_arg("vk_decode_filter: dtype %d", dtype);
-    if (kernel < VK_FILTER_AUTO || kernel > VK_FILTER_DENSE) return fail_arg("vk_decode_filter: kernel %d", kernel);
+    if (kernel < VK_FILTER_AUTO || kernel > VK_FILTER_DENSE_ONEPASS) return fail_arg("vk_decode_filter: kernel %d", kernel);
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_decode_filter: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_decode_filter: batch %d > 65535", batch);
     if ((long)H.tiles * batch > 0x7fffffffL) return fail_code(VK_E_LIMIT, "vk_decode_filter: %d x %d tiles", H.tiles, batch);
@@ -1310,7 +1310,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels,
     const bool ml = A.multi_label != 0;
     if (pick_dense(kernel, conf_thres)) {
 #define VK_DL_T(T)                                                                                  \
-        if (ml && pairs_ok(H, sizeof(T)) && !getenv("VK_NO_PAIRS")) return launch_decode_filter_pairs<T>(H, A, total_tiles, stream); \
+        if (ml && kernel != VK_FILTER_DENSE_ONEPASS && pairs_ok(H, sizeof(T))) return launch_decode_filter_pairs<T>(H, A, total_tiles, stream); \
         return ml ? launch_decode_filter_lanes<T, true>(H, A, total_tiles, stream)                   \
                   : launch_decode_filter_lanes<T, false>(H, A, total_tiles, stream)
         VK_BY_DTYPE(dtype, VK_DL_T);
@@ -1364,7 +1364,7 @@ extern "C" int vk_filter_pred(const void* pred, int dtype, int batch, int rows, 
     if (!pred || batch < 0 || rows <= 0 || nc < 1) return fail_arg("vk_filter_pred: null/negative argument");
     if (bad_dtype(dtype)) return fail_arg("vk_filter_pred: dtype %d", dtype);
     if (reinterpret_cast<uintptr_t>(pred) & (elem_size(dtype) - 1)) return fail_arg("vk_filter_pred: pred is misaligned");
-    if (kernel < VK_FILTER_AUTO || kernel > VK_FILTER_DENSE) return fail_arg("vk_filter_pred: kernel %d", kernel);
+    if (kernel < VK_FILTER_AUTO || kernel > VK_FILTER_DENSE_ONEPASS) return fail_arg("vk_filter_pred: kernel %d", kernel);
     if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail_arg("vk_filter_pred: conf_thres %g outside [0,1]", conf_thres);
     if (batch > 65535) return fail_code(VK_E_LIMIT, "vk_filter_pred: batch %d > 65535", batch);
     const int segs = ceil_div(rows, kTileS);

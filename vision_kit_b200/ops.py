@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import (VK_BF16, VK_CONV_PERSISTENT, VK_CONV_TILE, VK_CTRL_WORDS, VK_F16, VK_F32, VK_FILTER_AUTO,
-                   VK_FILTER_DENSE, VK_FILTER_SPARSE, VK_HEAD_V5, VK_HEAD_V7, VK_LB_BF16_NCHW,
+                   VK_FILTER_DENSE, VK_FILTER_DENSE_ONEPASS, VK_FILTER_SPARSE, VK_HEAD_V5, VK_HEAD_V7, VK_LB_BF16_NCHW,
                    VK_LB_F32_NCHW, VK_LB_U8_NHWC, VK_MAX_ANCHORS, VK_MAX_LEVELS, VkCandBuf, VkHeadCfg, VkLbDesc,
                    VkLbGeom)
 
@@ -23,15 +23,16 @@ MAX_WH = 7680          # utils/image_proc.py:107
 LIST_CAP = 8192        # entries of the per-image top list the NMS kernel sorts from
 _DTYPE = {torch.float32: VK_F32, torch.float16: VK_F16, torch.bfloat16: VK_BF16}
 _KERNEL = {"auto": VK_FILTER_AUTO, "sparse": VK_FILTER_SPARSE, "dense": VK_FILTER_DENSE,
+           "dense_onepass": VK_FILTER_DENSE_ONEPASS,
            None: VK_FILTER_AUTO, VK_FILTER_AUTO: VK_FILTER_AUTO, VK_FILTER_SPARSE: VK_FILTER_SPARSE,
-           VK_FILTER_DENSE: VK_FILTER_DENSE}
+           VK_FILTER_DENSE: VK_FILTER_DENSE, VK_FILTER_DENSE_ONEPASS: VK_FILTER_DENSE_ONEPASS}
 
 
 def expects_dense(kernel, conf_thres: float) -> bool:
     """The library's rule for the filter kernel (and for whether a candidate buffer wants the top list of
     vk_nms_batched's selection pass: eval thresholds leave ~240 k candidates per image)."""
     k = _KERNEL[kernel]
-    return k == VK_FILTER_DENSE or (k == VK_FILTER_AUTO and float(conf_thres) < 0.05)
+    return k in (VK_FILTER_DENSE, VK_FILTER_DENSE_ONEPASS) or (k == VK_FILTER_AUTO and float(conf_thres) < 0.05)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
