@@ -171,7 +171,7 @@ int vk_decode_filter_segments(const VkHeadCfg* cfg); /* for vk_decode_filter */
 #define VK_FILTER_AUTO 0
 #define VK_FILTER_SPARSE 1
 #define VK_FILTER_DENSE 2
-#define VK_FILTER_DENSE_ONEPASS 3   /* DENSE without the pre-test phase (sigmoid on every logit): the round-2 baseline, kept for measurements and as the kernel of odd grids */
+#define VK_FILTER_DENSE_ONEPASS 3   /* DENSE without the pre-test phase (sigmoid on every logit): kept for measurements */
 
 /* class_mask: dev uint32[(nc+31)/32] bitmap of allowed classes or NULL (classes=None). */
 int vk_filter_pred(const void* pred, int dtype, int batch, int rows, int nc, float conf_thres,

@@ -35,4 +35,11 @@ for name, levels, conf, ml, k in (("eval ML f32", lv, 0.001, True, "dense"), ("e
                                   ("eval ML f32 one-pass", lv, 0.001, True, "dense_onepass"), ("best-class dense f32", lv, 0.01, False, "dense")):
     buf = ops.decode_filter(cfg, levels, conf, ml, kernel=k)
     out.append(f"{name} {timeit(lambda: ops.decode_filter(cfg, levels, conf, ml, buf=buf, kernel=k)):7.1f} us")
+# an odd grid (608: 76 / 38 / 19): the pairs kernel loads the two rows of a lane separately
+grids6 = [(608 // s, 608 // s) for s in synth.STRIDES]
+cfg6 = ops.head_cfg("v5", 80, synth.V5_ANCHORS, synth.STRIDES, grids6)
+lv6 = [torch.from_numpy(x).to(dev) for x in synth.head_logits(B, seed=2, clusters=20, img=608)]
+for name, k in (("608 eval ML f32", "dense"), ("608 one-pass", "dense_onepass")):
+    buf = ops.decode_filter(cfg6, lv6, 0.001, True, kernel=k)
+    out.append(f"{name} {timeit(lambda: ops.decode_filter(cfg6, lv6, 0.001, True, buf=buf, kernel=k)):7.1f} us")
 print(f"{tag:24s} " + "   ".join(out) + f"   ({int(buf.counts.sum())} cand)")

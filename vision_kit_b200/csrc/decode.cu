@@ -795,8 +795,8 @@ decode_filter_lanes_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
 }
 
 // ---------------------------------------------------------------------------------------
-// Multi-label dense filter, two phases ("pairs" kernel; the default at eval thresholds when every plane has an even
-// number of rows and the level pointers are aligned for two-element loads -- the lanes kernel above otherwise).
+// Multi-label dense filter, two phases ("pairs" kernel; the default at eval thresholds; VK_FILTER_DENSE_ONEPASS
+// selects the lanes kernel above instead).
 // The one-phase loop spends two MUFUs and two POPCs per (row, class) pair although only ~1 pair in 8 becomes a
 // candidate at eval thresholds (XU pipe 61% busy, 4900 issue slots per tile).  Here the transcendentals run on
 // candidates only:
@@ -870,7 +870,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     return v;
 }
 
-template <class T>
+// VEC: every plane has an even number of rows and the level pointers are aligned for two-element loads (the host
+// checks): one load per pair.  Otherwise (odd grids such as 13x13, 19x19, 21x21) the two rows are loaded separately.
+template <class T, bool VEC>
 __global__ void __launch_bounds__(32 * kLaneWarps, VK_PAIRS_BPS)
 decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles) {
     typedef typename Pair<T>::type T2;
@@ -882,17 +884,23 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     const LogitLocator<T> L{H};
     const LogitTileRef<T> q = L.locate(t);
     const int nc = A.nc;
-    const int np = q.nynx >> 1;                           // pairs per plane (nynx is even: checked by the host)
-    const bool v = 2 * lane < q.nvalid;                   // nvalid is even as well: a pair is inside or outside
-    // Pairs past the end of a ragged tile read pair 0 instead (no per-load predicate) and carry obj = NaN.
-    const T2* const base = reinterpret_cast<const T2*>(q.base) + (v ? lane : 0);        // channel 0, the lane's pair
+    const int nynx = q.nynx;
+    const bool v0 = 2 * lane < q.nvalid, v1 = 2 * lane + 1 < q.nvalid;   // (VEC: nvalid is even, v0 == v1)
+    // Rows past the end of a ragged tile read row 0 of the tile instead (no per-load predicate) and carry obj = NaN.
+    const int j0 = v0 ? 2 * lane : 0;
+    const int d1 = v1 ? 1 : -j0;                          // the second row, relative to the first
+    const T* const base = q.base + j0;                    // channel 0, the lane's first row
+    auto ld2 = [&](const T* p) {
+        if (VEC) return Pair<T>::ld(reinterpret_cast<const T2*>(p));
+        return make_float2(ld_elem(p), ld_elem(p + d1));
+    };
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_warp[warp]);
     asm volatile("" : "+r"(sb));                          // one register, not re-derived
     // objectness (image_proc.py:99); rows at or under the threshold keep obj = 0 and never pass
-    const float2 o = Pair<T>::ld(base + (size_t)4 * np);
+    const float2 o = ld2(base + (size_t)4 * nynx);
     const float oa = sigmoidf_vk(o.x), ob = sigmoidf_vk(o.y);
-    const float obj0 = v ? (oa > A.conf ? oa : 0.0f) : __int_as_float(0x7fc00000);
-    const float obj1 = v ? (ob > A.conf ? ob : 0.0f) : __int_as_float(0x7fc00000);
+    const float obj0 = v0 ? (oa > A.conf ? oa : 0.0f) : __int_as_float(0x7fc00000);
+    const float obj1 = v1 ? (ob > A.conf ? ob : 0.0f) : __int_as_float(0x7fc00000);
     if (!__any_sync(0xffffffffu, obj0 > 0.0f || obj1 > 0.0f) && A.conf >= 0.0f) {         // no row passes :99
         if (lane == 0) {
             A.seg_count[(size_t)q.b * A.segs + q.seg] = 0;
@@ -904,8 +912,9 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     if (A.conf > 0.0f) {
         if (obj0 > 0.0f) thr0 = logit_floor(A.conf, obj0);
         if (obj1 > 0.0f) thr1 = logit_floor(A.conf, obj1);
-    } else if (v) {                                       // conf <= 0: even a product of 0 may pass, test every logit
-        thr0 = thr1 = __int_as_float(0x7fc00000);
+    } else {                                              // conf <= 0: even a product of 0 may pass, test every logit
+        if (v0) thr0 = __int_as_float(0x7fc00000);
+        if (v1) thr1 = __int_as_float(0x7fc00000);
     }
     sts32(sb + kPairObj + 8 * lane, __float_as_uint(obj0));
     sts32(sb + kPairObj + 8 * lane + 4, __float_as_uint(obj1));
@@ -932,17 +941,17 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
         }
         run += __popc(b);
     };
-    const T2* src = base + (size_t)5 * np;                // class plane being fetched
+    const T* src = base + (size_t)5 * nynx;               // class plane being fetched
     float2 x[8];
     auto fetch = [&](int c0, float2* a) {
         if (c0 + 8 <= nc) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { a[u] = Pair<T>::ld(src); src += np; }
+            for (int u = 0; u < 8; ++u) { a[u] = ld2(src); src += nynx; }
         } else {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                a[u] = c0 + u < nc ? Pair<T>::ld(src) : make_float2(0.0f, 0.0f);
-                src += np;
+                a[u] = c0 + u < nc ? ld2(src) : make_float2(0.0f, 0.0f);
+                src += nynx;
             }
         }
     };
@@ -995,8 +1004,7 @@ decode_filter_pairs_kernel(const HeadDev H, const FilterArgs A, int total_tiles)
     if (hit) {
         const PlaneGeom geom{H.variant, H.nx[q.l], q.s0, H.stride[q.l], H.anchors[q.l][2 * q.a], H.anchors[q.l][2 * q.a + 1]};
         float4* boxes = A.boxes + (size_t)q.b * A.rows + q.row0 + 2 * lane;
-        const float2 l0 = Pair<T>::ld(base), l1 = Pair<T>::ld(base + np), l2 = Pair<T>::ld(base + 2 * (size_t)np),
-                     l3 = Pair<T>::ld(base + 3 * (size_t)np);
+        const float2 l0 = ld2(base), l1 = ld2(base + nynx), l2 = ld2(base + 2 * (size_t)nynx), l3 = ld2(base + 3 * (size_t)nynx);
         if (hit & 0xffu) boxes[0] = geom.box(l0.x, l1.x, l2.x, l3.x, q.s0 + 2 * lane);
         if (hit >> 8) boxes[1] = geom.box(l0.y, l1.y, l2.y, l3.y, q.s0 + 2 * lane + 1);
     }
@@ -1269,7 +1277,9 @@ static bool pairs_ok(const HeadDev& H, size_t elem) {
 }
 template <class T>
 static int launch_decode_filter_pairs(const HeadDev& H, const FilterArgs& A, int total_tiles, cudaStream_t stream) {
-    decode_filter_pairs_kernel<T><<<ceil_div(total_tiles, kLaneWarps), 32 * kLaneWarps, 0, stream>>>(H, A, total_tiles);
+    const int grid = ceil_div(total_tiles, kLaneWarps);
+    if (pairs_ok(H, sizeof(T))) decode_filter_pairs_kernel<T, true><<<grid, 32 * kLaneWarps, 0, stream>>>(H, A, total_tiles);
+    else decode_filter_pairs_kernel<T, false><<<grid, 32 * kLaneWarps, 0, stream>>>(H, A, total_tiles);
     count_launch();
     return check_launch("decode_filter_pairs_kernel");
 }
@@ -1310,7 +1320,7 @@ extern "C" int vk_decode_filter(const VkHeadCfg* cfg, const void* const* levels,
     const bool ml = A.multi_label != 0;
     if (pick_dense(kernel, conf_thres)) {
 #define VK_DL_T(T)                                                                                  \
-        if (ml && kernel != VK_FILTER_DENSE_ONEPASS && pairs_ok(H, sizeof(T))) return launch_decode_filter_pairs<T>(H, A, total_tiles, stream); \
+        if (ml && kernel != VK_FILTER_DENSE_ONEPASS) return launch_decode_filter_pairs<T>(H, A, total_tiles, stream); \
         return ml ? launch_decode_filter_lanes<T, true>(H, A, total_tiles, stream)                   \
                   : launch_decode_filter_lanes<T, false>(H, A, total_tiles, stream)
         VK_BY_DTYPE(dtype, VK_DL_T);
