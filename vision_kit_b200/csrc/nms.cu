@@ -295,19 +295,22 @@ __device__ __forceinline__ float box_area(const float4 b) {
 // The division is only evaluated when a 1e-6-wide guard band around the threshold cannot
 // decide: fl(inter/den) > thr is implied by inter > fl(den*thr)*(1+1e-6) and excluded by
 // inter < fl(den*thr)*(1-1e-6) (each product/quotient is within 2^-24 relative of exact).
+// (Written without early returns: the callers run four of these per lane as independent chains, and a return per
+// comparison turned them into divergent branches.  Only the rare undecided case branches, to the division.)
 __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b,
                                             const float ab, const float thr) {
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
-    if (!(inter > 0.f)) return false;  // 0/x is 0, -0 or NaN: never > thr (thr >= 0)
+    const bool pos = inter > 0.f;      // otherwise 0/x is 0, -0 or NaN: never > thr (thr >= 0)
     const float den = __fsub_rn(__fadd_rn(aa, ab), inter);
     const float t = __fmul_rn(den, thr);
-    if (t > 1e-30f && den < 1e30f) {   // den > 0 and no under/overflow in the products
-        if (inter > __fmul_rn(t, 1.000001f)) return true;
-        if (inter < __fmul_rn(t, 0.999999f)) return false;
-    }
-    return __fdiv_rn(inter, den) > thr;
+    const bool ok = t > 1e-30f && den < 1e30f;   // den > 0 and no under/overflow in the products
+    const bool hi = inter > __fmul_rn(t, 1.000001f);
+    const bool lo = inter < __fmul_rn(t, 0.999999f);
+    bool r = pos && ok && hi;
+    if (pos && !(ok && (hi || lo))) r = __fdiv_rn(inter, den) > thr;
+    return r;
 }
 
 #ifdef VK_NMS_PROFILE
@@ -329,6 +332,7 @@ struct ChunkCtx {
     int nc, agnostic, max_det, rank_base;
     bool cut, want_keep;
     float thr;
+    uint32_t* done;                   // agnostic pruning: bitmap of the rows that are decided, or null
 };
 
 // One chunk of <= 256 sorted candidates [chunk0, chunk0 + cn) of the stage against the kept list.
@@ -341,7 +345,12 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
     const uint16_t* ccls = C.scls + chunk0;
     for (int i = tid; i < kHash / 2; i += T) C.XB.ccnt2[i] = 0u;
     for (int i = tid; i < kChunk; i += T) {
-        C.XB.state[i] = (i < cn) ? 0 : 2;                     // rows past the end never matter
+        int st0 = (i < cn) ? 0 : 2;                           // rows past the end never matter
+        if (C.done != nullptr && i < cn) {                    // agnostic: the row was decided by an earlier chunk of this
+            const uint32_t row = C.sidx[chunk0 + i] / (uint32_t)C.nc;      // stage, this candidate goes the same way
+            if ((C.done[row >> 5] >> (row & 31)) & 1u) st0 = 2;
+        }
+        C.XB.state[i] = (uint8_t)st0;
 #pragma unroll
         for (int wd = 0; wd < kChunkWords; ++wd) C.XB.pred[i * kChunkWords + wd] = 0u;
     }
@@ -439,21 +448,26 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
             }
         }
         __syncthreads();
-        // 2: warp tile = (32-row block rb, 32-column word wd <= rb): 36 tiles
-        for (int t = warp; t < 36; t += NW) {
-            int rb = 0, wd = t;
+        // 2: warp task = (32-row block rb, 32-column word wd <= rb, half of the word): 72 half tiles.  (Whole tiles
+        //    were 36 tasks on 32 warps: two rounds, the second one four tiles wide; halves take 2.25 rounds of half
+        //    the length.  An agnostic eval image spends most of its time here: all pairs of 256 boxes per chunk.)
+        uint16_t* const pred16 = reinterpret_cast<uint16_t*>(C.XB.pred);
+        for (int t = warp; t < 72; t += NW) {
+            const int half = t & 1;
+            int rb = 0, wd = t >> 1;
             while (wd > rb) { wd -= rb + 1; ++rb; }
             const int i = rb * 32 + lane;
+            const int j0 = wd * 32 + 16 * half;
             uint32_t m = 0;
             if (i < cn && C.XB.state[i] == 0) {
                 const float4 ib = cbox[i];
                 const float ia = box_area(ib);
-                const int jn = min(32, i - wd * 32);       // columns j < i only
+                const int jn = min(16, i - j0);             // columns j < i only
                 for (int bit = 0; bit < jn; bit += 4) {     // four independent chains per step
                     bool hit[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int j = wd * 32 + bit + u;
+                        const int j = j0 + bit + u;
                         hit[u] = false;
                         if (bit + u < jn && C.XB.state[j] == 0) {      // already removed: cannot suppress
                             const float4 jb = cbox[j];
@@ -465,7 +479,7 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
                         if (hit[u]) m |= 1u << (bit + u);
                 }
             }
-            C.XB.pred[i * kChunkWords + wd] = m;
+            pred16[(i * kChunkWords + wd) * 2 + half] = (uint16_t)m;      // (little-endian halves of the 32-bit word)
         }
     }
     __syncthreads();
@@ -528,6 +542,16 @@ __device__ __forceinline__ int nms_chunk(const ChunkCtx& C, int chunk0, int cn, 
             o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
             o[4] = __uint_as_float(unorder_key((uint32_t)(ck >> 32)));
             o[5] = (float)cls16;
+        }
+    }
+    // agnostic pruning: every row of the chunk is decided now (kept, or removed by a kept box): later candidates of
+    // these rows -- same box, IoU(self, self) = 1 > thr for a box of positive finite area -- are removed with them,
+    // by the next chunks of this stage (above) and by the selection of the next stages
+    if (C.done != nullptr && tid < cn) {
+        const float a = box_area(cbox[tid]);
+        if (a > 0.f && a < INFINITY) {
+            const uint32_t row = C.sidx[chunk0 + tid] / (uint32_t)C.nc;
+            atomicOr(&C.done[row >> 5], 1u << (row & 31));
         }
     }
     const int kept = min(C.max_det, kept0 + total);
@@ -680,7 +704,8 @@ nms_kernel(const NmsArgs A) {
     int kept0 = 0;
     bool safe = A.nc <= 65535;
     const float half_wh = 0.5f * A.max_wh;
-    ChunkCtx CC{XB, keys, sbox, sidx, scls, boxes, dets, A.nc, A.agnostic, A.max_det, 0, cut, keep_out != nullptr, A.iou_thr};
+    ChunkCtx CC{XB, keys, sbox, sidx, scls, boxes, dets, A.nc, A.agnostic, A.max_det, 0, cut, keep_out != nullptr, A.iou_thr,
+                A.prune ? done : nullptr};
     VK_STAMP(1);
     int stamp = 2;
     while (rank_base < K && kept0 < A.max_det) {
