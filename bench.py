@@ -346,44 +346,54 @@ def main():
     sptr = lambda s: C.c_void_p(s.cuda_stream)
     L = pipe._lib
 
-    def eager_step(ev=None):
-        """The captured step issued call by call, with CUDA events on the stream of each kernel:
-        [NMS of the previous batch] on the side stream beside [letterbox, filter of this batch]."""
-        s = pipe._graph_step & 1 if overlap else 0
+    def issue_step(ev, s, main):
+        """One step issued call by call on `main` (and the pipeline's side stream), in the order of the captured
+        step, with CUDA events around each kernel on the stream it runs on:
+        [NMS of the previous batch] on the side stream beside [letterbox, filter of this batch -> buffer set s]."""
         late = overlap and pipe.nms_fork == "after_preprocess"     # the NMS branch forks after the letterbox (as captured)
 
         def side_nms():
-            pipe._graph_step += 1
-            side.wait_stream(main_stream)
-            if ev: ev[3].record(side)
+            side.wait_stream(main)
+            ev[3].record(side)
             _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[s ^ 1], sptr(side)))
-            if ev: ev[4].record(side)
+            ev[4].record(side)
         if overlap and not late:
             side_nms()
-        if ev: ev[0].record(main_stream)
-        _lib.check("vk_letterbox_batch", L.vk_letterbox_batch(*pipe._lb_args, sptr(main_stream)))
-        if ev: ev[1].record(main_stream)
+        ev[0].record(main)
+        _lib.check("vk_letterbox_batch", L.vk_letterbox_batch(*pipe._lb_args, sptr(main)))
+        ev[1].record(main)
         if late:
             side_nms()
         _lib.check("vk_decode_filter", L.vk_decode_filter(pipe._cfg_ref, C.cast(pipe._lv_arr, C.c_void_p), pipe._lv_dt,
                                                             BATCH, pipe._conf, pipe._ml, pipe._mask_p, pipe._kernel,
-                                                            C.byref(pipe._cs[s]), sptr(main_stream)))
-        if ev: ev[2].record(main_stream)
+                                                            C.byref(pipe._cs[s]), sptr(main)))
+        ev[2].record(main)
         if overlap:
-            main_stream.wait_stream(side)
-            pipe._set = s
+            main.wait_stream(side)
         else:
-            if ev: ev[3].record(main_stream)
-            _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[0], sptr(main_stream)))
-            if ev: ev[4].record(main_stream)
+            ev[3].record(main)
+            _lib.check("vk_nms_batched", L.vk_nms_batched(*pipe._nms_args[0], sptr(main)))
+            ev[4].record(main)
+
+    def timed_graph(ev, s):
+        """The same step captured into its own CUDA graph with the five timing events as event-record nodes
+        (external events): a sampled step stays one graph launch, and the events see the kernels as they overlap."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            issue_step(ev, s, torch.cuda.current_stream())
+        return g
+
+    def replay_timed(g, s):
+        g.replay()
+        if overlap:                                        # the bookkeeping of DetectPipeline.replay()
+            pipe._graph_step += 1
+            pipe._set = s
+            pipe.cand, pipe.out = pipe._cands[s], pipe._outs[s ^ 1]
 
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     for _ in range(args.warmup):
         pipe.replay()
-    eager_step()
-    eager_step()
     torch.cuda.synchronize()
-    sampler.start()
 
     def barrier():
         if world > 1:
@@ -391,21 +401,32 @@ def main():
         torch.cuda.synchronize()
 
     # ---- timed region: K steps, device-resident inputs (626 MB per step > 126 MB L2).  Steps are CUDA-graph
-    # launches; every EVth step is the same step issued call by call with events around each kernel (on the
-    # stream it runs on), which is where the per-kernel durations of the roofline come from.
+    # launches; every EVth step (at most 16 of them) is a graph of the same step with event-record nodes around each
+    # kernel (on the stream it runs on), which is where the per-kernel durations of the roofline come from.
     K = args.steps
-    EV = 8
+    EV = max(8, -(-K // 16))
     sampled = [k for k in range(K) if k % EV == EV - 1] or [K - 1]      # short runs: the last step is the event step
-    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(5)] for k in sampled}
+    ev = {k: [torch.cuda.Event(enable_timing=True, external=True) for _ in range(5)] for k in sampled}
+    s0 = pipe._graph_step & 1 if overlap else 0
+    par = {k: ((s0 + k) & 1 if overlap else 0) for k in sampled}
+    evg = {k: timed_graph(ev[k], par[k]) for k in sampled}
+
+    def run_steps():
+        for k in range(K):
+            if k in evg:
+                replay_timed(evg[k], par[k])
+            else:
+                pipe.replay()
+    run_steps()                                            # one untimed pass of the very same sequence (first launches
+    if overlap and (K & 1):                                # of the event graphs), ending on the parity it started from
+        pipe.replay()
+    torch.cuda.synchronize()
+    sampler.start()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_issue0 = time.perf_counter()
     t_begin.record()
-    for k in range(K):
-        if k in ev:
-            eager_step(ev[k])
-        else:
-            pipe.replay()
+    run_steps()
     t_end.record()
     host_issue_us = (time.perf_counter() - t_issue0) / K * 1e6     # host time to enqueue one step (no waiting)
     barrier()
@@ -548,7 +569,7 @@ def main():
                    "l2": "inputs larger than L2: 627 MB read per step per GPU vs 126 MB L2, no flush needed",
                    "detections_per_step": n_dets, "candidates_per_step": n_cand,
                    "host_issue_us_per_step": round(host_issue_us, 1),
-                   "event_steps": f"every {EV}th step is issued call by call with CUDA events around each kernel"},
+                   "event_steps": f"every {EV}th step is a graph of the same step with CUDA event-record nodes around each kernel"},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "note": "PCIe-bound: the head's conv outputs (548 MB/step) are copied from host "
