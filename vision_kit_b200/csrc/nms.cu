@@ -209,45 +209,47 @@ nms_select_kernel(const NmsArgs A) {
         __syncwarp();
         staged = 0;
     };
-    // (the loads of a warp's next item are issued before the current one is examined)
-    struct Item { uint32_t slot0; int j0, cnt; };
+    // (the loads of a warp's next item are issued before the current one is examined; the two register buffers swap
+    // roles instead of being copied.)  Scores of candidates are positive floats (p > conf >= 0), whose bit patterns
+    // order like their ordered keys, so the test is one unsigned compare on the raw bits: key >= bound  <=>
+    // bits >= braw.  A lane's candidates of an item sit 32 slots apart from its first one: one base pointer and
+    // immediate offsets, and `32 u < rem` says which of them exist.
+    const uint32_t braw = bound > 0x80000000u ? bound - 0x80000000u : 0u;
+    struct Item { const uint2* p; int rem; };
     auto locate = [&](int item) {
         const int seg = seg_of(item);
-        return Item{(uint32_t)seg * (uint32_t)tile_cap, (item - s_pre[seg]) * kSelectPiece, s_cnt[seg]};
+        const int j0 = (item - s_pre[seg]) * kSelectPiece + lane;
+        return Item{cand + ((uint32_t)seg * (uint32_t)tile_cap + (uint32_t)j0), s_cnt[seg] - j0};
     };
     auto fetch = [&](const Item& it, uint2* sc) {
 #pragma unroll
+        for (int u = 0; u < 8; ++u) sc[u] = (32 * u < it.rem) ? it.p[32 * u] : make_uint2(0u, 0u);
+    };
+    auto examine = [&](const Item& cur, const uint2* sc) {
+#pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int jj = it.j0 + 32 * u + lane;
-            sc[u] = (jj < it.cnt) ? cand[it.slot0 + jj] : make_uint2(0u, 0u);
+            const bool take = 32 * u < cur.rem && sc[u].x >= braw;
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (m) {
+                if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)order_key(sc[u].x) << 32) | (uint32_t)~sc[u].y;
+                staged += __popc(m);
+                if (staged > kSelStage - 32) flush();
+            }
         }
     };
     if (first < items) {
-        Item cur = locate(first);
-        uint2 sc[8];
-        fetch(cur, sc);
-        for (int item = first; item < items; item += step) {
-            const bool more = item + step < items;
-            Item nxt = cur;
-            uint2 sn[8];
-            if (more) { nxt = locate(item + step); fetch(nxt, sn); }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jj = cur.j0 + 32 * u + lane;
-                const uint32_t key = order_key(sc[u].x);
-                const bool take = jj < cur.cnt && key >= bound;
-                const unsigned m = __ballot_sync(0xffffffffu, take);
-                if (m) {
-                    if (take) stage[staged + __popc(m & lt)] = ((unsigned long long)key << 32) | (uint32_t)~sc[u].y;
-                    staged += __popc(m);
-                    if (staged > kSelStage - 32) flush();
-                }
-            }
-            if (more) {
-                cur = nxt;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) sc[u] = sn[u];
-            }
+        Item ia = locate(first), ib = ia;
+        uint2 sa[8], sb[8];
+        fetch(ia, sa);
+        for (int item = first;; item += 2 * step) {
+            const bool more1 = item + step < items;
+            if (more1) { ib = locate(item + step); fetch(ib, sb); }
+            examine(ia, sa);
+            if (!more1) break;
+            const bool more2 = item + 2 * step < items;
+            if (more2) { ia = locate(item + 2 * step); fetch(ia, sa); }
+            examine(ib, sb);
+            if (!more2) break;
         }
     }
     if (staged) flush();
