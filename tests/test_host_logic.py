@@ -201,4 +201,6 @@ def test_filter_and_nms_argument_validation(vk_lib):
     assert vk_lib.vk_eval_match_smem_bytes(10, 100) == 100 * 6 * 4 + 10 * 100 * 4
     assert vk_lib.vk_eval_match_smem_bytes(0, 100) == 0
     assert ops.expects_dense("auto", 0.001) and not ops.expects_dense("auto", 0.25) and ops.expects_dense("dense", 0.25)
+    assert ops.expects_dense("dense_onepass", 0.25) and ops._KERNEL["dense_onepass"] == _lib.VK_FILTER_DENSE_ONEPASS == 3
+    assert vk_lib.vk_decode_filter(*args(0, 0.25, 4)) == -1 and b"kernel 4" in vk_lib.vk_last_error()
     assert _lib.C.sizeof(_lib.VkCandBuf) == 5 * 8 + 6 * 4
