@@ -204,3 +204,25 @@ def test_filter_and_nms_argument_validation(vk_lib):
     assert ops.expects_dense("dense_onepass", 0.25) and ops._KERNEL["dense_onepass"] == _lib.VK_FILTER_DENSE_ONEPASS == 3
     assert vk_lib.vk_decode_filter(*args(0, 0.25, 4)) == -1 and b"kernel 4" in vk_lib.vk_last_error()
     assert _lib.C.sizeof(_lib.VkCandBuf) == 5 * 8 + 6 * 4
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's CPU arm) runs without a GPU and prints ONE JSON line with the keys of
+    the bench contract: same metric / unit / config as our arm, `impl`, a `cpu_baseline` describing the run and an
+    `e2e` object that repeats the value with zero copies."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    baseline = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert d["impl"] == "reference" and d["metric"] == baseline["metric"] and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["config"]["workload"].startswith("configs[1]") and d["config"]["batch_per_gpu"] == 64
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
