@@ -540,9 +540,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["algorithmic_gbs"] / peak, "traffic": traffic_all.get(dom),
                 "peak_kind": f"of {peak_kind}",
-                "note": ("duration measured inside the step: the NMS of the previous batch runs beside it on the side "
-                         "stream and shares the SMs; kernels[*].ms_serial / share_serial are the same kernels issued one "
-                         "after the other (the arrangement of the ncu launch list in profiles/)"
+                "note": ("duration between the two event-record nodes around the kernel inside the captured step (the "
+                         "nodes add a few microseconds; the NMS branch of the previous batch forks "
+                         + ("after the letterbox" if pipe.nms_fork == "after_preprocess" else "before the letterbox and shares the SMs with it")
+                         + "); kernels[*].ms_serial / share_serial are the same kernels issued one after the other (the "
+                         "arrangement of the ncu launch list in profiles/); profiles/r2_kernels.txt has them graph-timed alone"
                          if overlap else "")}
 
     if rank != 0:
