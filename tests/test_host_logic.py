@@ -226,3 +226,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_pairs_kernel_pretest_error_budget():
+    """The dense multi-label filter drops a logit x without evaluating its sigmoid when x <= logit_floor(conf, obj)
+    (csrc/decode.cu).  That is only allowed if such a logit can never pass `fl(sigmoid_approx(x) * obj) > conf`,
+    where the approximate sigmoid is within 4e-7 (relative) of the true one and the product rounds once.  The floor is
+    restated here in float32 arithmetic step by step (lg2.approx modelled with a 2^-22 absolute error in either
+    direction) and the claim is checked in float64 for logits AT the floor -- the worst case, sigma is increasing --
+    with every error at its unfavourable end, over thresholds and objectness values from barely above conf to 1."""
+    f32 = np.float32
+    rng = np.random.default_rng(7)
+    worst = -np.inf
+    for conf in (1e-6, 1e-3, 0.01, 0.05, 0.25, 0.5, 0.9, 0.999):
+        obj = np.concatenate([conf * (1 + 10.0 ** rng.uniform(-7, 0, 4000)), rng.uniform(conf, 1, 4000), [1.0]])
+        obj = np.unique(np.minimum(obj, 1.0).astype(f32))
+        obj = obj[obj > f32(conf)]
+        s = np.minimum((f32(conf) / obj).astype(f32) * f32(0.999996), f32(0.999)).astype(f32)
+        u = ((f32(1.0) / s).astype(f32) - f32(1.0)).astype(f32)
+        for lg_err in (-2.0 ** -22, 2.0 ** -22):
+            l = (np.log2(u.astype(np.float64)) + lg_err).astype(f32)
+            floor = ((l * f32(-0.6931471805599453)).astype(f32) - f32(1e-3)).astype(f32)
+            x = floor.astype(np.float64)
+            sig = 1.0 / (1.0 + np.exp(-x))
+            p_max = sig * (1 + 4e-7) * obj.astype(np.float64) * (1 + 2.0 ** -24)     # the largest the kernel could compute
+            worst = max(worst, float(np.max(p_max / np.float64(f32(conf)))))
+            assert np.all(p_max <= np.float64(f32(conf))), (conf, float(np.max(p_max / conf)))
+    assert worst < 1.0 and worst > 0.99           # a margin, but not a loose one: the floor sits right under the cut
