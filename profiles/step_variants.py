@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Captured-step variants of config 3 on one GPU (tuning knobs read from the environment at capture time):
-python profiles/step_variants.py"""
+"""Captured step of config 3 on one GPU with both fork points of the NMS branch, VK_BATCH images per step (variant
+libraries via VK_B200_LIB): python profiles/step_variants.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,5 +20,5 @@ for fork in ("start", "after_preprocess"):
     e0.record()
     for _ in range(200): pipe.replay()
     e1.record(); torch.cuda.synchronize()
-    print(f"config 3 B={B} SEL_PER_SM={os.environ.get('VK_SEL_PER_SM','-')} NMS_LIST_T={os.environ.get('VK_NMS_LIST_T','-')} nms_fork={fork:16s}: {e0.elapsed_time(e1)/200*1e3:.1f} us/step", flush=True)
+    print(f"config 3 B={B} nms_fork={fork:16s}: {e0.elapsed_time(e1)/200*1e3:.1f} us/step", flush=True)
     del pipe
